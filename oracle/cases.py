@@ -1,0 +1,131 @@
+"""Golden-case catalogue shared by oracle/gen_golden.py (which runs the unmodified reference)
+and tests/ (which re-derive the same seeded inputs and compare).  TEST INFRASTRUCTURE ONLY.
+
+A case is a dict; inputs and weights are never stored, only re-generated from seeds through
+oracle/synth.py, so the fixtures under tests/golden/ hold reference OUTPUTS only.
+
+Case kinds (reference symbol each one pins):
+  layer       AdaAttnMultiHead.forward                      adaDecoder.py:162-206
+  adaattn     AdaAttN.forward                               adaDecoder.py:102-131
+  forloss     AdaAttnForLoss.forward                        adaDecoder.py:53-81
+  transformer AdaAttnTransformerMultiHead.forward (+decoder) adaDecoder.py:253-268, conv.py:96-100
+  decoder     Decoder.forward                               conv.py:96-100
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import synth
+
+LAYER_CASES = [
+    # name, B, C, heads, (h,w) content, (hs,ws) style, qk_gain, fcs_is_fc
+    dict(name="layer_c512_h8_16x16", kind="layer", B=2, C=512, H=8, hw=(16, 16), hsws=(16, 16), gain=1.0, seed=11),
+    dict(name="layer_c512_h8_ragged", kind="layer", B=1, C=512, H=8, hw=(9, 15), hsws=(11, 13), gain=1.0, seed=12),
+    dict(name="layer_c512_h8_cross", kind="layer", B=1, C=512, H=8, hw=(16, 24), hsws=(8, 8), gain=1.0, seed=13),
+    dict(name="layer_c512_h8_stress", kind="layer", B=1, C=512, H=8, hw=(16, 16), hsws=(12, 20), gain=4.0, seed=14),
+    dict(name="layer_c512_h4_12x12", kind="layer", B=1, C=512, H=4, hw=(12, 12), hsws=(12, 12), gain=1.0, seed=15),
+    dict(name="layer_c512_h1_8x8", kind="layer", B=1, C=512, H=1, hw=(8, 8), hsws=(8, 8), gain=1.0, seed=16),
+    dict(name="layer_c128_h2_20x20", kind="layer", B=2, C=128, H=2, hw=(20, 20), hsws=(20, 12), gain=1.0, seed=17),
+    dict(name="layer_c64_h1_2keys", kind="layer", B=1, C=64, H=1, hw=(6, 6), hsws=(1, 2), gain=1.0, seed=18),
+    dict(name="layer_c512_h8_selffcs", kind="layer", B=1, C=512, H=8, hw=(12, 12), hsws=(12, 12), gain=1.0, seed=19,
+         fcs_is_fc=True),
+]
+
+ADAATTN_CASES = [
+    dict(name="adaattn_c64_10x10", kind="adaattn", B=2, C=64, hw=(10, 10), hsws=(7, 9), seed=31),
+]
+
+FORLOSS_CASES = [
+    # AdaAttnForLoss shapes from train_image.py:52-58 at reduced spatial size: (v_dim, qk_dim)
+    dict(name="forloss_relu3_1", kind="forloss", B=1, v=256, qk=448, hw=(12, 12), hsws=(12, 12), seed=41),
+    dict(name="forloss_relu4_1", kind="forloss", B=2, v=512, qk=960, hw=(6, 6), hsws=(6, 6), seed=42),
+    dict(name="forloss_relu5_1", kind="forloss", B=1, v=512, qk=1472, hw=(3, 3), hsws=(3, 3), seed=43),
+]
+
+TRANSFORMER_CASES = [
+    dict(name="transformer_8x8", kind="transformer", B=1, hw=(8, 8), hsws=(8, 8), seed=51, sub=1, img_sub=1),
+    dict(name="transformer_b2_12x10", kind="transformer", B=2, hw=(12, 10), hsws=(6, 9), seed=52, sub=1, img_sub=2),
+    # cfg1-sized (512x512 image -> 64x64 tokens): outputs stored on a token / pixel sub-lattice
+    dict(name="transformer_64x64_sub", kind="transformer", B=1, hw=(64, 64), hsws=(64, 64), seed=53, sub=37,
+         img_sub=8),
+]
+
+DECODER_CASES = [
+    dict(name="decoder_5x7", kind="decoder", B=1, hw=(5, 7), seed=61),
+]
+
+ALL_CASES = LAYER_CASES + ADAATTN_CASES + FORLOSS_CASES + TRANSFORMER_CASES + DECODER_CASES
+
+
+def by_name(name: str) -> dict:
+    for c in ALL_CASES:
+        if c["name"] == name:
+            return c
+    raise KeyError(name)
+
+
+# --------------------------------------------------------------------------------------
+# seeded inputs (float64 numpy); the same arrays feed the reference, the oracle and the GPU path
+# --------------------------------------------------------------------------------------
+
+def layer_inputs(case: dict):
+    B, C = case["B"], case["C"]
+    h, w = case["hw"]
+    hs, ws = case["hsws"]
+    s = case["seed"]
+    fc = synth.features(s * 10 + 1, B, C, h, w)
+    fs = synth.features(s * 10 + 2, B, C, hs, ws)
+    fcs = fc if case.get("fcs_is_fc") else synth.features(s * 10 + 3, B, C, h, w, std=30.0, mean=-1.6)
+    sd = synth.mhada_layer_state(s, C, case["H"], qk_gain=case.get("gain", 1.0))
+    return fc, fs, fcs, sd
+
+
+def adaattn_inputs(case: dict):
+    B, C = case["B"], case["C"]
+    h, w = case["hw"]
+    hs, ws = case["hsws"]
+    s = case["seed"]
+    fc = synth.features(s * 10 + 1, B, C, h, w)
+    fs = synth.features(s * 10 + 2, B, C, hs, ws)
+    fcs = synth.features(s * 10 + 3, B, C, h, w, std=30.0)
+    return fc, fs, fcs, synth.adaattn_state(s, C)
+
+
+def forloss_inputs(case: dict):
+    B = case["B"]
+    h, w = case["hw"]
+    hs, ws = case["hsws"]
+    s = case["seed"]
+    # VGG relu features are non-negative; shift so most values are > 0 (lossfn.py:26-34 feeds relu maps)
+    c_x = np.abs(synth.features(s * 10 + 1, B, case["v"], h, w, std=2.0, mean=1.0))
+    s_x = np.abs(synth.features(s * 10 + 2, B, case["v"], hs, ws, std=2.0, mean=1.0))
+    c_1x = np.abs(synth.features(s * 10 + 3, B, case["qk"], h, w, std=2.0, mean=1.0))
+    s_1x = np.abs(synth.features(s * 10 + 4, B, case["qk"], hs, ws, std=2.0, mean=1.0))
+    return c_x, s_x, c_1x, s_1x
+
+
+def transformer_inputs(case: dict, num_layers: int = 3):
+    B = case["B"]
+    h, w = case["hw"]
+    hs, ws = case["hsws"]
+    s = case["seed"]
+    fc = [synth.features(s * 100 + i, B, 512, h, w) for i in range(num_layers)]
+    fs = [synth.features(s * 100 + 10 + i, B, 512, hs, ws) for i in range(num_layers)]
+    sd = synth.transformer_state(s)
+    return fc, fs, sd
+
+
+def decoder_inputs(case: dict):
+    h, w = case["hw"]
+    x = synth.features(case["seed"], case["B"], 512, h, w, std=29.0, mean=-1.6)
+    return x, synth.decoder_state(case["seed"])
+
+
+def token_sublattice(x: np.ndarray, sub: int) -> np.ndarray:
+    """(B,C,h,w) -> (B,C,ceil(h*w/sub)): every `sub`-th token in row-major order."""
+    b, c = x.shape[:2]
+    return x.reshape(b, c, -1)[:, :, ::sub]
+
+
+def pixel_sublattice(x: np.ndarray, sub: int) -> np.ndarray:
+    return x[:, :, ::sub, ::sub]

@@ -1,0 +1,119 @@
+"""The numpy oracle against the golden vectors produced by the unmodified reference
+(oracle/gen_golden.py).  CPU only.  This is what pins the oracle."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from oracle import cases, synth
+from oracle import mhada_oracle as O
+
+# golden arrays are the reference's float64 outputs rounded to float32 -> 2^-24 relative storage error
+STORE_RTOL = 2e-7
+
+
+def _check(got64, gold32, meta, key="out"):
+    e = O.errors(got64, gold32)
+    assert e["max_abs"] <= STORE_RTOL * max(meta[key]["absmax"], 1.0) + 1e-9, e
+    return e
+
+
+def _check_sums(got64, meta, key="out"):
+    # float64 sums recorded from the reference's float64 run: pins the oracle to ~1e-10
+    assert list(got64.shape) == meta[key]["shape"]
+    assert got64.sum() == pytest.approx(meta[key]["sum"], rel=1e-9, abs=1e-7 * meta[key]["absmax"])
+    assert (got64 * got64).sum() == pytest.approx(meta[key]["sumsq"], rel=1e-9)
+
+
+@pytest.mark.parametrize("case", cases.LAYER_CASES, ids=lambda c: c["name"])
+def test_layer_matches_reference(case, golden_index):
+    fc, fs, fcs, sd = cases.layer_inputs(case)
+    got = O.ada_attn_multi_head(fc, fs, fcs, sd, case["H"])
+    meta = golden_index[case["name"]]
+    _check(got, load_golden(case["name"])["out"], meta)
+    _check_sums(got, meta)
+
+
+@pytest.mark.parametrize("case", cases.ADAATTN_CASES, ids=lambda c: c["name"])
+def test_adaattn_matches_reference(case, golden_index):
+    fc, fs, fcs, sd = cases.adaattn_inputs(case)
+    got = O.ada_attn(fc, fs, fcs, sd)
+    meta = golden_index[case["name"]]
+    _check(got, load_golden(case["name"])["out"], meta)
+    _check_sums(got, meta)
+
+
+@pytest.mark.parametrize("case", cases.FORLOSS_CASES, ids=lambda c: c["name"])
+def test_forloss_matches_reference(case, golden_index):
+    got = O.ada_attn_for_loss(*cases.forloss_inputs(case))
+    meta = golden_index[case["name"]]
+    _check(got, load_golden(case["name"])["out"], meta)
+    _check_sums(got, meta)
+
+
+@pytest.mark.parametrize("case", cases.DECODER_CASES, ids=lambda c: c["name"])
+def test_decoder_matches_reference(case, golden_index):
+    x, sd = cases.decoder_inputs(case)
+    got = O.decoder(x, sd)
+    meta = golden_index[case["name"]]
+    _check(got, load_golden(case["name"])["out"], meta)
+    _check_sums(got, meta)
+
+
+@pytest.mark.parametrize("case", [c for c in cases.TRANSFORMER_CASES if c["hw"][0] <= 16], ids=lambda c: c["name"])
+def test_transformer_matches_reference(case, golden_index):
+    fc, fs, sd = cases.transformer_inputs(case)
+    fcs, cs = O.transformer_multi_head(fc, fs, sd)
+    meta = golden_index[case["name"]]
+    g = load_golden(case["name"])
+    _check(cases.token_sublattice(fcs, case["sub"]), g["fcs"], meta, "fcs")
+    _check(cases.pixel_sublattice(cs, case["img_sub"]), g["cs"], meta, "cs")
+    _check_sums(fcs, meta, "fcs")
+    _check_sums(cs, meta, "cs")
+
+
+def test_fp32_oracle_is_inside_reference_noise(golden_index):
+    """The oracle evaluated in float32 must sit within a few x of the reference's own
+    float32-vs-float64 deviation: it is the 'port' timed as cpu_baseline."""
+    case = cases.by_name("layer_c512_h8_16x16")
+    fc, fs, fcs, sd = cases.layer_inputs(case)
+    got = O.ada_attn_multi_head(fc, fs, fcs, sd, case["H"], dtype=np.float32)
+    e = O.errors(got, load_golden(case["name"])["out"])
+    floor = golden_index[case["name"]]["ref32_vs_ref64"]["max_abs"]
+    assert e["max_abs"] < max(5 * floor, 2e-3), (e, floor)
+
+
+def test_errors_and_validation():
+    with pytest.raises(ValueError):
+        O.ada_attn_multi_head(np.zeros((1, 6, 2, 2)), np.zeros((1, 6, 2, 2)), np.zeros((1, 6, 2, 2)), {}, 4)
+    with pytest.raises(ValueError):
+        O._activation("relu")
+    with pytest.raises(RuntimeError):
+        case = cases.by_name("layer_c64_h1_2keys")
+        fc, fs, fcs, sd = cases.layer_inputs(case)
+        O.ada_attn_multi_head(fc, np.concatenate([fs, fs]), fcs, sd, 1)
+
+
+def test_synth_is_bit_stable():
+    # literal bits: guards the "same seeds -> same inputs on any host" contract of the fixtures
+    u = synth.uniform01(7, (4,))
+    assert u.tolist() == synth.uniform01(7, (4,)).tolist()
+    assert [float.hex(v) for v in u] == EXPECTED_U7
+    f = synth.features(3, 1, 2, 2, 2)
+    assert f.shape == (1, 2, 2, 2) and np.isfinite(f).all()
+
+
+EXPECTED_U7 = ['0x1.38028f22c378bp-1', '0x1.02def267c57d3p-1', '0x1.7211ab3566398p-4', '0x1.698cfc3157b8ap-2']
+
+
+def test_transformer_cfg1_size_matches_reference(golden_index):
+    """BASELINE.json configs[0] size (512x512 image -> 64x64 tokens, 6 layers + decoder); the
+    golden holds the reference's output on a token / pixel sub-lattice."""
+    case = cases.by_name("transformer_64x64_sub")
+    fc, fs, sd = cases.transformer_inputs(case)
+    fcs, cs = O.transformer_multi_head(fc, fs, sd)
+    meta = golden_index[case["name"]]
+    g = load_golden(case["name"])
+    _check(cases.token_sublattice(fcs, case["sub"]), g["fcs"], meta, "fcs")
+    _check(cases.pixel_sublattice(cs, case["img_sub"]), g["cs"], meta, "cs")
+    _check_sums(fcs, meta, "fcs")
+    _check_sums(cs, meta, "cs")
