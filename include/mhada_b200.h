@@ -1,0 +1,152 @@
+/*
+ * mhada_b200.h -- C ABI of libmhada_b200.so: the B200 (sm_100a) MHAda forward hot path.
+ *
+ * The reference (Maboroshi0327/MHAda-Style-Transfer) is pure Python/PyTorch and has no FFI; the
+ * interface each entry point replaces is therefore a span of the reference's nn.Module code,
+ * cited per function as MHAdaSTr/network/<file>:<lines>.  INTEGRATION.md shows the ctypes binding
+ * a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - Every function returns 0 on success, a negative MHADA_ERR_* for a rejected argument and a
+ *     positive cudaError_t for a CUDA failure; mhada_last_error() gives the message (thread local).
+ *     Nothing throws across the boundary.
+ *   - All buffers are DEVICE pointers owned by the caller (inputs const, outputs and workspace
+ *     pre-allocated).  No allocation, no synchronisation, no default-stream use inside: every
+ *     launch goes on the caller's `stream` (a cudaStream_t passed as void*), so a sequence of calls
+ *     is CUDA-graph capturable.
+ *   - Feature maps are TOKEN-MAJOR: element (b, n, c) of a (B, C, h, w) map lives at
+ *     ((b * N) + n) * ld + c, n = y * w + x  (what torch calls channels_last; the reference ViT
+ *     already emits this memory order, MHAdaSTr/network/vit.py:163-166).  `ld` >= C is the row
+ *     pitch in elements.
+ *   - dtype: MHADA_F32 = the reference's arithmetic (true fp32 FFMA, never TF32);
+ *            MHADA_BF16 = bf16 storage, tcgen05 tensor-core math with fp32 accumulation.
+ *   - There is no CPU fallback: on a device that is not compute capability 10.x every compute
+ *     entry point returns MHADA_ERR_DEVICE.
+ */
+#ifndef MHADA_B200_H_
+#define MHADA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MHADA_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define MHADA_API __attribute__((visibility("default")))
+#else
+#define MHADA_API
+#endif
+
+typedef void* mhada_stream_t; /* cudaStream_t */
+
+enum mhada_dtype { MHADA_F32 = 0, MHADA_BF16 = 1 };
+
+enum mhada_status {
+    MHADA_OK = 0,
+    MHADA_ERR_ARG = -1,         /* null pointer, non-positive size, misaligned pointer / pitch   */
+    MHADA_ERR_UNSUPPORTED = -2, /* shape outside what the kernels implement (message says which) */
+    MHADA_ERR_DEVICE = -3,      /* current device is not sm_100                                  */
+    MHADA_ERR_WORKSPACE = -4,   /* workspace too small                                           */
+    MHADA_ERR_DRIVER = -5       /* cuTensorMapEncodeTiled unavailable / failed                   */
+};
+
+MHADA_API int mhada_abi_version(void);
+MHADA_API const char* mhada_last_error(void);
+/* 0 when the current CUDA device can run the kernels (compute capability 10.x). */
+MHADA_API int mhada_device_check(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * (1) Instance-norm statistics -- replaces the statistics half of nn.InstanceNorm2d(affine=False)
+ *     at MHAdaSTr/network/adaDecoder.py:147-149 (used :173, :178, :198): per (b, channel)
+ *     mean over the N tokens and rstd = 1/sqrt(biased_var + 1e-5).
+ *     x: [B, N, ld] (dtype), mean / rstd: float [B, C].
+ *     ws: float scratch of mhada_in_stats_workspace(B, N, C) bytes.
+ * ---------------------------------------------------------------------------------------------- */
+MHADA_API size_t mhada_in_stats_workspace(int B, int N, int C);
+MHADA_API int mhada_in_stats(const void* x, int dtype, int B, int N, int C, int ld, float* mean, float* rstd, void* ws,
+                   size_t ws_bytes, mhada_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (2) Per-head 1x1 projections -- replaces f_list / g_list / h_list applied to IN(fc), IN(fs), fs
+ *     at adaDecoder.py:173, :178, :182 (a grouped 1x1 convolution, groups = H, d = C / H):
+ *         Q  = Wf . IN(fc) + bf        K = Wg . IN(fs) + bg        V = Wh . fs + bh
+ *     Weights are passed packed: w float [3][H][d][d] (f, g, h; [out][in]), bias float [3][H][d].
+ *     Outputs (token-major, pitch C):
+ *         q  [B, Nc, C]   (bf16 path: pre-multiplied by log2(e) so the kernel can use exp2)
+ *         k  [B, Ns, C]
+ *         v  f32 path : [B, Ns, C]     centred values  V - mu_v
+ *            bf16 path: [B, Ns, 2C]    per head h the 2d columns [V - mu_v | (V - mu_v)^2]
+ *         mu_v float [B, C] = Wh . mean(fs) + bh   (added back by the attention epilogue; centring
+ *            is exact for M and for A.V^2 - M^2 and removes the bf16 cancellation)
+ *     ws (bf16 path): mhada_proj_workspace(B, H, d) bytes for the folded per-image weights.
+ * ---------------------------------------------------------------------------------------------- */
+MHADA_API size_t mhada_proj_workspace(int B, int H, int d);
+MHADA_API int mhada_proj(int dtype, const void* fc, const void* fs, const float* mean_c, const float* rstd_c,
+               const float* mean_s, const float* rstd_s, const float* w, const float* bias, int B, int Nc, int Ns,
+               int H, int d, void* q, void* k, void* v, float* mu_v, void* ws, size_t ws_bytes,
+               mhada_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (3) Streaming attention + fused AdaIN-style epilogue -- replaces adaDecoder.py:186-198
+ *     (and :70-81 of AdaAttnForLoss, :120-131 of AdaAttN):
+ *         A = softmax_rows(Q K^T)  (no 1/sqrt(d));  M = A V;  S = sqrt(max(A V^2 - M^2, 1e-6));
+ *         out[:, head] = S * IN(x)[:, head] + M (+ mu_v)
+ *     The Nc x Ns map A is never written anywhere.
+ *     f32 path : any dqk, dv; q/k may be given un-normalised with (q_mean, q_rstd) / (k_mean, k_rstd)
+ *                applied on load (AdaAttnForLoss); logits in natural units.
+ *     bf16 path: dqk = dv = 64 (the 8-head configuration every reference script uses), q in
+ *                log2 units, v = [V~ | V~^2] as written by mhada_proj; pitches fixed by C = H*64.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct mhada_attn_args {
+    int dtype;
+    int B, H, Nc, Ns, dqk, dv;
+    const void* q; /* [B, Nc, ldq], head h at column h*dqk */
+    const void* k; /* [B, Ns, ldk], head h at column h*dqk */
+    const void* v; /* f32: [B, Ns, ldv] head h at column h*dv;  bf16: [B, Ns, ldv] head h at column h*2*dv */
+    const void* x; /* [B, Nc, ldx] tensor whose instance norm is modulated (fcs), head h at column h*dv */
+    void* out;     /* [B, Nc, ldo] head h at column h*dv */
+    int ldq, ldk, ldv, ldx, ldo;
+    const float* x_mean; /* [B, H*dv] */
+    const float* x_rstd;
+    const float* mu_v;   /* [B, H*dv] or NULL */
+    const float* q_mean; /* f32 path only, [B, H*dqk] or NULL */
+    const float* q_rstd;
+    const float* k_mean;
+    const float* k_rstd;
+} mhada_attn_args;
+MHADA_API int mhada_attn(const mhada_attn_args* args, mhada_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (4) out_conv -- replaces torch.cat + nn.Conv2d(C, C, 1) at adaDecoder.py:202-205:
+ *         y[m, o] = sum_i x[m, i] * w[o, i] + bias[o],   x [M, ldx], y [M, ldy], w float [Cout][Cin].
+ *     bf16 path needs Cin % 64 == 0 and Cout % 64 == 0; ws = mhada_linear_workspace(Cout, Cin) bytes
+ *     (bf16 copy of w).
+ * ---------------------------------------------------------------------------------------------- */
+MHADA_API size_t mhada_linear_workspace(int dtype, int Cout, int Cin);
+MHADA_API int mhada_linear(int dtype, const void* x, int ldx, const float* w, const float* bias, int M, int Cin, int Cout,
+                 void* y, int ldy, void* ws, size_t ws_bytes, mhada_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (5) One whole layer -- replaces AdaAttnMultiHead.forward(fc, fs, fcs), adaDecoder.py:162-206.
+ *     fc, fcs [B, Nc, C]; fs [B, Ns, C]; out [B, Nc, C]; all token-major with pitch C, in `dtype`.
+ *     fcs may alias fc (layer 0 of the transformer, adaDecoder.py:262).  out must not alias inputs.
+ *     w_fgh / b_fgh as in (2); w_out float [C][C], b_out float [C]; both may be NULL together to
+ *     skip out_conv (the single-head AdaAttN, adaDecoder.py:102-131).
+ *     ws: mhada_layer_workspace(dtype, B, Nc, Ns, C, H) bytes.
+ * ---------------------------------------------------------------------------------------------- */
+MHADA_API size_t mhada_layer_workspace(int dtype, int B, int Nc, int Ns, int C, int H);
+MHADA_API int mhada_layer_forward(int dtype, const void* fc, const void* fs, const void* fcs, const float* w_fgh,
+                        const float* b_fgh, const float* w_out, const float* b_out, int B, int Nc, int Ns, int C,
+                        int H, void* out, void* ws, size_t ws_bytes, mhada_stream_t stream);
+
+/* Number of kernel launches the last mhada_layer_forward on this thread issued (bench bookkeeping). */
+MHADA_API int mhada_last_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MHADA_B200_H_ */

@@ -1,0 +1,13 @@
+"""B200-native MHAda forward hot path: a drop-in for the reference's `network` package surface on that
+path (MHAdaSTr/network/__init__.py:1-3, MHAdaSTr/network/adaDecoder.py).
+
+    from mhada_style_transfer_b200 import AdaAttnTransformerMultiHead, AdaAttnMultiHead
+
+Same constructors, forward signatures, attribute names and state_dict keys as the reference classes;
+the forward runs hand-written sm_100a kernels through the C ABI in include/mhada_b200.h.
+"""
+from .network import (AdaAttN, AdaAttnForLoss, AdaAttnMultiHead, AdaAttnTransformer,  # noqa: F401
+                      AdaAttnTransformerMultiHead, CosineSimilarity, Decoder, Softmax)
+
+__all__ = ["AdaAttnTransformer", "AdaAttnTransformerMultiHead", "AdaAttnForLoss", "AdaAttnMultiHead", "AdaAttN",
+           "Decoder", "Softmax", "CosineSimilarity"]

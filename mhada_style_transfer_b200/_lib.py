@@ -1,0 +1,82 @@
+"""ctypes binding of libmhada_b200.so (C ABI declared in include/mhada_b200.h).
+
+There is no CPU or PyTorch fallback: if the library is missing or the device is not a B200 the
+calls raise.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int, c_size_t, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmhada_b200.so")
+
+F32, BF16 = 0, 1
+ABI_VERSION = 1
+
+
+class AttnArgs(ctypes.Structure):
+    """mhada_attn_args (include/mhada_b200.h)."""
+    _fields_ = [
+        ("dtype", c_int),
+        ("B", c_int), ("H", c_int), ("Nc", c_int), ("Ns", c_int), ("dqk", c_int), ("dv", c_int),
+        ("q", c_void_p), ("k", c_void_p), ("v", c_void_p), ("x", c_void_p), ("out", c_void_p),
+        ("ldq", c_int), ("ldk", c_int), ("ldv", c_int), ("ldx", c_int), ("ldo", c_int),
+        ("x_mean", c_void_p), ("x_rstd", c_void_p), ("mu_v", c_void_p),
+        ("q_mean", c_void_p), ("q_rstd", c_void_p), ("k_mean", c_void_p), ("k_rstd", c_void_p),
+    ]
+
+
+# name -> (restype, argtypes); kept in one table so tests can check the export list against the header
+SIGNATURES = {
+    "mhada_abi_version": (c_int, []),
+    "mhada_last_error": (c_char_p, []),
+    "mhada_device_check": (c_int, []),
+    "mhada_last_launch_count": (c_int, []),
+    "mhada_in_stats_workspace": (c_size_t, [c_int, c_int, c_int]),
+    "mhada_in_stats": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t,
+                               c_void_p]),
+    "mhada_proj_workspace": (c_size_t, [c_int, c_int, c_int]),
+    "mhada_proj": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                           c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                           c_size_t, c_void_p]),
+    "mhada_attn": (c_int, [POINTER(AttnArgs), c_void_p]),
+    "mhada_linear_workspace": (c_size_t, [c_int, c_int, c_int]),
+    "mhada_linear": (c_int, [c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int,
+                             c_void_p, c_size_t, c_void_p]),
+    "mhada_layer_workspace": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),
+    "mhada_layer_forward": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                    c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+}
+
+_lib = None
+
+
+class MhadaError(RuntimeError):
+    def __init__(self, fn: str, code: int, msg: str):
+        super().__init__(f"{fn} failed with code {code}: {msg}")
+        self.code = code
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is not built (python -m mhada_style_transfer_b200.build). "
+                "The MHAda hot path has no CPU / PyTorch fallback.")
+        l = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        if l.mhada_abi_version() != ABI_VERSION:
+            raise RuntimeError(f"libmhada_b200.so ABI {l.mhada_abi_version()} != expected {ABI_VERSION}")
+        _lib = l
+    return _lib
+
+
+def check(fn: str, code: int) -> None:
+    if code != 0:
+        raise MhadaError(fn, code, lib().mhada_last_error().decode("utf-8", "replace"))

@@ -1,0 +1,238 @@
+// extern "C" surface of libmhada_b200.so (declared in include/mhada_b200.h): argument checks,
+// workspace carving and the per-layer launch sequence.  No torch types, no allocation, no syncs.
+#include "common.h"
+
+using namespace mh;
+
+namespace {
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+#define REQUIRE(cond, code, ...)      \
+    do {                              \
+        if (!(cond)) {                \
+            set_error(__VA_ARGS__);   \
+            return code;              \
+        }                             \
+    } while (0)
+
+size_t esize(int dtype) { return dtype == MHADA_BF16 ? 2 : 4; }
+
+struct LayerWs {
+    float *mean_c, *rstd_c, *mean_s, *rstd_s, *mean_x, *rstd_x, *mu_v;
+    void *stats_ws, *proj_ws, *q, *k, *v, *heads, *lin_ws;
+    size_t stats_bytes, proj_bytes, lin_bytes, total;
+};
+
+LayerWs carve(int dtype, int B, int Nc, int Ns, int C, int H, uint8_t* base) {
+    LayerWs w;
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        void* p = base ? base + off : nullptr;
+        off += align_up(bytes, 256);
+        return p;
+    };
+    const size_t sc = static_cast<size_t>(B) * C * sizeof(float);
+    w.mean_c = static_cast<float*>(take(sc)); w.rstd_c = static_cast<float*>(take(sc));
+    w.mean_s = static_cast<float*>(take(sc)); w.rstd_s = static_cast<float*>(take(sc));
+    w.mean_x = static_cast<float*>(take(sc)); w.rstd_x = static_cast<float*>(take(sc));
+    w.mu_v = static_cast<float*>(take(sc));
+    const int nmax = Nc > Ns ? Nc : Ns;
+    w.stats_bytes = stats_workspace(B, nmax, C);
+    // the split count depends on N; size for the larger of the two token counts and the smaller one too
+    size_t sb2 = stats_workspace(B, Nc < Ns ? Nc : Ns, C);
+    if (sb2 > w.stats_bytes) w.stats_bytes = sb2;
+    w.stats_ws = take(w.stats_bytes);
+    const int d = C / H;
+    w.proj_bytes = dtype == MHADA_BF16 ? proj_bf16_workspace(B, H, d) : 0;
+    w.proj_ws = take(w.proj_bytes);
+    const size_t e = esize(dtype);
+    w.q = take(static_cast<size_t>(B) * Nc * C * e);
+    w.k = take(static_cast<size_t>(B) * Ns * C * e);
+    w.v = take(static_cast<size_t>(B) * Ns * C * e * (dtype == MHADA_BF16 ? 2 : 1));
+    w.heads = take(static_cast<size_t>(B) * Nc * C * e);
+    w.lin_bytes = dtype == MHADA_BF16 ? linear_bf16_workspace(C, C) : 0;
+    w.lin_ws = take(w.lin_bytes);
+    w.total = off;
+    return w;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mhada_abi_version(void) { return MHADA_ABI_VERSION; }
+const char* mhada_last_error(void) { return last_error(); }
+int mhada_device_check(void) { return device_check(); }
+int mhada_last_launch_count(void) { return g_launches; }
+
+size_t mhada_in_stats_workspace(int B, int N, int C) {
+    if (B <= 0 || N <= 0 || C <= 0) return 0;
+    return stats_workspace(B, N, C);
+}
+
+int mhada_in_stats(const void* x, int dtype, int B, int N, int C, int ld, float* mean, float* rstd, void* ws,
+                   size_t ws_bytes, mhada_stream_t stream) {
+    REQUIRE(x && mean && rstd && ws, MHADA_ERR_ARG, "mhada_in_stats: null pointer");
+    REQUIRE(B > 0 && N > 0 && C > 0 && ld >= C, MHADA_ERR_ARG, "mhada_in_stats: bad sizes B=%d N=%d C=%d ld=%d", B, N, C, ld);
+    REQUIRE(dtype == MHADA_F32 || dtype == MHADA_BF16, MHADA_ERR_ARG, "mhada_in_stats: bad dtype %d", dtype);
+    const int vec = dtype == MHADA_BF16 ? 8 : 4;
+    REQUIRE(C % vec == 0 && ld % vec == 0 && aligned16(x), MHADA_ERR_ARG,
+            "mhada_in_stats: C and ld must be multiples of %d and x 16-byte aligned", vec);
+    REQUIRE(ws_bytes >= stats_workspace(B, N, C), MHADA_ERR_WORKSPACE, "mhada_in_stats: workspace %zu < %zu", ws_bytes,
+            stats_workspace(B, N, C));
+    if (int e = device_check()) return e;
+    return launch_stats(x, dtype, B, N, C, ld, mean, rstd, static_cast<float*>(ws), static_cast<cudaStream_t>(stream));
+}
+
+size_t mhada_proj_workspace(int B, int H, int d) {
+    if (B <= 0 || H <= 0 || d <= 0) return 0;
+    return proj_bf16_workspace(B, H, d);
+}
+
+int mhada_proj(int dtype, const void* fc, const void* fs, const float* mean_c, const float* rstd_c,
+               const float* mean_s, const float* rstd_s, const float* w, const float* bias, int B, int Nc, int Ns,
+               int H, int d, void* q, void* k, void* v, float* mu_v, void* ws, size_t ws_bytes,
+               mhada_stream_t stream) {
+    REQUIRE(fc && fs && mean_c && rstd_c && mean_s && rstd_s && w && bias && q && k && v && mu_v, MHADA_ERR_ARG,
+            "mhada_proj: null pointer");
+    REQUIRE(B > 0 && Nc > 0 && Ns > 0 && H > 0 && d > 0, MHADA_ERR_ARG, "mhada_proj: bad sizes");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (dtype == MHADA_F32) {
+        if (int e = device_check()) return e;
+        return launch_proj_f32(static_cast<const float*>(fc), static_cast<const float*>(fs), mean_c, rstd_c, mean_s,
+                               rstd_s, w, bias, B, Nc, Ns, H, d, static_cast<float*>(q), static_cast<float*>(k),
+                               static_cast<float*>(v), mu_v, s);
+    }
+    REQUIRE(dtype == MHADA_BF16, MHADA_ERR_ARG, "mhada_proj: bad dtype %d", dtype);
+    REQUIRE(d == 64, MHADA_ERR_UNSUPPORTED, "mhada_proj: the bf16 tensor-core path implements head_dim 64, got %d", d);
+    REQUIRE(ws && ws_bytes >= proj_bf16_workspace(B, H, d), MHADA_ERR_WORKSPACE, "mhada_proj: workspace too small");
+    REQUIRE(aligned16(fc) && aligned16(fs) && aligned16(q) && aligned16(k) && aligned16(v) && aligned16(ws),
+            MHADA_ERR_ARG, "mhada_proj: pointers must be 16-byte aligned");
+    if (int e = device_check()) return e;
+    return launch_proj_bf16(fc, fs, mean_c, rstd_c, mean_s, rstd_s, w, bias, B, Nc, Ns, H, d, q, k, v, mu_v, ws, s);
+}
+
+int mhada_attn(const mhada_attn_args* a, mhada_stream_t stream) {
+    REQUIRE(a, MHADA_ERR_ARG, "mhada_attn: null args");
+    REQUIRE(a->q && a->k && a->v && a->x && a->out && a->x_mean && a->x_rstd, MHADA_ERR_ARG, "mhada_attn: null pointer");
+    REQUIRE(a->B > 0 && a->H > 0 && a->Nc > 0 && a->Ns > 0 && a->dqk > 0 && a->dv > 0, MHADA_ERR_ARG,
+            "mhada_attn: bad sizes");
+    REQUIRE((a->q_mean == nullptr) == (a->q_rstd == nullptr) && (a->k_mean == nullptr) == (a->k_rstd == nullptr),
+            MHADA_ERR_ARG, "mhada_attn: mean/rstd must be given together");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (a->dtype == MHADA_F32) {
+        REQUIRE(a->ldq >= a->H * a->dqk && a->ldk >= a->H * a->dqk && a->ldv >= a->H * a->dv &&
+                    a->ldx >= a->H * a->dv && a->ldo >= a->H * a->dv,
+                MHADA_ERR_ARG, "mhada_attn: pitch smaller than H*d");
+        if (int e = device_check()) return e;
+        return launch_attn_f32(*a, s);
+    }
+    REQUIRE(a->dtype == MHADA_BF16, MHADA_ERR_ARG, "mhada_attn: bad dtype %d", a->dtype);
+    REQUIRE(a->dqk == 64 && a->dv == 64, MHADA_ERR_UNSUPPORTED,
+            "mhada_attn: the bf16 tensor-core path implements dqk = dv = 64, got %d / %d", a->dqk, a->dv);
+    REQUIRE(!a->q_mean && !a->k_mean, MHADA_ERR_UNSUPPORTED, "mhada_attn: normalise-on-load is f32-path only");
+    const int C = a->H * 64;
+    REQUIRE(a->ldq >= C && a->ldk >= C && a->ldv >= 2 * C && a->ldx >= C && a->ldo >= C, MHADA_ERR_ARG,
+            "mhada_attn: pitch smaller than the row");
+    REQUIRE(a->ldq % 8 == 0 && a->ldk % 8 == 0 && a->ldv % 8 == 0 && a->ldx % 8 == 0 && a->ldo % 8 == 0 &&
+                aligned16(a->q) && aligned16(a->k) && aligned16(a->v) && aligned16(a->x) && aligned16(a->out),
+            MHADA_ERR_ARG, "mhada_attn: bf16 pointers must be 16-byte aligned and pitches multiples of 8");
+    if (int e = device_check()) return e;
+    return launch_attn_bf16(*a, s);
+}
+
+size_t mhada_linear_workspace(int dtype, int Cout, int Cin) {
+    if (dtype != MHADA_BF16 || Cout <= 0 || Cin <= 0) return 0;
+    return linear_bf16_workspace(Cout, Cin);
+}
+
+int mhada_linear(int dtype, const void* x, int ldx, const float* w, const float* bias, int M, int Cin, int Cout,
+                 void* y, int ldy, void* ws, size_t ws_bytes, mhada_stream_t stream) {
+    REQUIRE(x && w && bias && y, MHADA_ERR_ARG, "mhada_linear: null pointer");
+    REQUIRE(M > 0 && Cin > 0 && Cout > 0 && ldx >= Cin && ldy >= Cout, MHADA_ERR_ARG, "mhada_linear: bad sizes");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (dtype == MHADA_F32) {
+        if (int e = device_check()) return e;
+        return launch_linear_f32(static_cast<const float*>(x), ldx, w, bias, M, Cin, Cout, static_cast<float*>(y), ldy, s);
+    }
+    REQUIRE(dtype == MHADA_BF16, MHADA_ERR_ARG, "mhada_linear: bad dtype %d", dtype);
+    REQUIRE(Cin % 64 == 0 && Cout % 64 == 0, MHADA_ERR_UNSUPPORTED,
+            "mhada_linear: bf16 path needs Cin and Cout multiples of 64, got %d / %d", Cin, Cout);
+    REQUIRE(ldx % 8 == 0 && ldy % 8 == 0 && aligned16(x) && aligned16(y) && aligned16(ws), MHADA_ERR_ARG,
+            "mhada_linear: bf16 pointers must be 16-byte aligned and pitches multiples of 8");
+    REQUIRE(ws && ws_bytes >= linear_bf16_workspace(Cout, Cin), MHADA_ERR_WORKSPACE, "mhada_linear: workspace too small");
+    if (int e = device_check()) return e;
+    return launch_linear_bf16(x, ldx, w, bias, M, Cin, Cout, y, ldy, ws, s);
+}
+
+size_t mhada_layer_workspace(int dtype, int B, int Nc, int Ns, int C, int H) {
+    if (B <= 0 || Nc <= 0 || Ns <= 0 || C <= 0 || H <= 0 || C % H != 0) return 0;
+    return carve(dtype, B, Nc, Ns, C, H, nullptr).total;
+}
+
+int mhada_layer_forward(int dtype, const void* fc, const void* fs, const void* fcs, const float* w_fgh,
+                        const float* b_fgh, const float* w_out, const float* b_out, int B, int Nc, int Ns, int C,
+                        int H, void* out, void* ws, size_t ws_bytes, mhada_stream_t stream) {
+    g_launches = 0;
+    REQUIRE(fc && fs && fcs && w_fgh && b_fgh && out && ws, MHADA_ERR_ARG, "mhada_layer_forward: null pointer");
+    REQUIRE((w_out == nullptr) == (b_out == nullptr), MHADA_ERR_ARG, "mhada_layer_forward: w_out/b_out must be given together");
+    REQUIRE(B > 0 && Nc > 0 && Ns > 0 && C > 0 && H > 0, MHADA_ERR_ARG, "mhada_layer_forward: bad sizes");
+    REQUIRE(C % H == 0, MHADA_ERR_ARG, "mhada_layer_forward: C=%d not divisible by H=%d", C, H);
+    REQUIRE(dtype == MHADA_F32 || dtype == MHADA_BF16, MHADA_ERR_ARG, "mhada_layer_forward: bad dtype %d", dtype);
+    REQUIRE(out != fc && out != fs && out != fcs, MHADA_ERR_ARG, "mhada_layer_forward: out must not alias an input");
+    const int d = C / H;
+    if (dtype == MHADA_BF16)
+        REQUIRE(d == 64, MHADA_ERR_UNSUPPORTED,
+                "mhada_layer_forward: the bf16 tensor-core path implements head_dim 64 (C/H = %d); use MHADA_F32", d);
+    REQUIRE(aligned16(fc) && aligned16(fs) && aligned16(fcs) && aligned16(out) && aligned16(ws), MHADA_ERR_ARG,
+            "mhada_layer_forward: pointers must be 16-byte aligned");
+    REQUIRE(C % (dtype == MHADA_BF16 ? 8 : 4) == 0, MHADA_ERR_ARG, "mhada_layer_forward: C must be a multiple of %d",
+            dtype == MHADA_BF16 ? 8 : 4);
+    LayerWs w = carve(dtype, B, Nc, Ns, C, H, static_cast<uint8_t*>(ws));
+    REQUIRE(ws_bytes >= w.total, MHADA_ERR_WORKSPACE, "mhada_layer_forward: workspace %zu < %zu", ws_bytes, w.total);
+    if (int e = device_check()) return e;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+
+    // (1) statistics of fc, fs and (unless it is the same tensor) fcs        adaDecoder.py:173,178,198
+    if (int e = launch_stats(fc, dtype, B, Nc, C, C, w.mean_c, w.rstd_c, static_cast<float*>(w.stats_ws), s)) return e;
+    if (int e = launch_stats(fs, dtype, B, Ns, C, C, w.mean_s, w.rstd_s, static_cast<float*>(w.stats_ws), s)) return e;
+    const float *mean_x = w.mean_c, *rstd_x = w.rstd_c;
+    if (fcs != fc) {
+        if (int e = launch_stats(fcs, dtype, B, Nc, C, C, w.mean_x, w.rstd_x, static_cast<float*>(w.stats_ws), s)) return e;
+        mean_x = w.mean_x;
+        rstd_x = w.rstd_x;
+    }
+    // (2) projections                                                        adaDecoder.py:173-183
+    if (dtype == MHADA_BF16) {
+        if (int e = launch_proj_bf16(fc, fs, w.mean_c, w.rstd_c, w.mean_s, w.rstd_s, w_fgh, b_fgh, B, Nc, Ns, H, d, w.q,
+                                     w.k, w.v, w.mu_v, w.proj_ws, s))
+            return e;
+    } else {
+        if (int e = launch_proj_f32(static_cast<const float*>(fc), static_cast<const float*>(fs), w.mean_c, w.rstd_c,
+                                    w.mean_s, w.rstd_s, w_fgh, b_fgh, B, Nc, Ns, H, d, static_cast<float*>(w.q),
+                                    static_cast<float*>(w.k), static_cast<float*>(w.v), w.mu_v, s))
+            return e;
+    }
+    // (3) attention + fused epilogue                                         adaDecoder.py:186-198
+    mhada_attn_args a{};
+    a.dtype = dtype; a.B = B; a.H = H; a.Nc = Nc; a.Ns = Ns; a.dqk = d; a.dv = d;
+    a.q = w.q; a.k = w.k; a.v = w.v; a.x = fcs;
+    a.out = w_out ? w.heads : out;
+    a.ldq = C; a.ldk = C; a.ldv = dtype == MHADA_BF16 ? 2 * C : C; a.ldx = C; a.ldo = C;
+    a.x_mean = mean_x; a.x_rstd = rstd_x; a.mu_v = w.mu_v;
+    if (int e = (dtype == MHADA_BF16 ? launch_attn_bf16(a, s) : launch_attn_f32(a, s))) return e;
+    // (4) out_conv                                                           adaDecoder.py:202-205
+    if (w_out) {
+        if (dtype == MHADA_BF16) {
+            if (int e = launch_linear_bf16(w.heads, C, w_out, b_out, B * Nc, C, C, out, C, w.lin_ws, s)) return e;
+        } else {
+            if (int e = launch_linear_f32(static_cast<const float*>(w.heads), C, w_out, b_out, B * Nc, C, C,
+                                          static_cast<float*>(out), C, s))
+                return e;
+        }
+    }
+    return 0;
+}
+
+}  // extern "C"

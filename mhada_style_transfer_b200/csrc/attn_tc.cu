@@ -1,0 +1,336 @@
+// K2 + K3 -- streaming MHAda attention on tcgen05 / TMEM / TMA with the AdaIN-style epilogue fused.
+//
+// Replaces MHAdaSTr/network/adaDecoder.py:186-198 for one head:
+//     A = softmax(Q K^T)   (no 1/sqrt(d); Q arrives pre-multiplied by log2 e -> exp2)
+//     M = A V ;  Var = A V^2 - M^2 ;  S = sqrt(clamp(Var, 1e-6)) ;  out = S * IN(fcs) + M
+// The Nc x Ns map never leaves the SM: S tiles live in TMEM, P overwrites S in place as bf16 and
+// is consumed straight from TMEM by the second MMA, which multiplies by V' = [V~ | V~^2] (128 wide)
+// so the mean and the second moment come out of ONE pass (V~ = V - mu_v, added back at the end).
+//
+// CTA = 2 query tiles of 128 rows x 1 head, 12 warps:
+//   warp 0       TMA producer: Q (once), K ring (3 x 16 KB), V' ring (3 x 32 KB), 128B swizzle
+//   warp 1       tcgen05.mma issuer (one elected lane)
+//   warp 2       TMEM allocator (512 columns: S0 | S1 | O0 | O1, 128 fp32 columns each)
+//   warp 3       stages the epilogue constants (mean/rstd of fcs, mu_v) into shared memory
+//   warps 4-7    softmax + epilogue for query tile 0 (thread = row; TMEM lane = row, no shuffles)
+//   warps 8-11   same for query tile 1 -- the two tiles ping-pong on the tensor core
+// MMA order per key tile j:  PV0(j) S0(j+1) PV1(j) S1(j+1), so while one warpgroup runs exp2 on its
+// tile the tensor core works for the other one.  Rescaling of O is lazy (only when a row max grows by
+// more than 2^8), done in place in TMEM by the softmax warps while no MMA touches that accumulator.
+//
+// Tensor-bound: algorithmic FLOPs = 6 * B * Nc * Ns * C per layer (2 QK^T + 2 AV + 2 AV^2).
+#include <math.h>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace mh {
+
+constexpr int AT_BM = 128;       // query rows per tile
+constexpr int AT_BN = 128;       // keys per tile
+constexpr int AT_D = 64;         // head dim (dqk = dv)
+constexpr int AT_DV2 = 128;      // [V~ | V~^2]
+constexpr int AT_KST = 3, AT_VST = 3;
+constexpr int AT_THREADS = 384;
+constexpr uint32_t AT_Q_BYTES = AT_BM * AT_D * 2;          // 16 KB per query tile
+constexpr uint32_t AT_K_BYTES = AT_BN * AT_D * 2;          // 16 KB
+constexpr uint32_t AT_V_BYTES = AT_BN * AT_DV2 * 2;        // 32 KB (two 64-column boxes)
+constexpr uint32_t AT_SMEM_DATA = 2 * AT_Q_BYTES + AT_KST * AT_K_BYTES + AT_VST * AT_V_BYTES;
+constexpr float AT_RESCALE_THRESHOLD = 8.0f;               // log2 units: P <= 2^8
+
+struct AttnTcParams {
+    const __nv_bfloat16* x;   // fcs [B, Nc, ldx]
+    __nv_bfloat16* out;       // [B, Nc, ldo]
+    const float *x_mean, *x_rstd, *mu_v;   // [B, H*64]
+    int H, Nc, Ns, ldx, ldo;
+};
+
+struct AttnBars {
+    uint64_t q_full;
+    uint64_t k_full[AT_KST], k_empty[AT_KST];
+    uint64_t v_full[AT_VST], v_empty[AT_VST];
+    uint64_t s_full[2], p_ready[2], o_full[2];
+    uint32_t tmem_slot;
+    float cst[3][AT_D];       // x_mean, x_rstd, mu_v of this (b, head)
+};
+
+__global__ void __launch_bounds__(AT_THREADS, 1)
+attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+               const __grid_constant__ CUtensorMap tmV, const AttnTcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem;
+    uint8_t* sK = sQ + 2 * AT_Q_BYTES;
+    uint8_t* sV = sK + AT_KST * AT_K_BYTES;
+    AttnBars* bars = reinterpret_cast<AttnBars*>(sV + AT_VST * AT_V_BYTES);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * (2 * AT_BM), h = blockIdx.y, b = blockIdx.z;
+    const int T = (p.Ns + AT_BN - 1) / AT_BN;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmQ);
+        tma_prefetch_desc(&tmK);
+        tma_prefetch_desc(&tmV);
+    }
+    if (warp == 1 && lane == 0) {
+        mbar_init(&bars->q_full, 1);
+        for (int s = 0; s < AT_KST; ++s) { mbar_init(&bars->k_full[s], 1); mbar_init(&bars->k_empty[s], 1); }
+        for (int s = 0; s < AT_VST; ++s) { mbar_init(&bars->v_full[s], 1); mbar_init(&bars->v_empty[s], 1); }
+        for (int t = 0; t < 2; ++t) {
+            mbar_init(&bars->s_full[t], 1);
+            mbar_init(&bars->p_ready[t], 4);     // one arrive per softmax warp
+            mbar_init(&bars->o_full[t], 1);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(&bars->tmem_slot, 512);
+        tmem_relinquish();
+    }
+    if (warp == 3) {
+        const size_t sidx = (static_cast<size_t>(b) * p.H + h) * AT_D;
+        for (int i = lane; i < AT_D; i += 32) {
+            bars->cst[0][i] = p.x_mean[sidx + i];
+            bars->cst[1][i] = p.x_rstd[sidx + i];
+            bars->cst[2][i] = p.mu_v ? p.mu_v[sidx + i] : 0.f;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = bars->tmem_slot;
+    // TMEM columns: S_t at t*128 (P_t aliases its first 64 columns), O_t at 256 + t*128
+
+    // Register hand-over: the setmaxnreg calls sit INSIDE the role branches (no join before the role
+    // code) so ptxas allocates each branch against its own budget.
+    if (warp < 4) {
+      setmaxnreg_dec<64>();
+      if (warp == 0) {
+        // ===================================================================== TMA producer
+        if (elect_one()) {
+            mbar_arrive_expect_tx(&bars->q_full, 2 * AT_Q_BYTES);
+            tma_load_3d(sQ, &tmQ, &bars->q_full, h * AT_D, q0, b);
+            tma_load_3d(sQ + AT_Q_BYTES, &tmQ, &bars->q_full, h * AT_D, q0 + AT_BM, b);
+            for (int j = 0; j < T; ++j) {
+                const int ks = j % AT_KST, vs = j % AT_VST;
+                mbar_wait(&bars->k_empty[ks], ((j / AT_KST) & 1) ^ 1);
+                mbar_arrive_expect_tx(&bars->k_full[ks], AT_K_BYTES);
+                tma_load_3d(sK + ks * AT_K_BYTES, &tmK, &bars->k_full[ks], h * AT_D, j * AT_BN, b);
+                mbar_wait(&bars->v_empty[vs], ((j / AT_VST) & 1) ^ 1);
+                mbar_arrive_expect_tx(&bars->v_full[vs], AT_V_BYTES);
+                uint8_t* v = sV + vs * AT_V_BYTES;
+                tma_load_3d(v, &tmV, &bars->v_full[vs], h * AT_DV2, j * AT_BN, b);
+                tma_load_3d(v + AT_V_BYTES / 2, &tmV, &bars->v_full[vs], h * AT_DV2 + 64, j * AT_BN, b);
+            }
+        }
+      } else if (warp == 1) {
+        // ===================================================================== MMA issuer
+        if (elect_one()) {
+            constexpr uint32_t idesc_s = make_idesc_bf16(AT_BM, AT_BN, 0, 0);     // S = Q K^T, both K-major
+            constexpr uint32_t idesc_o = make_idesc_bf16(AT_BM, AT_DV2, 0, 1);    // O += P V', V' MN-major
+            const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV);
+            auto issue_s = [&](int t, int ks) {
+                const uint64_t da = make_smem_desc(q_addr + t * AT_Q_BYTES, 16, 1024);
+                const uint64_t db = make_smem_desc(k_addr + ks * AT_K_BYTES, 16, 1024);
+#pragma unroll
+                for (int k = 0; k < AT_D / 16; ++k)
+                    umma_ss(tmem + t * 128, desc_advance(da, k * 32), desc_advance(db, k * 32), idesc_s, k != 0);
+            };
+            auto issue_pv = [&](int t, int vs, bool accumulate) {
+                // B = V' tile [128 keys][128 cols] as two [128][64] boxes: LBO = box stride, SBO = 8 key rows
+                const uint64_t db = make_smem_desc(v_addr + vs * AT_V_BYTES, AT_V_BYTES / 2, 1024);
+#pragma unroll
+                for (int k = 0; k < AT_BN / 16; ++k)
+                    umma_ts(tmem + 256 + t * 128, tmem + t * 128 + k * 8, desc_advance(db, k * 2048), idesc_o,
+                            (accumulate || k != 0) ? 1u : 0u);
+            };
+            mbar_wait(&bars->q_full, 0);
+            mbar_wait(&bars->k_full[0], 0);
+            tc_fence_after();
+            issue_s(0, 0);
+            umma_commit(&bars->s_full[0]);
+            issue_s(1, 0);
+            umma_commit(&bars->s_full[1]);
+            umma_commit(&bars->k_empty[0]);
+            for (int j = 0; j < T; ++j) {
+                const int vs = j % AT_VST;
+                const bool more = (j + 1 < T);
+                const int ks1 = (j + 1) % AT_KST;
+                mbar_wait(&bars->v_full[vs], (j / AT_VST) & 1);
+                if (more) mbar_wait(&bars->k_full[ks1], ((j + 1) / AT_KST) & 1);
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                    mbar_wait(&bars->p_ready[t], j & 1);
+                    tc_fence_after();
+                    issue_pv(t, vs, j != 0);
+                    if (t == 1) umma_commit(&bars->v_empty[vs]);
+                    if (more) {
+                        issue_s(t, ks1);
+                        umma_commit(&bars->s_full[t]);
+                        if (t == 1) umma_commit(&bars->k_empty[ks1]);
+                    } else {
+                        umma_commit(&bars->o_full[t]);
+                    }
+                }
+            }
+        }
+      }
+    } else {
+        setmaxnreg_inc<216>();
+        // ===================================================================== softmax + epilogue
+        const int t = (warp - 4) >> 2;           // query tile of this warpgroup
+        const int quarter = warp & 3;            // TMEM lane quarter this warp may touch
+        const int row = quarter * 32 + lane;
+        const uint32_t s_tm = tmem_addr(tmem, quarter * 32, t * 128);
+        const uint32_t o_tm = tmem_addr(tmem, quarter * 32, 256 + t * 128);
+        float m_used = -INFINITY, l = 0.f;
+
+        for (int j = 0; j < T; ++j) {
+            mbar_wait(&bars->s_full[t], j & 1);
+            tc_fence_after();
+            uint32_t s[128];
+            tmem_ld_x32(s_tm, s);
+            tmem_ld_x32(s_tm + 32, s + 32);
+            tmem_ld_x32(s_tm + 64, s + 64);
+            tmem_ld_x32(s_tm + 96, s + 96);
+            tmem_wait_ld();
+            const int valid = p.Ns - j * AT_BN;       // keys in this tile (tail tile: < 128)
+            if (valid < AT_BN) {
+#pragma unroll
+                for (int i = 0; i < 128; ++i)
+                    if (i >= valid) s[i] = 0xff800000u;   // -inf
+            }
+            float mx = __uint_as_float(s[0]);
+#pragma unroll
+            for (int i = 1; i < 128; ++i) mx = fmaxf(mx, __uint_as_float(s[i]));
+            if (j == 0) {
+                m_used = mx;
+            } else {
+                const bool grow = mx > m_used + AT_RESCALE_THRESHOLD;
+                if (__any_sync(0xffffffffu, grow)) {
+                    const float m_new = grow ? mx : m_used;
+                    const float sc = ex2_approx(m_used - m_new);    // 1 for rows that keep their max
+                    l *= sc;
+                    m_used = m_new;
+#pragma unroll 1
+                    for (int c = 0; c < AT_DV2; c += 32) {
+                        uint32_t o[32];
+                        tmem_ld_x32(o_tm + c, o);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * sc);
+                        tmem_st_x32(o_tm + c, o);
+                    }
+                }
+            }
+            // P = exp2(S - m), packed bf16x2, written over the first 64 columns of S
+            float lsum = 0.f;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t pk[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    float p0 = ex2_approx(__uint_as_float(s[c * 32 + 2 * i]) - m_used);
+                    float p1 = ex2_approx(__uint_as_float(s[c * 32 + 2 * i + 1]) - m_used);
+                    lsum += p0 + p1;
+                    pk[i] = pack_bf16x2(p0, p1);
+                }
+                tmem_st_x16(s_tm + c * 16, pk);
+            }
+            l += lsum;
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->p_ready[t]);
+        }
+
+        // ---- epilogue: O/l -> (M~, E~) -> sqrt(max(E~ - M~^2, 1e-6)) * IN(fcs) + M~ + mu_v
+        mbar_wait(&bars->o_full[t], 0);
+        tc_fence_after();
+        const float inv = 1.f / l;
+        const int n = q0 + t * AT_BM + row;
+        const size_t tok = static_cast<size_t>(b) * p.Nc + (n < p.Nc ? n : 0);
+        const __nv_bfloat16* xrow = p.x + tok * p.ldx + h * AT_D;
+        __nv_bfloat16* orow = p.out + tok * p.ldo + h * AT_D;
+#pragma unroll 1
+        for (int c = 0; c < AT_D; c += 32) {
+            uint32_t mm[32], ee[32];
+            tmem_ld_x32(o_tm + c, mm);
+            tmem_ld_x32(o_tm + AT_D + c, ee);
+            uint4 xv[4];
+            if (n < p.Nc) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) xv[i] = __ldg(reinterpret_cast<const uint4*>(xrow + c) + i);
+            }
+            tmem_wait_ld();
+            if (n < p.Nc) {
+                const uint32_t* xw = reinterpret_cast<const uint32_t*>(xv);
+                uint32_t ov[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    float r[2];
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int ch = c + 2 * i + e;
+                        const float m = __uint_as_float(mm[2 * i + e]) * inv;
+                        const float ex = __uint_as_float(ee[2 * i + e]) * inv;
+                        const float sd = sqrtf(fmaxf(ex - m * m, 1e-6f));
+                        const float xf = e == 0 ? bf16_lo(xw[i]) : bf16_hi(xw[i]);
+                        const float xn = (xf - bars->cst[0][ch]) * bars->cst[1][ch];
+                        r[e] = fmaf(sd, xn, m + bars->cst[2][ch]);
+                    }
+                    ov[i] = pack_bf16x2(r[0], r[1]);
+                }
+                uint4* dst = reinterpret_cast<uint4*>(orow + c);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) dst[i] = make_uint4(ov[4 * i], ov[4 * i + 1], ov[4 * i + 2], ov[4 * i + 3]);
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem, 512);
+}
+
+int launch_attn_bf16(const mhada_attn_args& a, cudaStream_t s) {
+    const int C = a.H * AT_D;
+    CUtensorMap tmQ, tmK, tmV;
+    {
+        uint64_t dims[3] = {static_cast<uint64_t>(C), static_cast<uint64_t>(a.Nc), static_cast<uint64_t>(a.B)};
+        uint64_t str[2] = {static_cast<uint64_t>(a.ldq) * 2, static_cast<uint64_t>(a.Nc) * a.ldq * 2};
+        uint32_t box[3] = {AT_D, AT_BM, 1};
+        if (int e = make_tmap_bf16(&tmQ, a.q, 3, dims, str, box)) return e;
+    }
+    {
+        uint64_t dims[3] = {static_cast<uint64_t>(C), static_cast<uint64_t>(a.Ns), static_cast<uint64_t>(a.B)};
+        uint64_t str[2] = {static_cast<uint64_t>(a.ldk) * 2, static_cast<uint64_t>(a.Ns) * a.ldk * 2};
+        uint32_t box[3] = {AT_D, AT_BN, 1};
+        if (int e = make_tmap_bf16(&tmK, a.k, 3, dims, str, box)) return e;
+    }
+    {
+        uint64_t dims[3] = {static_cast<uint64_t>(2 * C), static_cast<uint64_t>(a.Ns), static_cast<uint64_t>(a.B)};
+        uint64_t str[2] = {static_cast<uint64_t>(a.ldv) * 2, static_cast<uint64_t>(a.Ns) * a.ldv * 2};
+        uint32_t box[3] = {64, AT_BN, 1};
+        if (int e = make_tmap_bf16(&tmV, a.v, 3, dims, str, box)) return e;
+    }
+    AttnTcParams p;
+    p.x = static_cast<const __nv_bfloat16*>(a.x);
+    p.out = static_cast<__nv_bfloat16*>(a.out);
+    p.x_mean = a.x_mean; p.x_rstd = a.x_rstd; p.mu_v = a.mu_v;
+    p.H = a.H; p.Nc = a.Nc; p.Ns = a.Ns; p.ldx = a.ldx; p.ldo = a.ldo;
+    constexpr size_t smem = AT_SMEM_DATA + sizeof(AttnBars) + 1024;
+    static bool attr_done = false;
+    if (!attr_done) {
+        if (int e = check_cuda(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                    static_cast<int>(smem)), "attn smem attr"))
+            return e;
+        attr_done = true;
+    }
+    dim3 grid((a.Nc + 2 * AT_BM - 1) / (2 * AT_BM), a.H, a.B);
+    attn_tc_kernel<<<grid, AT_THREADS, smem, s>>>(tmQ, tmK, tmV, p);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "attn_tc launch");
+}
+
+}  // namespace mh

@@ -1,0 +1,53 @@
+// Host-side plumbing shared by the kernel translation units: error reporting, device check,
+// TMA tensor-map construction (through the driver entry point, so libcuda is not a link-time
+// dependency and the library loads on a box without a GPU), launch counting.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/mhada_b200.h"
+
+namespace mh {
+
+void set_error(const char* fmt, ...);
+const char* last_error();
+int check_cuda(cudaError_t e, const char* what);   // 0 or the error (message recorded)
+int device_check();
+
+extern thread_local int g_launches;
+inline void count_launch() { ++g_launches; }
+
+// bf16 tensor map, up to 3 dims, dims[0] innermost (contiguous).  strides_bytes[i] = byte pitch of
+// dim i+1.  box[i] = tile extent.  128B swizzle when box[0]*2 == 128, else none.
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                   const uint64_t* strides_bytes, const uint32_t* box);
+
+// ---- launchers (one per kernel family); all return 0 / error code ------------------------------
+size_t stats_workspace(int B, int N, int C);
+int launch_stats(const void* x, int dtype, int B, int N, int C, int ld, float* mean, float* rstd, float* ws,
+                 cudaStream_t s);
+
+// f32 SIMT path
+int launch_proj_f32(const float* fc, const float* fs, const float* mean_c, const float* rstd_c,
+                    const float* mean_s, const float* rstd_s, const float* w, const float* bias, int B, int Nc,
+                    int Ns, int H, int d, float* q, float* k, float* v, float* mu_v, cudaStream_t s);
+int launch_attn_f32(const mhada_attn_args& a, cudaStream_t s);
+int launch_linear_f32(const float* x, int ldx, const float* w, const float* bias, int M, int Cin, int Cout, float* y,
+                      int ldy, cudaStream_t s);
+
+// bf16 tcgen05 path
+size_t proj_bf16_workspace(int B, int H, int d);
+int launch_proj_bf16(const void* fc, const void* fs, const float* mean_c, const float* rstd_c, const float* mean_s,
+                     const float* rstd_s, const float* w, const float* bias, int B, int Nc, int Ns, int H, int d,
+                     void* q, void* k, void* v, float* mu_v, void* ws, cudaStream_t s);
+int launch_attn_bf16(const mhada_attn_args& a, cudaStream_t s);
+size_t linear_bf16_workspace(int Cout, int Cin);
+int launch_linear_bf16(const void* x, int ldx, const float* w, const float* bias, int M, int Cin, int Cout, void* y,
+                       int ldy, void* ws, cudaStream_t s);
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace mh

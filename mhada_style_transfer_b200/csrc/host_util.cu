@@ -1,0 +1,92 @@
+// Error reporting, device check and TMA tensor-map construction.
+#include <stdarg.h>
+#include <stdio.h>
+#include <mutex>
+
+#include "common.h"
+
+namespace mh {
+
+static thread_local char g_err[512] = "";
+thread_local int g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+const char* last_error() { return g_err; }
+
+int check_cuda(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return 0;
+    set_error("%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+    return static_cast<int>(e);
+}
+
+int device_check() {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) {
+        set_error("no CUDA device: %s", cudaGetErrorString(e));
+        (void)cudaGetLastError();
+        return MHADA_ERR_DEVICE;
+    }
+    int major = 0;
+    e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (e != cudaSuccess || major != 10) {
+        set_error("libmhada_b200 needs an sm_100 (B200) device, found compute capability major %d", major);
+        (void)cudaGetLastError();
+        return MHADA_ERR_DEVICE;
+    }
+    return 0;
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+        (void)cudaGetLastError();
+    });
+    return fn;
+}
+
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled not available from the driver");
+        return MHADA_ERR_DRIVER;
+    }
+    cuuint64_t gdim[3];
+    cuuint64_t gstr[2];
+    cuuint32_t bx[3], es[3];
+    for (int i = 0; i < rank; ++i) {
+        gdim[i] = dims[i];
+        bx[i] = box[i];
+        es[i] = 1;
+    }
+    for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+    CUtensorMapSwizzle sw = (box[0] * 2 == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE;
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base),
+                     gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu,%llu,%llu box %u,%u,%u)",
+                  static_cast<int>(r), rank, (unsigned long long)gdim[0], (unsigned long long)(rank > 1 ? gdim[1] : 0),
+                  (unsigned long long)(rank > 2 ? gdim[2] : 0), bx[0], rank > 1 ? bx[1] : 0, rank > 2 ? bx[2] : 0);
+        return MHADA_ERR_DRIVER;
+    }
+    return 0;
+}
+
+}  // namespace mh

@@ -1,0 +1,309 @@
+// The fp32 path: true-fp32 FFMA kernels (never TF32) that reproduce the reference's arithmetic
+// for BASELINE.json configs[0] and serve as the on-device yardstick for the tensor-core path.
+//
+//   grouped_linear_f32 : per-head 1x1 convs f/g/h with the instance norm applied on load
+//                        (adaDecoder.py:173, :178, :182) and out_conv (adaDecoder.py:205)
+//   attn_f32           : streaming softmax(Q K^T) [V, V^2] + sqrt(max(E - M^2, 1e-6)) * IN(x) + M
+//                        (adaDecoder.py:186-198; AdaAttnForLoss :70-81), any dqk / dv
+//
+// Both are shared-memory tiled SIMT kernels (64x64 output tile, 4x4 register micro-tile).
+#include <math.h>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace mh {
+
+constexpr int TILE = 64;
+constexpr int KC = 32;  // reduction chunk staged in shared memory
+
+// ------------------------------------------------------------------------------------------------
+// y[m, g*dout + o] = sum_i w[g][o][i] * xin[m, g*din + i] + bias[g][o]
+//   mode 0: xin = x   mode 1: xin = (x - mean) * rstd   mode 2: xin = x - mean  (bias ignored -> centred V)
+// rows m = b * rows_per_batch + n;  mean / rstd are [B, G*din].
+// grid (ceil(M/64), ceil(dout/64), G)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) grouped_linear_f32_kernel(const float* __restrict__ x, int ldx,
+                                                                 const float* __restrict__ w,
+                                                                 const float* __restrict__ bias,
+                                                                 const float* __restrict__ mean,
+                                                                 const float* __restrict__ rstd, int mode, int M,
+                                                                 int rows_per_batch, int din, int dout,
+                                                                 float* __restrict__ y, int ldy) {
+    __shared__ float xs[KC][TILE + 1];
+    __shared__ float ws[KC][TILE + 1];
+    const int g = blockIdx.z;
+    const int m0 = blockIdx.x * TILE, o0 = blockIdx.y * TILE;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const float* wg = w + static_cast<size_t>(g) * dout * din;
+    const int cin0 = g * din;
+
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (int k0 = 0; k0 < din; k0 += KC) {
+        // stage x tile [64 rows][32 k] and w tile [64 outs][32 k]; consecutive threads walk k (contiguous)
+        for (int e = threadIdx.x; e < TILE * KC; e += 256) {
+            int r = e / KC, kk = e % KC;
+            int m = m0 + r, k = k0 + kk;
+            float xv = 0.f;
+            if (m < M && k < din) {
+                xv = __ldg(x + static_cast<size_t>(m) * ldx + cin0 + k);
+                if (mode != 0) {
+                    int b = m / rows_per_batch;
+                    float mu = __ldg(mean + static_cast<size_t>(b) * gridDim.z * din + cin0 + k);
+                    xv -= mu;
+                    if (mode == 1) xv *= __ldg(rstd + static_cast<size_t>(b) * gridDim.z * din + cin0 + k);
+                }
+            }
+            xs[kk][r] = xv;
+            int o = o0 + r;
+            ws[kk][r] = (o < dout && k < din) ? __ldg(wg + static_cast<size_t>(o) * din + k) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int kk = 0; kk < KC; ++kk) {
+            float a[4], bb[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = xs[kk][ty + 16 * i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bb[j] = ws[kk][tx + 16 * j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int m = m0 + ty + 16 * i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int o = o0 + tx + 16 * j;
+            if (o >= dout) continue;
+            float bv = (mode == 2 || bias == nullptr) ? 0.f : __ldg(bias + static_cast<size_t>(g) * dout + o);
+            y[static_cast<size_t>(m) * ldy + g * dout + o] = acc[i][j] + bv;
+        }
+    }
+}
+
+// mu_v[b, g*d + o] = sum_i wh[g][o][i] * mean_s[b, g*d + i] + bh[g][o]      (tiny)
+__global__ void muv_kernel(const float* __restrict__ wh, const float* __restrict__ bh,
+                           const float* __restrict__ mean_s, int B, int H, int d, float* __restrict__ mu_v) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int C = H * d;
+    if (i >= B * C) return;
+    int b = i / C, c = i % C, g = c / d, o = c % d;
+    const float* wr = wh + (static_cast<size_t>(g) * d + o) * d;
+    const float* mu = mean_s + static_cast<size_t>(b) * C + g * d;
+    float a = 0.f;
+    for (int k = 0; k < d; ++k) a = fmaf(wr[k], mu[k], a);
+    mu_v[i] = a + bh[g * d + o];
+}
+
+int launch_proj_f32(const float* fc, const float* fs, const float* mean_c, const float* rstd_c,
+                    const float* mean_s, const float* rstd_s, const float* w, const float* bias, int B, int Nc,
+                    int Ns, int H, int d, float* q, float* k, float* v, float* mu_v, cudaStream_t s) {
+    const int C = H * d;
+    const size_t wsz = static_cast<size_t>(H) * d * d, bsz = static_cast<size_t>(H) * d;
+    dim3 gq((B * Nc + TILE - 1) / TILE, (d + TILE - 1) / TILE, H), gk((B * Ns + TILE - 1) / TILE, (d + TILE - 1) / TILE, H);
+    grouped_linear_f32_kernel<<<gq, 256, 0, s>>>(fc, C, w, bias, mean_c, rstd_c, 1, B * Nc, Nc, d, d, q, C);
+    count_launch();
+    grouped_linear_f32_kernel<<<gk, 256, 0, s>>>(fs, C, w + wsz, bias + bsz, mean_s, rstd_s, 1, B * Ns, Ns, d, d, k, C);
+    count_launch();
+    grouped_linear_f32_kernel<<<gk, 256, 0, s>>>(fs, C, w + 2 * wsz, nullptr, mean_s, nullptr, 2, B * Ns, Ns, d, d, v, C);
+    count_launch();
+    muv_kernel<<<(B * C + 255) / 256, 256, 0, s>>>(w + 2 * wsz, bias + 2 * bsz, mean_s, B, H, d, mu_v);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "proj_f32 launch");
+}
+
+int launch_linear_f32(const float* x, int ldx, const float* w, const float* bias, int M, int Cin, int Cout, float* y,
+                      int ldy, cudaStream_t s) {
+    dim3 g((M + TILE - 1) / TILE, (Cout + TILE - 1) / TILE, 1);
+    grouped_linear_f32_kernel<<<g, 256, 0, s>>>(x, ldx, w, bias, nullptr, nullptr, 0, M, M, Cin, Cout, y, ldy);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "linear_f32 launch");
+}
+
+// ------------------------------------------------------------------------------------------------
+// Streaming attention, fp32.  grid (ceil(Nc/64), ceil(dv/64), B*H), 256 threads as 16x16;
+// thread (ty, tx) owns rows ty+16i and columns tx+16j of every 64x64 tile.
+// ------------------------------------------------------------------------------------------------
+struct AttnF32Params {
+    const float *q, *k, *v, *x;
+    float* out;
+    const float *x_mean, *x_rstd, *mu_v, *q_mean, *q_rstd, *k_mean, *k_rstd;
+    int H, Nc, Ns, dqk, dv, ldq, ldk, ldv, ldx, ldo;
+};
+
+__global__ void __launch_bounds__(256) attn_f32_kernel(const AttnF32Params p) {
+    __shared__ float Ps[TILE][TILE + 1];
+    __shared__ union {
+        struct {
+            float q[KC][TILE + 1];
+            float k[KC][TILE + 1];
+        } qk;
+        float v[TILE][TILE + 1];
+    } sm;
+
+    const int bh = blockIdx.z, b = bh / p.H, h = bh % p.H;
+    const int q0 = blockIdx.x * TILE, c0 = blockIdx.y * TILE;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const float* qb = p.q + static_cast<size_t>(b) * p.Nc * p.ldq + h * p.dqk;
+    const float* kb = p.k + static_cast<size_t>(b) * p.Ns * p.ldk + h * p.dqk;
+    const float* vb = p.v + static_cast<size_t>(b) * p.Ns * p.ldv + h * p.dv;
+    const float* qmu = p.q_mean ? p.q_mean + static_cast<size_t>(b) * p.H * p.dqk + h * p.dqk : nullptr;
+    const float* qrs = p.q_mean ? p.q_rstd + static_cast<size_t>(b) * p.H * p.dqk + h * p.dqk : nullptr;
+    const float* kmu = p.k_mean ? p.k_mean + static_cast<size_t>(b) * p.H * p.dqk + h * p.dqk : nullptr;
+    const float* krs = p.k_mean ? p.k_rstd + static_cast<size_t>(b) * p.H * p.dqk + h * p.dqk : nullptr;
+
+    float om[4][4], oe[4][4], mrow[4], lrow[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        mrow[i] = -INFINITY;
+        lrow[i] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) om[i][j] = oe[i][j] = 0.f;
+    }
+
+    for (int k0 = 0; k0 < p.Ns; k0 += TILE) {
+        // ---- S = Q K^T for this key tile
+        float s[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
+        for (int d0 = 0; d0 < p.dqk; d0 += KC) {
+            for (int e = threadIdx.x; e < TILE * KC; e += 256) {
+                int r = e / KC, dd = e % KC, d = d0 + dd;
+                float qv = 0.f, kv = 0.f;
+                if (d < p.dqk) {
+                    if (q0 + r < p.Nc) {
+                        qv = __ldg(qb + static_cast<size_t>(q0 + r) * p.ldq + d);
+                        if (qmu) qv = (qv - __ldg(qmu + d)) * __ldg(qrs + d);
+                    }
+                    if (k0 + r < p.Ns) {
+                        kv = __ldg(kb + static_cast<size_t>(k0 + r) * p.ldk + d);
+                        if (kmu) kv = (kv - __ldg(kmu + d)) * __ldg(krs + d);
+                    }
+                }
+                sm.qk.q[dd][r] = qv;
+                sm.qk.k[dd][r] = kv;
+            }
+            __syncthreads();
+#pragma unroll 8
+            for (int dd = 0; dd < KC; ++dd) {
+                float a[4], bb[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) a[i] = sm.qk.q[dd][ty + 16 * i];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) bb[j] = sm.qk.k[dd][tx + 16 * j];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) s[i][j] = fmaf(a[i], bb[j], s[i][j]);
+            }
+            __syncthreads();
+        }
+        // ---- online softmax (rows are shared by the 16 threads with equal ty = one half warp)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float mx = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (k0 + tx + 16 * j >= p.Ns) s[i][j] = -INFINITY;
+                mx = fmaxf(mx, s[i][j]);
+            }
+#pragma unroll
+            for (int o = 8; o >= 1; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            float mnew = fmaxf(mrow[i], mx);  // finite: every tile has >= 1 valid key
+            float scale = expf(mrow[i] - mnew);
+            float rs = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float e = expf(s[i][j] - mnew);
+                rs += e;
+                Ps[ty + 16 * i][tx + 16 * j] = e;
+            }
+#pragma unroll
+            for (int o = 8; o >= 1; o >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, o);
+            lrow[i] = lrow[i] * scale + rs;
+            mrow[i] = mnew;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                om[i][j] *= scale;
+                oe[i][j] *= scale;
+            }
+        }
+        // ---- stage V tile [64 keys][64 value columns]
+        for (int e = threadIdx.x; e < TILE * TILE; e += 256) {
+            int r = e / TILE, c = e % TILE;
+            float vv = 0.f;
+            if (k0 + r < p.Ns && c0 + c < p.dv) vv = __ldg(vb + static_cast<size_t>(k0 + r) * p.ldv + c0 + c);
+            sm.v[r][c] = vv;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int kk = 0; kk < TILE; ++kk) {
+            float a[4], vv[4], v2[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = Ps[ty + 16 * i][kk];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                vv[j] = sm.v[kk][tx + 16 * j];
+                v2[j] = vv[j] * vv[j];
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    om[i][j] = fmaf(a[i], vv[j], om[i][j]);
+                    oe[i][j] = fmaf(a[i], v2[j], oe[i][j]);
+                }
+        }
+        __syncthreads();
+    }
+    // ---- epilogue: S * IN(x) + M   (adaDecoder.py:190-198)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int n = q0 + ty + 16 * i;
+        if (n >= p.Nc) continue;
+        float inv = 1.f / lrow[i];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int c = c0 + tx + 16 * j;
+            if (c >= p.dv) continue;
+            int ch = h * p.dv + c;
+            float m = om[i][j] * inv, e = oe[i][j] * inv;
+            float sd = sqrtf(fmaxf(e - m * m, 1e-6f));
+            size_t sidx = static_cast<size_t>(b) * p.H * p.dv + ch;
+            float xn = (__ldg(p.x + (static_cast<size_t>(b) * p.Nc + n) * p.ldx + ch) - __ldg(p.x_mean + sidx)) *
+                       __ldg(p.x_rstd + sidx);
+            float mu = p.mu_v ? __ldg(p.mu_v + sidx) : 0.f;
+            p.out[(static_cast<size_t>(b) * p.Nc + n) * p.ldo + ch] = fmaf(sd, xn, m + mu);
+        }
+    }
+}
+
+int launch_attn_f32(const mhada_attn_args& a, cudaStream_t s) {
+    AttnF32Params p;
+    p.q = static_cast<const float*>(a.q); p.k = static_cast<const float*>(a.k);
+    p.v = static_cast<const float*>(a.v); p.x = static_cast<const float*>(a.x);
+    p.out = static_cast<float*>(a.out);
+    p.x_mean = a.x_mean; p.x_rstd = a.x_rstd; p.mu_v = a.mu_v;
+    p.q_mean = a.q_mean; p.q_rstd = a.q_rstd; p.k_mean = a.k_mean; p.k_rstd = a.k_rstd;
+    p.H = a.H; p.Nc = a.Nc; p.Ns = a.Ns; p.dqk = a.dqk; p.dv = a.dv;
+    p.ldq = a.ldq; p.ldk = a.ldk; p.ldv = a.ldv; p.ldx = a.ldx; p.ldo = a.ldo;
+    dim3 grid((a.Nc + TILE - 1) / TILE, (a.dv + TILE - 1) / TILE, a.B * a.H);
+    attn_f32_kernel<<<grid, 256, 0, s>>>(p);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "attn_f32 launch");
+}
+
+}  // namespace mh

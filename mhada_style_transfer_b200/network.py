@@ -1,0 +1,437 @@
+"""Host-side mirror of the reference's MHAda modules (MHAdaSTr/network/adaDecoder.py, conv.py).
+
+Same class names, constructor signatures, attribute names, state_dict keys (318 for the default
+AdaAttnTransformerMultiHead), return values and ValueErrors as the reference, so a checkpoint
+written by the reference loads with strict=True and `adaFormer(fc, fs)` in infer_image.py /
+infer_video.py / infer_time.py keeps working.  The forward does not run PyTorch ops for the hot
+path: it hands device pointers to libmhada_b200.so (C ABI, include/mhada_b200.h) on the current
+CUDA stream.  PyTorch is used for memory, streams and the decoder convolutions only.
+
+Precision (`module.precision`, default "auto"):
+  "fp32"  true-fp32 SIMT kernels (the reference's arithmetic; any head_dim)
+  "bf16"  tcgen05 tensor-core kernels, bf16 storage / fp32 accumulate (head_dim 64)
+  "auto"  bf16 path when the inputs are bf16/fp16 and head_dim == 64, else fp32 path
+There is no CPU path: CPU tensors raise.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Sequence
+
+import torch
+import torch.nn as nn
+from torch.nn import functional as F
+
+from . import _lib
+
+__all__ = ["Softmax", "CosineSimilarity", "AdaAttnForLoss", "AdaAttN", "AdaAttnMultiHead", "AdaAttnTransformer",
+           "AdaAttnTransformerMultiHead", "Decoder", "set_precision"]
+
+
+# ------------------------------------------------------------------------------------------------
+# small helpers
+# ------------------------------------------------------------------------------------------------
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+_WORKSPACES: dict = {}
+
+
+def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
+    """One growing scratch buffer per (device, stream): launches on a stream are ordered, so layers
+    that run back to back on it can share the buffer."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    buf = _WORKSPACES.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
+        _WORKSPACES[key] = buf
+    return buf
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if not t.is_cuda:
+            raise RuntimeError("mhada_style_transfer_b200 runs on a B200 GPU only: got a CPU tensor "
+                               "(there is no CPU fallback; use the reference package on CPU)")
+
+
+def _no_autograd(module: nn.Module, *tensors):
+    if torch.is_grad_enabled() and (any(t.requires_grad for t in tensors) or
+                                    any(p.requires_grad for p in module.parameters())):
+        raise RuntimeError("the B200 MHAda path is forward-only in this round: call it under torch.no_grad() "
+                           "(the reference inference scripts do, e.g. infer_image.py:82)")
+
+
+def _token_major(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """(B,C,h,w) with any strides -> contiguous (B,h,w,C) of `dtype` (one fused copy, or none when the
+    tensor already is channels_last in that dtype, which is what the reference ViT emits)."""
+    t = x.permute(0, 2, 3, 1)
+    if t.dtype == dtype and t.is_contiguous():
+        return t
+    out = torch.empty(t.shape, dtype=dtype, device=x.device)
+    out.copy_(t)
+    return out
+
+
+def _same_tensor(a: torch.Tensor, b: torch.Tensor) -> bool:
+    return a is b or (a.data_ptr() == b.data_ptr() and a.shape == b.shape and a.stride() == b.stride()
+                      and a.dtype == b.dtype)
+
+
+def _code(dtype: torch.dtype) -> int:
+    return _lib.BF16 if dtype == torch.bfloat16 else _lib.F32
+
+
+def _resolve_precision(precision: str, head_dim: int, *inputs) -> torch.dtype:
+    if precision not in ("auto", "fp32", "bf16"):
+        raise ValueError(f"Unknown precision: {precision}")
+    if precision == "fp32":
+        return torch.float32
+    if precision == "bf16":
+        if head_dim != 64:
+            raise NotImplementedError(f"the bf16 tensor-core path implements head_dim 64, got {head_dim}; "
+                                      "use precision='fp32'")
+        return torch.bfloat16
+    low = all(t.dtype in (torch.bfloat16, torch.float16) for t in inputs)
+    return torch.bfloat16 if (low and head_dim == 64) else torch.float32
+
+
+def _layer_forward(dt: torch.dtype, tfc, tfs, tfcs, w_fgh, b_fgh, w_out, b_out, num_heads: int, out=None):
+    """Token-major tensors in, token-major tensor out: AdaAttnMultiHead.forward, adaDecoder.py:162-206."""
+    L = _lib.lib()
+    B, h, w, C = tfc.shape
+    Nc, Ns = h * w, tfs.shape[1] * tfs.shape[2]
+    if out is None:
+        out = torch.empty((B, h, w, C), dtype=dt, device=tfc.device)
+    code = _code(dt)
+    nbytes = L.mhada_layer_workspace(code, B, Nc, Ns, C, num_heads)
+    ws = _workspace(tfc.device, nbytes)
+    with torch.cuda.device(tfc.device):
+        rc = L.mhada_layer_forward(code, _ptr(tfc), _ptr(tfs), _ptr(tfcs), _ptr(w_fgh), _ptr(b_fgh), _ptr(w_out),
+                                   _ptr(b_out), B, Nc, Ns, C, num_heads, _ptr(out), _ptr(ws), ws.numel(), _stream())
+    _lib.check("mhada_layer_forward", rc)
+    return out
+
+
+class _PackedWeights:
+    """Packs per-head conv weights into the [3][H][d][d] / [3][H][d] fp32 buffers the ABI takes; re-packs
+    only when a parameter was modified (version counter) or moved."""
+
+    def __init__(self):
+        self.key = None
+        self.tensors = None
+
+    def get(self, groups: Sequence[Sequence[nn.Conv2d]], out_conv):
+        params = [p for g in groups for m in g for p in (m.weight, m.bias)]
+        if out_conv is not None:
+            params += [out_conv.weight, out_conv.bias]
+        key = tuple((p.data_ptr(), p._version, p.device) for p in params)
+        if key != self.key:
+            with torch.no_grad():
+                w = torch.stack([torch.stack([m.weight.reshape(m.weight.shape[0], -1) for m in g]) for g in groups])
+                b = torch.stack([torch.stack([m.bias for m in g]) for g in groups])
+                w = w.float().contiguous()
+                b = b.float().contiguous()
+                wo = out_conv.weight.reshape(out_conv.weight.shape[0], -1).float().contiguous() if out_conv is not None else None
+                bo = out_conv.bias.float().contiguous() if out_conv is not None else None
+            self.tensors = (w, b, wo, bo)
+            self.key = key
+        return self.tensors
+
+
+# ------------------------------------------------------------------------------------------------
+# activation markers (adaDecoder.py:11-34).  They carry no parameters; the kernels implement softmax.
+# ------------------------------------------------------------------------------------------------
+
+class Softmax(nn.Module):
+    """Marker for softmax(bmm(q, k)) -- computed inside the streaming attention kernels."""
+
+    def forward(self, q, k):  # pragma: no cover - the attention map is never materialised on this path
+        raise RuntimeError("the N x N attention map is never materialised on the B200 path")
+
+
+class CosineSimilarity(nn.Module):
+    """Marker for the 'cosine' activation (adaDecoder.py:20-34); accepted by the constructors like the
+    reference, not implemented by the kernels yet (no reference script uses it)."""
+
+    def forward(self, q, k):  # pragma: no cover
+        raise NotImplementedError("activation='cosine' is not implemented on the B200 path yet")
+
+
+def _make_activation(activation: str) -> nn.Module:
+    if activation == "softmax":
+        return Softmax()
+    if activation == "cosine":
+        return CosineSimilarity()
+    raise ValueError(f"Unknown activation function: {activation}")
+
+
+def _check_activation(m: nn.Module):
+    if isinstance(m, CosineSimilarity):
+        raise NotImplementedError("activation='cosine' is not implemented on the B200 path yet")
+
+
+# ------------------------------------------------------------------------------------------------
+# AdaAttnForLoss (adaDecoder.py:38-81): parameter free, Q/K width != V width
+# ------------------------------------------------------------------------------------------------
+
+class AdaAttnForLoss(nn.Module):
+    def __init__(self, v_dim, qk_dim, activation="softmax"):
+        super().__init__()
+        self.norm_q = nn.InstanceNorm2d(qk_dim, affine=False)
+        self.norm_k = nn.InstanceNorm2d(qk_dim, affine=False)
+        self.norm_v = nn.InstanceNorm2d(v_dim, affine=False)
+        self.activation = _make_activation(activation)
+
+    def forward(self, c_x, s_x, c_1x, s_1x):
+        _require_cuda(c_x, s_x, c_1x, s_1x)
+        _no_autograd(self, c_x, s_x, c_1x, s_1x)
+        _check_activation(self.activation)
+        L = _lib.lib()
+        dt = torch.float32
+        tq, tk, tv, tx = (_token_major(t, dt) for t in (c_1x, s_1x, s_x, c_x))
+        B, h, w, dv = tx.shape
+        dqk = tq.shape[3]
+        Nc, Ns = tq.shape[1] * tq.shape[2], tk.shape[1] * tk.shape[2]
+        if tv.shape[1] * tv.shape[2] != Ns or h * w != Nc or tk.shape[3] != dqk or tv.shape[3] != dv:
+            raise RuntimeError("AdaAttnForLoss: inconsistent shapes")
+        dev = tx.device
+        stats = torch.empty((6, B, max(dqk, dv)), dtype=torch.float32, device=dev)
+        st = _stream()
+        with torch.cuda.device(dev):
+            for i, (t, n, c) in enumerate(((tq, Nc, dqk), (tk, Ns, dqk), (tx, Nc, dv))):
+                nb = L.mhada_in_stats_workspace(B, n, c)
+                ws = _workspace(dev, nb)
+                mean = stats[2 * i].view(-1)[: B * c]
+                rstd = stats[2 * i + 1].view(-1)[: B * c]
+                _lib.check("mhada_in_stats", L.mhada_in_stats(_ptr(t), _lib.F32, B, n, c, c, _ptr(mean), _ptr(rstd),
+                                                              _ptr(ws), ws.numel(), st))
+            out = torch.empty((B, h, w, dv), dtype=dt, device=dev)
+            a = _lib.AttnArgs()
+            a.dtype = _lib.F32
+            a.B, a.H, a.Nc, a.Ns, a.dqk, a.dv = B, 1, Nc, Ns, dqk, dv
+            a.q, a.k, a.v, a.x, a.out = tq.data_ptr(), tk.data_ptr(), tv.data_ptr(), tx.data_ptr(), out.data_ptr()
+            a.ldq, a.ldk, a.ldv, a.ldx, a.ldo = dqk, dqk, dv, dv, dv
+            a.q_mean, a.q_rstd = stats[0].data_ptr(), stats[1].data_ptr()
+            a.k_mean, a.k_rstd = stats[2].data_ptr(), stats[3].data_ptr()
+            a.x_mean, a.x_rstd = stats[4].data_ptr(), stats[5].data_ptr()
+            a.mu_v = None
+            _lib.check("mhada_attn", L.mhada_attn(ctypes.byref(a), st))
+        res = out.permute(0, 3, 1, 2)
+        return res if res.dtype == c_x.dtype else res.to(c_x.dtype)
+
+
+# ------------------------------------------------------------------------------------------------
+# AdaAttN (adaDecoder.py:85-131): single head, learnable f/g/h, no out_conv
+# ------------------------------------------------------------------------------------------------
+
+class AdaAttN(nn.Module):
+    def __init__(self, qkv_dim, activation="softmax"):
+        super().__init__()
+        self.f = nn.Conv2d(qkv_dim, qkv_dim, 1)
+        self.g = nn.Conv2d(qkv_dim, qkv_dim, 1)
+        self.h = nn.Conv2d(qkv_dim, qkv_dim, 1)
+        self.norm_q = nn.InstanceNorm2d(qkv_dim, affine=False)
+        self.norm_k = nn.InstanceNorm2d(qkv_dim, affine=False)
+        self.norm_v = nn.InstanceNorm2d(qkv_dim, affine=False)
+        self.activation = _make_activation(activation)
+        self.precision = "auto"
+        self._packed = _PackedWeights()
+
+    def forward(self, fc: torch.Tensor, fs: torch.Tensor, fcs: torch.Tensor):
+        _require_cuda(fc, fs, fcs)
+        _no_autograd(self, fc, fs, fcs)
+        _check_activation(self.activation)
+        dt = _resolve_precision(self.precision, fc.shape[1], fc, fs, fcs)
+        w, b, _, _ = self._packed.get([[self.f], [self.g], [self.h]], None)
+        tfc, tfs = _token_major(fc, dt), _token_major(fs, dt)
+        tfcs = tfc if _same_tensor(fc, fcs) else _token_major(fcs, dt)
+        out = _layer_forward(dt, tfc, tfs, tfcs, w, b, None, None, 1).permute(0, 3, 1, 2)
+        return out if out.dtype == fc.dtype else out.to(fc.dtype)
+
+
+# ------------------------------------------------------------------------------------------------
+# AdaAttnMultiHead (adaDecoder.py:134-206): the hot path
+# ------------------------------------------------------------------------------------------------
+
+class AdaAttnMultiHead(nn.Module):
+    def __init__(self, qkv_dim, num_heads, activation="softmax"):
+        super().__init__()
+        if qkv_dim % num_heads != 0:
+            raise ValueError("qkv_dim 必須能被 num_heads 整除")   # same message as adaDecoder.py:138
+        self.num_heads = num_heads
+        self.head_dim = qkv_dim // num_heads
+        d = self.head_dim
+        self.f_list = nn.ModuleList([nn.Conv2d(d, d, kernel_size=1) for _ in range(num_heads)])
+        self.g_list = nn.ModuleList([nn.Conv2d(d, d, kernel_size=1) for _ in range(num_heads)])
+        self.h_list = nn.ModuleList([nn.Conv2d(d, d, kernel_size=1) for _ in range(num_heads)])
+        # parameter-free; kept so the attribute surface matches the reference
+        self.norm_q_list = nn.ModuleList([nn.InstanceNorm2d(d, affine=False) for _ in range(num_heads)])
+        self.norm_k_list = nn.ModuleList([nn.InstanceNorm2d(d, affine=False) for _ in range(num_heads)])
+        self.norm_v_out_list = nn.ModuleList([nn.InstanceNorm2d(d, affine=False) for _ in range(num_heads)])
+        self.out_conv = nn.Conv2d(qkv_dim, qkv_dim, kernel_size=1)
+        self.activation = _make_activation(activation)
+        self.precision = "auto"
+        self._packed = _PackedWeights()
+
+    def packed_weights(self):
+        return self._packed.get([self.f_list, self.g_list, self.h_list], self.out_conv)
+
+    def _check_shapes(self, fc, fs, fcs):
+        C = self.num_heads * self.head_dim
+        if fc.dim() != 4 or fs.dim() != 4 or fcs.dim() != 4:
+            raise RuntimeError("fc, fs and fcs must be (b, qkv_dim, h, w)")
+        if fc.shape[1] != C or fs.shape[1] != C or fcs.shape[1] != C:
+            raise RuntimeError(f"expected {C} channels, got {fc.shape[1]}, {fs.shape[1]}, {fcs.shape[1]}")
+        if fs.shape[0] != fc.shape[0]:
+            # the reference reshapes K/V with the content batch (adaDecoder.py:177-183) and fails the same way
+            raise RuntimeError(f"style batch {fs.shape[0]} must equal content batch {fc.shape[0]}")
+        if fcs.shape != fc.shape:
+            raise RuntimeError("fcs must have the shape of fc")
+
+    def forward_tokens(self, dt, tfc, tfs, tfcs, out=None):
+        """Token-major entry used by the transformer to chain layers without layout round trips."""
+        w, b, wo, bo = self.packed_weights()
+        return _layer_forward(dt, tfc, tfs, tfcs, w, b, wo, bo, self.num_heads, out)
+
+    def forward(self, fc: torch.Tensor, fs: torch.Tensor, fcs: torch.Tensor):
+        self._check_shapes(fc, fs, fcs)
+        _require_cuda(fc, fs, fcs)
+        _no_autograd(self, fc, fs, fcs)
+        _check_activation(self.activation)
+        dt = _resolve_precision(self.precision, self.head_dim, fc, fs, fcs)
+        tfc, tfs = _token_major(fc, dt), _token_major(fs, dt)
+        tfcs = tfc if _same_tensor(fc, fcs) else _token_major(fcs, dt)
+        out = self.forward_tokens(dt, tfc, tfs, tfcs).permute(0, 3, 1, 2)
+        return out if out.dtype == fc.dtype else out.to(fc.dtype)
+
+
+# ------------------------------------------------------------------------------------------------
+# Decoder (conv.py:23-100): boundary neighbour, runs on cuDNN through PyTorch (channels_last)
+# ------------------------------------------------------------------------------------------------
+
+class _PadConv(nn.Module):
+    """ReflectionPad2d(k//2) + Conv2d (the reference's `Conv`, conv.py:23-33): keys `conv.weight/bias`."""
+
+    def __init__(self, in_channels: int, out_channels: int, kernel_size: int, stride: int):
+        super().__init__()
+        self.pad = nn.ReflectionPad2d(kernel_size // 2)
+        self.conv = nn.Conv2d(in_channels, out_channels, kernel_size, stride)
+        self._shadow = {}
+
+    def _weights(self, dtype):
+        if dtype == self.conv.weight.dtype:
+            return self.conv.weight, self.conv.bias
+        key = (dtype, self.conv.weight._version, self.conv.bias._version, self.conv.weight.data_ptr())
+        if self._shadow.get("key") != key:
+            self._shadow = {"key": key,
+                            "w": self.conv.weight.detach().to(dtype).contiguous(memory_format=torch.channels_last),
+                            "b": self.conv.bias.detach().to(dtype)}
+        return self._shadow["w"], self._shadow["b"]
+
+    def forward(self, x):
+        w, b = self._weights(x.dtype)
+        return F.conv2d(self.pad(x), w, b, self.conv.stride)
+
+
+class _ConvBlock(nn.Module):
+    """ConvReLU / ConvReluInterpolate (conv.py:36-45, :61-72): key `conv.conv.*`."""
+
+    def __init__(self, in_channels: int, out_channels: int, scale_factor: float = 0.0):
+        super().__init__()
+        self.conv = _PadConv(in_channels, out_channels, 3, 1)
+        self.relu = nn.ReLU()
+        self.scale_factor = scale_factor
+
+    def forward(self, x):
+        x = self.relu(self.conv(x))
+        if self.scale_factor:
+            x = F.interpolate(x, scale_factor=self.scale_factor, mode="bilinear", align_corners=False)
+        return x
+
+
+class Decoder(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.conv1 = nn.Sequential(_ConvBlock(512, 256, 2), _ConvBlock(256, 256), _ConvBlock(256, 256),
+                                   _ConvBlock(256, 256), _ConvBlock(256, 128, 2))
+        self.conv2 = nn.Sequential(_ConvBlock(128, 128), _ConvBlock(128, 64, 2))
+        self.conv3 = nn.Sequential(_ConvBlock(64, 64), _ConvBlock(64, 3))
+
+    def forward(self, fcs: torch.Tensor):
+        if fcs.is_cuda and fcs.dtype == torch.float32:
+            # the fp32 path promises the reference's fp32 arithmetic: keep cuDNN off TF32 here
+            with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+                return self.conv3(self.conv2(self.conv1(fcs)))
+        return self.conv3(self.conv2(self.conv1(fcs)))
+
+
+# ------------------------------------------------------------------------------------------------
+# Transformers (adaDecoder.py:209-268)
+# ------------------------------------------------------------------------------------------------
+
+class AdaAttnTransformer(nn.Module):
+    def __init__(self, num_layers: int = 3, qkv_dim: int = 512, activation: str = "softmax"):
+        super().__init__()
+        self.num_layers = num_layers
+        self.adaAttNs = nn.ModuleList([AdaAttN(qkv_dim, activation) for _ in range(num_layers)])
+        self.decoder = Decoder()
+
+    def forward(self, fc: List[torch.Tensor], fs: List[torch.Tensor]) -> torch.Tensor:
+        fcs = fc[0]
+        for i in range(self.num_layers):
+            fcs = self.adaAttNs[i](fc[i], fs[i], fcs)
+        return self.decoder(fcs)
+
+
+class AdaAttnTransformerMultiHead(nn.Module):
+    def __init__(self, num_layers: int = 3, qkv_dim: int = 512, num_heads: int = 8, activation: str = "softmax"):
+        super().__init__()
+        self.num_layers = num_layers
+        self.adaAttnHead = nn.ModuleList(
+            [AdaAttnMultiHead(qkv_dim=qkv_dim, num_heads=num_heads, activation=activation)
+             for _ in range(num_layers * 2)])
+        self.decoder = Decoder()
+        self.precision = "auto"
+
+    def forward(self, *args):
+        # model(fc_list, fs_list) or model((fc_list, fs_list)) -- adaDecoder.py:253-260
+        if len(args) == 1:
+            fc, fs = args[0]
+        else:
+            fc, fs = args
+        L0 = self.adaAttnHead[0]
+        for i in range(self.num_layers):
+            L0._check_shapes(fc[i], fs[i], fc[0])
+        _require_cuda(*fc, *fs)
+        _no_autograd(self, *fc, *fs)
+        _check_activation(L0.activation)
+        in_dtype = fc[0].dtype
+        dt = _resolve_precision(self.precision, L0.head_dim, *fc[: self.num_layers], *fs[: self.num_layers])
+        tfc = [_token_major(t, dt) for t in fc[: self.num_layers]]
+        tfs = [_token_major(t, dt) for t in fs[: self.num_layers]]
+        fcs = tfc[0]                                                         # :262
+        for i in range(self.num_layers):                                     # :263-265
+            fcs = self.adaAttnHead[2 * i].forward_tokens(dt, tfc[i], tfs[i], fcs)
+            fcs = self.adaAttnHead[2 * i + 1].forward_tokens(dt, fcs, tfs[i], fcs)
+        fcs = fcs.permute(0, 3, 1, 2)            # (B,C,h,w) view over channels_last memory
+        cs = self.decoder(fcs)                   # :267
+        if dt != in_dtype:
+            fcs, cs = fcs.to(in_dtype), cs.to(in_dtype)
+        return fcs, cs
+
+
+def set_precision(module: nn.Module, precision: str) -> nn.Module:
+    """Set `.precision` on a module tree ("auto" | "fp32" | "bf16")."""
+    if precision not in ("auto", "fp32", "bf16"):
+        raise ValueError(f"Unknown precision: {precision}")
+    for m in module.modules():
+        if hasattr(m, "precision"):
+            m.precision = precision
+    return module

@@ -1,0 +1,220 @@
+"""Module-level parity on the B200 against the golden vectors made by the unmodified reference
+(tests/golden, oracle/gen_golden.py) and, at BASELINE.json sizes, against the oracle and through
+size-independent properties.  Tolerances are BASELINE.json's: fp32 path max-abs <= 1e-3 (scaled with
+the output range where the reference's own fp32-vs-fp64 deviation is already larger), bf16 path
+<= 2e-2 relative (max-abs / absmax)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import cases, synth
+from oracle import mhada_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+import mhada_style_transfer_b200 as M  # noqa: E402
+from mhada_style_transfer_b200.network import set_precision  # noqa: E402
+
+DEV = "cuda:0"
+FP32_MAX_ABS = 1e-3
+BF16_REL = 2e-2
+
+
+def dev(x, dtype=torch.float32):
+    return torch.from_numpy(np.ascontiguousarray(x)).to(dtype).to(DEV)
+
+
+def fp32_tol(meta_key):
+    # 1e-3 max-abs, or 3x the reference's own fp32-vs-fp64 deviation on this case when that is larger
+    return max(FP32_MAX_ABS, 3.0 * meta_key["max_abs"])
+
+
+def build_layer(case, sd):
+    m = M.AdaAttnMultiHead(case["C"], case["H"])
+    m.load_state_dict(synth.to_torch(sd, torch.float32), strict=True)
+    return m.to(DEV).eval()
+
+
+@pytest.mark.parametrize("case", cases.LAYER_CASES, ids=lambda c: c["name"])
+def test_layer_fp32_vs_reference_golden(case, golden_index):
+    fc, fs, fcs, sd = cases.layer_inputs(case)
+    m = build_layer(case, sd)
+    tfc, tfs = dev(fc), dev(fs)
+    tfcs = tfc if case.get("fcs_is_fc") else dev(fcs)
+    with torch.no_grad():
+        out = m(tfc, tfs, tfcs)
+    assert out.shape == tfc.shape and out.dtype == torch.float32
+    e = O.errors(out.cpu().numpy(), load_golden(case["name"])["out"])
+    assert e["max_abs"] <= fp32_tol(golden_index[case["name"]]["ref32_vs_ref64"]), e
+
+
+@pytest.mark.parametrize("case", [c for c in cases.LAYER_CASES if c["C"] // c["H"] == 64], ids=lambda c: c["name"])
+def test_layer_bf16_vs_reference_golden(case, golden_index):
+    fc, fs, fcs, sd = cases.layer_inputs(case)
+    m = build_layer(case, sd)
+    m.precision = "bf16"
+    tfc, tfs = dev(fc), dev(fs)
+    tfcs = tfc if case.get("fcs_is_fc") else dev(fcs)
+    with torch.no_grad():
+        out = m(tfc, tfs, tfcs)
+    assert out.dtype == torch.float32
+    e = O.errors(out.cpu().numpy(), load_golden(case["name"])["out"])
+    # the stress case multiplies the logits by 16: bf16 Q/K rounding then moves probability mass
+    tol = BF16_REL if case.get("gain", 1.0) == 1.0 else 8e-2
+    assert e["max_abs_rel"] <= tol, e
+    # bf16 tensors in -> bf16 out on the "auto" path
+    m.precision = "auto"
+    with torch.no_grad():
+        ob = m(tfc.bfloat16(), tfs.bfloat16(), tfcs.bfloat16())
+    assert ob.dtype == torch.bfloat16
+    eb = O.errors(ob.float().cpu().numpy(), load_golden(case["name"])["out"])
+    assert eb["max_abs_rel"] <= 2 * tol, eb
+
+
+def test_layer_accepts_nchw_and_channels_last():
+    case = cases.by_name("layer_c512_h8_ragged")
+    fc, fs, fcs, sd = cases.layer_inputs(case)
+    m = build_layer(case, sd)
+    a = [dev(x) for x in (fc, fs, fcs)]
+    b = [t.contiguous(memory_format=torch.channels_last) for t in a]
+    with torch.no_grad():
+        o1, o2 = m(*a), m(*b)
+    assert torch.equal(o1, o2)
+
+
+@pytest.mark.parametrize("case", cases.ADAATTN_CASES, ids=lambda c: c["name"])
+def test_adaattn_fp32(case, golden_index):
+    fc, fs, fcs, sd = cases.adaattn_inputs(case)
+    m = M.AdaAttN(case["C"])
+    m.load_state_dict(synth.to_torch(sd, torch.float32), strict=True)
+    m = m.to(DEV).eval()
+    with torch.no_grad():
+        out = m(dev(fc), dev(fs), dev(fcs))
+    e = O.errors(out.cpu().numpy(), load_golden(case["name"])["out"])
+    assert e["max_abs"] <= fp32_tol(golden_index[case["name"]]["ref32_vs_ref64"]), e
+
+
+@pytest.mark.parametrize("case", cases.FORLOSS_CASES, ids=lambda c: c["name"])
+def test_forloss_fp32(case, golden_index):
+    args = [dev(a) for a in cases.forloss_inputs(case)]
+    m = M.AdaAttnForLoss(case["v"], case["qk"]).to(DEV).eval()
+    with torch.no_grad():
+        out = m(*args)
+    e = O.errors(out.cpu().numpy(), load_golden(case["name"])["out"])
+    assert e["max_abs"] <= fp32_tol(golden_index[case["name"]]["ref32_vs_ref64"]), e
+
+
+def build_transformer(sd, precision="auto"):
+    m = M.AdaAttnTransformerMultiHead()
+    m.load_state_dict(synth.to_torch(sd, torch.float32), strict=True)
+    m = m.to(DEV).eval()
+    return set_precision(m, precision)
+
+
+@pytest.mark.parametrize("case", cases.TRANSFORMER_CASES, ids=lambda c: c["name"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_transformer_vs_reference_golden(case, precision, golden_index):
+    """6 MHAda layers + decoder (adaDecoder.py:253-268); transformer_64x64_sub is BASELINE configs[0]'s
+    size (512x512 image -> 4096 tokens)."""
+    fc, fs, sd = cases.transformer_inputs(case)
+    m = build_transformer(sd, precision)
+    with torch.no_grad():
+        fcs, cs = m([dev(x) for x in fc], [dev(x) for x in fs])          # call form 1
+        fcs2, cs2 = m(([dev(x) for x in fc], [dev(x) for x in fs]))      # call form 2 (ptflops style)
+    assert torch.equal(fcs, fcs2) and torch.equal(cs, cs2)
+    B = case["B"]
+    h, w = case["hw"]
+    assert fcs.shape == (B, 512, h, w) and cs.shape == (B, 3, 8 * h, 8 * w)
+    g = load_golden(case["name"])
+    meta = golden_index[case["name"]]
+    ef = O.errors(cases.token_sublattice(fcs.cpu().numpy(), case["sub"]), g["fcs"])
+    ec = O.errors(cases.pixel_sublattice(cs.cpu().numpy(), case["img_sub"]), g["cs"])
+    if precision == "fp32":
+        assert ef["max_abs"] <= fp32_tol(meta["fcs_ref32_vs_ref64"]), ef
+        assert ec["max_abs_rel"] <= 1e-4, ec
+    else:
+        assert ef["max_abs_rel"] <= BF16_REL, ef
+        assert ec["max_abs_rel"] <= BF16_REL, ec
+
+
+# ---------------------------------------------------------------------------------------------------
+# BASELINE.json sizes: oracle where it finishes in seconds, properties above that
+# ---------------------------------------------------------------------------------------------------
+
+def test_layer_512px_vs_oracle():
+    """One layer at configs[0]/[1] size (64x64 tokens) against the float64 oracle, both paths."""
+    case = dict(B=1, C=512, H=8, hw=(64, 64), hsws=(64, 64), seed=71, gain=1.0)
+    fc, fs, fcs, sd = cases.layer_inputs(case)
+    want = O.ada_attn_multi_head(fc, fs, fcs, sd, 8)
+    m = build_layer(case, sd)
+    with torch.no_grad():
+        o32 = m(dev(fc), dev(fs), dev(fcs))
+        m.precision = "bf16"
+        o16 = m(dev(fc), dev(fs), dev(fcs))
+    e32, e16 = O.errors(o32.cpu().numpy(), want), O.errors(o16.cpu().numpy(), want)
+    assert e32["max_abs"] <= FP32_MAX_ABS, e32
+    assert e16["max_abs_rel"] <= BF16_REL, e16
+
+
+@pytest.mark.parametrize("B,hw,hsws", [(8, (64, 64), (64, 64)), (1, (128, 128), (128, 128)), (1, (135, 240), (64, 64))])
+def test_full_size_properties(B, hw, hsws):
+    """configs[1] (batch 8 @512^2), configs[2] (1024^2 -> 16384 tokens), configs[3] (1080p frame x 512^2
+    style): (a) tensor-core path vs fp32 SIMT path -- two independent implementations -- within the bf16
+    tolerance on a token sub-lattice; (b) images are independent: element 0 of the batch equals the B=1 run
+    bit for bit; (c) constant style => S = sqrt(1e-6), M = V: out = 1e-3 * IN(fcs) + const, closed form."""
+    case = dict(B=B, C=512, H=8, hw=hw, hsws=hsws, seed=81, gain=1.0)
+    fc, fs, fcs, sd = cases.layer_inputs(case)
+    m = build_layer(case, sd)
+    tfc, tfs, tfcs = dev(fc, torch.bfloat16), dev(fs, torch.bfloat16), dev(fcs, torch.bfloat16)
+    with torch.no_grad():
+        o16 = m(tfc, tfs, tfcs)                                   # auto -> tensor cores
+        m.precision = "fp32"
+        # fp32 path on a query subset keeps the SIMT run short at 16k / 32k tokens
+        rows = min(hw[0], 8)
+        o32 = m(tfc[:1, :, :rows].float(), tfs[:1].float(), tfcs[:1, :, :rows].float())
+    # (a) NOTE: instance-norm statistics of fc / fcs are taken over the tokens present, so compare on a
+    # run where both paths see the same content tokens
+    with torch.no_grad():
+        m.precision = "bf16"
+        o16_sub = m(tfc[:1, :, :rows], tfs[:1], tfcs[:1, :, :rows])
+    e = O.errors(o16_sub.float().cpu().numpy(), o32.cpu().numpy())
+    assert e["max_abs_rel"] <= BF16_REL, e
+    # (b)
+    with torch.no_grad():
+        o1 = m(tfc[:1], tfs[:1], tfcs[:1])
+    assert torch.equal(o1, o16[:1])
+    # (c)
+    const_fs = tfs[:1, :, :1, :1].expand(-1, -1, hsws[0], hsws[1]).contiguous()
+    with torch.no_grad():
+        oc = m(tfc[:1], const_fs, tfcs[:1]).float()
+        m.precision = "fp32"
+        oc32 = m(tfc[:1, :, :rows].float(), const_fs.float(), tfcs[:1, :, :rows].float())
+    x = tfcs[:1].float()
+    xin = (x - x.mean((2, 3), keepdim=True)) / torch.sqrt(x.var((2, 3), unbiased=False, keepdim=True) + 1e-5)
+    # heads output before out_conv: 1e-3 * IN(fcs) + V (V = Wh fs0 + bh, constant per channel)
+    v = torch.cat([torch.nn.functional.conv2d(const_fs[:, i * 64:(i + 1) * 64, :1, :1].float(), m.h_list[i].weight,
+                                              m.h_list[i].bias) for i in range(8)], dim=1)
+    heads = 1e-3 * xin + v
+    want = torch.nn.functional.conv2d(heads, m.out_conv.weight, m.out_conv.bias)
+    ec = O.errors(oc.cpu().numpy(), want.cpu().numpy())
+    assert ec["max_abs_rel"] <= BF16_REL, ec
+    xs = tfcs[:1, :, :rows].float()
+    xin_s = (xs - xs.mean((2, 3), keepdim=True)) / torch.sqrt(xs.var((2, 3), unbiased=False, keepdim=True) + 1e-5)
+    want_s = torch.nn.functional.conv2d(1e-3 * xin_s + v, m.out_conv.weight, m.out_conv.bias)
+    ec32 = O.errors(oc32.cpu().numpy(), want_s.cpu().numpy())
+    assert ec32["max_abs"] <= 2e-3, ec32
+
+
+def test_errors_on_device():
+    m = M.AdaAttnMultiHead(512, 8, activation="cosine").to(DEV)
+    x = torch.zeros(1, 512, 4, 4, device=DEV)
+    with torch.no_grad(), pytest.raises(NotImplementedError):
+        m(x, x, x)
+    m = M.AdaAttnMultiHead(512, 8).to(DEV)
+    with pytest.raises(RuntimeError, match="forward-only"):
+        m(x, x, x)                      # grad mode with trainable parameters
+    m4 = M.AdaAttnMultiHead(512, 4).to(DEV)
+    m4.precision = "bf16"
+    with torch.no_grad(), pytest.raises(NotImplementedError):
+        m4(x, x, x)

@@ -1,0 +1,222 @@
+"""Stage-level parity on the B200, every call going through the C ABI (include/mhada_b200.h),
+each stage against the numpy oracle on the same seeded inputs."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mhada_oracle as O
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+
+from mhada_style_transfer_b200 import _lib  # noqa: E402
+import gpu_util as G  # noqa: E402
+
+F32, BF16 = _lib.F32, _lib.BF16
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _lib_loaded():
+    L = _lib.lib()
+    assert L.mhada_device_check() == 0, L.mhada_last_error()
+    return L
+
+
+# ------------------------------------------------------------------------------------------------ stats
+@pytest.mark.parametrize("code", [F32, BF16])
+@pytest.mark.parametrize("B,C,hw", [(2, 512, (16, 16)), (1, 512, (9, 15)), (3, 64, (7, 5)), (1, 1472, (3, 3)),
+                                    (8, 512, (64, 64)), (1, 512, (135, 240))])
+def test_in_stats(code, B, C, hw):
+    x = synth.features(100 + B + C, B, C, *hw)
+    x[:, :7] += 4000.0          # |mean| >> std on a few channels: exercises the pivoted accumulation
+    xt = G.to_tokens(x, code)
+    xr = G.from_tokens(xt, hw)  # what the kernel actually saw (bf16-rounded on that path)
+    mean, rstd = G.stats(xt, code)
+    em, er = O.instance_norm_stats(xr)
+    assert np.abs(mean.cpu().numpy() - em).max() <= 2e-6 * np.abs(em).max() + 1e-4
+    assert (np.abs(rstd.cpu().numpy() - er) / er).max() <= 2e-5
+
+
+# ------------------------------------------------------------------------------------------------ linear
+@pytest.mark.parametrize("code,M,Cin,Cout", [(F32, 300, 512, 512), (F32, 77, 96, 40), (BF16, 300, 512, 512),
+                                             (BF16, 4096, 512, 512), (BF16, 130, 128, 64), (BF16, 128, 64, 192)])
+def test_linear(code, M, Cin, Cout):
+    L = _lib.lib()
+    x = synth.bellish(7, (M, Cin), 0.0, 30.0)
+    w = synth.uniform(8, (Cout, Cin), -0.05, 0.05)
+    b = synth.uniform(9, (Cout,), -1, 1)
+    xt = torch.from_numpy(x).float().to(G.DEV).to(G.tdt(code)).contiguous()
+    y = torch.empty(M, Cout, dtype=G.tdt(code), device=G.DEV)
+    wsb = G.ws(L.mhada_linear_workspace(code, Cout, Cin))
+    _lib.check("mhada_linear", L.mhada_linear(code, G.ptr(xt), Cin, G.ptr(G.f32(w)), G.ptr(G.f32(b)), M, Cin, Cout,
+                                              G.ptr(y), Cout, G.ptr(wsb), wsb.numel(), G.stream()))
+    if code == BF16:
+        want = xt.float().cpu().numpy().astype(np.float64) @ G.bf16_round(w).T + b
+        tol = 6e-3      # output rounding to bf16 (2^-9 relative) on |y| up to absmax
+    else:
+        want = x.astype(np.float32).astype(np.float64) @ w.astype(np.float32).astype(np.float64).T + b
+        tol = 2e-6
+    e = O.errors(y.float().cpu().numpy(), want)
+    assert e["max_abs_rel"] <= tol, e
+
+
+# ------------------------------------------------------------------------------------------------ projections
+def _proj_case(code, B, H, hw, hsws, seed=3):
+    L = _lib.lib()
+    d, C = 64, H * 64
+    fc = synth.features(seed, B, C, *hw)
+    fs = synth.features(seed + 1, B, C, *hsws)
+    sd = synth.mhada_layer_state(seed, C, H)
+    tfc, tfs = G.to_tokens(fc, code), G.to_tokens(fs, code)
+    fcr, fsr = G.from_tokens(tfc, hw), G.from_tokens(tfs, hsws)
+    mc, rc = G.stats(tfc, code)
+    ms, rs = G.stats(tfs, code)
+    w, b = G.pack_fgh(sd, H)
+    Nc, Ns = hw[0] * hw[1], hsws[0] * hsws[1]
+    dt = G.tdt(code)
+    q = torch.empty(B, Nc, C, dtype=dt, device=G.DEV)
+    k = torch.empty(B, Ns, C, dtype=dt, device=G.DEV)
+    v = torch.empty(B, Ns, C * (2 if code == BF16 else 1), dtype=dt, device=G.DEV)
+    muv = torch.empty(B, C, dtype=torch.float32, device=G.DEV)
+    wsb = G.ws(L.mhada_proj_workspace(B, H, d))
+    _lib.check("mhada_proj", L.mhada_proj(code, G.ptr(tfc), G.ptr(tfs), G.ptr(mc), G.ptr(rc), G.ptr(ms), G.ptr(rs),
+                                          G.ptr(w), G.ptr(b), B, Nc, Ns, H, d, G.ptr(q), G.ptr(k), G.ptr(v),
+                                          G.ptr(muv), G.ptr(wsb), wsb.numel(), G.stream()))
+    # oracle on the tensors the kernels saw
+    eq = np.zeros((B, C) + tuple(hw)); ek = np.zeros((B, C) + tuple(hsws)); ev = np.zeros_like(ek)
+    for i in range(H):
+        sl = slice(i * d, (i + 1) * d)
+        eq[:, sl] = O.conv1x1(O.instance_norm(fcr[:, sl]), sd[f"f_list.{i}.weight"], sd[f"f_list.{i}.bias"])
+        ek[:, sl] = O.conv1x1(O.instance_norm(fsr[:, sl]), sd[f"g_list.{i}.weight"], sd[f"g_list.{i}.bias"])
+        ev[:, sl] = O.conv1x1(fsr[:, sl], sd[f"h_list.{i}.weight"], sd[f"h_list.{i}.bias"])
+    return dict(q=q, k=k, v=v, muv=muv, eq=eq, ek=ek, ev=ev, hw=hw, hsws=hsws, B=B, C=C, H=H)
+
+
+@pytest.mark.parametrize("B,H,hw,hsws", [(2, 8, (16, 16), (16, 16)), (1, 8, (9, 15), (11, 13)), (1, 2, (20, 20), (5, 4))])
+def test_proj_f32(B, H, hw, hsws):
+    r = _proj_case(F32, B, H, hw, hsws)
+    assert O.errors(G.from_tokens(r["q"], hw), r["eq"])["max_abs_rel"] < 5e-6
+    assert O.errors(G.from_tokens(r["k"], hsws), r["ek"])["max_abs_rel"] < 5e-6
+    vfull = G.from_tokens(r["v"], hsws) + r["muv"].cpu().numpy().astype(np.float64)[:, :, None, None]
+    assert O.errors(vfull, r["ev"])["max_abs_rel"] < 5e-6
+    # V~ is centred: its token mean is ~0 relative to its spread
+    vc = G.from_tokens(r["v"], hsws)
+    assert np.abs(vc.mean(axis=(2, 3))).max() < 1e-3 * vc.std()
+
+
+@pytest.mark.parametrize("B,H,hw,hsws", [(2, 8, (16, 16), (16, 16)), (1, 8, (9, 15), (11, 13)), (1, 2, (20, 20), (5, 4))])
+def test_proj_bf16(B, H, hw, hsws):
+    r = _proj_case(BF16, B, H, hw, hsws)
+    C, d = r["C"], 64
+    log2e = 1.4426950408889634
+    # bf16 weights x bf16 inputs, fp32 accumulate, bf16 output rounding: ~2^-8 relative per element
+    assert O.errors(G.from_tokens(r["q"], hw), r["eq"] * log2e)["max_abs_rel"] < 1.5e-2
+    assert O.errors(G.from_tokens(r["k"], hsws), r["ek"])["max_abs_rel"] < 1.5e-2
+    vp = r["v"].float().cpu().numpy().astype(np.float64).reshape(B, -1, r["H"], 2, d)       # [B,Ns,H,2,d]
+    vt = vp[:, :, :, 0].reshape(B, -1, C).transpose(0, 2, 1).reshape(r["ev"].shape)
+    v2 = vp[:, :, :, 1].reshape(B, -1, C).transpose(0, 2, 1).reshape(r["ev"].shape)
+    vfull = vt + r["muv"].cpu().numpy().astype(np.float64)[:, :, None, None]
+    assert O.errors(vfull, r["ev"])["max_abs_rel"] < 1.5e-2
+    assert O.errors(v2, vt * vt)["max_abs_rel"] < 1e-2           # second half is the square of the first
+
+
+# ------------------------------------------------------------------------------------------------ attention
+def _attn_expected(q, k, v, x, xm, xr, muv, H, dqk, dv, base2: bool):
+    """float64 evaluation of adaDecoder.py:186-198 on token-major arrays."""
+    B, Nc, _ = q.shape
+    out = np.zeros((B, Nc, H * dv))
+    for h in range(H):
+        qq = q[:, :, h * dqk:(h + 1) * dqk]
+        kk = k[:, :, h * dqk:(h + 1) * dqk]
+        vv = v[:, :, h * dv:(h + 1) * dv]
+        s = qq @ kk.transpose(0, 2, 1)
+        if base2:
+            s = s * np.log(2.0)
+        s = s - s.max(-1, keepdims=True)
+        a = np.exp(s)
+        a /= a.sum(-1, keepdims=True)
+        m = a @ vv
+        var = a @ (vv * vv) - m * m
+        sd = np.sqrt(np.maximum(var, 1e-6))
+        sl = slice(h * dv, (h + 1) * dv)
+        xn = (x[:, :, sl] - xm[:, None, sl]) * xr[:, None, sl]
+        out[:, :, sl] = sd * xn + m + (muv[:, None, sl] if muv is not None else 0.0)
+    return out
+
+
+@pytest.mark.parametrize("B,H,Nc,Ns,dqk,dv", [(2, 8, 256, 256, 64, 64), (1, 8, 135, 143, 64, 64), (1, 1, 144, 144, 448, 256),
+                                              (2, 1, 36, 36, 960, 512), (1, 2, 100, 3, 16, 24), (1, 4, 200, 1000, 128, 128)])
+def test_attn_f32(B, H, Nc, Ns, dqk, dv):
+    L = _lib.lib()
+    q = synth.bellish(1, (B, Nc, H * dqk), 0, 0.6)
+    k = synth.bellish(2, (B, Ns, H * dqk), 0, 0.6)
+    v = synth.bellish(3, (B, Ns, H * dv), 0, 40.0)
+    x = synth.bellish(4, (B, Nc, H * dv), 2.0, 30.0)
+    muv = synth.uniform(5, (B, H * dv), -3, 3)
+    tq, tk, tv, tx = (G.f32(a) for a in (q, k, v, x))
+    xm, xr = G.stats(tx, F32)
+    out = torch.empty(B, Nc, H * dv, dtype=torch.float32, device=G.DEV)
+    a = _lib.AttnArgs()
+    a.dtype = F32
+    a.B, a.H, a.Nc, a.Ns, a.dqk, a.dv = B, H, Nc, Ns, dqk, dv
+    a.q, a.k, a.v, a.x, a.out = tq.data_ptr(), tk.data_ptr(), tv.data_ptr(), tx.data_ptr(), out.data_ptr()
+    a.ldq, a.ldk, a.ldv, a.ldx, a.ldo = H * dqk, H * dqk, H * dv, H * dv, H * dv
+    keep = G.f32(muv)
+    a.x_mean, a.x_rstd, a.mu_v = xm.data_ptr(), xr.data_ptr(), keep.data_ptr()
+    _lib.check("mhada_attn", L.mhada_attn(ctypes.byref(a), G.stream()))
+    f = lambda z: z.astype(np.float32).astype(np.float64)
+    want = _attn_expected(f(q), f(k), f(v), f(x), xm.cpu().numpy().astype(np.float64),
+                          xr.cpu().numpy().astype(np.float64), f(muv), H, dqk, dv, base2=False)
+    e = O.errors(out.cpu().numpy(), want)
+    assert e["max_abs_rel"] < 2e-5, e
+
+
+@pytest.mark.parametrize("B,H,Nc,Ns,gain", [(1, 1, 128, 128, 0.5), (1, 1, 256, 128, 0.5), (1, 1, 128, 384, 0.5),
+                                            (2, 8, 256, 256, 0.6), (1, 8, 135, 143, 0.6), (1, 2, 300, 1000, 0.6),
+                                            (1, 2, 512, 700, 2.0), (1, 8, 4096, 4096, 0.6), (1, 1, 70, 1, 0.6)])
+def test_attn_bf16(B, H, Nc, Ns, gain):
+    """tcgen05 kernel against a float64 evaluation on the SAME bf16-rounded operands: what is left is
+    the bf16 rounding of P, fp32 accumulation and the bf16 output rounding."""
+    L = _lib.lib()
+    d = 64
+    C = H * d
+    bf = lambda a: torch.from_numpy(a).float().to(G.DEV).to(torch.bfloat16).contiguous()
+    q = synth.bellish(11, (B, Nc, C), 0, gain)          # log2 units: logits std ~ gain^2 * 8
+    k = synth.bellish(12, (B, Ns, C), 0, gain)
+    vt = synth.bellish(13, (B, Ns, H, d), 0, 40.0)
+    x = synth.bellish(14, (B, Nc, C), 2.0, 30.0)
+    muv = synth.uniform(15, (B, C), -3, 3)
+    tq, tk, tx = bf(q), bf(k), bf(x)
+    tvt = bf(vt)
+    tv = torch.cat([tvt, (tvt.float() ** 2).to(torch.bfloat16)], dim=3).reshape(B, Ns, 2 * C).contiguous()
+    xm, xr = G.stats(tx, BF16)
+    tmu = G.f32(muv)
+    out = torch.empty(B, Nc, C, dtype=torch.bfloat16, device=G.DEV)
+    a = _lib.AttnArgs()
+    a.dtype = BF16
+    a.B, a.H, a.Nc, a.Ns, a.dqk, a.dv = B, H, Nc, Ns, d, d
+    a.q, a.k, a.v, a.x, a.out = tq.data_ptr(), tk.data_ptr(), tv.data_ptr(), tx.data_ptr(), out.data_ptr()
+    a.ldq, a.ldk, a.ldv, a.ldx, a.ldo = C, C, 2 * C, C, C
+    a.x_mean, a.x_rstd, a.mu_v = xm.data_ptr(), xr.data_ptr(), tmu.data_ptr()
+    _lib.check("mhada_attn", L.mhada_attn(ctypes.byref(a), G.stream()))
+    torch.cuda.synchronize()
+    n = lambda t: t.float().cpu().numpy().astype(np.float64)
+    # the kernel's second moment uses the bf16-rounded squares; mirror that in the expectation
+    vv = n(tvt).reshape(B, Ns, C)
+    v2 = n(tv).reshape(B, Ns, H, 2, d)[:, :, :, 1].reshape(B, Ns, C)
+    want = np.zeros((B, Nc, C))
+    for h in range(H):
+        sl = slice(h * d, (h + 1) * d)
+        s = (n(tq)[:, :, sl] @ n(tk)[:, :, sl].transpose(0, 2, 1)) * np.log(2.0)
+        s -= s.max(-1, keepdims=True)
+        p = np.exp(s)
+        p /= p.sum(-1, keepdims=True)
+        m = p @ vv[:, :, sl]
+        var = p @ v2[:, :, sl] - m * m
+        sd = np.sqrt(np.maximum(var, 1e-6))
+        xn = (n(tx)[:, :, sl] - n(xm)[:, None, sl]) * n(xr)[:, None, sl]
+        want[:, :, sl] = sd * xn + m + muv.astype(np.float32).astype(np.float64)[:, None, sl]
+    e = O.errors(n(out), want)
+    assert e["max_abs_rel"] < 1.2e-2 and e["fro_rel"] < 4e-3, e

@@ -1,0 +1,97 @@
+"""Host-side mirror of the reference module surface + the C-ABI library (CPU only, no compute)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import ROOT
+from oracle import synth
+
+import mhada_style_transfer_b200 as M
+from mhada_style_transfer_b200 import _lib, build as build_mod
+
+
+@pytest.fixture(scope="module")
+def lib():
+    build_mod.build()
+    return _lib.lib()
+
+
+def test_state_dict_is_reference_compatible():
+    # 318 keys, same names / shapes / order as the reference (SURVEY.md §5 checkpoint row)
+    m = M.AdaAttnTransformerMultiHead()
+    sd = synth.to_torch(synth.transformer_state(5), torch.float32)
+    assert len(sd) == 318
+    assert list(m.state_dict().keys()) == list(sd.keys())
+    assert m.load_state_dict(sd, strict=True).missing_keys == []
+    for k, v in m.state_dict().items():
+        assert tuple(v.shape) == tuple(sd[k].shape), k
+    # single layer / single head variants
+    l = M.AdaAttnMultiHead(512, 8)
+    l.load_state_dict(synth.to_torch(synth.mhada_layer_state(3, 512, 8), torch.float32), strict=True)
+    a = M.AdaAttN(64)
+    a.load_state_dict(synth.to_torch(synth.adaattn_state(3, 64), torch.float32), strict=True)
+    assert M.AdaAttnForLoss(256, 448).state_dict() == {}
+
+
+def test_attribute_surface():
+    l = M.AdaAttnMultiHead(512, 8)
+    for name in ("num_heads", "head_dim", "f_list", "g_list", "h_list", "norm_q_list", "norm_k_list",
+                 "norm_v_out_list", "out_conv", "activation"):
+        assert hasattr(l, name), name
+    assert l.num_heads == 8 and l.head_dim == 64 and len(l.f_list) == 8
+    assert l.f_list[0].weight.shape == (64, 64, 1, 1) and l.out_conv.weight.shape == (512, 512, 1, 1)
+    t = M.AdaAttnTransformerMultiHead(num_layers=2, qkv_dim=256, num_heads=4)
+    assert t.num_layers == 2 and len(t.adaAttnHead) == 4 and hasattr(t, "decoder")
+    assert M.AdaAttnTransformer().num_layers == 3
+
+
+def test_constructor_errors_match_reference():
+    with pytest.raises(ValueError):
+        M.AdaAttnMultiHead(512, 7)                      # adaDecoder.py:137-138
+    with pytest.raises(ValueError, match="Unknown activation"):
+        M.AdaAttnMultiHead(512, 8, activation="relu")   # adaDecoder.py:160
+    with pytest.raises(ValueError, match="Unknown activation"):
+        M.AdaAttnForLoss(64, 64, "tanh")
+    M.AdaAttnMultiHead(512, 8, activation="cosine")     # accepted at construction like the reference
+
+
+def test_no_cpu_fallback():
+    m = M.AdaAttnMultiHead(128, 2)
+    x = torch.zeros(1, 128, 4, 4)
+    with torch.no_grad(), pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(x, x, x)
+    with pytest.raises(RuntimeError):
+        m(x, torch.zeros(2, 128, 4, 4), x)              # batch mismatch (adaDecoder.py:177-183)
+
+
+def test_library_exports_every_declared_symbol(lib):
+    header = open(os.path.join(ROOT, "include", "mhada_b200.h")).read()
+    declared = set(re.findall(r"MHADA_API\s+[\w\s\*]+?\b(mhada_\w+)\s*\(", header))
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.mhada_abi_version() == 1
+
+
+def test_abi_rejects_without_gpu_or_bad_args(lib):
+    # argument validation happens before any CUDA call, so it is testable on a CPU box
+    rc = lib.mhada_in_stats(None, 0, 1, 1, 4, 4, None, None, None, 0, None)
+    assert rc == -1 and b"null" in lib.mhada_last_error()
+    assert lib.mhada_layer_workspace(_lib.BF16, 8, 4096, 4096, 512, 8) > 0
+    assert lib.mhada_layer_workspace(_lib.BF16, 8, 4096, 4096, 512, 7) == 0
+    buf = (ctypes.c_float * 64)()
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    rc = lib.mhada_layer_forward(_lib.BF16, p, p, p, p, p, None, None, 1, 4, 4, 512, 4, p, p, 1 << 30, None)
+    assert rc == -1   # out aliases an input
+    if not torch.cuda.is_available():
+        assert lib.mhada_device_check() == -3
+
+
+def test_workspace_formula_matches_design(lib):
+    # bf16, cfg2: Q,K,heads [8,4096,512] bf16 + V' [8,4096,1024] bf16 dominate
+    n = lib.mhada_layer_workspace(_lib.BF16, 8, 4096, 4096, 512, 8)
+    tensors = 8 * 4096 * 512 * 2 * 5
+    assert tensors <= n <= tensors + (8 << 20)
