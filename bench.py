@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""bench.py -- images/sec of the MHAda forward hot path (BASELINE.json metric) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload cfg2|cfg3|cfg1]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (N=1 default) = BASELINE.json configs[1]: batch 8 of 512x512 content/style (ViT feature maps
+3 x [8,512,64,64] each), bf16, MHAda x6 + decoder.  One step = one forward of
+AdaAttnTransformerMultiHead over one batch per GPU (weak scaling: 8 images per GPU, sharded by image,
+no data-path collective; outputs gathered to rank 0 over NCCL at the end of every step).
+
+One JSON line on rank 0:
+  value     images/s, inputs resident in HBM, device-timed (CUDA events), max over ranks
+  e2e       images/s through the public module call with HOST (pinned) inputs: H2D of the six feature
+            maps and D2H of the decoded images inside the timed region
+  roofline  the attention kernel (tcgen05): algorithmic FLOPs 6*B*Nc*Ns*C per launch / its device time
+            measured with CUDA events on the launching stream INSIDE the timed region
+  cpu_baseline  the PyTorch-CPU port of the reference path (oracle/torch_port.py) on this box's cores
+--impl reference times that CPU port alone (the reference is Python and cannot travel to the GPU box).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: (batch per GPU, content tokens h,w, style tokens h,w, dtype)
+    "cfg2": dict(B=8, hw=(64, 64), hsws=(64, 64), dtype="bf16",
+                 desc="BASELINE configs[1]: batch 8 of 512x512 content/style, bf16, MHAda x6 + decoder"),
+    "cfg3": dict(B=1, hw=(128, 128), hsws=(128, 128), dtype="bf16",
+                 desc="BASELINE configs[2]: 1024x1024 content/style (16384 tokens), bf16, MHAda x6 + decoder"),
+    "cfg1": dict(B=1, hw=(64, 64), hsws=(64, 64), dtype="fp32",
+                 desc="BASELINE configs[0]: single 512x512 content/style, fp32, MHAda x6 + decoder"),
+}
+C, H, LAYERS = 512, 8, 3
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"bf16_tflops": p["bf16_tflops"], "bf16_tflops_sustained": p.get("bf16_tflops_sustained"),
+                "hbm_gbs": p["hbm_gbs"], "source": "measured (MEASURED_PEAKS.json)"}
+    return {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0,
+            "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, reasons, mx, pw = [], set(), None, []
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1]); pw.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        # "under load" = the upper half of the samples (the sampler also sees the idle edges)
+        sm.sort()
+        load = sm[len(sm) // 2:] if sm else []
+        return {"sm_mhz": (load[len(load) // 2] if load else None), "sm_max_mhz": mx,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_features(wl, device, seed):
+    """Synthetic ViT feature maps with the reference's random-init statistics (std ~85): three levels
+    for content and style, channels_last memory like the reference ViT emits (vit.py:163-166)."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    B = wl["B"]
+    dt = torch.bfloat16 if wl["dtype"] == "bf16" else torch.float32
+
+    def one(hw):
+        x = torch.randn(B, hw[0], hw[1], C, generator=g) * 85.0 + 1.3      # token-major memory
+        return x.to(dt)
+
+    fc = [one(wl["hw"]) for _ in range(LAYERS)]
+    fs = [one(wl["hsws"]) for _ in range(LAYERS)]
+    return fc, fs
+
+
+def build_model(wl, device):
+    import mhada_style_transfer_b200 as M
+    from mhada_style_transfer_b200.network import set_precision
+    from oracle import synth
+    m = M.AdaAttnTransformerMultiHead(num_layers=LAYERS, qkv_dim=C, num_heads=H)
+    m.load_state_dict(synth.to_torch(synth.transformer_state(1234), torch.float32), strict=True)
+    m = m.to(device).eval()
+    return set_precision(m, "bf16" if wl["dtype"] == "bf16" else "fp32")
+
+
+def cpu_port_run(wl, images: int, steps: int, warmup: int, budget_s: float):
+    """Times oracle/torch_port.py (the reference's CPU path, re-stated) on `images` images per step."""
+    from oracle import synth, torch_port
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = torch_port.prepare(synth.transformer_state(1234))
+    g = torch.Generator().manual_seed(0)
+    hw, hs = wl["hw"], wl["hsws"]
+    fc = [torch.randn(images, C, hw[0], hw[1], generator=g) * 85 + 1.3 for _ in range(LAYERS)]
+    fs = [torch.randn(images, C, hs[0], hs[1], generator=g) * 85 + 1.3 for _ in range(LAYERS)]
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            torch_port.transformer(fc, fs, sd)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+            if sum(times) > budget_s and len(times) >= 1:
+                break
+    return times
+
+
+def run_reference(args, wl, rank):
+    if rank != 0:
+        return
+    images = 1
+    times = cpu_port_run(wl, images, args.steps, args.warmup, budget_s=240.0)
+    sec = sum(times) / len(times)
+    val = images / sec
+    line = {
+        "impl": "reference", "metric": "images_per_sec", "value": round(val, 4), "unit": "images/s",
+        "n_gpus": args.gpus, "steps": len(times), "warmup": args.warmup, "ms_per_step": round(sec * 1e3, 2),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["desc"], "hot_path": "AdaAttnTransformerMultiHead forward (MHAda x6 + decoder)"},
+        "cpu_baseline": {"value": round(val, 4), "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"{images} image(s) of the workload per step (the reference processes a batch "
+                                   "head by head; its img/s does not grow with batch, BASELINE.md §2)"},
+        "e2e": {"value": round(val, 4), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, wl, rank)
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the MHAda path has no CPU fallback (use --impl reference for the CPU port)")
+    import torch.distributed as dist
+    from mhada_style_transfer_b200 import _lib
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    L = _lib.lib()
+    _lib.check("mhada_device_check", L.mhada_device_check())
+
+    B = wl["B"]
+    Nc, Ns = wl["hw"][0] * wl["hw"][1], wl["hsws"][0] * wl["hsws"][1]
+    model = build_model(wl, device)
+    fc_h, fs_h = make_features(wl, device, seed=rank)
+    fc_h = [t.pin_memory() for t in fc_h]
+    fs_h = [t.pin_memory() for t in fs_h]
+    # device-resident inputs for `value` (NCHW views over token-major memory = channels_last)
+    fc_d = [t.to(device).permute(0, 3, 1, 2) for t in fc_h]
+    fs_d = [t.to(device).permute(0, 3, 1, 2) for t in fs_h]
+    gather_buf = None
+    if world > 1:
+        gather_buf = [torch.empty((B, 3, 8 * wl["hw"][0], 8 * wl["hw"][1]), dtype=fc_d[0].dtype, device=device)
+                      for _ in range(world)] if rank == 0 else None
+
+    def step_device():
+        fcs, cs = model(fc_d, fs_d)
+        if world > 1:
+            dist.gather(cs.contiguous(), gather_buf, dst=0)     # the only collective: final gather over NVLink
+        return cs
+
+    cs_host = torch.empty((B, 3, 8 * wl["hw"][0], 8 * wl["hw"][1]), dtype=fc_d[0].dtype).pin_memory()
+
+    def step_e2e():
+        fc = [t.to(device, non_blocking=True).permute(0, 3, 1, 2) for t in fc_h]
+        fs = [t.to(device, non_blocking=True).permute(0, 3, 1, 2) for t in fs_h]
+        fcs, cs = model(fc, fs)
+        if world > 1:
+            dist.gather(cs.contiguous(), gather_buf, dst=0)
+        cs_host.copy_(cs, non_blocking=True)
+        return cs
+
+    def timed(fn, steps, warmup, profile=False):
+        with torch.no_grad():
+            for _ in range(warmup):
+                fn()
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            if profile:
+                L.mhada_profile_begin()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            attn_ms, attn_n = ctypes.c_float(0), ctypes.c_int(0)
+            if profile:
+                _lib.check("mhada_profile_end", L.mhada_profile_end(ctypes.byref(attn_ms), ctypes.byref(attn_n)))
+        if world > 1:
+            t = torch.tensor([ms], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, attn_ms.value, attn_n.value
+
+    # count my kernel launches in one step (6 layers)
+    with torch.no_grad():
+        step_device()
+    launches_per_layer = L.mhada_last_launch_count()
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms_total, attn_ms, attn_n = timed(step_device, args.steps, args.warmup, profile=True)
+    clocks = sampler.stop() if sampler else None
+    ms_e2e, _, _ = timed(step_e2e, args.steps, max(3, args.warmup // 2))
+
+    images = B * world * args.steps
+    value = images / (ms_total * 1e-3)
+    e2e_value = images / (ms_e2e * 1e-3)
+    esz = 2 if wl["dtype"] == "bf16" else 4
+    h2d = sum(t.numel() for t in fc_h + fs_h) * esz
+    d2h = cs_host.numel() * esz
+
+    pk = peaks()
+    flops_per_launch = 6.0 * B * Nc * Ns * C
+    attn_avg_ms = attn_ms / max(attn_n, 1)
+    if wl["dtype"] == "bf16":
+        achieved = flops_per_launch / (attn_avg_ms * 1e-3) / 1e12
+        # the attention kernel runs inside a long step under the power cap -> sustained peak
+        roof = {"bound": "tensor", "kernel": "attn_tc_kernel", "achieved": round(achieved, 1),
+                "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                "frac": round(achieved / pk["bf16_tflops_sustained"], 4),
+                "frac_of_burst_peak": round(achieved / pk["bf16_tflops"], 4), "peak_burst": pk["bf16_tflops"],
+                "peak_source": pk["source"] + ", sustained (kernel timed inside a long step)",
+                "algorithmic_flops_per_launch": flops_per_launch, "avg_launch_ms": round(attn_avg_ms, 4),
+                "launches_timed": attn_n, "share_of_step": round(attn_ms / ms_total, 4), "traffic": None}
+    else:
+        achieved = flops_per_launch / (attn_avg_ms * 1e-3) / 1e12
+        roof = {"bound": "fp32-simt", "kernel": "attn_f32_kernel", "achieved": round(achieved, 2), "peak": None,
+                "unit": "TFLOP/s", "frac": None, "avg_launch_ms": round(attn_avg_ms, 4), "launches_timed": attn_n,
+                "share_of_step": round(attn_ms / ms_total, 4), "traffic": None,
+                "note": "fp32 parity path (FFMA); the roofline claim is made on the bf16 workload"}
+
+    if rank == 0:
+        line = {
+            "metric": "images_per_sec", "value": round(value, 2), "unit": "images/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 4),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": wl["dtype"], "data": "synthetic",
+            "config": {"workload": wl["desc"], "images_per_gpu_per_step": B, "tokens": [Nc, Ns], "heads": H,
+                       "channels": C, "layers": 2 * LAYERS, "sharding": "by image, one process per GPU, final gather",
+                       "l2": f"inputs {h2d / 1e6:.0f} MB/step + {L.mhada_layer_workspace(_lib.BF16 if esz == 2 else _lib.F32, B, Nc, Ns, C, H) / 1e6:.0f} MB workspace exceed the 126 MB L2"},
+            "e2e": {"value": round(e2e_value, 2), "unit": "images/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": round(ms_e2e / args.steps, 4)},
+            "gpu_launches": launches_per_layer * 2 * LAYERS * args.steps,
+            "gpu_launches_per_step": launches_per_layer * 2 * LAYERS,
+            "roofline": roof, "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            times = cpu_port_run(wl, 1, steps=3, warmup=1, budget_s=25.0)
+            sec = sum(times) / len(times)
+            line["cpu_baseline"] = {"value": round(1.0 / sec, 4), "unit": "images/s", "cores": torch.get_num_threads(),
+                                    "kind": "port", "sample": f"{len(times)} x 1 image of the workload (fp32, "
+                                    "oracle/torch_port.py = the reference's ATen op sequence) after 1 warm-up"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -146,6 +146,16 @@ MHADA_API int mhada_layer_forward(int dtype, const void* fc, const void* fs, con
 /* Number of kernel launches the last mhada_layer_forward on this thread issued (bench bookkeeping). */
 MHADA_API int mhada_last_launch_count(void);
 
+/* ------------------------------------------------------------------------------------------------
+ * (6) Kernel timing for the roofline line of bench.py (no reference counterpart).
+ *     Between mhada_profile_begin() and mhada_profile_end() every attention launch issued from this
+ *     thread (by mhada_attn or mhada_layer_forward) is bracketed by cudaEventRecord on the caller's
+ *     stream.  mhada_profile_end() waits for those events and returns the summed device time (ms) and
+ *     the number of launches.  Not graph-capturable while enabled.
+ * ---------------------------------------------------------------------------------------------- */
+MHADA_API int mhada_profile_begin(void);
+MHADA_API int mhada_profile_end(float* attn_ms_total, int* attn_launches);
+
 #ifdef __cplusplus
 }
 #endif

@@ -34,6 +34,8 @@ SIGNATURES = {
     "mhada_last_error": (c_char_p, []),
     "mhada_device_check": (c_int, []),
     "mhada_last_launch_count": (c_int, []),
+    "mhada_profile_begin": (c_int, []),
+    "mhada_profile_end": (c_int, [POINTER(c_float), POINTER(c_int)]),
     "mhada_in_stats_workspace": (c_size_t, [c_int, c_int, c_int]),
     "mhada_in_stats": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t,
                                c_void_p]),

@@ -1,5 +1,7 @@
 // extern "C" surface of libmhada_b200.so (declared in include/mhada_b200.h): argument checks,
 // workspace carving and the per-layer launch sequence.  No torch types, no allocation, no syncs.
+#include <vector>
+
 #include "common.h"
 
 using namespace mh;
@@ -57,9 +59,60 @@ LayerWs carve(int dtype, int B, int Nc, int Ns, int C, int H, uint8_t* base) {
     return w;
 }
 
+// ---- optional event bracketing of the attention launches (mhada_profile_*)
+struct Profiler {
+    bool on = false;
+    std::vector<cudaEvent_t> ev;   // pairs: start, stop
+    size_t used = 0;
+};
+thread_local Profiler g_prof;
+
+int attn_dispatch(const mhada_attn_args& a, cudaStream_t s) {
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (g_prof.on) {
+        if (g_prof.used + 2 > g_prof.ev.size()) {
+            for (int i = 0; i < 2; ++i) {
+                cudaEvent_t e;
+                if (int err = check_cuda(cudaEventCreate(&e), "cudaEventCreate")) return err;
+                g_prof.ev.push_back(e);
+            }
+        }
+        e0 = g_prof.ev[g_prof.used];
+        e1 = g_prof.ev[g_prof.used + 1];
+        g_prof.used += 2;
+        cudaEventRecord(e0, s);
+    }
+    int rc = a.dtype == MHADA_BF16 ? launch_attn_bf16(a, s) : launch_attn_f32(a, s);
+    if (e1) cudaEventRecord(e1, s);
+    return rc;
+}
+
 }  // namespace
 
 extern "C" {
+
+int mhada_profile_begin(void) {
+    g_prof.on = true;
+    g_prof.used = 0;
+    return 0;
+}
+
+int mhada_profile_end(float* attn_ms_total, int* attn_launches) {
+    g_prof.on = false;
+    float total = 0.f;
+    int n = 0;
+    for (size_t i = 0; i + 1 < g_prof.used; i += 2) {
+        if (int e = check_cuda(cudaEventSynchronize(g_prof.ev[i + 1]), "cudaEventSynchronize")) return e;
+        float ms = 0.f;
+        if (int e = check_cuda(cudaEventElapsedTime(&ms, g_prof.ev[i], g_prof.ev[i + 1]), "cudaEventElapsedTime")) return e;
+        total += ms;
+        ++n;
+    }
+    g_prof.used = 0;
+    if (attn_ms_total) *attn_ms_total = total;
+    if (attn_launches) *attn_launches = n;
+    return 0;
+}
 
 int mhada_abi_version(void) { return MHADA_ABI_VERSION; }
 const char* mhada_last_error(void) { return last_error(); }
@@ -126,7 +179,7 @@ int mhada_attn(const mhada_attn_args* a, mhada_stream_t stream) {
                     a->ldx >= a->H * a->dv && a->ldo >= a->H * a->dv,
                 MHADA_ERR_ARG, "mhada_attn: pitch smaller than H*d");
         if (int e = device_check()) return e;
-        return launch_attn_f32(*a, s);
+        return attn_dispatch(*a, s);
     }
     REQUIRE(a->dtype == MHADA_BF16, MHADA_ERR_ARG, "mhada_attn: bad dtype %d", a->dtype);
     REQUIRE(a->dqk == 64 && a->dv == 64, MHADA_ERR_UNSUPPORTED,
@@ -139,7 +192,7 @@ int mhada_attn(const mhada_attn_args* a, mhada_stream_t stream) {
                 aligned16(a->q) && aligned16(a->k) && aligned16(a->v) && aligned16(a->x) && aligned16(a->out),
             MHADA_ERR_ARG, "mhada_attn: bf16 pointers must be 16-byte aligned and pitches multiples of 8");
     if (int e = device_check()) return e;
-    return launch_attn_bf16(*a, s);
+    return attn_dispatch(*a, s);
 }
 
 size_t mhada_linear_workspace(int dtype, int Cout, int Cin) {
@@ -221,7 +274,7 @@ int mhada_layer_forward(int dtype, const void* fc, const void* fs, const void* f
     a.out = w_out ? w.heads : out;
     a.ldq = C; a.ldk = C; a.ldv = dtype == MHADA_BF16 ? 2 * C : C; a.ldx = C; a.ldo = C;
     a.x_mean = mean_x; a.x_rstd = rstd_x; a.mu_v = w.mu_v;
-    if (int e = (dtype == MHADA_BF16 ? launch_attn_bf16(a, s) : launch_attn_f32(a, s))) return e;
+    if (int e = attn_dispatch(a, s)) return e;
     // (4) out_conv                                                           adaDecoder.py:202-205
     if (w_out) {
         if (dtype == MHADA_BF16) {

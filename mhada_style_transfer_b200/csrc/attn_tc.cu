@@ -233,8 +233,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 for (int i = 0; i < 16; ++i) {
                     float p0 = ex2_approx(__uint_as_float(s[c * 32 + 2 * i]) - m_used);
                     float p1 = ex2_approx(__uint_as_float(s[c * 32 + 2 * i + 1]) - m_used);
-                    lsum += p0 + p1;
                     pk[i] = pack_bf16x2(p0, p1);
+                    // the row sum must use the ROUNDED weights the MMA sees: with l = sum(p) but
+                    // M, E built from bf16(p), Var = E - M^2 picks up eps * M^2 (eps = 2^-9) and
+                    // sqrt() of that is percent-level when the attention is peaked
+                    lsum += bf16_lo(pk[i]) + bf16_hi(pk[i]);
                 }
                 tmem_st_x16(s_tm + c * 16, pk);
             }

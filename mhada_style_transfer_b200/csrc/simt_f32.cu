@@ -17,6 +17,18 @@ namespace mh {
 constexpr int TILE = 64;
 constexpr int KC = 32;  // reduction chunk staged in shared memory
 
+// Compensated (Kahan) add of a short fp32 partial sum into a long-running one.  Dot products are
+// accumulated in short chunks (8 or 32 terms, small magnitude) and the chunks are folded in with the
+// rounding error carried along: the logits / out_conv sums then sit ~10x closer to the float64 result
+// than a single 64..512-term fp32 chain, which is what the <= 1e-3 max-abs budget of the fp32 path needs
+// (the reference's CPU sgemm gets the same effect from its many SIMD-lane accumulators).
+__device__ __forceinline__ void kahan_add(float& sum, float& comp, float term) {
+    float y = term - comp;
+    float u = sum + y;
+    comp = (u - sum) - y;
+    sum = u;
+}
+
 // ------------------------------------------------------------------------------------------------
 // y[m, g*dout + o] = sum_i w[g][o][i] * xin[m, g*din + i] + bias[g][o]
 //   mode 0: xin = x   mode 1: xin = (x - mean) * rstd   mode 2: xin = x - mean  (bias ignored -> centred V)
@@ -38,11 +50,11 @@ __global__ void __launch_bounds__(256) grouped_linear_f32_kernel(const float* __
     const float* wg = w + static_cast<size_t>(g) * dout * din;
     const int cin0 = g * din;
 
-    float acc[4][4];
+    float acc[4][4], cmp[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        for (int j = 0; j < 4; ++j) acc[i][j] = cmp[i][j] = 0.f;
 
     for (int k0 = 0; k0 < din; k0 += KC) {
         // stage x tile [64 rows][32 k] and w tile [64 outs][32 k]; consecutive threads walk k (contiguous)
@@ -64,6 +76,11 @@ __global__ void __launch_bounds__(256) grouped_linear_f32_kernel(const float* __
             ws[kk][r] = (o < dout && k < din) ? __ldg(wg + static_cast<size_t>(o) * din + k) : 0.f;
         }
         __syncthreads();
+        float part[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) part[i][j] = 0.f;
 #pragma unroll 8
         for (int kk = 0; kk < KC; ++kk) {
             float a[4], bb[4];
@@ -74,8 +91,12 @@ __global__ void __launch_bounds__(256) grouped_linear_f32_kernel(const float* __
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+                for (int j = 0; j < 4; ++j) part[i][j] = fmaf(a[i], bb[j], part[i][j]);
         }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) kahan_add(acc[i][j], cmp[i][j], part[i][j]);
         __syncthreads();
     }
 #pragma unroll
@@ -174,11 +195,11 @@ __global__ void __launch_bounds__(256) attn_f32_kernel(const AttnF32Params p) {
 
     for (int k0 = 0; k0 < p.Ns; k0 += TILE) {
         // ---- S = Q K^T for this key tile
-        float s[4][4];
+        float s[4][4], sc[4][4];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
+            for (int j = 0; j < 4; ++j) s[i][j] = sc[i][j] = 0.f;
         for (int d0 = 0; d0 < p.dqk; d0 += KC) {
             for (int e = threadIdx.x; e < TILE * KC; e += 256) {
                 int r = e / KC, dd = e % KC, d = d0 + dd;
@@ -197,17 +218,29 @@ __global__ void __launch_bounds__(256) attn_f32_kernel(const AttnF32Params p) {
                 sm.qk.k[dd][r] = kv;
             }
             __syncthreads();
-#pragma unroll 8
-            for (int dd = 0; dd < KC; ++dd) {
-                float a[4], bb[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) a[i] = sm.qk.q[dd][ty + 16 * i];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) bb[j] = sm.qk.k[dd][tx + 16 * j];
+#pragma unroll 1
+            for (int d1 = 0; d1 < KC; d1 += 8) {
+                float part[4][4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) s[i][j] = fmaf(a[i], bb[j], s[i][j]);
+                    for (int j = 0; j < 4; ++j) part[i][j] = 0.f;
+#pragma unroll
+                for (int dd = d1; dd < d1 + 8; ++dd) {
+                    float a[4], bb[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) a[i] = sm.qk.q[dd][ty + 16 * i];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) bb[j] = sm.qk.k[dd][tx + 16 * j];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) part[i][j] = fmaf(a[i], bb[j], part[i][j]);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) kahan_add(s[i][j], sc[i][j], part[i][j]);
             }
             __syncthreads();
         }

@@ -135,12 +135,15 @@ __global__ void stats_final_kernel(const T* __restrict__ x, const float* __restr
     rstd[i] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(kInEps)));
 }
 
-static int stats_splits(int B, int N) {
-    // aim at >= 2 CTAs per SM over the whole grid, at least 64 tokens per split
-    int want = (2 * 148 + B - 1) / B;
-    int max_splits = (N + 63) / 64;
-    int s = want < max_splits ? want : max_splits;
-    return s < 1 ? 1 : s;
+// Tokens per split depend on N only (never on B), so the statistics of an image -- and with them the
+// whole layer -- are bit-identical whatever batch the image is part of.  At most 128 splits.
+static int stats_tokens_per_split(int N) {
+    int t = (N + 127) / 128;
+    return t < 64 ? 64 : t;
+}
+static int stats_splits(int /*B*/, int N) {
+    int t = stats_tokens_per_split(N);
+    return (N + t - 1) / t;
 }
 
 size_t stats_workspace(int B, int N, int C) {
@@ -150,7 +153,7 @@ size_t stats_workspace(int B, int N, int C) {
 int launch_stats(const void* x, int dtype, int B, int N, int C, int ld, float* mean, float* rstd, float* ws,
                  cudaStream_t s) {
     const int splits = stats_splits(B, N);
-    const int tps = (N + splits - 1) / splits;
+    const int tps = stats_tokens_per_split(N);
     if (dtype == MHADA_BF16) {
         dim3 grid((C + 32 * 8 - 1) / (32 * 8), splits, B);
         stats_partial_kernel<__nv_bfloat16><<<grid, kStatsThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(x), N, C, ld, tps, ws);

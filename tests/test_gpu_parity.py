@@ -190,6 +190,11 @@ def test_full_size_properties(B, hw, hsws):
         oc = m(tfc[:1], const_fs, tfcs[:1]).float()
         m.precision = "fp32"
         oc32 = m(tfc[:1, :, :rows].float(), const_fs.float(), tfcs[:1, :, :rows].float())
+    with torch.no_grad():
+        _check_constant_style(m, tfcs, const_fs, rows, oc, oc32)
+
+
+def _check_constant_style(m, tfcs, const_fs, rows, oc, oc32):
     x = tfcs[:1].float()
     xin = (x - x.mean((2, 3), keepdim=True)) / torch.sqrt(x.var((2, 3), unbiased=False, keepdim=True) + 1e-5)
     # heads output before out_conv: 1e-3 * IN(fcs) + V (V = Wh fs0 + bh, constant per channel)

@@ -50,8 +50,10 @@ def test_linear(code, M, Cin, Cout):
     xt = torch.from_numpy(x).float().to(G.DEV).to(G.tdt(code)).contiguous()
     y = torch.empty(M, Cout, dtype=G.tdt(code), device=G.DEV)
     wsb = G.ws(L.mhada_linear_workspace(code, Cout, Cin))
-    _lib.check("mhada_linear", L.mhada_linear(code, G.ptr(xt), Cin, G.ptr(G.f32(w)), G.ptr(G.f32(b)), M, Cin, Cout,
+    tw, tb = G.f32(w), G.f32(b)        # keep the device tensors alive across the call
+    _lib.check("mhada_linear", L.mhada_linear(code, G.ptr(xt), Cin, G.ptr(tw), G.ptr(tb), M, Cin, Cout,
                                               G.ptr(y), Cout, G.ptr(wsb), wsb.numel(), G.stream()))
+    torch.cuda.synchronize()
     if code == BF16:
         want = xt.float().cpu().numpy().astype(np.float64) @ G.bf16_round(w).T + b
         tol = 6e-3      # output rounding to bf16 (2^-9 relative) on |y| up to absmax
@@ -150,8 +152,9 @@ def _attn_expected(q, k, v, x, xm, xr, muv, H, dqk, dv, base2: bool):
                                               (2, 1, 36, 36, 960, 512), (1, 2, 100, 3, 16, 24), (1, 4, 200, 1000, 128, 128)])
 def test_attn_f32(B, H, Nc, Ns, dqk, dv):
     L = _lib.lib()
-    q = synth.bellish(1, (B, Nc, H * dqk), 0, 0.6)
-    k = synth.bellish(2, (B, Ns, H * dqk), 0, 0.6)
+    sig = 3.0 ** 0.5 / dqk ** 0.25                      # logits std ~3 whatever dqk is
+    q = synth.bellish(1, (B, Nc, H * dqk), 0, sig)
+    k = synth.bellish(2, (B, Ns, H * dqk), 0, sig)
     v = synth.bellish(3, (B, Ns, H * dv), 0, 40.0)
     x = synth.bellish(4, (B, Nc, H * dv), 2.0, 30.0)
     muv = synth.uniform(5, (B, H * dv), -3, 3)

@@ -117,3 +117,21 @@ def test_transformer_cfg1_size_matches_reference(golden_index):
     _check(cases.pixel_sublattice(cs, case["img_sub"]), g["cs"], meta, "cs")
     _check_sums(fcs, meta, "fcs")
     _check_sums(cs, meta, "cs")
+
+
+def test_torch_port_matches_reference(golden_index):
+    """oracle/torch_port.py (the CPU port bench.py times as cpu_baseline / --impl reference) against the
+    same golden vectors, at the reference's native float32."""
+    import torch
+    from oracle import torch_port
+    case = cases.by_name("transformer_b2_12x10")
+    fc, fs, sd = cases.transformer_inputs(case)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).float()
+    with torch.no_grad():
+        fcs, cs = torch_port.transformer([t(x) for x in fc], [t(x) for x in fs], torch_port.prepare(sd))
+    g = load_golden(case["name"])
+    meta = golden_index[case["name"]]
+    ef = O.errors(cases.token_sublattice(fcs.numpy(), case["sub"]), g["fcs"])
+    ec = O.errors(cases.pixel_sublattice(cs.numpy(), case["img_sub"]), g["cs"])
+    assert ef["max_abs"] <= 5 * meta["fcs_ref32_vs_ref64"]["max_abs"] + 1e-4, ef
+    assert ec["max_abs_rel"] <= 1e-4, ec
