@@ -184,13 +184,15 @@ __global__ void __launch_bounds__(256) attn_f32_kernel(const AttnF32Params p) {
     const float* kmu = p.k_mean ? p.k_mean + static_cast<size_t>(b) * p.H * p.dqk + h * p.dqk : nullptr;
     const float* krs = p.k_mean ? p.k_rstd + static_cast<size_t>(b) * p.H * p.dqk + h * p.dqk : nullptr;
 
-    float om[4][4], oe[4][4], mrow[4], lrow[4];
+    // running (unnormalised) A.V and A.V^2 with their Kahan compensation terms: a plain fp32 chain over
+    // Ns = 4096..32400 keys drifts by ~sqrt(Ns) ulp, which alone would eat the 1e-3 max-abs budget
+    float om[4][4], oe[4][4], cm[4][4], ce[4][4], mrow[4], lrow[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         mrow[i] = -INFINITY;
         lrow[i] = 0.f;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) om[i][j] = oe[i][j] = 0.f;
+        for (int j = 0; j < 4; ++j) om[i][j] = oe[i][j] = cm[i][j] = ce[i][j] = 0.f;
     }
 
     for (int k0 = 0; k0 < p.Ns; k0 += TILE) {
@@ -266,12 +268,12 @@ __global__ void __launch_bounds__(256) attn_f32_kernel(const AttnF32Params p) {
             }
 #pragma unroll
             for (int o = 8; o >= 1; o >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, o);
-            lrow[i] = lrow[i] * scale + rs;
+            lrow[i] = lrow[i] * scale + rs;   // 64..500 additions of O(1..64) terms: ~1e-6 relative at worst
             mrow[i] = mnew;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                om[i][j] *= scale;
-                oe[i][j] *= scale;
+                om[i][j] *= scale; cm[i][j] *= scale;
+                oe[i][j] *= scale; ce[i][j] *= scale;
             }
         }
         // ---- stage V tile [64 keys][64 value columns]
@@ -282,22 +284,36 @@ __global__ void __launch_bounds__(256) attn_f32_kernel(const AttnF32Params p) {
             sm.v[r][c] = vv;
         }
         __syncthreads();
+        {
+            float pm[4][4], pe[4][4];       // this tile's 64-key partial sums
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) pm[i][j] = pe[i][j] = 0.f;
 #pragma unroll 4
-        for (int kk = 0; kk < TILE; ++kk) {
-            float a[4], vv[4], v2[4];
+            for (int kk = 0; kk < TILE; ++kk) {
+                float a[4], vv[4], v2[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) a[i] = Ps[ty + 16 * i][kk];
+                for (int i = 0; i < 4; ++i) a[i] = Ps[ty + 16 * i][kk];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                vv[j] = sm.v[kk][tx + 16 * j];
-                v2[j] = vv[j] * vv[j];
+                for (int j = 0; j < 4; ++j) {
+                    vv[j] = sm.v[kk][tx + 16 * j];
+                    v2[j] = vv[j] * vv[j];
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        pm[i][j] = fmaf(a[i], vv[j], pm[i][j]);
+                        pe[i][j] = fmaf(a[i], v2[j], pe[i][j]);
+                    }
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    om[i][j] = fmaf(a[i], vv[j], om[i][j]);
-                    oe[i][j] = fmaf(a[i], v2[j], oe[i][j]);
+                    kahan_add(om[i][j], cm[i][j], pm[i][j]);
+                    kahan_add(oe[i][j], ce[i][j], pe[i][j]);
                 }
         }
         __syncthreads();

@@ -30,6 +30,17 @@ def fp32_tol(meta_key):
     return max(FP32_MAX_ABS, 3.0 * meta_key["max_abs"])
 
 
+def bf16_tol(case):
+    """2e-2 (BASELINE.json) from ~100 tokens up.  Below that every output averages over too few keys /
+    tokens for the independent bf16 roundings to cancel: an exact-arithmetic emulation of the same
+    roundings (tools/error_budget.py) gives 2.0e-2 at 64 tokens and 1.4e-2 at 4096, so the tiny fixtures
+    get 4e-2.  The stress case multiplies the logits by 16 (bf16 Q/K rounding then moves probability mass)."""
+    if case.get("gain", 1.0) != 1.0:
+        return 8e-2
+    ntok = min(case["hw"][0] * case["hw"][1], case["hsws"][0] * case["hsws"][1])
+    return BF16_REL if ntok >= 100 else 4e-2
+
+
 def build_layer(case, sd):
     m = M.AdaAttnMultiHead(case["C"], case["H"])
     m.load_state_dict(synth.to_torch(sd, torch.float32), strict=True)
@@ -60,8 +71,7 @@ def test_layer_bf16_vs_reference_golden(case, golden_index):
         out = m(tfc, tfs, tfcs)
     assert out.dtype == torch.float32
     e = O.errors(out.cpu().numpy(), load_golden(case["name"])["out"])
-    # the stress case multiplies the logits by 16: bf16 Q/K rounding then moves probability mass
-    tol = BF16_REL if case.get("gain", 1.0) == 1.0 else 8e-2
+    tol = bf16_tol(case)
     assert e["max_abs_rel"] <= tol, e
     # bf16 tensors in -> bf16 out on the "auto" path
     m.precision = "auto"
@@ -134,8 +144,8 @@ def test_transformer_vs_reference_golden(case, precision, golden_index):
         assert ef["max_abs"] <= fp32_tol(meta["fcs_ref32_vs_ref64"]), ef
         assert ec["max_abs_rel"] <= 1e-4, ec
     else:
-        assert ef["max_abs_rel"] <= BF16_REL, ef
-        assert ec["max_abs_rel"] <= BF16_REL, ec
+        assert ef["max_abs_rel"] <= bf16_tol(case), ef
+        assert ec["max_abs_rel"] <= bf16_tol(case), ec
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -195,20 +205,24 @@ def test_full_size_properties(B, hw, hsws):
 
 
 def _check_constant_style(m, tfcs, const_fs, rows, oc, oc32):
-    x = tfcs[:1].float()
-    xin = (x - x.mean((2, 3), keepdim=True)) / torch.sqrt(x.var((2, 3), unbiased=False, keepdim=True) + 1e-5)
-    # heads output before out_conv: 1e-3 * IN(fcs) + V (V = Wh fs0 + bh, constant per channel)
-    v = torch.cat([torch.nn.functional.conv2d(const_fs[:, i * 64:(i + 1) * 64, :1, :1].float(), m.h_list[i].weight,
-                                              m.h_list[i].bias) for i in range(8)], dim=1)
-    heads = 1e-3 * xin + v
-    want = torch.nn.functional.conv2d(heads, m.out_conv.weight, m.out_conv.bias)
-    ec = O.errors(oc.cpu().numpy(), want.cpu().numpy())
+    """Expected value in float64 on the CPU (torch's GPU convs would use TF32)."""
+    f64 = lambda t: t.detach().double().cpu()
+    wh = torch.stack([f64(m.h_list[i].weight).reshape(64, 64) for i in range(8)])           # [8,64,64]
+    bh = torch.stack([f64(m.h_list[i].bias) for i in range(8)])
+    fs0 = f64(const_fs[0, :, 0, 0]).reshape(8, 64)
+    v = (torch.einsum("hoi,hi->ho", wh, fs0) + bh).reshape(1, 512, 1, 1)                    # V, constant per channel
+    wo, bo = f64(m.out_conv.weight).reshape(512, 512), f64(m.out_conv.bias)
+
+    def closed_form(x):
+        x = f64(x)
+        xin = (x - x.mean((2, 3), keepdim=True)) / torch.sqrt(x.var((2, 3), unbiased=False, keepdim=True) + 1e-5)
+        heads = 1e-3 * xin + v                     # S = sqrt(1e-6), M = V
+        return torch.einsum("oc,bchw->bohw", wo, heads) + bo.reshape(1, -1, 1, 1)
+
+    ec = O.errors(oc.cpu().numpy(), closed_form(tfcs[:1]).numpy())
     assert ec["max_abs_rel"] <= BF16_REL, ec
-    xs = tfcs[:1, :, :rows].float()
-    xin_s = (xs - xs.mean((2, 3), keepdim=True)) / torch.sqrt(xs.var((2, 3), unbiased=False, keepdim=True) + 1e-5)
-    want_s = torch.nn.functional.conv2d(1e-3 * xin_s + v, m.out_conv.weight, m.out_conv.bias)
-    ec32 = O.errors(oc32.cpu().numpy(), want_s.cpu().numpy())
-    assert ec32["max_abs"] <= 2e-3, ec32
+    ec32 = O.errors(oc32.cpu().numpy(), closed_form(tfcs[:1, :, :rows]).numpy())
+    assert ec32["max_abs"] <= FP32_MAX_ABS, ec32
 
 
 def test_errors_on_device():

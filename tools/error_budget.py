@@ -1,0 +1,80 @@
+"""CPU emulation of the bf16 tensor-core pipeline with per-stage rounding toggles: which roundings
+dominate the parity error against the float64 oracle?  Development aid (numpy/torch CPU only)."""
+import sys, os, itertools
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import cases, mhada_oracle as O
+
+def rnd(x, kind):
+    if kind is None: return x
+    t = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+    if kind == "bf16": return t.to(torch.bfloat16).float().numpy().astype(np.float64)
+    if kind == "fp16": return t.to(torch.float16).float().numpy().astype(np.float64)
+    if kind == "split": # two bf16 terms
+        hi = t.to(torch.bfloat16).float(); lo = (t - hi).to(torch.bfloat16).float()
+        return (hi + lo).numpy().astype(np.float64)
+    raise ValueError(kind)
+
+def layer(fc, fs, fcs, sd, prefix, H, cfg):
+    b, c, h, w = fc.shape; d = c // H; hs, ws = fs.shape[2:]
+    fc_r, fs_r, fcs_r = rnd(fc, cfg["inp"]), rnd(fs, cfg["inp"]), rnd(fcs, cfg["inp"])
+    mc, rc = O.instance_norm_stats(fc_r); ms, rs = O.instance_norm_stats(fs_r); mx, rx = O.instance_norm_stats(fcs_r)
+    heads = []
+    for i in range(H):
+        sl = slice(i*d, (i+1)*d)
+        wf = sd[f"{prefix}f_list.{i}.weight"].reshape(d, d); bf = sd[f"{prefix}f_list.{i}.bias"]
+        wg = sd[f"{prefix}g_list.{i}.weight"].reshape(d, d); bg = sd[f"{prefix}g_list.{i}.bias"]
+        wh = sd[f"{prefix}h_list.{i}.weight"].reshape(d, d); bh = sd[f"{prefix}h_list.{i}.bias"]
+        out_q = []
+        Q = np.zeros((b, h*w, d)); K = np.zeros((b, hs*ws, d)); V = np.zeros((b, hs*ws, d)); muv = np.zeros((b, d))
+        for bi in range(b):
+            wq = rnd(wf * rc[bi, sl][None, :], cfg["w"]); bq = bf - wq @ mc[bi, sl]
+            wk = rnd(wg * rs[bi, sl][None, :], cfg["w"]); bk = bg - wk @ ms[bi, sl]
+            wv = rnd(wh, cfg["w"]); bv = -wv @ ms[bi, sl]
+            xc = fc_r[bi, sl].reshape(d, -1).T; xs = fs_r[bi, sl].reshape(d, -1).T
+            Q[bi] = xc @ wq.T + bq; K[bi] = xs @ wk.T + bk; V[bi] = xs @ wv.T + bv; muv[bi] = bh - bv
+        Q = rnd(Q * np.log2(np.e), cfg["qk"]); K = rnd(K, cfg["qk"])
+        V2 = rnd(V * V, cfg["v"]); V = rnd(V, cfg["v"])
+        S = Q @ K.transpose(0, 2, 1)
+        S = S - S.max(-1, keepdims=True)
+        P = rnd(np.exp2(S), cfg["p"])
+        l = P.sum(-1, keepdims=True)
+        M = (P @ V) / l; E = (P @ V2) / l
+        sd_ = np.sqrt(np.maximum(E - M*M, 1e-6))
+        xn = (fcs_r[:, sl].reshape(b, d, -1).transpose(0, 2, 1) - mx[:, None, sl]) * rx[:, None, sl]
+        heads.append(rnd(sd_ * xn + M + muv[:, None, :], cfg["heads"]))
+    cat = np.concatenate(heads, axis=2)   # [b, N, C]
+    wo = rnd(sd[f"{prefix}out_conv.weight"].reshape(c, c), cfg["w"]); bo = sd[f"{prefix}out_conv.bias"]
+    y = rnd(cat @ wo.T + bo, cfg["out"])
+    return y.transpose(0, 2, 1).reshape(b, c, h, w)
+
+def run(case, cfg):
+    fc, fs, sd = cases.transformer_inputs(case)
+    fcs = fc[0]
+    for i in range(3):
+        fcs = layer(fc[i], fs[i], fcs, sd, f"adaAttnHead.{2*i}.", 8, cfg)
+        fcs = layer(fcs, fs[i], fcs, sd, f"adaAttnHead.{2*i+1}.", 8, cfg)
+    return fcs
+
+if __name__ == "__main__":
+    name = sys.argv[1] if len(sys.argv) > 1 else "transformer_8x8"
+    case = cases.by_name(name)
+    fc, fs, sd = cases.transformer_inputs(case)
+    want, _ = O.transformer_multi_head(fc, fs, sd, decode=False)
+    base = dict(inp=None, w=None, qk=None, v=None, p=None, heads=None, out=None)
+    allbf = dict(inp="bf16", w="bf16", qk="bf16", v="bf16", p="bf16", heads="bf16", out="bf16")
+    def show(tag, cfg):
+        e = O.errors(run(case, cfg), want)
+        print(f"{tag:42s} max_abs_rel {e['max_abs_rel']:.4f}  fro_rel {e['fro_rel']:.4f}")
+    show("exact restatement", base)
+    show("all bf16 (current kernels)", allbf)
+    for k in base:
+        show(f"only {k} bf16", dict(base, **{k: "bf16"}))
+    for k in base:
+        show(f"all bf16 except {k} exact", dict(allbf, **{k: None}))
+    show("all bf16, qk fp16", dict(allbf, qk="fp16"))
+    show("all bf16, qk fp16, w split", dict(allbf, qk="fp16", w="split"))
+    show("qk fp16, w split, inp exact", dict(allbf, qk="fp16", w="split", inp=None))
+    show("qk fp16, w split, inp exact, out exact", dict(allbf, qk="fp16", w="split", inp=None, out=None))
+    show("qk fp16, w split, inp/out/heads exact", dict(allbf, qk="fp16", w="split", inp=None, out=None, heads=None))
+    show("qk split, w split, inp/out exact", dict(allbf, qk="split", w="split", inp=None, out=None))
