@@ -44,6 +44,7 @@ SIGNATURES = {
                            c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                            c_size_t, c_void_p]),
     "mhada_attn": (c_int, [POINTER(AttnArgs), c_void_p]),
+    "mhada_debug_attn_trace": (c_int, [POINTER(AttnArgs), c_void_p, c_void_p]),
     "mhada_linear_workspace": (c_size_t, [c_int, c_int, c_int]),
     "mhada_linear": (c_int, [c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int,
                              c_void_p, c_size_t, c_void_p]),

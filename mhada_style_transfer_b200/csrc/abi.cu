@@ -195,6 +195,14 @@ int mhada_attn(const mhada_attn_args* a, mhada_stream_t stream) {
     return attn_dispatch(*a, s);
 }
 
+int mhada_debug_attn_trace(const mhada_attn_args* a, long long* trace, mhada_stream_t stream) {
+    REQUIRE(a && trace, MHADA_ERR_ARG, "mhada_debug_attn_trace: null pointer");
+    REQUIRE(a->dtype == MHADA_BF16 && a->dqk == 64 && a->dv == 64, MHADA_ERR_UNSUPPORTED,
+            "mhada_debug_attn_trace: bf16 / head_dim 64 only");
+    if (int e = device_check()) return e;
+    return launch_attn_bf16_impl(*a, trace, static_cast<cudaStream_t>(stream));
+}
+
 size_t mhada_linear_workspace(int dtype, int Cout, int Cin) {
     if (dtype != MHADA_BF16 || Cout <= 0 || Cin <= 0) return 0;
     return linear_bf16_workspace(Cout, Cin);

@@ -38,11 +38,18 @@ constexpr uint32_t AT_V_BYTES = AT_BN * AT_DV2 * 2;        // 32 KB (two 64-colu
 constexpr uint32_t AT_SMEM_DATA = 2 * AT_Q_BYTES + AT_KST * AT_K_BYTES + AT_VST * AT_V_BYTES;
 constexpr float AT_RESCALE_THRESHOLD = 8.0f;               // log2 units: P <= 2^8
 
+// Trace slots (development aid, attn_tc_kernel<true> only): clock64() stamps of CTA (0,0,0).
+//   softmax WG t, iteration j: trace[(t*64 + j)*8 + e], e = 0 S ready, 1 S in registers, 2 max/rescale done,
+//                              3 P stores issued, 4 P arrived
+//   MMA thread:                trace[(2*64 + j)*8 + e], e = 0/2 P_t ready seen (t=0/1), 1/3 PV_t+S_t issued
+constexpr int AT_TRACE_WORDS = 3 * 64 * 8;
+
 struct AttnTcParams {
     const __nv_bfloat16* x;   // fcs [B, Nc, ldx]
     __nv_bfloat16* out;       // [B, Nc, ldo]
     const float *x_mean, *x_rstd, *mu_v;   // [B, H*64]
     int H, Nc, Ns, ldx, ldo;
+    long long* trace;         // AT_TRACE_WORDS entries or nullptr
 };
 
 struct AttnBars {
@@ -54,6 +61,7 @@ struct AttnBars {
     float cst[3][AT_D];       // x_mean, x_rstd, mu_v of this (b, head)
 };
 
+template <bool TRACE>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const AttnTcParams p) {
@@ -67,6 +75,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * (2 * AT_BM), h = blockIdx.y, b = blockIdx.z;
     const int T = (p.Ns + AT_BN - 1) / AT_BN;
+    const bool tracing = TRACE && p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+    auto stamp = [&](int role, int j, int e) {
+        if (TRACE && tracing && j < 64) p.trace[(role * 64 + j) * 8 + e] = clock64();
+    };
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmQ);
@@ -163,6 +175,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 for (int t = 0; t < 2; ++t) {
                     mbar_wait(&bars->p_ready[t], j & 1);
                     tc_fence_after();
+                    stamp(2, j, 2 * t);
                     issue_pv(t, vs, j != 0);
                     if (t == 1) umma_commit(&bars->v_empty[vs]);
                     if (more) {
@@ -172,6 +185,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                     } else {
                         umma_commit(&bars->o_full[t]);
                     }
+                    stamp(2, j, 2 * t + 1);
                 }
             }
         }
@@ -189,21 +203,29 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         for (int j = 0; j < T; ++j) {
             mbar_wait(&bars->s_full[t], j & 1);
             tc_fence_after();
+            const bool tr = TRACE && quarter == 0 && lane == 0;
+            if (tr) stamp(t, j, 0);
             uint32_t s[128];
             tmem_ld_x32(s_tm, s);
             tmem_ld_x32(s_tm + 32, s + 32);
             tmem_ld_x32(s_tm + 64, s + 64);
             tmem_ld_x32(s_tm + 96, s + 96);
             tmem_wait_ld();
+            if (tr) stamp(t, j, 1);
             const int valid = p.Ns - j * AT_BN;       // keys in this tile (tail tile: < 128)
             if (valid < AT_BN) {
 #pragma unroll
                 for (int i = 0; i < 128; ++i)
                     if (i >= valid) s[i] = 0xff800000u;   // -inf
             }
-            float mx = __uint_as_float(s[0]);
+            // row max: 8 independent chains (a single 127-deep FMNMX chain costs ~4 cycles per link)
+            float mxa[8];
 #pragma unroll
-            for (int i = 1; i < 128; ++i) mx = fmaxf(mx, __uint_as_float(s[i]));
+            for (int i = 0; i < 8; ++i) mxa[i] = __uint_as_float(s[i]);
+#pragma unroll
+            for (int i = 8; i < 128; ++i) mxa[i & 7] = fmaxf(mxa[i & 7], __uint_as_float(s[i]));
+            const float mx = fmaxf(fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])),
+                                   fmaxf(fmaxf(mxa[4], mxa[5]), fmaxf(mxa[6], mxa[7])));
             if (j == 0) {
                 m_used = mx;
             } else {
@@ -224,28 +246,34 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                     }
                 }
             }
-            // P = exp2(S - m), packed bf16x2, written over the first 64 columns of S
-            float lsum = 0.f;
+            if (tr) stamp(t, j, 2);
+            // P = exp2(S - m), packed bf16x2, written over the first 64 columns of S.
+            // Packed f32x2 adds (FADD2) for the subtraction and for the row sum; four independent sum chains.
+            // The row sum uses the ROUNDED weights the MMA sees: with l = sum(p) but M, E built from bf16(p),
+            // Var = E - M^2 picks up eps * M^2 (eps ~ 2^-9) and sqrt() of that is percent-level when the
+            // attention is peaked.
+            const float2 neg_m = make_float2(-m_used, -m_used);
+            float2 la = make_float2(0.f, 0.f), lb = make_float2(0.f, 0.f);
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 uint32_t pk[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    float p0 = ex2_approx(__uint_as_float(s[c * 32 + 2 * i]) - m_used);
-                    float p1 = ex2_approx(__uint_as_float(s[c * 32 + 2 * i + 1]) - m_used);
-                    pk[i] = pack_bf16x2(p0, p1);
-                    // the row sum must use the ROUNDED weights the MMA sees: with l = sum(p) but
-                    // M, E built from bf16(p), Var = E - M^2 picks up eps * M^2 (eps = 2^-9) and
-                    // sqrt() of that is percent-level when the attention is peaked
-                    lsum += bf16_lo(pk[i]) + bf16_hi(pk[i]);
+                    const float2 x = __fadd2_rn(make_float2(__uint_as_float(s[c * 32 + 2 * i]),
+                                                            __uint_as_float(s[c * 32 + 2 * i + 1])), neg_m);
+                    pk[i] = pack_bf16x2(ex2_approx(x.x), ex2_approx(x.y));
+                    const float2 r = make_float2(bf16_lo(pk[i]), bf16_hi(pk[i]));
+                    if (i & 1) la = __fadd2_rn(la, r); else lb = __fadd2_rn(lb, r);
                 }
                 tmem_st_x16(s_tm + c * 16, pk);
             }
-            l += lsum;
+            l += (la.x + la.y) + (lb.x + lb.y);
+            if (tr) stamp(t, j, 3);
             tmem_wait_st();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars->p_ready[t]);
+            if (tr) stamp(t, j, 4);
         }
 
         // ---- epilogue: O/l -> (M~, E~) -> sqrt(max(E~ - M~^2, 1e-6)) * IN(fcs) + M~ + mu_v
@@ -296,7 +324,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     if (warp == 2) tmem_dealloc(tmem, 512);
 }
 
-int launch_attn_bf16(const mhada_attn_args& a, cudaStream_t s) {
+int launch_attn_bf16_impl(const mhada_attn_args& a, long long* trace, cudaStream_t s);
+int launch_attn_bf16(const mhada_attn_args& a, cudaStream_t s) { return launch_attn_bf16_impl(a, nullptr, s); }
+
+int launch_attn_bf16_impl(const mhada_attn_args& a, long long* trace, cudaStream_t s) {
     const int C = a.H * AT_D;
     CUtensorMap tmQ, tmK, tmV;
     {
@@ -322,16 +353,23 @@ int launch_attn_bf16(const mhada_attn_args& a, cudaStream_t s) {
     p.out = static_cast<__nv_bfloat16*>(a.out);
     p.x_mean = a.x_mean; p.x_rstd = a.x_rstd; p.mu_v = a.mu_v;
     p.H = a.H; p.Nc = a.Nc; p.Ns = a.Ns; p.ldx = a.ldx; p.ldo = a.ldo;
+    p.trace = trace;
     constexpr size_t smem = AT_SMEM_DATA + sizeof(AttnBars) + 1024;
     static bool attr_done = false;
     if (!attr_done) {
-        if (int e = check_cuda(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        if (int e = check_cuda(cudaFuncSetAttribute(attn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                    static_cast<int>(smem)), "attn smem attr"))
+            return e;
+        if (int e = check_cuda(cudaFuncSetAttribute(attn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                     static_cast<int>(smem)), "attn smem attr"))
             return e;
         attr_done = true;
     }
     dim3 grid((a.Nc + 2 * AT_BM - 1) / (2 * AT_BM), a.H, a.B);
-    attn_tc_kernel<<<grid, AT_THREADS, smem, s>>>(tmQ, tmK, tmV, p);
+    if (trace)
+        attn_tc_kernel<true><<<grid, AT_THREADS, smem, s>>>(tmQ, tmK, tmV, p);
+    else
+        attn_tc_kernel<false><<<grid, AT_THREADS, smem, s>>>(tmQ, tmK, tmV, p);
     count_launch();
     return check_cuda(cudaGetLastError(), "attn_tc launch");
 }

@@ -44,6 +44,7 @@ int launch_proj_bf16(const void* fc, const void* fs, const float* mean_c, const 
                      const float* rstd_s, const float* w, const float* bias, int B, int Nc, int Ns, int H, int d,
                      void* q, void* k, void* v, float* mu_v, void* ws, cudaStream_t s);
 int launch_attn_bf16(const mhada_attn_args& a, cudaStream_t s);
+int launch_attn_bf16_impl(const mhada_attn_args& a, long long* trace, cudaStream_t s);   // trace: 3*64*8 slots or null
 size_t linear_bf16_workspace(int Cout, int Cin);
 int launch_linear_bf16(const void* x, int ldx, const float* w, const float* bias, int M, int Cin, int Cout, void* y,
                        int ldy, void* ws, cudaStream_t s);
