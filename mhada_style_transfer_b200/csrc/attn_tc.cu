@@ -7,16 +7,19 @@
 // is consumed straight from TMEM by the second MMA, which multiplies by V' = [V~ | V~^2] (128 wide)
 // so the mean and the second moment come out of ONE pass (V~ = V - mu_v, added back at the end).
 //
-// CTA = 2 query tiles of 128 rows x 1 head, 12 warps:
-//   warp 0       TMA producer: Q (once), K ring (3 x 16 KB), V' ring (3 x 32 KB), 128B swizzle
+// CTA = 2 query tiles of 128 rows x 1 head, key tiles of 64, 12 warps:
+//   warp 0       TMA producer: Q (once), K ring (4 x 8 KB), V' ring (4 x 16 KB), 128B swizzle
 //   warp 1       tcgen05.mma issuer (one elected lane)
-//   warp 2       TMEM allocator (512 columns: S0 | S1 | O0 | O1, 128 fp32 columns each)
+//   warp 2       TMEM allocator (512 columns; per query tile t: S buffers at t*256 + {0, 64}, O at t*256 + 128)
 //   warp 3       stages the epilogue constants (mean/rstd of fcs, mu_v) into shared memory
 //   warps 4-7    softmax + epilogue for query tile 0 (thread = row; TMEM lane = row, no shuffles)
-//   warps 8-11   same for query tile 1 -- the two tiles ping-pong on the tensor core
-// MMA order per key tile j:  PV0(j) S0(j+1) PV1(j) S1(j+1), so while one warpgroup runs exp2 on its
-// tile the tensor core works for the other one.  Rescaling of O is lazy (only when a row max grows by
-// more than 2^8), done in place in TMEM by the softmax warps while no MMA touches that accumulator.
+//   warps 8-11   same for query tile 1
+// Pipeline (measured motivation in DESIGN.md, attention section): S is DOUBLE-BUFFERED in TMEM, so
+// S(j+1), S(j+2) are computed while the softmax warps still work on tile j -- they do not wait for the
+// tensor core in steady state, and the exp2 (MUFU) units, which bound this head_dim-64 problem, stay busy.
+// MMA issue order per key tile j and query tile t:  [P_t(j) ready]  PV_t(j)  S_t(j+2).
+// Rescaling of O is lazy (only when a row max grows by more than 2^8) and done in place in TMEM by the
+// softmax warps after waiting for the last PV into that accumulator.
 //
 // Tensor-bound: algorithmic FLOPs = 6 * B * Nc * Ns * C per layer (2 QK^T + 2 AV + 2 AV^2).
 #include <math.h>
@@ -27,14 +30,14 @@
 namespace mh {
 
 constexpr int AT_BM = 128;       // query rows per tile
-constexpr int AT_BN = 128;       // keys per tile
+constexpr int AT_BN = 64;        // keys per tile
 constexpr int AT_D = 64;         // head dim (dqk = dv)
 constexpr int AT_DV2 = 128;      // [V~ | V~^2]
-constexpr int AT_KST = 3, AT_VST = 3;
+constexpr int AT_KST = 4, AT_VST = 4;
 constexpr int AT_THREADS = 384;
 constexpr uint32_t AT_Q_BYTES = AT_BM * AT_D * 2;          // 16 KB per query tile
-constexpr uint32_t AT_K_BYTES = AT_BN * AT_D * 2;          // 16 KB
-constexpr uint32_t AT_V_BYTES = AT_BN * AT_DV2 * 2;        // 32 KB (two 64-column boxes)
+constexpr uint32_t AT_K_BYTES = AT_BN * AT_D * 2;          // 8 KB
+constexpr uint32_t AT_V_BYTES = AT_BN * AT_DV2 * 2;        // 16 KB (two 64-column boxes)
 constexpr uint32_t AT_SMEM_DATA = 2 * AT_Q_BYTES + AT_KST * AT_K_BYTES + AT_VST * AT_V_BYTES;
 constexpr float AT_RESCALE_THRESHOLD = 8.0f;               // log2 units: P <= 2^8
 
@@ -42,7 +45,7 @@ constexpr float AT_RESCALE_THRESHOLD = 8.0f;               // log2 units: P <= 2
 //   softmax WG t, iteration j: trace[(t*64 + j)*8 + e], e = 0 S ready, 1 S in registers, 2 max/rescale done,
 //                              3 P stores issued, 4 P arrived
 //   MMA thread:                trace[(2*64 + j)*8 + e], e = 0/2 P_t ready seen (t=0/1), 1/3 PV_t+S_t issued
-constexpr int AT_TRACE_WORDS = 3 * 64 * 8;
+constexpr int AT_TRACE_WORDS = 4 * 64 * 8;   // role 3 = TMA producer: e0 K(j+2) issued, e1 V(j) slot free, e2 V(j) issued
 
 struct AttnTcParams {
     const __nv_bfloat16* x;   // fcs [B, Nc, ldx]
@@ -56,7 +59,9 @@ struct AttnBars {
     uint64_t q_full;
     uint64_t k_full[AT_KST], k_empty[AT_KST];
     uint64_t v_full[AT_VST], v_empty[AT_VST];
-    uint64_t s_full[2], p_ready[2], o_full[2];
+    uint64_t s_full[2][2];    // [query tile][S buffer]
+    uint64_t p_ready[2][2];
+    uint64_t pv_done[2];      // one phase per key tile: PV_t(j) retired (O_t quiescent until P_t(j+1) arrives)
     uint32_t tmem_slot;
     float cst[3][AT_D];       // x_mean, x_rstd, mu_v of this (b, head)
 };
@@ -90,9 +95,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         for (int s = 0; s < AT_KST; ++s) { mbar_init(&bars->k_full[s], 1); mbar_init(&bars->k_empty[s], 1); }
         for (int s = 0; s < AT_VST; ++s) { mbar_init(&bars->v_full[s], 1); mbar_init(&bars->v_empty[s], 1); }
         for (int t = 0; t < 2; ++t) {
-            mbar_init(&bars->s_full[t], 1);
-            mbar_init(&bars->p_ready[t], 4);     // one arrive per softmax warp
-            mbar_init(&bars->o_full[t], 1);
+            for (int u = 0; u < 2; ++u) {
+                mbar_init(&bars->s_full[t][u], 1);
+                mbar_init(&bars->p_ready[t][u], 4);     // one arrive per softmax warp
+            }
+            mbar_init(&bars->pv_done[t], 1);
         }
         fence_mbar_init();
     }
@@ -112,7 +119,6 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = bars->tmem_slot;
-    // TMEM columns: S_t at t*128 (P_t aliases its first 64 columns), O_t at 256 + t*128
 
     // Register hand-over: the setmaxnreg calls sit INSIDE the role branches (no join before the role
     // code) so ptxas allocates each branch against its own budget.
@@ -124,16 +130,25 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             mbar_arrive_expect_tx(&bars->q_full, 2 * AT_Q_BYTES);
             tma_load_3d(sQ, &tmQ, &bars->q_full, h * AT_D, q0, b);
             tma_load_3d(sQ + AT_Q_BYTES, &tmQ, &bars->q_full, h * AT_D, q0 + AT_BM, b);
-            for (int j = 0; j < T; ++j) {
-                const int ks = j % AT_KST, vs = j % AT_VST;
+            auto load_k = [&](int j) {
+                const int ks = j % AT_KST;
                 mbar_wait(&bars->k_empty[ks], ((j / AT_KST) & 1) ^ 1);
                 mbar_arrive_expect_tx(&bars->k_full[ks], AT_K_BYTES);
                 tma_load_3d(sK + ks * AT_K_BYTES, &tmK, &bars->k_full[ks], h * AT_D, j * AT_BN, b);
+            };
+            load_k(0);
+            if (T > 1) load_k(1);
+            for (int j = 0; j < T; ++j) {
+                if (j + 2 < T) load_k(j + 2);          // S runs two key tiles ahead of PV
+                stamp(3, j, 0);
+                const int vs = j % AT_VST;
                 mbar_wait(&bars->v_empty[vs], ((j / AT_VST) & 1) ^ 1);
+                stamp(3, j, 1);
                 mbar_arrive_expect_tx(&bars->v_full[vs], AT_V_BYTES);
                 uint8_t* v = sV + vs * AT_V_BYTES;
                 tma_load_3d(v, &tmV, &bars->v_full[vs], h * AT_DV2, j * AT_BN, b);
                 tma_load_3d(v + AT_V_BYTES / 2, &tmV, &bars->v_full[vs], h * AT_DV2 + 64, j * AT_BN, b);
+                stamp(3, j, 2);
             }
         }
       } else if (warp == 1) {
@@ -142,48 +157,55 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             constexpr uint32_t idesc_s = make_idesc_bf16(AT_BM, AT_BN, 0, 0);     // S = Q K^T, both K-major
             constexpr uint32_t idesc_o = make_idesc_bf16(AT_BM, AT_DV2, 0, 1);    // O += P V', V' MN-major
             const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV);
-            auto issue_s = [&](int t, int ks) {
+            auto issue_s = [&](int t, int j) {         // S_t(j) -> S buffer j&1 of query tile t
+                const int ks = j % AT_KST;
                 const uint64_t da = make_smem_desc(q_addr + t * AT_Q_BYTES, 16, 1024);
                 const uint64_t db = make_smem_desc(k_addr + ks * AT_K_BYTES, 16, 1024);
+                const uint32_t d_tm = tmem + t * 256 + (j & 1) * 64;
 #pragma unroll
                 for (int k = 0; k < AT_D / 16; ++k)
-                    umma_ss(tmem + t * 128, desc_advance(da, k * 32), desc_advance(db, k * 32), idesc_s, k != 0);
+                    umma_ss(d_tm, desc_advance(da, k * 32), desc_advance(db, k * 32), idesc_s, k != 0);
+                umma_commit(&bars->s_full[t][j & 1]);
             };
-            auto issue_pv = [&](int t, int vs, bool accumulate) {
-                // B = V' tile [128 keys][128 cols] as two [128][64] boxes: LBO = box stride, SBO = 8 key rows
+            auto issue_pv = [&](int t, int j) {
+                // B = V' tile [64 keys][128 cols] as two [64][64] boxes: LBO = box stride, SBO = 8 key rows
+                const int vs = j % AT_VST;
                 const uint64_t db = make_smem_desc(v_addr + vs * AT_V_BYTES, AT_V_BYTES / 2, 1024);
+                const uint32_t a_tm = tmem + t * 256 + (j & 1) * 64;      // P_t(j) aliases S buffer j&1
 #pragma unroll
                 for (int k = 0; k < AT_BN / 16; ++k)
-                    umma_ts(tmem + 256 + t * 128, tmem + t * 128 + k * 8, desc_advance(db, k * 2048), idesc_o,
-                            (accumulate || k != 0) ? 1u : 0u);
+                    umma_ts(tmem + t * 256 + 128, a_tm + k * 8, desc_advance(db, k * 2048), idesc_o,
+                            (j != 0 || k != 0) ? 1u : 0u);
+                umma_commit(&bars->pv_done[t]);
             };
             mbar_wait(&bars->q_full, 0);
-            mbar_wait(&bars->k_full[0], 0);
-            tc_fence_after();
-            issue_s(0, 0);
-            umma_commit(&bars->s_full[0]);
-            issue_s(1, 0);
-            umma_commit(&bars->s_full[1]);
-            umma_commit(&bars->k_empty[0]);
+            for (int j = 0; j < 2 && j < T; ++j) {
+                mbar_wait(&bars->k_full[j % AT_KST], 0);
+                tc_fence_after();
+                issue_s(0, j);
+                issue_s(1, j);
+                umma_commit(&bars->k_empty[j % AT_KST]);
+            }
             for (int j = 0; j < T; ++j) {
                 const int vs = j % AT_VST;
-                const bool more = (j + 1 < T);
-                const int ks1 = (j + 1) % AT_KST;
+                const bool more = (j + 2 < T);
                 mbar_wait(&bars->v_full[vs], (j / AT_VST) & 1);
-                if (more) mbar_wait(&bars->k_full[ks1], ((j + 1) / AT_KST) & 1);
+                stamp(2, j, 4);
 #pragma unroll
                 for (int t = 0; t < 2; ++t) {
-                    mbar_wait(&bars->p_ready[t], j & 1);
+                    mbar_wait(&bars->p_ready[t][j & 1], (j >> 1) & 1);
                     tc_fence_after();
                     stamp(2, j, 2 * t);
-                    issue_pv(t, vs, j != 0);
+                    issue_pv(t, j);
                     if (t == 1) umma_commit(&bars->v_empty[vs]);
                     if (more) {
-                        issue_s(t, ks1);
-                        umma_commit(&bars->s_full[t]);
-                        if (t == 1) umma_commit(&bars->k_empty[ks1]);
-                    } else {
-                        umma_commit(&bars->o_full[t]);
+                        if (t == 0) {
+                            mbar_wait(&bars->k_full[(j + 2) % AT_KST], ((j + 2) / AT_KST) & 1);
+                            tc_fence_after();
+                            stamp(2, j, 5);
+                        }
+                        issue_s(t, j + 2);
+                        if (t == 1) umma_commit(&bars->k_empty[(j + 2) % AT_KST]);
                     }
                     stamp(2, j, 2 * t + 1);
                 }
@@ -196,34 +218,33 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         const int t = (warp - 4) >> 2;           // query tile of this warpgroup
         const int quarter = warp & 3;            // TMEM lane quarter this warp may touch
         const int row = quarter * 32 + lane;
-        const uint32_t s_tm = tmem_addr(tmem, quarter * 32, t * 128);
-        const uint32_t o_tm = tmem_addr(tmem, quarter * 32, 256 + t * 128);
+        const uint32_t s_tm = tmem_addr(tmem, quarter * 32, t * 256);
+        const uint32_t o_tm = tmem_addr(tmem, quarter * 32, t * 256 + 128);
         float m_used = -INFINITY, l = 0.f;
 
         for (int j = 0; j < T; ++j) {
-            mbar_wait(&bars->s_full[t], j & 1);
+            const uint32_t sb_tm = s_tm + (j & 1) * 64;
+            mbar_wait(&bars->s_full[t][j & 1], (j >> 1) & 1);
             tc_fence_after();
             const bool tr = TRACE && quarter == 0 && lane == 0;
             if (tr) stamp(t, j, 0);
-            uint32_t s[128];
-            tmem_ld_x32(s_tm, s);
-            tmem_ld_x32(s_tm + 32, s + 32);
-            tmem_ld_x32(s_tm + 64, s + 64);
-            tmem_ld_x32(s_tm + 96, s + 96);
+            uint32_t s[64];
+            tmem_ld_x32(sb_tm, s);
+            tmem_ld_x32(sb_tm + 32, s + 32);
             tmem_wait_ld();
             if (tr) stamp(t, j, 1);
-            const int valid = p.Ns - j * AT_BN;       // keys in this tile (tail tile: < 128)
+            const int valid = p.Ns - j * AT_BN;       // keys in this tile (tail tile: < 64)
             if (valid < AT_BN) {
 #pragma unroll
-                for (int i = 0; i < 128; ++i)
+                for (int i = 0; i < 64; ++i)
                     if (i >= valid) s[i] = 0xff800000u;   // -inf
             }
-            // row max: 8 independent chains (a single 127-deep FMNMX chain costs ~4 cycles per link)
+            // row max: 8 independent chains (a single deep FMNMX chain costs ~4 cycles per link)
             float mxa[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) mxa[i] = __uint_as_float(s[i]);
 #pragma unroll
-            for (int i = 8; i < 128; ++i) mxa[i & 7] = fmaxf(mxa[i & 7], __uint_as_float(s[i]));
+            for (int i = 8; i < 64; ++i) mxa[i & 7] = fmaxf(mxa[i & 7], __uint_as_float(s[i]));
             const float mx = fmaxf(fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])),
                                    fmaxf(fmaxf(mxa[4], mxa[5]), fmaxf(mxa[6], mxa[7])));
             if (j == 0) {
@@ -235,6 +256,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                     const float sc = ex2_approx(m_used - m_new);    // 1 for rows that keep their max
                     l *= sc;
                     m_used = m_new;
+                    // O_t may only be touched once PV_t(j-1) has retired; PV_t(j) cannot start before our P arrives
+                    mbar_wait(&bars->pv_done[t], (j - 1) & 1);
+                    tc_fence_after();
 #pragma unroll 1
                     for (int c = 0; c < AT_DV2; c += 32) {
                         uint32_t o[32];
@@ -247,7 +271,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 }
             }
             if (tr) stamp(t, j, 2);
-            // P = exp2(S - m), packed bf16x2, written over the first 64 columns of S.
+            // P = exp2(S - m), packed bf16x2, written over the first 32 columns of this S buffer.
             // Packed f32x2 adds (FADD2) for the subtraction and for the row sum; four independent sum chains.
             // The row sum uses the ROUNDED weights the MMA sees: with l = sum(p) but M, E built from bf16(p),
             // Var = E - M^2 picks up eps * M^2 (eps ~ 2^-9) and sqrt() of that is percent-level when the
@@ -255,7 +279,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             const float2 neg_m = make_float2(-m_used, -m_used);
             float2 la = make_float2(0.f, 0.f), lb = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < 2; ++c) {
                 uint32_t pk[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
@@ -265,19 +289,22 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                     const float2 r = make_float2(bf16_lo(pk[i]), bf16_hi(pk[i]));
                     if (i & 1) la = __fadd2_rn(la, r); else lb = __fadd2_rn(lb, r);
                 }
-                tmem_st_x16(s_tm + c * 16, pk);
+                tmem_st_x16(sb_tm + c * 16, pk);
             }
             l += (la.x + la.y) + (lb.x + lb.y);
             if (tr) stamp(t, j, 3);
             tmem_wait_st();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&bars->p_ready[t]);
+            if (lane == 0) mbar_arrive(&bars->p_ready[t][j & 1]);
             if (tr) stamp(t, j, 4);
         }
 
         // ---- epilogue: O/l -> (M~, E~) -> sqrt(max(E~ - M~^2, 1e-6)) * IN(fcs) + M~ + mu_v
-        mbar_wait(&bars->o_full[t], 0);
+        // a parity wait is only valid within one phase of the barrier: S(T-1) being loaded proves PV(T-3)
+        // retired, so first wait for phase T-2, then for the last one
+        if (T >= 2) mbar_wait(&bars->pv_done[t], (T - 2) & 1);
+        mbar_wait(&bars->pv_done[t], (T - 1) & 1);
         tc_fence_after();
         const float inv = 1.f / l;
         const int n = q0 + t * AT_BM + row;
@@ -324,7 +351,6 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     if (warp == 2) tmem_dealloc(tmem, 512);
 }
 
-int launch_attn_bf16_impl(const mhada_attn_args& a, long long* trace, cudaStream_t s);
 int launch_attn_bf16(const mhada_attn_args& a, cudaStream_t s) { return launch_attn_bf16_impl(a, nullptr, s); }
 
 int launch_attn_bf16_impl(const mhada_attn_args& a, long long* trace, cudaStream_t s) {

@@ -15,7 +15,7 @@ def main():
     x = (torch.randn(B, Nc, C, device=dev, generator=g) * 30).bfloat16()
     st = torch.zeros(3, B, C, device=dev); st[1] = 1.0
     out = torch.empty_like(x)
-    trace = torch.zeros(3 * 64 * 8, dtype=torch.int64, device=dev)
+    trace = torch.zeros(4 * 64 * 8, dtype=torch.int64, device=dev)
     a = _lib.AttnArgs(); a.dtype = _lib.BF16
     a.B, a.H, a.Nc, a.Ns, a.dqk, a.dv = B, H, Nc, Ns, d, d
     a.q, a.k, a.v, a.x, a.out = q.data_ptr(), k.data_ptr(), v.data_ptr(), x.data_ptr(), out.data_ptr()
@@ -25,13 +25,13 @@ def main():
     for _ in range(2):
         _lib.check("trace", L.mhada_debug_attn_trace(ctypes.byref(a), ctypes.c_void_p(trace.data_ptr()), stream))
     torch.cuda.synchronize()
-    t = trace.cpu().numpy().reshape(3, 64, 8)
+    t = trace.cpu().numpy().reshape(4, 64, 8)
     t0 = t[0, 0, 0]
-    T = Ns // 128
+    T = Ns // 64
     print("softmax WG0/WG1: [S ready, S in regs, max done, P st issued, P arrived]; MMA: [P0 seen, PV0+S0 issued, P1 seen, PV1+S1 issued]  (cycles rel. to first S0 ready)")
-    for j in list(range(0, 6)) + list(range(T - 3, T)):
+    for j in list(range(0, 8)) + list(range(T - 3, T)):
         r = lambda role, n: " ".join(f"{int(x - t0):7d}" for x in t[role, j, :n])
-        print(f"j={j:2d} WG0 {r(0,5)} | WG1 {r(1,5)} | MMA {r(2,4)}")
+        print(f"j={j:2d} WG0 {r(0,5)} | WG1 {r(1,5)} | MMA {r(2,6)} | TMA {r(3,3)}")
     d0 = np.diff(t[0, :T, 0]); d1 = np.diff(t[1, :T, 0])
     print("period WG0 mean", d0[2:].mean(), "WG1", d1[2:].mean())
     for name, role in (("WG0", 0), ("WG1", 1)):
