@@ -143,6 +143,16 @@ MHADA_API int mhada_layer_forward(int dtype, const void* fc, const void* fs, con
                         const float* b_fgh, const float* w_out, const float* b_out, int B, int Nc, int Ns, int C,
                         int H, void* out, void* ws, size_t ws_bytes, mhada_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * (5b) Decoder glue -- replaces nn.ReflectionPad2d(1) (MHAdaSTr/network/conv.py:26-27) and, when
+ *     `upsample` != 0, the F.interpolate(scale_factor=2, mode="bilinear", align_corners=False) that
+ *     precedes it (conv.py:71), in one pass over channels_last activations:
+ *         x [B, H, W, C]  ->  y [B, Ho + 2, Wo + 2, C],   Ho, Wo = H, W or 2H, 2W.
+ *     C must be a multiple of 8 (bf16) / 4 (f32); pointers 16-byte aligned.
+ * ---------------------------------------------------------------------------------------------- */
+MHADA_API int mhada_pad_reflect(int dtype, const void* x, int B, int H, int W, int C, int upsample, void* y,
+                                mhada_stream_t stream);
+
 /* Number of kernel launches the last mhada_layer_forward on this thread issued (bench bookkeeping). */
 MHADA_API int mhada_last_launch_count(void);
 

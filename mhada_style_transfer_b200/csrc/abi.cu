@@ -227,6 +227,18 @@ int mhada_linear(int dtype, const void* x, int ldx, const float* w, const float*
     return launch_linear_bf16(x, ldx, w, bias, M, Cin, Cout, y, ldy, ws, s);
 }
 
+int mhada_pad_reflect(int dtype, const void* x, int B, int H, int W, int C, int upsample, void* y,
+                      mhada_stream_t stream) {
+    REQUIRE(x && y, MHADA_ERR_ARG, "mhada_pad_reflect: null pointer");
+    REQUIRE(dtype == MHADA_F32 || dtype == MHADA_BF16, MHADA_ERR_ARG, "mhada_pad_reflect: bad dtype %d", dtype);
+    REQUIRE(B > 0 && H > 1 && W > 1 && C > 0, MHADA_ERR_ARG,
+            "mhada_pad_reflect: bad sizes B=%d H=%d W=%d C=%d (reflection needs H, W >= 2)", B, H, W, C);
+    REQUIRE(C % (dtype == MHADA_BF16 ? 8 : 4) == 0 && aligned16(x) && aligned16(y), MHADA_ERR_ARG,
+            "mhada_pad_reflect: C must be a multiple of %d and pointers 16-byte aligned", dtype == MHADA_BF16 ? 8 : 4);
+    if (int e = device_check()) return e;
+    return launch_pad_reflect(dtype, x, B, H, W, C, upsample, y, static_cast<cudaStream_t>(stream));
+}
+
 size_t mhada_layer_workspace(int dtype, int B, int Nc, int Ns, int C, int H) {
     if (B <= 0 || Nc <= 0 || Ns <= 0 || C <= 0 || H <= 0 || C % H != 0) return 0;
     return carve(dtype, B, Nc, Ns, C, H, nullptr).total;

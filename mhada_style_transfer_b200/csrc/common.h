@@ -49,6 +49,9 @@ size_t linear_bf16_workspace(int Cout, int Cin);
 int launch_linear_bf16(const void* x, int ldx, const float* w, const float* bias, int M, int Cin, int Cout, void* y,
                        int ldy, void* ws, cudaStream_t s);
 
+// decoder glue
+int launch_pad_reflect(int dtype, const void* x, int B, int H, int W, int C, int upsample, void* y, cudaStream_t s);
+
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 }  // namespace mh

@@ -356,7 +356,41 @@ class _ConvBlock(nn.Module):
         return x
 
 
+def _pad_reflect(x_tok: torch.Tensor, upsample: bool) -> torch.Tensor:
+    """[B,H,W,C] contiguous -> [B,Ho+2,Wo+2,C]: ReflectionPad2d(1) (+ x2 bilinear first) in one kernel."""
+    L = _lib.lib()
+    B, H, W, C = x_tok.shape
+    Ho, Wo = (2 * H, 2 * W) if upsample else (H, W)
+    y = torch.empty((B, Ho + 2, Wo + 2, C), dtype=x_tok.dtype, device=x_tok.device)
+    with torch.cuda.device(x_tok.device):
+        rc = L.mhada_pad_reflect(_code(x_tok.dtype), _ptr(x_tok), B, H, W, C, 1 if upsample else 0, _ptr(y), _stream())
+    _lib.check("mhada_pad_reflect", rc)
+    return y
+
+
+_CUDNN_RELU_OK = {}
+
+
+def _conv3x3_relu(xp_nchw: torch.Tensor, w: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """3x3 conv (input already padded) + bias + ReLU.  cuDNN's fused conv-bias-relu when it accepts the
+    shape, else conv2d + relu_.  Library call: the decoder convolutions are the boundary neighbour."""
+    key = (xp_nchw.dtype, w.shape[0], w.shape[1])
+    if _CUDNN_RELU_OK.get(key, True):
+        try:
+            y = torch.cudnn_convolution_relu(xp_nchw, w, b, (1, 1), (0, 0), (1, 1), 1)
+            _CUDNN_RELU_OK[key] = True
+            return y
+        except RuntimeError:
+            _CUDNN_RELU_OK[key] = False
+    return F.conv2d(xp_nchw, w, b).relu_()
+
+
 class Decoder(nn.Module):
+    """Decoder.forward (conv.py:75-100).  On the GPU every block runs as
+        [fused reflect-pad (+ x2 bilinear of the previous block)] -> cuDNN NHWC conv3x3 + bias + ReLU
+    so activations stay channels_last and each one is written once and read once between convolutions.
+    CPU tensors take the plain PyTorch path (the decoder is not part of the no-fallback hot path)."""
+
     def __init__(self):
         super().__init__()
         self.conv1 = nn.Sequential(_ConvBlock(512, 256, 2), _ConvBlock(256, 256), _ConvBlock(256, 256),
@@ -364,12 +398,35 @@ class Decoder(nn.Module):
         self.conv2 = nn.Sequential(_ConvBlock(128, 128), _ConvBlock(128, 64, 2))
         self.conv3 = nn.Sequential(_ConvBlock(64, 64), _ConvBlock(64, 3))
 
+    def _blocks(self):
+        return [*self.conv1, *self.conv2, *self.conv3]
+
     def forward(self, fcs: torch.Tensor):
-        if fcs.is_cuda and fcs.dtype == torch.float32:
-            # the fp32 path promises the reference's fp32 arithmetic: keep cuDNN off TF32 here
-            with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
-                return self.conv3(self.conv2(self.conv1(fcs)))
-        return self.conv3(self.conv2(self.conv1(fcs)))
+        if not fcs.is_cuda:
+            return self.conv3(self.conv2(self.conv1(fcs)))
+        if fcs.dtype not in (torch.float32, torch.bfloat16):
+            fcs = fcs.to(torch.bfloat16)
+        if fcs.shape[2] < 2 or fcs.shape[3] < 2:
+            raise RuntimeError("Decoder needs at least 2x2 feature maps (ReflectionPad2d(1))")
+        x = _token_major(fcs, fcs.dtype)                    # [B,h,w,512]
+        up = False
+        ctx = torch.backends.cudnn.flags(enabled=True, allow_tf32=False) if x.dtype == torch.float32 else _NullCtx()
+        with ctx:                                            # fp32 path: the reference's fp32 arithmetic, not TF32
+            for blk in self._blocks():
+                xp = _pad_reflect(x, up)                     # conv.py:26-27 (+ :71 of the previous block)
+                w, b = blk.conv._weights(x.dtype)
+                y = _conv3x3_relu(xp.permute(0, 3, 1, 2), w, b)
+                x = _token_major(y, y.dtype)                 # no copy when cuDNN answered in channels_last
+                up = bool(blk.scale_factor)
+        return x.permute(0, 3, 1, 2)
+
+
+class _NullCtx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
 
 
 # ------------------------------------------------------------------------------------------------

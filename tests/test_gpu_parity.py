@@ -115,6 +115,21 @@ def test_forloss_fp32(case, golden_index):
     assert e["max_abs"] <= fp32_tol(golden_index[case["name"]]["ref32_vs_ref64"]), e
 
 
+@pytest.mark.parametrize("case", cases.DECODER_CASES, ids=lambda c: c["name"])
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 2e-2)])
+def test_decoder_vs_reference_golden(case, dtype, tol, golden_index):
+    """Decoder.forward (conv.py:96-100): fused reflect-pad / up-sample kernels + cuDNN convolutions."""
+    x, sd = cases.decoder_inputs(case)
+    m = M.Decoder()
+    m.load_state_dict({k[len("decoder."):]: v for k, v in synth.to_torch(sd, torch.float32).items()}, strict=True)
+    m = m.to(DEV).eval()
+    with torch.no_grad():
+        out = m(dev(x, dtype))
+    assert out.shape == (case["B"], 3, 8 * case["hw"][0], 8 * case["hw"][1])
+    e = O.errors(out.float().cpu().numpy(), load_golden(case["name"])["out"])
+    assert e["max_abs_rel"] <= tol, e
+
+
 def build_transformer(sd, precision="auto"):
     m = M.AdaAttnTransformerMultiHead()
     m.load_state_dict(synth.to_torch(sd, torch.float32), strict=True)

@@ -223,3 +223,22 @@ def test_attn_bf16(B, H, Nc, Ns, gain):
         want[:, :, sl] = sd * xn + m + muv.astype(np.float32).astype(np.float64)[:, None, sl]
     e = O.errors(n(out), want)
     assert e["max_abs_rel"] < 1.2e-2 and e["fro_rel"] < 4e-3, e
+
+
+# ------------------------------------------------------------------------------------------------ decoder glue
+@pytest.mark.parametrize("code", [F32, BF16])
+@pytest.mark.parametrize("B,H,W,C,up", [(2, 5, 7, 64, 0), (1, 5, 7, 64, 1), (1, 2, 2, 8, 1), (2, 16, 12, 256, 1),
+                                        (1, 64, 64, 512, 0)])
+def test_pad_reflect(code, B, H, W, C, up):
+    """mhada_pad_reflect against the oracle's reflection_pad1 / bilinear_up2 (conv.py:26-27, :71)."""
+    L = _lib.lib()
+    x = synth.bellish(21, (B, C, H, W), 0.5, 3.0)
+    xt = G.to_tokens(x, code).reshape(B, H, W, C)
+    xr = xt.float().cpu().numpy().astype(np.float64).transpose(0, 3, 1, 2)
+    Ho, Wo = (2 * H, 2 * W) if up else (H, W)
+    y = torch.empty(B, Ho + 2, Wo + 2, C, dtype=G.tdt(code), device=G.DEV)
+    _lib.check("mhada_pad_reflect", L.mhada_pad_reflect(code, G.ptr(xt), B, H, W, C, up, G.ptr(y), G.stream()))
+    want = O.reflection_pad1(O.bilinear_up2(xr) if up else xr)
+    got = y.float().cpu().numpy().astype(np.float64).transpose(0, 3, 1, 2)
+    e = O.errors(got, want)
+    assert e["max_abs_rel"] <= (4e-3 if (code == BF16 and up) else 1e-6), e
