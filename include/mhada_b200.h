@@ -155,6 +155,8 @@ MHADA_API int mhada_pad_reflect(int dtype, const void* x, int B, int H, int W, i
 
 /* Number of kernel launches the last mhada_layer_forward on this thread issued (bench bookkeeping). */
 MHADA_API int mhada_last_launch_count(void);
+/* Kernel launches issued by this library from this thread since it was loaded (monotonic). */
+MHADA_API long long mhada_total_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------
  * (6) Kernel timing for the roofline line of bench.py (no reference counterpart).

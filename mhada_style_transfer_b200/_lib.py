@@ -34,6 +34,7 @@ SIGNATURES = {
     "mhada_last_error": (c_char_p, []),
     "mhada_device_check": (c_int, []),
     "mhada_last_launch_count": (c_int, []),
+    "mhada_total_launch_count": (ctypes.c_longlong, []),
     "mhada_profile_begin": (c_int, []),
     "mhada_profile_end": (c_int, [POINTER(c_float), POINTER(c_int)]),
     "mhada_in_stats_workspace": (c_size_t, [c_int, c_int, c_int]),

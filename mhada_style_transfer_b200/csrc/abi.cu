@@ -118,6 +118,7 @@ int mhada_abi_version(void) { return MHADA_ABI_VERSION; }
 const char* mhada_last_error(void) { return last_error(); }
 int mhada_device_check(void) { return device_check(); }
 int mhada_last_launch_count(void) { return g_launches; }
+long long mhada_total_launch_count(void) { return g_launches_total; }
 
 size_t mhada_in_stats_workspace(int B, int N, int C) {
     if (B <= 0 || N <= 0 || C <= 0) return 0;

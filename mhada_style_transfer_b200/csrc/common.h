@@ -18,7 +18,8 @@ int check_cuda(cudaError_t e, const char* what);   // 0 or the error (message re
 int device_check();
 
 extern thread_local int g_launches;
-inline void count_launch() { ++g_launches; }
+extern thread_local long long g_launches_total;
+inline void count_launch() { ++g_launches; ++g_launches_total; }
 
 // bf16 tensor map, up to 3 dims, dims[0] innermost (contiguous).  strides_bytes[i] = byte pitch of
 // dim i+1.  box[i] = tile extent.  128B swizzle when box[0]*2 == 128, else none.

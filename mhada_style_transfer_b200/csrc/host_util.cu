@@ -9,6 +9,7 @@ namespace mh {
 
 static thread_local char g_err[512] = "";
 thread_local int g_launches = 0;
+thread_local long long g_launches_total = 0;
 
 void set_error(const char* fmt, ...) {
     va_list ap;
