@@ -62,6 +62,7 @@ struct AttnBars {
     uint64_t s_full[2][2];    // [query tile][S buffer]
     uint64_t p_ready[2][2];
     uint64_t pv_done[2];      // one phase per key tile: PV_t(j) retired (O_t quiescent until P_t(j+1) arrives)
+    uint64_t o_full[2];       // single phase: the last PV_t retired
     uint32_t tmem_slot;
     float cst[3][AT_D];       // x_mean, x_rstd, mu_v of this (b, head)
 };
@@ -100,6 +101,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 mbar_init(&bars->p_ready[t][u], 4);     // one arrive per softmax warp
             }
             mbar_init(&bars->pv_done[t], 1);
+            mbar_init(&bars->o_full[t], 1);
         }
         fence_mbar_init();
     }
@@ -177,6 +179,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                     umma_ts(tmem + t * 256 + 128, a_tm + k * 8, desc_advance(db, k * 2048), idesc_o,
                             (j != 0 || k != 0) ? 1u : 0u);
                 umma_commit(&bars->pv_done[t]);
+                if (j == T - 1) umma_commit(&bars->o_full[t]);
             };
             mbar_wait(&bars->q_full, 0);
             for (int j = 0; j < 2 && j < T; ++j) {
@@ -301,10 +304,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         }
 
         // ---- epilogue: O/l -> (M~, E~) -> sqrt(max(E~ - M~^2, 1e-6)) * IN(fcs) + M~ + mu_v
-        // a parity wait is only valid within one phase of the barrier: S(T-1) being loaded proves PV(T-3)
-        // retired, so first wait for phase T-2, then for the last one
-        if (T >= 2) mbar_wait(&bars->pv_done[t], (T - 2) & 1);
-        mbar_wait(&bars->pv_done[t], (T - 1) & 1);
+        // (pv_done cannot be used here: a parity wait is only meaningful while the barrier is at most one
+        // phase ahead, and a late warp may find both PV(T-2) and PV(T-1) retired -- o_full has a single phase)
+        mbar_wait(&bars->o_full[t], 0);
         tc_fence_after();
         const float inv = 1.f / l;
         const int n = q0 + t * AT_BM + row;
