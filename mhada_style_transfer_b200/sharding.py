@@ -1,0 +1,68 @@
+"""Image / frame sharding across the GPUs of one box.
+
+The MHAda path has no exchange step: every image (or video frame, given the style features) is independent
+(`AdaAttnMultiHead.forward` is batch-independent, adaDecoder.py:162-206; infer_video.py:73-118 processes frames
+one by one).  So the batch is partitioned contiguously over ranks, one process per GPU, and the ONLY collective
+is the gather of the results.  Works with any torch.distributed backend (NCCL on the B200 box, gloo in the CPU
+tests).
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n_items: int, world_size: int) -> List[Tuple[int, int]]:
+    """Contiguous, balanced partition of range(n_items): the first n % world ranks get one extra item."""
+    if n_items < 0 or world_size <= 0:
+        raise ValueError("n_items must be >= 0 and world_size > 0")
+    base, extra = divmod(n_items, world_size)
+    bounds, start = [], 0
+    for r in range(world_size):
+        size = base + (1 if r < extra else 0)
+        bounds.append((start, start + size))
+        start += size
+    return bounds
+
+
+def shard_range(n_items: int, rank: int, world_size: int) -> Tuple[int, int]:
+    return shard_bounds(n_items, world_size)[rank]
+
+
+def gather_batches(local: torch.Tensor, n_items: int, dst: int = 0, group=None):
+    """Gather per-rank result shards (dim 0 = images of this rank's shard_range) into the full batch on `dst`.
+    Shards may be uneven or empty: they are padded to the largest shard for the collective and trimmed after.
+    Returns the (n_items, ...) tensor on rank `dst`, None elsewhere."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    bounds = shard_bounds(n_items, world)
+    largest = max(e - s for s, e in bounds)
+    if largest == 0:
+        return local[:0] if rank == dst else None
+    pad = largest - local.shape[0]
+    send = local.contiguous()
+    if pad:
+        send = torch.cat([send, send.new_zeros((pad,) + tuple(send.shape[1:]))], dim=0)
+    bufs = [torch.empty_like(send) for _ in range(world)] if rank == dst else None
+    dist.gather(send, bufs, dst=dst, group=group)
+    if rank != dst:
+        return None
+    return torch.cat([b[: e - s] for b, (s, e) in zip(bufs, bounds)], dim=0)
+
+
+def run_sharded(model: Callable, fc: Sequence[torch.Tensor], fs: Sequence[torch.Tensor], dst: int = 0, group=None):
+    """`model(fc, fs) -> (fcs, cs)` on this rank's slice of the batch; decoded images gathered on `dst`.
+    fc / fs are lists of (B, C, h, w) feature maps holding the WHOLE batch (every rank passes the same B)."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    n = fc[0].shape[0]
+    s, e = shard_range(n, rank, world)
+    if e > s:
+        _, cs = model([t[s:e] for t in fc], [t[s:e] for t in fs])
+    else:  # more ranks than images: contribute an empty shard of the right trailing shape
+        with torch.no_grad():
+            _, probe = model([t[:1] for t in fc], [t[:1] for t in fs])
+        cs = probe[:0]
+    return gather_batches(cs, n, dst=dst, group=group)

@@ -1,0 +1,74 @@
+"""Host-side sharding / gather logic of the N > 1 path on CPU: world_size 2 (and 3, uneven) over gloo.
+The model is a stand-in with the module's call signature; the kernels themselves are covered by -m gpu."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from mhada_style_transfer_b200.sharding import gather_batches, run_sharded, shard_bounds, shard_range
+
+
+def test_shard_bounds_cover_and_balance():
+    for n in (0, 1, 7, 8, 9, 64):
+        for w in (1, 2, 3, 8):
+            b = shard_bounds(n, w)
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+            sizes = [e - s for s, e in b]
+            assert max(sizes) - min(sizes) <= 1
+    assert shard_range(9, 0, 2) == (0, 5) and shard_range(9, 1, 2) == (5, 9)
+    with pytest.raises(ValueError):
+        shard_bounds(4, 0)
+
+
+def _fake_model(fc, fs):
+    # per-image function of the inputs (like MHAda + decoder: no coupling across the batch)
+    fcs = fc[0] * 2.0 + fs[0].mean(dim=(1, 2, 3), keepdim=True)
+    cs = torch.stack([fcs[:, :3].sum(dim=(1, 2, 3))] * 4, dim=1).reshape(-1, 1, 2, 2) + fc[1][:, :1, :2, :2]
+    return fcs, cs
+
+
+def _worker(rank, world, port, n_images, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(0)
+    fc = [torch.randn(n_images, 8, 4, 4, generator=g) for _ in range(3)]
+    fs = [torch.randn(n_images, 8, 3, 3, generator=g) for _ in range(3)]
+    got = run_sharded(_fake_model, fc, fs, dst=0)
+    if rank == 0:
+        want = _fake_model(fc, fs)[1]
+        q.put((tuple(got.shape), bool(torch.equal(got, want))))
+    else:
+        assert got is None
+    # an uneven explicit gather too
+    s, e = shard_range(n_images, rank, world)
+    full = torch.arange(n_images * 3, dtype=torch.float32).reshape(n_images, 3)
+    out = gather_batches(full[s:e], n_images, dst=0)
+    if rank == 0:
+        q.put(bool(torch.equal(out, full)))
+    dist.destroy_process_group()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+@pytest.mark.parametrize("world,n_images", [(2, 8), (2, 5), (3, 2)])
+def test_sharded_run_matches_unsharded(world, n_images):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_images, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    shape, same = q.get(timeout=10)
+    assert shape == (n_images, 1, 2, 2) and same
+    assert q.get(timeout=10) is True

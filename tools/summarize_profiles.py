@@ -1,0 +1,96 @@
+"""Turn gpurun_out/launches.csv and gpurun_out/prof_attn.ncu-rep into the committed summaries under profiles/."""
+import collections
+import csv
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+out_dir = os.path.join(ROOT, "profiles")
+os.makedirs(out_dir, exist_ok=True)
+
+# ---- launch list
+lines = [l for l in open(os.path.join(ROOT, "gpurun_out", "launches.csv")) if not l.startswith("==")]
+rows = list(csv.DictReader(lines))
+agg = collections.OrderedDict()
+tot = 0.0
+for r in rows:
+    name = r["Kernel Name"].split("(")[0][:90]
+    t = float(r["Metric Value"]) / 1e3   # us
+    a = agg.setdefault(name, [0, 0.0])
+    a[0] += 1
+    a[1] += t
+    tot += t
+with open(os.path.join(out_dir, f"{tag}_launches_summary.md"), "w") as f:
+    f.write(f"# {tag}: kernel launch list of `python bench.py --steps 2 --warmup 1 --no-cpu-baseline`\n\n")
+    f.write("Command: `ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv` (B200, cfg2 = batch 8 of 512x512, bf16).\n"
+            "Times are cold-cache and serialised by ncu: read the SHARES, not the absolutes. "
+            f"{len(rows)} launches captured (3 steps + set-up copies), total {tot / 1e3:.2f} ms.\n\n")
+    f.write("| share | total us | launches | avg us | kernel |\n|---:|---:|---:|---:|---|\n")
+    for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        f.write(f"| {100 * t / tot:5.1f}% | {t:9.1f} | {n} | {t / n:7.1f} | `{k}` |\n")
+    mine = sum(t for k, (n, t) in agg.items() if k.startswith("mh::") or "mh::" in k)
+    f.write(f"\nKernels of this repo (`mh::*`): {100 * mine / tot:.1f}% of the captured device time; "
+            "the rest is cuDNN convolutions of the decoder and PyTorch copies.\n")
+import shutil
+shutil.copy(os.path.join(ROOT, "gpurun_out", "launches.csv"), os.path.join(out_dir, f"{tag}_launches.csv"))
+
+# ---- attention kernel, ncu --set full
+rep = os.path.join(ROOT, "gpurun_out", "prof_attn.ncu-rep")
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rr = list(csv.reader(raw.splitlines()))
+hdr, units, data = rr[0], rr[1], rr[2:]
+want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__bytes_read.sum.per_second",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
+        "sm__cycles_elapsed.avg", "sm__cycles_elapsed.avg.per_second", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "lts__t_bytes.sum", "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+        "smsp__inst_executed.sum", "launch__shared_mem_per_block_dynamic"]
+with open(os.path.join(out_dir, f"{tag}_attn_tc_ncu.md"), "w") as f:
+    f.write(f"# {tag}: `mh::attn_tc_kernel` under `ncu --set full --clock-control none` (B200)\n\n")
+    f.write("Workload: cfg2 layer (B=8, H=8, Nc=Ns=4096, d=64): grid 1024 CTAs x 384 threads. "
+            "Algorithmic FLOPs per launch = 6*B*Nc*Ns*C = 412.3 GFLOP; algorithmic HBM bytes = Q 33.5 + K 33.5 + V' 67.1 + fcs 33.5 MB read, 33.5 MB written.\n\n")
+    f.write("| metric | unit | " + " | ".join(f"launch {i}" for i in range(len(data))) + " |\n|---|---|" + "---:|" * len(data) + "\n")
+    for w in want:
+        if w in hdr:
+            i = hdr.index(w)
+            f.write(f"| `{w}` | {units[i]} | " + " | ".join(d[i] for d in data) + " |\n")
+    src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    sr = list(csv.reader(src.splitlines()))
+    sh = sr[1]
+    ix = {h: i for i, h in enumerate(sh)}
+    body, seen = [], set()
+    for r in sr[2:]:
+        if len(r) != len(sh) or r[0] == "Address":
+            continue
+        if r[0] in seen:
+            break
+        seen.add(r[0])
+        body.append(r)
+    stalls = [h for h in sh if h.startswith("stall_") and "Not Issued" not in h]
+    total = sum(int(r[ix["# Samples"]]) for r in body)
+    f.write(f"\n## Warp-stall samples by reason (first profiled launch, {total} samples)\n\n| reason | samples | share |\n|---|---:|---:|\n")
+    c = collections.Counter()
+    for r in body:
+        for h in stalls:
+            c[h] += int(r[ix[h]])
+    for h, n in c.most_common(10):
+        f.write(f"| {h} | {n} | {100 * n / max(total, 1):.1f}% |\n")
+    f.write("\n## Hottest SASS instructions\n\n| samples | executed | instruction | top stall |\n|---:|---:|---|---|\n")
+    for r in sorted(body, key=lambda r: -int(r[ix["# Samples"]]))[:25]:
+        s = {h: int(r[ix[h]]) for h in stalls if int(r[ix[h]]) > 0}
+        top = max(s.items(), key=lambda kv: kv[1])[0] if s else ""
+        f.write(f"| {r[ix['# Samples']]} | {r[ix['Instructions Executed']]} | `{r[ix['Source']].strip()[:70]}` | {top} |\n")
+    ops = collections.Counter()
+    for r in body:
+        src_ = r[ix["Source"]].strip().split()
+        if not src_:
+            continue
+        op = src_[1] if src_[0].startswith("@") and len(src_) > 1 else src_[0]
+        if op.startswith(("UTC", "UTMA", "LDTM", "STTM", "MUFU", "SYNCS", "FMNMX", "FADD2", "F2FP", "UBLKCP")):
+            ops[op.split(".")[0] + ("." + op.split(".")[1] if "." in op and op.startswith(("MUFU", "LDTM", "STTM")) else "")] += 1
+    f.write("\n## Blackwell-native instructions present in the SASS (static counts)\n\n" +
+            ", ".join(f"`{k}` x{v}" for k, v in sorted(ops.items())) + "\n")
+print("written", os.listdir(out_dir))
