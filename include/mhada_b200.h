@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define MHADA_ABI_VERSION 1
+#define MHADA_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define MHADA_API __attribute__((visibility("default")))
@@ -137,11 +137,14 @@ MHADA_API int mhada_linear(int dtype, const void* x, int ldx, const float* w, co
  *     w_fgh / b_fgh as in (2); w_out float [C][C], b_out float [C]; both may be NULL together to
  *     skip out_conv (the single-head AdaAttN, adaDecoder.py:102-131).
  *     ws: mhada_layer_workspace(dtype, B, Nc, Ns, C, H) bytes.
+ *     flags: MHADA_REUSE_FS_STATS when `fs` and `ws` are the ones passed to the previous call on this stream
+ *     (the two layers of a level share fs, adaDecoder.py:264-265): its statistics are not recomputed.
  * ---------------------------------------------------------------------------------------------- */
+#define MHADA_REUSE_FS_STATS 1
 MHADA_API size_t mhada_layer_workspace(int dtype, int B, int Nc, int Ns, int C, int H);
 MHADA_API int mhada_layer_forward(int dtype, const void* fc, const void* fs, const void* fcs, const float* w_fgh,
                         const float* b_fgh, const float* w_out, const float* b_out, int B, int Nc, int Ns, int C,
-                        int H, void* out, void* ws, size_t ws_bytes, mhada_stream_t stream);
+                        int H, int flags, void* out, void* ws, size_t ws_bytes, mhada_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * (5b) Decoder glue -- replaces nn.ReflectionPad2d(1) (MHAdaSTr/network/conv.py:26-27) and, when

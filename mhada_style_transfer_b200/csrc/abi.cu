@@ -247,7 +247,7 @@ size_t mhada_layer_workspace(int dtype, int B, int Nc, int Ns, int C, int H) {
 
 int mhada_layer_forward(int dtype, const void* fc, const void* fs, const void* fcs, const float* w_fgh,
                         const float* b_fgh, const float* w_out, const float* b_out, int B, int Nc, int Ns, int C,
-                        int H, void* out, void* ws, size_t ws_bytes, mhada_stream_t stream) {
+                        int H, int flags, void* out, void* ws, size_t ws_bytes, mhada_stream_t stream) {
     g_launches = 0;
     REQUIRE(fc && fs && fcs && w_fgh && b_fgh && out && ws, MHADA_ERR_ARG, "mhada_layer_forward: null pointer");
     REQUIRE((w_out == nullptr) == (b_out == nullptr), MHADA_ERR_ARG, "mhada_layer_forward: w_out/b_out must be given together");
@@ -268,14 +268,24 @@ int mhada_layer_forward(int dtype, const void* fc, const void* fs, const void* f
     if (int e = device_check()) return e;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
 
-    // (1) statistics of fc, fs and (unless it is the same tensor) fcs        adaDecoder.py:173,178,198
-    if (int e = launch_stats(fc, dtype, B, Nc, C, C, w.mean_c, w.rstd_c, static_cast<float*>(w.stats_ws), s)) return e;
-    if (int e = launch_stats(fs, dtype, B, Ns, C, C, w.mean_s, w.rstd_s, static_cast<float*>(w.stats_ws), s)) return e;
+    // (1) statistics of fc, fs and (unless it is the same tensor) fcs, one launch   adaDecoder.py:173,178,198
+    //     MHADA_REUSE_FS_STATS: fs (and this workspace) are the ones of the previous call, so mean_s / rstd_s
+    //     are still valid -- the two layers of a level share fs (adaDecoder.py:264-265)
     const float *mean_x = w.mean_c, *rstd_x = w.rstd_c;
-    if (fcs != fc) {
-        if (int e = launch_stats(fcs, dtype, B, Nc, C, C, w.mean_x, w.rstd_x, static_cast<float*>(w.stats_ws), s)) return e;
-        mean_x = w.mean_x;
-        rstd_x = w.rstd_x;
+    {
+        const void* xs[3];
+        float* ms[3];
+        float* rs[3];
+        int ns[3];
+        int n = 0;
+        xs[n] = fc; ms[n] = w.mean_c; rs[n] = w.rstd_c; ns[n] = Nc; ++n;
+        if (!(flags & MHADA_REUSE_FS_STATS)) { xs[n] = fs; ms[n] = w.mean_s; rs[n] = w.rstd_s; ns[n] = Ns; ++n; }
+        if (fcs != fc) {
+            xs[n] = fcs; ms[n] = w.mean_x; rs[n] = w.rstd_x; ns[n] = Nc; ++n;
+            mean_x = w.mean_x;
+            rstd_x = w.rstd_x;
+        }
+        if (int e = launch_stats_multi(n, xs, ns, ms, rs, dtype, B, C, C, static_cast<float*>(w.stats_ws), s)) return e;
     }
     // (2) projections                                                        adaDecoder.py:173-183
     if (dtype == MHADA_BF16) {

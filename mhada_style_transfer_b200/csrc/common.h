@@ -30,6 +30,9 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 size_t stats_workspace(int B, int N, int C);
 int launch_stats(const void* x, int dtype, int B, int N, int C, int ld, float* mean, float* rstd, float* ws,
                  cudaStream_t s);
+// up to 3 tensors with the same B, C, ld (fc, fs, fcs of a layer) in one launch of each pass
+int launch_stats_multi(int n, const void* const* x, const int* N, float* const* mean, float* const* rstd, int dtype,
+                       int B, int C, int ld, float* ws, cudaStream_t s);
 
 // f32 SIMT path
 int launch_proj_f32(const float* fc, const float* fs, const float* mean_c, const float* rstd_c,

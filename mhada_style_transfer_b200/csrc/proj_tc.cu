@@ -25,34 +25,42 @@ size_t proj_bf16_workspace(int B, int H, int d) {
     return fold_w_bytes(B, H, d) + align_up(static_cast<size_t>(3) * B * H * d * 4, 256);
 }
 
-// grid (H, B, 3), block d threads: thread o folds output row o of (which, b, h)
-__global__ void fold_kernel(const float* __restrict__ w, const float* __restrict__ bias,
-                            const float* __restrict__ mean_c, const float* __restrict__ rstd_c,
-                            const float* __restrict__ mean_s, const float* __restrict__ rstd_s, int B, int H, int d,
-                            __nv_bfloat16* __restrict__ wf, float* __restrict__ bf, float* __restrict__ mu_v) {
-    const int h = blockIdx.x, b = blockIdx.y, which = blockIdx.z, o = threadIdx.x;
-    if (o >= d) return;
+// grid (H, B, 3), 256 threads = 8 warps: warp w folds output rows w, w+8, ...; lanes walk the input channels,
+// so every global read / write is a contiguous row segment
+__global__ void __launch_bounds__(256) fold_kernel(const float* __restrict__ w, const float* __restrict__ bias,
+                                                   const float* __restrict__ mean_c, const float* __restrict__ rstd_c,
+                                                   const float* __restrict__ mean_s, const float* __restrict__ rstd_s,
+                                                   int B, int H, int d, __nv_bfloat16* __restrict__ wf,
+                                                   float* __restrict__ bf, float* __restrict__ mu_v) {
+    const int h = blockIdx.x, b = blockIdx.y, which = blockIdx.z;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int C = H * d;
-    const float* wr = w + ((static_cast<size_t>(which) * H + h) * d + o) * d;
-    const float bo = bias[(static_cast<size_t>(which) * H + h) * d + o];
     const float* mu = (which == 0 ? mean_c : mean_s) + static_cast<size_t>(b) * C + h * d;
     const float* rs = (which == 0 ? rstd_c : rstd_s) + static_cast<size_t>(b) * C + h * d;
-    __nv_bfloat16* dst = wf + (((static_cast<size_t>(which) * B + b) * H + h) * d + o) * d;
     const float gain = which == 0 ? kLog2e : 1.f;
-    float acc = 0.f;
-    for (int i = 0; i < d; ++i) {
-        float wv = wr[i] * gain;
-        if (which != 2) wv *= rs[i];
-        __nv_bfloat16 wb = __float2bfloat16_rn(wv);
-        dst[i] = wb;
-        acc = fmaf(__bfloat162float(wb), mu[i], acc);
-    }
-    const size_t bi = ((static_cast<size_t>(which) * B + b) * H + h) * d + o;
-    if (which == 2) {
-        bf[bi] = -acc;                                   // V~ = Wh y - Wh mu_s
-        mu_v[static_cast<size_t>(b) * C + h * d + o] = acc + bo;   // what the epilogue adds back
-    } else {
-        bf[bi] = bo * gain - acc;
+    for (int o = warp; o < d; o += 8) {
+        const float* wr = w + ((static_cast<size_t>(which) * H + h) * d + o) * d;
+        __nv_bfloat16* dst = wf + (((static_cast<size_t>(which) * B + b) * H + h) * d + o) * d;
+        float acc = 0.f;
+        for (int i = lane; i < d; i += 32) {
+            float wv = wr[i] * gain;
+            if (which != 2) wv *= rs[i];
+            const __nv_bfloat16 wb = __float2bfloat16_rn(wv);
+            dst[i] = wb;
+            acc = fmaf(__bfloat162float(wb), mu[i], acc);     // bias from the ROUNDED weights: centring cancels exactly
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+        if (lane == 0) {
+            const float bo = bias[(static_cast<size_t>(which) * H + h) * d + o];
+            const size_t bi = ((static_cast<size_t>(which) * B + b) * H + h) * d + o;
+            if (which == 2) {
+                bf[bi] = -acc;                                             // V~ = Wh y - Wh mu_s
+                mu_v[static_cast<size_t>(b) * C + h * d + o] = acc + bo;   // what the epilogue adds back
+            } else {
+                bf[bi] = bo * gain - acc;
+            }
+        }
     }
 }
 
@@ -182,7 +190,7 @@ int launch_proj_bf16(const void* fc, const void* fs, const float* mean_c, const 
                      void* q, void* k, void* v, float* mu_v, void* ws, cudaStream_t s) {
     __nv_bfloat16* wf = static_cast<__nv_bfloat16*>(ws);
     float* bf = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + fold_w_bytes(B, H, d));
-    fold_kernel<<<dim3(H, B, 3), d, 0, s>>>(w, bias, mean_c, rstd_c, mean_s, rstd_s, B, H, d, wf, bf, mu_v);
+    fold_kernel<<<dim3(H, B, 3), 256, 0, s>>>(w, bias, mean_c, rstd_c, mean_s, rstd_s, B, H, d, wf, bf, mu_v);
     count_launch();
 
     const int C = H * d;

@@ -41,17 +41,32 @@ struct VecIO<__nv_bfloat16> {
     }
 };
 
-// grid (channel chunks, splits, B)
+// Up to three tensors (fc, fs, fcs of one layer) go through ONE launch of each pass.
+#define MH_SEL3(arr, i) ((i) == 0 ? (arr)[0] : ((i) == 1 ? (arr)[1] : (arr)[2]))   // no local copy of the params
+struct StatsJob {
+    const void* x[3];
+    float* mean[3];
+    float* rstd[3];
+    int N[3];
+    int tps[3];        // tokens per split
+    int splits[3];
+    int n;             // tensors in this job
+    int max_splits;
+};
+
+// grid (channel chunks, max_splits, B * n_tensors)
 template <typename T>
-__global__ void __launch_bounds__(kStatsThreads) stats_partial_kernel(const T* __restrict__ x, int N, int C, int ld,
-                                                                      int tokens_per_split,
+__global__ void __launch_bounds__(kStatsThreads) stats_partial_kernel(const StatsJob job, int B, int C, int ld,
                                                                       float* __restrict__ partial) {
     constexpr int VEC = VecIO<T>::VEC;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int c0 = (blockIdx.x * 32 + lane) * VEC;
-    const int split = blockIdx.y, splits = gridDim.y, b = blockIdx.z;
+    const int ti = blockIdx.z / B, b = blockIdx.z % B;
+    const int split = blockIdx.y;
+    if (split >= MH_SEL3(job.splits, ti)) return;
+    const int N = MH_SEL3(job.N, ti), tokens_per_split = MH_SEL3(job.tps, ti);
     const bool active = c0 < C;
-    const T* xb = x + static_cast<size_t>(b) * N * ld + c0;
+    const T* xb = static_cast<const T*>(MH_SEL3(job.x, ti)) + static_cast<size_t>(b) * N * ld + c0;
 
     float piv[VEC], s1[VEC], s2[VEC];
 #pragma unroll
@@ -96,7 +111,7 @@ __global__ void __launch_bounds__(kStatsThreads) stats_partial_kernel(const T* _
     }
     __syncthreads();
     if (warp == 0 && active) {
-        float* dst = partial + ((static_cast<size_t>(b) * splits + split) * C + c0) * 2;
+        float* dst = partial + (((static_cast<size_t>(ti) * B + b) * job.max_splits + split) * C + c0) * 2;
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
             float a = 0.f, q = 0.f;
@@ -112,17 +127,19 @@ __global__ void __launch_bounds__(kStatsThreads) stats_partial_kernel(const T* _
 }
 
 template <typename T>
-__global__ void stats_final_kernel(const T* __restrict__ x, const float* __restrict__ partial, int B, int N, int C,
-                                   int ld, int splits, float* __restrict__ mean, float* __restrict__ rstd) {
+__global__ void stats_final_kernel(const StatsJob job, const float* __restrict__ partial, int B, int C, int ld) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= B * C) return;
-    int b = i / C, c = i % C;
+    if (i >= job.n * B * C) return;
+    const int ti = i / (B * C), r = i % (B * C), b = r / C, c = r % C;
+    const int N = MH_SEL3(job.N, ti);
+    const int nsplit = MH_SEL3(job.splits, ti);
     double a = 0.0, q = 0.0;
-    for (int s = 0; s < splits; ++s) {
-        const float* p = partial + ((static_cast<size_t>(b) * splits + s) * C + c) * 2;
+    for (int s = 0; s < nsplit; ++s) {
+        const float* p = partial + (((static_cast<size_t>(ti) * B + b) * job.max_splits + s) * C + c) * 2;
         a += p[0];
         q += p[1];
     }
+    const T* x = static_cast<const T*>(MH_SEL3(job.x, ti));
     double piv;
     if constexpr (sizeof(T) == 2)
         piv = __bfloat162float(x[static_cast<size_t>(b) * N * ld + c]);
@@ -131,43 +148,62 @@ __global__ void stats_final_kernel(const T* __restrict__ x, const float* __restr
     double m = a / N;
     double var = q / N - m * m;
     if (var < 0.0) var = 0.0;
-    mean[i] = static_cast<float>(piv + m);
-    rstd[i] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(kInEps)));
+    MH_SEL3(job.mean, ti)[r] = static_cast<float>(piv + m);
+    MH_SEL3(job.rstd, ti)[r] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(kInEps)));
 }
 
 // Tokens per split depend on N only (never on B), so the statistics of an image -- and with them the
-// whole layer -- are bit-identical whatever batch the image is part of.  At most 128 splits.
+// whole layer -- are bit-identical whatever batch the image is part of.  At most 16 splits: each CTA
+// streams >= 64 tokens with four 16-byte loads in flight per lane.
 static int stats_tokens_per_split(int N) {
-    int t = (N + 127) / 128;
+    int t = (N + 15) / 16;
     return t < 64 ? 64 : t;
 }
-static int stats_splits(int /*B*/, int N) {
+static int stats_splits(int N) {
     int t = stats_tokens_per_split(N);
     return (N + t - 1) / t;
 }
 
 size_t stats_workspace(int B, int N, int C) {
-    return static_cast<size_t>(B) * stats_splits(B, N) * C * 2 * sizeof(float);
+    // room for three tensors of up to N tokens (one launch serves fc, fs and fcs of a layer)
+    return static_cast<size_t>(3) * B * 16 * C * 2 * sizeof(float);
+}
+
+int launch_stats_multi(int n, const void* const* x, const int* N, float* const* mean, float* const* rstd, int dtype,
+                       int B, int C, int ld, float* ws, cudaStream_t s) {
+    StatsJob job{};
+    job.n = n;
+    job.max_splits = 0;
+    for (int i = 0; i < n; ++i) {
+        job.x[i] = x[i]; job.mean[i] = mean[i]; job.rstd[i] = rstd[i]; job.N[i] = N[i];
+        job.tps[i] = stats_tokens_per_split(N[i]);
+        job.splits[i] = stats_splits(N[i]);
+        if (job.splits[i] > job.max_splits) job.max_splits = job.splits[i];
+    }
+    const int vec = dtype == MHADA_BF16 ? 8 : 4;
+    dim3 grid((C + 32 * vec - 1) / (32 * vec), job.max_splits, B * n);
+    const int fin_blocks = (n * B * C + 255) / 256;
+    if (dtype == MHADA_BF16) {
+        stats_partial_kernel<__nv_bfloat16><<<grid, kStatsThreads, 0, s>>>(job, B, C, ld, ws);
+        count_launch();
+        stats_final_kernel<__nv_bfloat16><<<fin_blocks, 256, 0, s>>>(job, ws, B, C, ld);
+        count_launch();
+    } else {
+        stats_partial_kernel<float><<<grid, kStatsThreads, 0, s>>>(job, B, C, ld, ws);
+        count_launch();
+        stats_final_kernel<float><<<fin_blocks, 256, 0, s>>>(job, ws, B, C, ld);
+        count_launch();
+    }
+    return check_cuda(cudaGetLastError(), "stats launch");
 }
 
 int launch_stats(const void* x, int dtype, int B, int N, int C, int ld, float* mean, float* rstd, float* ws,
                  cudaStream_t s) {
-    const int splits = stats_splits(B, N);
-    const int tps = stats_tokens_per_split(N);
-    if (dtype == MHADA_BF16) {
-        dim3 grid((C + 32 * 8 - 1) / (32 * 8), splits, B);
-        stats_partial_kernel<__nv_bfloat16><<<grid, kStatsThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(x), N, C, ld, tps, ws);
-        count_launch();
-        stats_final_kernel<__nv_bfloat16><<<(B * C + 255) / 256, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(x), ws, B, N, C, ld, splits, mean, rstd);
-        count_launch();
-    } else {
-        dim3 grid((C + 32 * 4 - 1) / (32 * 4), splits, B);
-        stats_partial_kernel<float><<<grid, kStatsThreads, 0, s>>>(static_cast<const float*>(x), N, C, ld, tps, ws);
-        count_launch();
-        stats_final_kernel<float><<<(B * C + 255) / 256, 256, 0, s>>>(static_cast<const float*>(x), ws, B, N, C, ld, splits, mean, rstd);
-        count_launch();
-    }
-    return check_cuda(cudaGetLastError(), "stats launch");
+    const void* xs[1] = {x};
+    float* ms[1] = {mean};
+    float* rs[1] = {rstd};
+    int ns[1] = {N};
+    return launch_stats_multi(1, xs, ns, ms, rs, dtype, B, C, ld, ws, s);
 }
 
 }  // namespace mh

@@ -102,7 +102,8 @@ def _resolve_precision(precision: str, head_dim: int, *inputs) -> torch.dtype:
     return torch.bfloat16 if (low and head_dim == 64) else torch.float32
 
 
-def _layer_forward(dt: torch.dtype, tfc, tfs, tfcs, w_fgh, b_fgh, w_out, b_out, num_heads: int, out=None):
+def _layer_forward(dt: torch.dtype, tfc, tfs, tfcs, w_fgh, b_fgh, w_out, b_out, num_heads: int, out=None,
+                   flags: int = 0):
     """Token-major tensors in, token-major tensor out: AdaAttnMultiHead.forward, adaDecoder.py:162-206."""
     L = _lib.lib()
     B, h, w, C = tfc.shape
@@ -114,7 +115,8 @@ def _layer_forward(dt: torch.dtype, tfc, tfs, tfcs, w_fgh, b_fgh, w_out, b_out, 
     ws = _workspace(tfc.device, nbytes)
     with torch.cuda.device(tfc.device):
         rc = L.mhada_layer_forward(code, _ptr(tfc), _ptr(tfs), _ptr(tfcs), _ptr(w_fgh), _ptr(b_fgh), _ptr(w_out),
-                                   _ptr(b_out), B, Nc, Ns, C, num_heads, _ptr(out), _ptr(ws), ws.numel(), _stream())
+                                   _ptr(b_out), B, Nc, Ns, C, num_heads, flags, _ptr(out), _ptr(ws), ws.numel(),
+                                   _stream())
     _lib.check("mhada_layer_forward", rc)
     return out
 
@@ -295,10 +297,12 @@ class AdaAttnMultiHead(nn.Module):
         if fcs.shape != fc.shape:
             raise RuntimeError("fcs must have the shape of fc")
 
-    def forward_tokens(self, dt, tfc, tfs, tfcs, out=None):
-        """Token-major entry used by the transformer to chain layers without layout round trips."""
+    def forward_tokens(self, dt, tfc, tfs, tfcs, out=None, reuse_fs_stats: bool = False):
+        """Token-major entry used by the transformer to chain layers without layout round trips.
+        reuse_fs_stats: `tfs` is the tensor the previous layer call on this stream used (same workspace)."""
         w, b, wo, bo = self.packed_weights()
-        return _layer_forward(dt, tfc, tfs, tfcs, w, b, wo, bo, self.num_heads, out)
+        return _layer_forward(dt, tfc, tfs, tfcs, w, b, wo, bo, self.num_heads, out,
+                              _lib.REUSE_FS_STATS if reuse_fs_stats else 0)
 
     def forward(self, fc: torch.Tensor, fs: torch.Tensor, fcs: torch.Tensor):
         self._check_shapes(fc, fs, fcs)
@@ -476,7 +480,7 @@ class AdaAttnTransformerMultiHead(nn.Module):
         fcs = tfc[0]                                                         # :262
         for i in range(self.num_layers):                                     # :263-265
             fcs = self.adaAttnHead[2 * i].forward_tokens(dt, tfc[i], tfs[i], fcs)
-            fcs = self.adaAttnHead[2 * i + 1].forward_tokens(dt, fcs, tfs[i], fcs)
+            fcs = self.adaAttnHead[2 * i + 1].forward_tokens(dt, fcs, tfs[i], fcs, reuse_fs_stats=True)
         fcs = fcs.permute(0, 3, 1, 2)            # (B,C,h,w) view over channels_last memory
         cs = self.decoder(fcs)                   # :267
         if dt != in_dtype:

@@ -73,7 +73,7 @@ def test_library_exports_every_declared_symbol(lib):
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.mhada_abi_version() == 1
+    assert lib.mhada_abi_version() == _lib.ABI_VERSION == 2
 
 
 def test_abi_rejects_without_gpu_or_bad_args(lib):
@@ -84,7 +84,7 @@ def test_abi_rejects_without_gpu_or_bad_args(lib):
     assert lib.mhada_layer_workspace(_lib.BF16, 8, 4096, 4096, 512, 7) == 0
     buf = (ctypes.c_float * 64)()
     p = ctypes.cast(buf, ctypes.c_void_p)
-    rc = lib.mhada_layer_forward(_lib.BF16, p, p, p, p, p, None, None, 1, 4, 4, 512, 4, p, p, 1 << 30, None)
+    rc = lib.mhada_layer_forward(_lib.BF16, p, p, p, p, p, None, None, 1, 4, 4, 512, 4, 0, p, p, 1 << 30, None)
     assert rc == -1   # out aliases an input
     if not torch.cuda.is_available():
         assert lib.mhada_device_check() == -3

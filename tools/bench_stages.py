@@ -45,7 +45,7 @@ def main():
     st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
     def layer():
-        _lib.check("layer", L.mhada_layer_forward(code, P(fc), P(fs), P(fcs), P(w), P(b), P(wo), P(bo), B, Nc, Ns, C, H,
+        _lib.check("layer", L.mhada_layer_forward(code, P(fc), P(fs), P(fcs), P(w), P(b), P(wo), P(bo), B, Nc, Ns, C, H, 0,
                                                   P(out), P(ws), ws.numel(), st))
 
     # stage pieces (re-using the layer's own buffers through the public stage entry points)
