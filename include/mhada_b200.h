@@ -169,7 +169,7 @@ MHADA_API long long mhada_total_launch_count(void);
  *     the number of launches.  Not graph-capturable while enabled.
  * ---------------------------------------------------------------------------------------------- */
 /* Development aid: runs the bf16 attention kernel with clock64() stamps of CTA (0,0,0) written to
- * `trace` (device, 4*64*8 int64; layout in csrc/attn_tc.cu).  Same results as mhada_attn. */
+ * `trace` (device, 4*64*8 + 3*4096 int64; layout in csrc/attn_tc.cu).  Same results as mhada_attn. */
 MHADA_API int mhada_debug_attn_trace(const mhada_attn_args* args, long long* trace, mhada_stream_t stream);
 MHADA_API int mhada_profile_begin(void);
 MHADA_API int mhada_profile_end(float* attn_ms_total, int* attn_launches);

@@ -18,7 +18,7 @@ SOURCES = ["host_util.cu", "stats.cu", "simt_f32.cu", "linear_tc.cu", "proj_tc.c
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
-]
+] + os.environ.get("MHADA_NVCC_EXTRA", "").split()
 
 
 def _nvcc() -> str:
