@@ -9,6 +9,7 @@ using namespace mh;
 namespace {
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+bool aligned32(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31) == 0; }
 
 #define REQUIRE(cond, code, ...)      \
     do {                              \
@@ -161,8 +162,8 @@ int mhada_proj(int dtype, const void* fc, const void* fs, const float* mean_c, c
     REQUIRE(dtype == MHADA_BF16, MHADA_ERR_ARG, "mhada_proj: bad dtype %d", dtype);
     REQUIRE(d == 64, MHADA_ERR_UNSUPPORTED, "mhada_proj: the bf16 tensor-core path implements head_dim 64, got %d", d);
     REQUIRE(ws && ws_bytes >= proj_bf16_workspace(B, H, d), MHADA_ERR_WORKSPACE, "mhada_proj: workspace too small");
-    REQUIRE(aligned16(fc) && aligned16(fs) && aligned16(q) && aligned16(k) && aligned16(v) && aligned16(ws),
-            MHADA_ERR_ARG, "mhada_proj: pointers must be 16-byte aligned");
+    REQUIRE(aligned16(fc) && aligned16(fs) && aligned32(q) && aligned32(k) && aligned32(v) && aligned16(ws),
+            MHADA_ERR_ARG, "mhada_proj: inputs must be 16-byte aligned, outputs 32-byte aligned");
     if (int e = device_check()) return e;
     return launch_proj_bf16(fc, fs, mean_c, rstd_c, mean_s, rstd_s, w, bias, B, Nc, Ns, H, d, q, k, v, mu_v, ws, s);
 }
@@ -189,9 +190,10 @@ int mhada_attn(const mhada_attn_args* a, mhada_stream_t stream) {
     const int C = a->H * 64;
     REQUIRE(a->ldq >= C && a->ldk >= C && a->ldv >= 2 * C && a->ldx >= C && a->ldo >= C, MHADA_ERR_ARG,
             "mhada_attn: pitch smaller than the row");
-    REQUIRE(a->ldq % 8 == 0 && a->ldk % 8 == 0 && a->ldv % 8 == 0 && a->ldx % 8 == 0 && a->ldo % 8 == 0 &&
-                aligned16(a->q) && aligned16(a->k) && aligned16(a->v) && aligned16(a->x) && aligned16(a->out),
-            MHADA_ERR_ARG, "mhada_attn: bf16 pointers must be 16-byte aligned and pitches multiples of 8");
+    REQUIRE(a->ldq % 8 == 0 && a->ldk % 8 == 0 && a->ldv % 8 == 0 && a->ldx % 8 == 0 && a->ldo % 16 == 0 &&
+                aligned16(a->q) && aligned16(a->k) && aligned16(a->v) && aligned16(a->x) && aligned32(a->out),
+            MHADA_ERR_ARG,
+            "mhada_attn: bf16 inputs must be 16-byte aligned with pitches multiples of 8; out 32-byte aligned, ldo a multiple of 16");
     if (int e = device_check()) return e;
     return attn_dispatch(*a, s);
 }
@@ -221,8 +223,8 @@ int mhada_linear(int dtype, const void* x, int ldx, const float* w, const float*
     REQUIRE(dtype == MHADA_BF16, MHADA_ERR_ARG, "mhada_linear: bad dtype %d", dtype);
     REQUIRE(Cin % 64 == 0 && Cout % 64 == 0, MHADA_ERR_UNSUPPORTED,
             "mhada_linear: bf16 path needs Cin and Cout multiples of 64, got %d / %d", Cin, Cout);
-    REQUIRE(ldx % 8 == 0 && ldy % 8 == 0 && aligned16(x) && aligned16(y) && aligned16(ws), MHADA_ERR_ARG,
-            "mhada_linear: bf16 pointers must be 16-byte aligned and pitches multiples of 8");
+    REQUIRE(ldx % 8 == 0 && ldy % 16 == 0 && aligned16(x) && aligned32(y) && aligned16(ws), MHADA_ERR_ARG,
+            "mhada_linear: x 16-byte aligned with ldx a multiple of 8; y 32-byte aligned with ldy a multiple of 16");
     REQUIRE(ws && ws_bytes >= linear_bf16_workspace(Cout, Cin), MHADA_ERR_WORKSPACE, "mhada_linear: workspace too small");
     if (int e = device_check()) return e;
     return launch_linear_bf16(x, ldx, w, bias, M, Cin, Cout, y, ldy, ws, s);
@@ -259,8 +261,9 @@ int mhada_layer_forward(int dtype, const void* fc, const void* fs, const void* f
     if (dtype == MHADA_BF16)
         REQUIRE(d == 64, MHADA_ERR_UNSUPPORTED,
                 "mhada_layer_forward: the bf16 tensor-core path implements head_dim 64 (C/H = %d); use MHADA_F32", d);
-    REQUIRE(aligned16(fc) && aligned16(fs) && aligned16(fcs) && aligned16(out) && aligned16(ws), MHADA_ERR_ARG,
-            "mhada_layer_forward: pointers must be 16-byte aligned");
+    REQUIRE(aligned16(fc) && aligned16(fs) && aligned16(fcs) && aligned32(out) && aligned32(ws), MHADA_ERR_ARG,
+            "mhada_layer_forward: inputs must be 16-byte aligned, out and ws 32-byte aligned");
+    if (dtype == MHADA_BF16) REQUIRE(C % 16 == 0, MHADA_ERR_ARG, "mhada_layer_forward: bf16 path needs C %% 16 == 0");
     REQUIRE(C % (dtype == MHADA_BF16 ? 8 : 4) == 0, MHADA_ERR_ARG, "mhada_layer_forward: C must be a multiple of %d",
             dtype == MHADA_BF16 ? 8 : 4);
     LayerWs w = carve(dtype, B, Nc, Ns, C, H, static_cast<uint8_t*>(ws));

@@ -399,9 +399,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                     ov[i] = pack_bf16x2(r[0], r[1]);
                 }
                 if (row_ok) {
-                    uint4* dst = reinterpret_cast<uint4*>(orow + c);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) dst[i] = make_uint4(ov[4 * i], ov[4 * i + 1], ov[4 * i + 2], ov[4 * i + 3]);
+                    st_global_256(orow + c, ov);
+                    st_global_256(orow + c + 16, ov + 8);
                 }
             }
             tc_fence_before();

@@ -13,7 +13,12 @@
 
 namespace mh {
 
-constexpr int LIN_BM = 128, LIN_BK = 64, LIN_STAGES = 4, LIN_THREADS = 192;
+// 2 stages on purpose: 64 KB of shared memory per CTA lets three CTAs share an SM, so one CTA's pipeline fill and
+// epilogue overlap the others' main loops (r1: 4 stages = 1 CTA/SM = 52 us on cfg2, 7 serial waves)
+#ifndef MHADA_LIN_STAGES
+#define MHADA_LIN_STAGES 2
+#endif
+constexpr int LIN_BM = 128, LIN_BK = 64, LIN_STAGES = MHADA_LIN_STAGES, LIN_THREADS = 192;
 
 __global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) {
     size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
@@ -21,7 +26,7 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16*
 }
 
 template <int BN>
-__global__ void __launch_bounds__(LIN_THREADS, 1)
+__global__ void __launch_bounds__(LIN_THREADS)
 linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const float* __restrict__ bias, __nv_bfloat16* __restrict__ y, int ldy, int M, int ktiles) {
     constexpr uint32_t A_BYTES = LIN_BM * LIN_BK * 2, B_BYTES = BN * LIN_BK * 2, STAGE = A_BYTES + B_BYTES;
@@ -105,9 +110,9 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     float v1 = __uint_as_float(r[2 * i + 1]) + __ldg(bias + n0 + c + 2 * i + 1);
                     o[i] = pack_bf16x2(v0, v1);
                 }
-                uint4* dst = reinterpret_cast<uint4*>(y + static_cast<size_t>(m) * ldy + n0 + c);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) dst[i] = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+                __nv_bfloat16* dst = y + static_cast<size_t>(m) * ldy + n0 + c;
+                st_global_256(dst, o);
+                st_global_256(dst + 16, o + 8);
             }
         }
         tc_fence_before();

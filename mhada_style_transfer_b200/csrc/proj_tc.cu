@@ -156,18 +156,14 @@ proj_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
                     }
                     if (!is_v) {
                         __nv_bfloat16* o = (t == 0 ? out0 : out1) + (static_cast<size_t>(b) * N + n) * C + h * PRJ_D + c;
-                        uint4* dst = reinterpret_cast<uint4*>(o);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) dst[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+                        st_global_256(o, lo);
+                        st_global_256(o + 16, lo + 8);
                     } else {
                         __nv_bfloat16* o = out1 + (static_cast<size_t>(b) * N + n) * (2 * C) + h * (2 * PRJ_D) + c;
-                        uint4* d0 = reinterpret_cast<uint4*>(o);
-                        uint4* d1 = reinterpret_cast<uint4*>(o + PRJ_D);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            d0[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
-                            d1[i] = make_uint4(sq[4 * i], sq[4 * i + 1], sq[4 * i + 2], sq[4 * i + 3]);
-                        }
+                        st_global_256(o, lo);
+                        st_global_256(o + 16, lo + 8);
+                        st_global_256(o + PRJ_D, sq);
+                        st_global_256(o + PRJ_D + 16, sq + 8);
                     }
                 }
             }

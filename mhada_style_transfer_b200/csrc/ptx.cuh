@@ -239,6 +239,14 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
 
+// 256-bit global store (sm_100 STG.E.256): one full 32-byte sector per lane, so a thread-per-row epilogue
+// whose lanes are a row pitch apart still writes whole sectors (16-byte stores were half-sector writes)
+__device__ __forceinline__ void st_global_256(void* p, const uint32_t* r) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]),
+                 "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+
 // register budget hand-over between warpgroups
 template <int N>
 __device__ __forceinline__ void setmaxnreg_inc() {

@@ -77,13 +77,13 @@ __global__ void __launch_bounds__(kStatsThreads) stats_partial_kernel(const Stat
     const int t_end = min(N, t_begin + tokens_per_split);
     if (active) {
         int t = t_begin + warp;
-        // 4 tokens in flight per lane: 4 independent 16 B loads before any use
-        for (; t + 3 * kStatsWarps < t_end; t += 4 * kStatsWarps) {
-            float a[4][VEC];
+        // 8 tokens in flight per lane: 8 independent 16 B loads before any use
+        for (; t + 7 * kStatsWarps < t_end; t += 8 * kStatsWarps) {
+            float a[8][VEC];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) VecIO<T>::load(xb + static_cast<size_t>(t + u * kStatsWarps) * ld, a[u]);
+            for (int u = 0; u < 8; ++u) VecIO<T>::load(xb + static_cast<size_t>(t + u * kStatsWarps) * ld, a[u]);
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
+            for (int u = 0; u < 8; ++u)
 #pragma unroll
                 for (int v = 0; v < VEC; ++v) {
                     float d = a[u][v] - piv[v];
@@ -153,10 +153,10 @@ __global__ void stats_final_kernel(const StatsJob job, const float* __restrict__
 }
 
 // Tokens per split depend on N only (never on B), so the statistics of an image -- and with them the
-// whole layer -- are bit-identical whatever batch the image is part of.  At most 16 splits: each CTA
-// streams >= 64 tokens with four 16-byte loads in flight per lane.
+// whole layer -- are bit-identical whatever batch the image is part of.  At most 32 splits: each CTA
+// streams >= 64 tokens with eight 16-byte loads in flight per lane.
 static int stats_tokens_per_split(int N) {
-    int t = (N + 15) / 16;
+    int t = (N + 31) / 32;
     return t < 64 ? 64 : t;
 }
 static int stats_splits(int N) {
@@ -166,7 +166,7 @@ static int stats_splits(int N) {
 
 size_t stats_workspace(int B, int N, int C) {
     // room for three tensors of up to N tokens (one launch serves fc, fs and fcs of a layer)
-    return static_cast<size_t>(3) * B * 16 * C * 2 * sizeof(float);
+    return static_cast<size_t>(3) * B * 32 * C * 2 * sizeof(float);
 }
 
 int launch_stats_multi(int n, const void* const* x, const int* N, float* const* mean, float* const* rstd, int dtype,
