@@ -319,6 +319,13 @@ def main():
     d2h = cs_host[0].numel() * esz
 
     pk = peaks()
+    traffic = None            # DRAM bytes per launch of the attention kernel from the committed ncu capture (cfg2 only)
+    try:
+        prof = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.endswith("_attn_tc_ncu.json"))
+        if prof and args.workload == "cfg2":
+            traffic = json.load(open(os.path.join(ROOT, "profiles", prof[-1]))).get("dram_bytes_per_launch")
+    except OSError:
+        pass
     flops_per_launch = 6.0 * B * Nc * Ns * C
     attn_avg_ms = attn_ms / max(attn_n, 1)
     if wl["dtype"] == "bf16":
@@ -330,7 +337,8 @@ def main():
                 "frac_of_burst_peak": round(achieved / pk["bf16_tflops"], 4), "peak_burst": pk["bf16_tflops"],
                 "peak_source": pk["source"] + ", sustained (kernel timed inside a long step)",
                 "algorithmic_flops_per_launch": flops_per_launch, "avg_launch_ms": round(attn_avg_ms, 4),
-                "launches_timed": attn_n, "share_of_step": round(attn_ms / ms_total, 4), "traffic": None}
+                "launches_timed": attn_n, "share_of_step": round(attn_ms / ms_total, 4), "traffic": traffic,
+                "traffic_unit": "bytes/launch (dram read+write, ncu)", "algorithmic_bytes_per_launch": 2.0 * B * C * (2 * Nc + 3 * Ns)}
     else:
         achieved = flops_per_launch / (attn_avg_ms * 1e-3) / 1e12
         roof = {"bound": "fp32-simt", "kernel": "attn_f32_kernel", "achieved": round(achieved, 2), "peak": None,

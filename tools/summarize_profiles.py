@@ -93,4 +93,18 @@ with open(os.path.join(out_dir, f"{tag}_attn_tc_ncu.md"), "w") as f:
             ops[op.split(".")[0] + ("." + op.split(".")[1] if "." in op and op.startswith(("MUFU", "LDTM", "STTM")) else "")] += 1
     f.write("\n## Blackwell-native instructions present in the SASS (static counts)\n\n" +
             ", ".join(f"`{k}` x{v}" for k, v in sorted(ops.items())) + "\n")
+import json
+def col(name):
+    return [float(d[hdr.index(name)]) for d in data] if name in hdr else []
+rd, wr, dur = col("dram__bytes_read.sum"), col("dram__bytes_write.sum"), col("gpu__time_duration.sum")
+unit_r = units[hdr.index("dram__bytes_read.sum")]
+scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}.get(unit_r, 1e6)
+json.dump({"kernel": "attn_tc_kernel", "workload": "cfg2 layer (B=8, H=8, Nc=Ns=4096)",
+           "dram_bytes_per_launch": (sum(rd) / len(rd) + sum(wr) / len(wr)) * scale if rd else None,
+           "dram_read_bytes": sum(rd) / len(rd) * scale if rd else None, "dram_write_bytes": sum(wr) / len(wr) * scale if wr else None,
+           "ncu_duration_us": sum(dur) / len(dur) if dur else None,
+           "tensor_pipe_active_pct": col("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"),
+           "xu_pipe_pct": col("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active"),
+           "source": f"profiles/{tag}_attn_tc_ncu.md (ncu --set full --clock-control none)"},
+          open(os.path.join(out_dir, f"{tag}_attn_tc_ncu.json"), "w"), indent=1)
 print("written", os.listdir(out_dir))
