@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define MHADA_ABI_VERSION 2
+#define MHADA_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define MHADA_API __attribute__((visibility("default")))
@@ -84,10 +84,12 @@ MHADA_API int mhada_in_stats(const void* x, int dtype, int B, int N, int C, int 
  *            is exact for M and for A.V^2 - M^2 and removes the bf16 cancellation)
  *     ws (bf16 path): mhada_proj_workspace(B, H, d) bytes for the folded per-image weights.
  * ---------------------------------------------------------------------------------------------- */
-MHADA_API size_t mhada_proj_workspace(int B, int H, int d);
-MHADA_API int mhada_proj(int dtype, const void* fc, const void* fs, const float* mean_c, const float* rstd_c,
-               const float* mean_s, const float* rstd_s, const float* w, const float* bias, int B, int Nc, int Ns,
-               int H, int d, void* q, void* k, void* v, float* mu_v, void* ws, size_t ws_bytes,
+#define MHADA_PROJ_Q 1  /* Q from fc (content batch B)         */
+#define MHADA_PROJ_KV 2 /* K, V, mu_v from fs (style batch Bs) */
+MHADA_API size_t mhada_proj_workspace(int B, int H, int d);   /* B = max(B, Bs) */
+MHADA_API int mhada_proj(int dtype, int parts, const void* fc, const void* fs, const float* mean_c, const float* rstd_c,
+               const float* mean_s, const float* rstd_s, const float* w, const float* bias, int B, int Bs, int Nc,
+               int Ns, int H, int d, void* q, void* k, void* v, float* mu_v, void* ws, size_t ws_bytes,
                mhada_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
@@ -117,6 +119,9 @@ typedef struct mhada_attn_args {
     const float* q_rstd;
     const float* k_mean;
     const float* k_rstd;
+    int kv_batch;        /* batch of k / v / mu_v (/ k_mean, k_rstd): 0 or B = one per image; 1 = one style shared by
+                            all B images (the reference cannot do this, adaDecoder.py:177-183; infer_video.py uses one
+                            style for every frame) */
 } mhada_attn_args;
 MHADA_API int mhada_attn(const mhada_attn_args* args, mhada_stream_t stream);
 
@@ -145,6 +150,24 @@ MHADA_API size_t mhada_layer_workspace(int dtype, int B, int Nc, int Ns, int C, 
 MHADA_API int mhada_layer_forward(int dtype, const void* fc, const void* fs, const void* fcs, const float* w_fgh,
                         const float* b_fgh, const float* w_out, const float* b_out, int B, int Nc, int Ns, int C,
                         int H, int flags, void* out, void* ws, size_t ws_bytes, mhada_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (5a) Style-side cache (no counterpart in the reference, which recomputes the style side of every
+ *     layer for every frame, infer_video.py:91-92).  K, V and mu_v of a layer depend on fs and on the layer's g / h
+ *     weights only: mhada_style_precompute() runs the fs statistics and the K / V projections once and stores
+ *     [K | V (bf16: V') | mu_v] in `cache` (mhada_style_cache_bytes); mhada_layer_forward_cached() then runs the
+ *     content side only (stats of fc / fcs, Q projection, attention, out_conv).  Bs = 1 serves any content batch B.
+ *     Results are bit-identical to mhada_layer_forward on the same fs.
+ *     ws for precompute: mhada_layer_workspace(dtype, Bs, Ns, Ns, C, H) bytes.
+ * ---------------------------------------------------------------------------------------------- */
+MHADA_API size_t mhada_style_cache_bytes(int dtype, int Bs, int Ns, int C, int H);
+MHADA_API int mhada_style_precompute(int dtype, const void* fs, const float* w_fgh, const float* b_fgh, int Bs, int Ns,
+                                     int C, int H, void* cache, size_t cache_bytes, void* ws, size_t ws_bytes,
+                                     mhada_stream_t stream);
+MHADA_API int mhada_layer_forward_cached(int dtype, const void* fc, const void* fcs, const void* cache, int Bs,
+                                         const float* w_fgh, const float* b_fgh, const float* w_out,
+                                         const float* b_out, int B, int Nc, int Ns, int C, int H, void* out, void* ws,
+                                         size_t ws_bytes, mhada_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * (5b) Decoder glue -- replaces nn.ReflectionPad2d(1) (MHAdaSTr/network/conv.py:26-27) and, when

@@ -7,7 +7,7 @@ Same constructors, forward signatures, attribute names and state_dict keys as th
 the forward runs hand-written sm_100a kernels through the C ABI in include/mhada_b200.h.
 """
 from .network import (AdaAttN, AdaAttnForLoss, AdaAttnMultiHead, AdaAttnTransformer,  # noqa: F401
-                      AdaAttnTransformerMultiHead, CosineSimilarity, Decoder, Softmax)
+                      AdaAttnTransformerMultiHead, CosineSimilarity, Decoder, Softmax, StyleCache)
 
 __all__ = ["AdaAttnTransformer", "AdaAttnTransformerMultiHead", "AdaAttnForLoss", "AdaAttnMultiHead", "AdaAttN",
-           "Decoder", "Softmax", "CosineSimilarity"]
+           "Decoder", "Softmax", "CosineSimilarity", "StyleCache"]

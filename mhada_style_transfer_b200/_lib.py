@@ -13,7 +13,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libmhada_b200.so")
 
 F32, BF16 = 0, 1
-ABI_VERSION = 2
+ABI_VERSION = 3
+PROJ_Q, PROJ_KV = 1, 2
 REUSE_FS_STATS = 1
 
 
@@ -26,6 +27,7 @@ class AttnArgs(ctypes.Structure):
         ("ldq", c_int), ("ldk", c_int), ("ldv", c_int), ("ldx", c_int), ("ldo", c_int),
         ("x_mean", c_void_p), ("x_rstd", c_void_p), ("mu_v", c_void_p),
         ("q_mean", c_void_p), ("q_rstd", c_void_p), ("k_mean", c_void_p), ("k_rstd", c_void_p),
+        ("kv_batch", c_int),
     ]
 
 
@@ -42,14 +44,20 @@ SIGNATURES = {
     "mhada_in_stats": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t,
                                c_void_p]),
     "mhada_proj_workspace": (c_size_t, [c_int, c_int, c_int]),
-    "mhada_proj": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                           c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+    "mhada_proj": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                           c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                            c_size_t, c_void_p]),
     "mhada_attn": (c_int, [POINTER(AttnArgs), c_void_p]),
     "mhada_debug_attn_trace": (c_int, [POINTER(AttnArgs), c_void_p, c_void_p]),
     "mhada_linear_workspace": (c_size_t, [c_int, c_int, c_int]),
     "mhada_linear": (c_int, [c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int,
                              c_void_p, c_size_t, c_void_p]),
+    "mhada_style_cache_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    "mhada_style_precompute": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_size_t,
+                                       c_void_p, c_size_t, c_void_p]),
+    "mhada_layer_forward_cached": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                                           c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t,
+                                           c_void_p]),
     "mhada_pad_reflect": (c_int, [c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "mhada_layer_workspace": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "mhada_layer_forward": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

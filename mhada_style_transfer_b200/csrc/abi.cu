@@ -88,6 +88,111 @@ int attn_dispatch(const mhada_attn_args& a, cudaStream_t s) {
     return rc;
 }
 
+struct StyleCacheView {
+    void *k, *v;
+    float* mu_v;
+    size_t total;
+};
+
+StyleCacheView carve_cache(int dtype, int Bs, int Ns, int C, uint8_t* base) {
+    StyleCacheView c;
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        void* p = base ? base + off : nullptr;
+        off += align_up(bytes, 256);
+        return p;
+    };
+    const size_t e = esize(dtype);
+    c.k = take(static_cast<size_t>(Bs) * Ns * C * e);
+    c.v = take(static_cast<size_t>(Bs) * Ns * C * e * (dtype == MHADA_BF16 ? 2 : 1));
+    c.mu_v = static_cast<float*>(take(static_cast<size_t>(Bs) * C * sizeof(float)));
+    c.total = off;
+    return c;
+}
+
+int attn_dispatch(const mhada_attn_args& a, cudaStream_t s);
+
+// One MHAda layer.  cache == nullptr: the style side (fs statistics, K, V, mu_v) is computed into the workspace;
+// otherwise it is read from `cache` (style batch Bs = 1 or B) and fs is not touched.
+int layer_impl(const char* who, int dtype, const void* fc, const void* fs, const void* fcs, const void* cache, int Bs,
+               const float* w_fgh, const float* b_fgh, const float* w_out, const float* b_out, int B, int Nc, int Ns,
+               int C, int H, int flags, void* out, void* ws, size_t ws_bytes, mhada_stream_t stream) {
+    g_launches = 0;
+    REQUIRE(fc && fcs && w_fgh && b_fgh && out && ws, MHADA_ERR_ARG, "%s: null pointer", who);
+    REQUIRE((w_out == nullptr) == (b_out == nullptr), MHADA_ERR_ARG, "%s: w_out/b_out must be given together", who);
+    REQUIRE(B > 0 && Nc > 0 && Ns > 0 && C > 0 && H > 0, MHADA_ERR_ARG, "%s: bad sizes", who);
+    REQUIRE(C % H == 0, MHADA_ERR_ARG, "%s: C=%d not divisible by H=%d", who, C, H);
+    REQUIRE(dtype == MHADA_F32 || dtype == MHADA_BF16, MHADA_ERR_ARG, "%s: bad dtype %d", who, dtype);
+    REQUIRE(out != fc && out != fs && out != fcs, MHADA_ERR_ARG, "%s: out must not alias an input", who);
+    const int d = C / H;
+    if (dtype == MHADA_BF16)
+        REQUIRE(d == 64, MHADA_ERR_UNSUPPORTED,
+                "%s: the bf16 tensor-core path implements head_dim 64 (C/H = %d); use MHADA_F32", who, d);
+    REQUIRE(aligned16(fc) && (!fs || aligned16(fs)) && aligned16(fcs) && aligned32(out) && aligned32(ws), MHADA_ERR_ARG,
+            "%s: inputs must be 16-byte aligned, out and ws 32-byte aligned", who);
+    if (dtype == MHADA_BF16) REQUIRE(C % 16 == 0, MHADA_ERR_ARG, "%s: bf16 path needs C %% 16 == 0", who);
+    REQUIRE(C % (dtype == MHADA_BF16 ? 8 : 4) == 0, MHADA_ERR_ARG, "%s: C must be a multiple of %d", who,
+            dtype == MHADA_BF16 ? 8 : 4);
+    LayerWs w = carve(dtype, B, Nc, Ns, C, H, static_cast<uint8_t*>(ws));
+    REQUIRE(ws_bytes >= w.total, MHADA_ERR_WORKSPACE, "%s: workspace %zu < %zu", who, ws_bytes, w.total);
+    if (int e = device_check()) return e;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    StyleCacheView cv{};
+    if (cache) cv = carve_cache(dtype, Bs, Ns, C, static_cast<uint8_t*>(const_cast<void*>(cache)));
+
+    // (1) statistics of fc, fs and (unless it is the same tensor) fcs, one launch   adaDecoder.py:173,178,198
+    //     MHADA_REUSE_FS_STATS: fs (and this workspace) are the ones of the previous call, so mean_s / rstd_s
+    //     are still valid -- the two layers of a level share fs (adaDecoder.py:264-265)
+    const float *mean_x = w.mean_c, *rstd_x = w.rstd_c;
+    {
+        const void* xs[3];
+        float* ms[3];
+        float* rs[3];
+        int ns[3];
+        int n = 0;
+        xs[n] = fc; ms[n] = w.mean_c; rs[n] = w.rstd_c; ns[n] = Nc; ++n;
+        if (!cache && !(flags & MHADA_REUSE_FS_STATS)) { xs[n] = fs; ms[n] = w.mean_s; rs[n] = w.rstd_s; ns[n] = Ns; ++n; }
+        if (fcs != fc) {
+            xs[n] = fcs; ms[n] = w.mean_x; rs[n] = w.rstd_x; ns[n] = Nc; ++n;
+            mean_x = w.mean_x;
+            rstd_x = w.rstd_x;
+        }
+        if (int e = launch_stats_multi(n, xs, ns, ms, rs, dtype, B, C, C, static_cast<float*>(w.stats_ws), s)) return e;
+    }
+    // (2) projections                                                        adaDecoder.py:173-183
+    const int parts = cache ? MHADA_PROJ_Q : (MHADA_PROJ_Q | MHADA_PROJ_KV);
+    if (dtype == MHADA_BF16) {
+        if (int e = launch_proj_bf16(parts, fc, fs, w.mean_c, w.rstd_c, w.mean_s, w.rstd_s, w_fgh, b_fgh, B, cache ? 0 : B, Nc, Ns,
+                                     H, d, w.q, w.k, w.v, w.mu_v, w.proj_ws, s))
+            return e;
+    } else {
+        if (int e = launch_proj_f32(parts, static_cast<const float*>(fc), static_cast<const float*>(fs), w.mean_c, w.rstd_c,
+                                    w.mean_s, w.rstd_s, w_fgh, b_fgh, B, cache ? 0 : B, Nc, Ns, H, d, static_cast<float*>(w.q),
+                                    static_cast<float*>(w.k), static_cast<float*>(w.v), w.mu_v, s))
+            return e;
+    }
+    // (3) attention + fused epilogue                                         adaDecoder.py:186-198
+    mhada_attn_args a{};
+    a.dtype = dtype; a.B = B; a.H = H; a.Nc = Nc; a.Ns = Ns; a.dqk = d; a.dv = d;
+    a.q = w.q; a.k = cache ? cv.k : w.k; a.v = cache ? cv.v : w.v; a.x = fcs;
+    a.out = w_out ? w.heads : out;
+    a.ldq = C; a.ldk = C; a.ldv = dtype == MHADA_BF16 ? 2 * C : C; a.ldx = C; a.ldo = C;
+    a.x_mean = mean_x; a.x_rstd = rstd_x; a.mu_v = cache ? cv.mu_v : w.mu_v;
+    a.kv_batch = cache ? Bs : B;
+    if (int e = attn_dispatch(a, s)) return e;
+    // (4) out_conv                                                           adaDecoder.py:202-205
+    if (w_out) {
+        if (dtype == MHADA_BF16) {
+            if (int e = launch_linear_bf16(w.heads, C, w_out, b_out, B * Nc, C, C, out, C, w.lin_ws, s)) return e;
+        } else {
+            if (int e = launch_linear_f32(static_cast<const float*>(w.heads), C, w_out, b_out, B * Nc, C, C,
+                                          static_cast<float*>(out), C, s))
+                return e;
+        }
+    }
+    return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -145,27 +250,33 @@ size_t mhada_proj_workspace(int B, int H, int d) {
     return proj_bf16_workspace(B, H, d);
 }
 
-int mhada_proj(int dtype, const void* fc, const void* fs, const float* mean_c, const float* rstd_c,
-               const float* mean_s, const float* rstd_s, const float* w, const float* bias, int B, int Nc, int Ns,
-               int H, int d, void* q, void* k, void* v, float* mu_v, void* ws, size_t ws_bytes,
+int mhada_proj(int dtype, int parts, const void* fc, const void* fs, const float* mean_c, const float* rstd_c,
+               const float* mean_s, const float* rstd_s, const float* w, const float* bias, int B, int Bs, int Nc,
+               int Ns, int H, int d, void* q, void* k, void* v, float* mu_v, void* ws, size_t ws_bytes,
                mhada_stream_t stream) {
-    REQUIRE(fc && fs && mean_c && rstd_c && mean_s && rstd_s && w && bias && q && k && v && mu_v, MHADA_ERR_ARG,
-            "mhada_proj: null pointer");
-    REQUIRE(B > 0 && Nc > 0 && Ns > 0 && H > 0 && d > 0, MHADA_ERR_ARG, "mhada_proj: bad sizes");
+    REQUIRE(parts >= 1 && parts <= 3, MHADA_ERR_ARG, "mhada_proj: parts must be MHADA_PROJ_Q | MHADA_PROJ_KV");
+    REQUIRE(w && bias, MHADA_ERR_ARG, "mhada_proj: null weights");
+    if (parts & MHADA_PROJ_Q) REQUIRE(fc && mean_c && rstd_c && q && B > 0 && Nc > 0, MHADA_ERR_ARG, "mhada_proj: Q side incomplete");
+    if (parts & MHADA_PROJ_KV)
+        REQUIRE(fs && mean_s && rstd_s && k && v && mu_v && Bs > 0 && Ns > 0, MHADA_ERR_ARG, "mhada_proj: K/V side incomplete");
+    REQUIRE(H > 0 && d > 0, MHADA_ERR_ARG, "mhada_proj: bad sizes");
+    if (!(parts & MHADA_PROJ_Q)) B = 0;
+    if (!(parts & MHADA_PROJ_KV)) Bs = 0;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (dtype == MHADA_F32) {
         if (int e = device_check()) return e;
-        return launch_proj_f32(static_cast<const float*>(fc), static_cast<const float*>(fs), mean_c, rstd_c, mean_s,
-                               rstd_s, w, bias, B, Nc, Ns, H, d, static_cast<float*>(q), static_cast<float*>(k),
+        return launch_proj_f32(parts, static_cast<const float*>(fc), static_cast<const float*>(fs), mean_c, rstd_c, mean_s,
+                               rstd_s, w, bias, B, Bs, Nc, Ns, H, d, static_cast<float*>(q), static_cast<float*>(k),
                                static_cast<float*>(v), mu_v, s);
     }
     REQUIRE(dtype == MHADA_BF16, MHADA_ERR_ARG, "mhada_proj: bad dtype %d", dtype);
     REQUIRE(d == 64, MHADA_ERR_UNSUPPORTED, "mhada_proj: the bf16 tensor-core path implements head_dim 64, got %d", d);
-    REQUIRE(ws && ws_bytes >= proj_bf16_workspace(B, H, d), MHADA_ERR_WORKSPACE, "mhada_proj: workspace too small");
-    REQUIRE(aligned16(fc) && aligned16(fs) && aligned32(q) && aligned32(k) && aligned32(v) && aligned16(ws),
+    REQUIRE(ws && ws_bytes >= proj_bf16_workspace(B > Bs ? B : Bs, H, d), MHADA_ERR_WORKSPACE, "mhada_proj: workspace too small");
+    REQUIRE((!(parts & 1) || (aligned16(fc) && aligned32(q))) && (!(parts & 2) || (aligned16(fs) && aligned32(k) && aligned32(v))) &&
+                aligned16(ws),
             MHADA_ERR_ARG, "mhada_proj: inputs must be 16-byte aligned, outputs 32-byte aligned");
     if (int e = device_check()) return e;
-    return launch_proj_bf16(fc, fs, mean_c, rstd_c, mean_s, rstd_s, w, bias, B, Nc, Ns, H, d, q, k, v, mu_v, ws, s);
+    return launch_proj_bf16(parts, fc, fs, mean_c, rstd_c, mean_s, rstd_s, w, bias, B, Bs, Nc, Ns, H, d, q, k, v, mu_v, ws, s);
 }
 
 int mhada_attn(const mhada_attn_args* a, mhada_stream_t stream) {
@@ -173,6 +284,8 @@ int mhada_attn(const mhada_attn_args* a, mhada_stream_t stream) {
     REQUIRE(a->q && a->k && a->v && a->x && a->out && a->x_mean && a->x_rstd, MHADA_ERR_ARG, "mhada_attn: null pointer");
     REQUIRE(a->B > 0 && a->H > 0 && a->Nc > 0 && a->Ns > 0 && a->dqk > 0 && a->dv > 0, MHADA_ERR_ARG,
             "mhada_attn: bad sizes");
+    REQUIRE(a->kv_batch == 0 || a->kv_batch == 1 || a->kv_batch == a->B, MHADA_ERR_ARG,
+            "mhada_attn: kv_batch must be 0, 1 or B");
     REQUIRE((a->q_mean == nullptr) == (a->q_rstd == nullptr) && (a->k_mean == nullptr) == (a->k_rstd == nullptr),
             MHADA_ERR_ARG, "mhada_attn: mean/rstd must be given together");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -247,79 +360,52 @@ size_t mhada_layer_workspace(int dtype, int B, int Nc, int Ns, int C, int H) {
     return carve(dtype, B, Nc, Ns, C, H, nullptr).total;
 }
 
+size_t mhada_style_cache_bytes(int dtype, int Bs, int Ns, int C, int H) {
+    if (Bs <= 0 || Ns <= 0 || C <= 0 || H <= 0 || C % H != 0) return 0;
+    return carve_cache(dtype, Bs, Ns, C, nullptr).total;
+}
+
 int mhada_layer_forward(int dtype, const void* fc, const void* fs, const void* fcs, const float* w_fgh,
                         const float* b_fgh, const float* w_out, const float* b_out, int B, int Nc, int Ns, int C,
                         int H, int flags, void* out, void* ws, size_t ws_bytes, mhada_stream_t stream) {
+    REQUIRE(fs, MHADA_ERR_ARG, "mhada_layer_forward: null pointer");
+    return layer_impl("mhada_layer_forward", dtype, fc, fs, fcs, nullptr, B, w_fgh, b_fgh, w_out, b_out, B, Nc, Ns, C, H,
+                      flags, out, ws, ws_bytes, stream);
+}
+
+int mhada_layer_forward_cached(int dtype, const void* fc, const void* fcs, const void* cache, int Bs,
+                               const float* w_fgh, const float* b_fgh, const float* w_out, const float* b_out, int B,
+                               int Nc, int Ns, int C, int H, void* out, void* ws, size_t ws_bytes,
+                               mhada_stream_t stream) {
+    REQUIRE(cache && aligned32(cache), MHADA_ERR_ARG, "mhada_layer_forward_cached: cache must be a 32-byte aligned pointer");
+    REQUIRE(Bs == 1 || Bs == B, MHADA_ERR_ARG, "mhada_layer_forward_cached: style batch %d must be 1 or the content batch %d", Bs, B);
+    return layer_impl("mhada_layer_forward_cached", dtype, fc, nullptr, fcs, cache, Bs, w_fgh, b_fgh, w_out, b_out, B, Nc, Ns,
+                      C, H, 0, out, ws, ws_bytes, stream);
+}
+
+int mhada_style_precompute(int dtype, const void* fs, const float* w_fgh, const float* b_fgh, int Bs, int Ns, int C,
+                           int H, void* cache, size_t cache_bytes, void* ws, size_t ws_bytes, mhada_stream_t stream) {
     g_launches = 0;
-    REQUIRE(fc && fs && fcs && w_fgh && b_fgh && out && ws, MHADA_ERR_ARG, "mhada_layer_forward: null pointer");
-    REQUIRE((w_out == nullptr) == (b_out == nullptr), MHADA_ERR_ARG, "mhada_layer_forward: w_out/b_out must be given together");
-    REQUIRE(B > 0 && Nc > 0 && Ns > 0 && C > 0 && H > 0, MHADA_ERR_ARG, "mhada_layer_forward: bad sizes");
-    REQUIRE(C % H == 0, MHADA_ERR_ARG, "mhada_layer_forward: C=%d not divisible by H=%d", C, H);
-    REQUIRE(dtype == MHADA_F32 || dtype == MHADA_BF16, MHADA_ERR_ARG, "mhada_layer_forward: bad dtype %d", dtype);
-    REQUIRE(out != fc && out != fs && out != fcs, MHADA_ERR_ARG, "mhada_layer_forward: out must not alias an input");
+    REQUIRE(fs && w_fgh && b_fgh && cache && ws, MHADA_ERR_ARG, "mhada_style_precompute: null pointer");
+    REQUIRE(Bs > 0 && Ns > 0 && C > 0 && H > 0 && C % H == 0, MHADA_ERR_ARG, "mhada_style_precompute: bad sizes");
+    REQUIRE(dtype == MHADA_F32 || dtype == MHADA_BF16, MHADA_ERR_ARG, "mhada_style_precompute: bad dtype %d", dtype);
     const int d = C / H;
     if (dtype == MHADA_BF16)
-        REQUIRE(d == 64, MHADA_ERR_UNSUPPORTED,
-                "mhada_layer_forward: the bf16 tensor-core path implements head_dim 64 (C/H = %d); use MHADA_F32", d);
-    REQUIRE(aligned16(fc) && aligned16(fs) && aligned16(fcs) && aligned32(out) && aligned32(ws), MHADA_ERR_ARG,
-            "mhada_layer_forward: inputs must be 16-byte aligned, out and ws 32-byte aligned");
-    if (dtype == MHADA_BF16) REQUIRE(C % 16 == 0, MHADA_ERR_ARG, "mhada_layer_forward: bf16 path needs C %% 16 == 0");
-    REQUIRE(C % (dtype == MHADA_BF16 ? 8 : 4) == 0, MHADA_ERR_ARG, "mhada_layer_forward: C must be a multiple of %d",
-            dtype == MHADA_BF16 ? 8 : 4);
-    LayerWs w = carve(dtype, B, Nc, Ns, C, H, static_cast<uint8_t*>(ws));
-    REQUIRE(ws_bytes >= w.total, MHADA_ERR_WORKSPACE, "mhada_layer_forward: workspace %zu < %zu", ws_bytes, w.total);
+        REQUIRE(d == 64 && C % 16 == 0, MHADA_ERR_UNSUPPORTED,
+                "mhada_style_precompute: the bf16 tensor-core path implements head_dim 64 (C/H = %d)", d);
+    REQUIRE(aligned16(fs) && aligned32(cache) && aligned32(ws), MHADA_ERR_ARG, "mhada_style_precompute: misaligned pointer");
+    StyleCacheView cv = carve_cache(dtype, Bs, Ns, C, static_cast<uint8_t*>(cache));
+    REQUIRE(cache_bytes >= cv.total, MHADA_ERR_WORKSPACE, "mhada_style_precompute: cache %zu < %zu", cache_bytes, cv.total);
+    LayerWs w = carve(dtype, Bs, Ns, Ns, C, H, static_cast<uint8_t*>(ws));
+    REQUIRE(ws_bytes >= w.total, MHADA_ERR_WORKSPACE, "mhada_style_precompute: workspace %zu < %zu", ws_bytes, w.total);
     if (int e = device_check()) return e;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-
-    // (1) statistics of fc, fs and (unless it is the same tensor) fcs, one launch   adaDecoder.py:173,178,198
-    //     MHADA_REUSE_FS_STATS: fs (and this workspace) are the ones of the previous call, so mean_s / rstd_s
-    //     are still valid -- the two layers of a level share fs (adaDecoder.py:264-265)
-    const float *mean_x = w.mean_c, *rstd_x = w.rstd_c;
-    {
-        const void* xs[3];
-        float* ms[3];
-        float* rs[3];
-        int ns[3];
-        int n = 0;
-        xs[n] = fc; ms[n] = w.mean_c; rs[n] = w.rstd_c; ns[n] = Nc; ++n;
-        if (!(flags & MHADA_REUSE_FS_STATS)) { xs[n] = fs; ms[n] = w.mean_s; rs[n] = w.rstd_s; ns[n] = Ns; ++n; }
-        if (fcs != fc) {
-            xs[n] = fcs; ms[n] = w.mean_x; rs[n] = w.rstd_x; ns[n] = Nc; ++n;
-            mean_x = w.mean_x;
-            rstd_x = w.rstd_x;
-        }
-        if (int e = launch_stats_multi(n, xs, ns, ms, rs, dtype, B, C, C, static_cast<float*>(w.stats_ws), s)) return e;
-    }
-    // (2) projections                                                        adaDecoder.py:173-183
-    if (dtype == MHADA_BF16) {
-        if (int e = launch_proj_bf16(fc, fs, w.mean_c, w.rstd_c, w.mean_s, w.rstd_s, w_fgh, b_fgh, B, Nc, Ns, H, d, w.q,
-                                     w.k, w.v, w.mu_v, w.proj_ws, s))
-            return e;
-    } else {
-        if (int e = launch_proj_f32(static_cast<const float*>(fc), static_cast<const float*>(fs), w.mean_c, w.rstd_c,
-                                    w.mean_s, w.rstd_s, w_fgh, b_fgh, B, Nc, Ns, H, d, static_cast<float*>(w.q),
-                                    static_cast<float*>(w.k), static_cast<float*>(w.v), w.mu_v, s))
-            return e;
-    }
-    // (3) attention + fused epilogue                                         adaDecoder.py:186-198
-    mhada_attn_args a{};
-    a.dtype = dtype; a.B = B; a.H = H; a.Nc = Nc; a.Ns = Ns; a.dqk = d; a.dv = d;
-    a.q = w.q; a.k = w.k; a.v = w.v; a.x = fcs;
-    a.out = w_out ? w.heads : out;
-    a.ldq = C; a.ldk = C; a.ldv = dtype == MHADA_BF16 ? 2 * C : C; a.ldx = C; a.ldo = C;
-    a.x_mean = mean_x; a.x_rstd = rstd_x; a.mu_v = w.mu_v;
-    if (int e = attn_dispatch(a, s)) return e;
-    // (4) out_conv                                                           adaDecoder.py:202-205
-    if (w_out) {
-        if (dtype == MHADA_BF16) {
-            if (int e = launch_linear_bf16(w.heads, C, w_out, b_out, B * Nc, C, C, out, C, w.lin_ws, s)) return e;
-        } else {
-            if (int e = launch_linear_f32(static_cast<const float*>(w.heads), C, w_out, b_out, B * Nc, C, C,
-                                          static_cast<float*>(out), C, s))
-                return e;
-        }
-    }
-    return 0;
+    if (int e = launch_stats(fs, dtype, Bs, Ns, C, C, w.mean_s, w.rstd_s, static_cast<float*>(w.stats_ws), s)) return e;
+    if (dtype == MHADA_BF16)
+        return launch_proj_bf16(MHADA_PROJ_KV, nullptr, fs, nullptr, nullptr, w.mean_s, w.rstd_s, w_fgh, b_fgh, 0, Bs, 0, Ns, H,
+                                d, nullptr, cv.k, cv.v, cv.mu_v, w.proj_ws, s);
+    return launch_proj_f32(MHADA_PROJ_KV, nullptr, static_cast<const float*>(fs), nullptr, nullptr, w.mean_s, w.rstd_s, w_fgh,
+                           b_fgh, 0, Bs, 0, Ns, H, d, nullptr, static_cast<float*>(cv.k), static_cast<float*>(cv.v), cv.mu_v, s);
 }
 
 }  // extern "C"

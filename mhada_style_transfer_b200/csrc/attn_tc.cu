@@ -56,6 +56,7 @@ struct AttnTcParams {
     __nv_bfloat16* out;       // [B, Nc, ldo]
     const float *x_mean, *x_rstd, *mu_v;   // [B, H*64]
     int B, H, Nc, Ns, ldx, ldo;
+    int kv_shared;            // 1: one K / V' / mu_v set (style) serves every image of the batch
     long long* trace;         // AT_TRACE_WORDS entries or nullptr
 };
 
@@ -141,11 +142,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++n) {
                 const int qx = it % XT, h = (it / XT) % p.H, b = it / (XT * p.H);
                 const int q0 = qx * (2 * AT_BM), g0 = n * T;
+                const int bkv = p.kv_shared ? 0 : b;
                 auto load_k = [&](int j) {
                     const int g = g0 + j, ks = g % AT_KST;
                     mbar_wait(&bars->k_empty[ks], ((g / AT_KST) & 1) ^ 1);
                     mbar_arrive_expect_tx(&bars->k_full[ks], AT_K_BYTES);
-                    tma_load_3d(sK + ks * AT_K_BYTES, &tmK, &bars->k_full[ks], h * AT_D, j * AT_BN, b);
+                    tma_load_3d(sK + ks * AT_K_BYTES, &tmK, &bars->k_full[ks], h * AT_D, j * AT_BN, bkv);
                 };
                 mbar_wait(&bars->q_empty, (n & 1) ^ 1);      // all S MMAs of the previous item have read Q
                 mbar_arrive_expect_tx(&bars->q_full, 2 * AT_Q_BYTES);
@@ -161,8 +163,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                     if (n == 0) stamp(3, j, 1);
                     mbar_arrive_expect_tx(&bars->v_full[vs], AT_V_BYTES);
                     uint8_t* v = sV + vs * AT_V_BYTES;
-                    tma_load_3d(v, &tmV, &bars->v_full[vs], h * AT_DV2, j * AT_BN, b);
-                    tma_load_3d(v + AT_V_BYTES / 2, &tmV, &bars->v_full[vs], h * AT_DV2 + 64, j * AT_BN, b);
+                    tma_load_3d(v, &tmV, &bars->v_full[vs], h * AT_DV2, j * AT_BN, bkv);
+                    tma_load_3d(v + AT_V_BYTES / 2, &tmV, &bars->v_full[vs], h * AT_DV2 + 64, j * AT_BN, bkv);
                     if (n == 0) stamp(3, j, 2);
                 }
             }
@@ -267,7 +269,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                     bars->cst[t][0][wg_tid] = p.x_mean[sidx + wg_tid];
                     bars->cst[t][1][wg_tid] = p.x_rstd[sidx + wg_tid];
                 } else {
-                    bars->cst[t][2][wg_tid - AT_D] = p.mu_v ? p.mu_v[sidx + wg_tid - AT_D] : 0.f;
+                    const size_t vidx = (static_cast<size_t>(p.kv_shared ? 0 : b) * p.H + h) * AT_D;
+                    bars->cst[t][2][wg_tid - AT_D] = p.mu_v ? p.mu_v[vidx + wg_tid - AT_D] : 0.f;
                 }
             }
             const int nrow = q0 + t * AT_BM + row;
@@ -418,6 +421,7 @@ int launch_attn_bf16(const mhada_attn_args& a, cudaStream_t s) { return launch_a
 
 int launch_attn_bf16_impl(const mhada_attn_args& a, long long* trace, cudaStream_t s) {
     const int C = a.H * AT_D;
+    const int kvB = a.kv_batch == 1 ? 1 : a.B;       // style batch: 1 = shared by all images
     CUtensorMap tmQ, tmK, tmV;
     {
         uint64_t dims[3] = {static_cast<uint64_t>(C), static_cast<uint64_t>(a.Nc), static_cast<uint64_t>(a.B)};
@@ -426,13 +430,13 @@ int launch_attn_bf16_impl(const mhada_attn_args& a, long long* trace, cudaStream
         if (int e = make_tmap_bf16(&tmQ, a.q, 3, dims, str, box)) return e;
     }
     {
-        uint64_t dims[3] = {static_cast<uint64_t>(C), static_cast<uint64_t>(a.Ns), static_cast<uint64_t>(a.B)};
+        uint64_t dims[3] = {static_cast<uint64_t>(C), static_cast<uint64_t>(a.Ns), static_cast<uint64_t>(kvB)};
         uint64_t str[2] = {static_cast<uint64_t>(a.ldk) * 2, static_cast<uint64_t>(a.Ns) * a.ldk * 2};
         uint32_t box[3] = {AT_D, AT_BN, 1};
         if (int e = make_tmap_bf16(&tmK, a.k, 3, dims, str, box)) return e;
     }
     {
-        uint64_t dims[3] = {static_cast<uint64_t>(2 * C), static_cast<uint64_t>(a.Ns), static_cast<uint64_t>(a.B)};
+        uint64_t dims[3] = {static_cast<uint64_t>(2 * C), static_cast<uint64_t>(a.Ns), static_cast<uint64_t>(kvB)};
         uint64_t str[2] = {static_cast<uint64_t>(a.ldv) * 2, static_cast<uint64_t>(a.Ns) * a.ldv * 2};
         uint32_t box[3] = {64, AT_BN, 1};
         if (int e = make_tmap_bf16(&tmV, a.v, 3, dims, str, box)) return e;
@@ -442,6 +446,7 @@ int launch_attn_bf16_impl(const mhada_attn_args& a, long long* trace, cudaStream
     p.out = static_cast<__nv_bfloat16*>(a.out);
     p.x_mean = a.x_mean; p.x_rstd = a.x_rstd; p.mu_v = a.mu_v;
     p.B = a.B; p.H = a.H; p.Nc = a.Nc; p.Ns = a.Ns; p.ldx = a.ldx; p.ldo = a.ldo;
+    p.kv_shared = (a.kv_batch == 1 && a.B > 1) ? 1 : 0;
     p.trace = trace;
     constexpr size_t smem = AT_SMEM_DATA + sizeof(AttnBars) + 1024;
     static bool attr_done = false;

@@ -35,8 +35,9 @@ int launch_stats_multi(int n, const void* const* x, const int* N, float* const* 
                        int B, int C, int ld, float* ws, cudaStream_t s);
 
 // f32 SIMT path
-int launch_proj_f32(const float* fc, const float* fs, const float* mean_c, const float* rstd_c,
-                    const float* mean_s, const float* rstd_s, const float* w, const float* bias, int B, int Nc,
+// parts: 1 = Q (content batch B), 2 = K, V (style batch Bs)
+int launch_proj_f32(int parts, const float* fc, const float* fs, const float* mean_c, const float* rstd_c,
+                    const float* mean_s, const float* rstd_s, const float* w, const float* bias, int B, int Bs, int Nc,
                     int Ns, int H, int d, float* q, float* k, float* v, float* mu_v, cudaStream_t s);
 int launch_attn_f32(const mhada_attn_args& a, cudaStream_t s);
 int launch_linear_f32(const float* x, int ldx, const float* w, const float* bias, int M, int Cin, int Cout, float* y,
@@ -44,9 +45,9 @@ int launch_linear_f32(const float* x, int ldx, const float* w, const float* bias
 
 // bf16 tcgen05 path
 size_t proj_bf16_workspace(int B, int H, int d);
-int launch_proj_bf16(const void* fc, const void* fs, const float* mean_c, const float* rstd_c, const float* mean_s,
-                     const float* rstd_s, const float* w, const float* bias, int B, int Nc, int Ns, int H, int d,
-                     void* q, void* k, void* v, float* mu_v, void* ws, cudaStream_t s);
+int launch_proj_bf16(int parts, const void* fc, const void* fs, const float* mean_c, const float* rstd_c,
+                     const float* mean_s, const float* rstd_s, const float* w, const float* bias, int B, int Bs, int Nc,
+                     int Ns, int H, int d, void* q, void* k, void* v, float* mu_v, void* ws, cudaStream_t s);
 int launch_attn_bf16(const mhada_attn_args& a, cudaStream_t s);
 int launch_attn_bf16_impl(const mhada_attn_args& a, long long* trace, cudaStream_t s);   // trace: 3*64*8 slots or null
 size_t linear_bf16_workspace(int Cout, int Cin);

@@ -25,14 +25,16 @@ size_t proj_bf16_workspace(int B, int H, int d) {
     return fold_w_bytes(B, H, d) + align_up(static_cast<size_t>(3) * B * H * d * 4, 256);
 }
 
-// grid (H, B, 3), 256 threads = 8 warps: warp w folds output rows w, w+8, ...; lanes walk the input channels,
-// so every global read / write is a contiguous row segment
+// grid (H, batch of this part, number of projections), 256 threads = 8 warps: warp w folds output rows w, w+8, ...;
+// lanes walk the input channels, so every global read / write is a contiguous row segment.
+// which = which0 + blockIdx.z: 0 = f (content side, batch B), 1 = g, 2 = h (style side, batch Bs).  B here is the
+// batch STRIDE of the folded-weight workspace ([3][B][H][d][d]), the same for both sides.
 __global__ void __launch_bounds__(256) fold_kernel(const float* __restrict__ w, const float* __restrict__ bias,
                                                    const float* __restrict__ mean_c, const float* __restrict__ rstd_c,
                                                    const float* __restrict__ mean_s, const float* __restrict__ rstd_s,
-                                                   int B, int H, int d, __nv_bfloat16* __restrict__ wf,
+                                                   int which0, int B, int H, int d, __nv_bfloat16* __restrict__ wf,
                                                    float* __restrict__ bf, float* __restrict__ mu_v) {
-    const int h = blockIdx.x, b = blockIdx.y, which = blockIdx.z;
+    const int h = blockIdx.x, b = blockIdx.y, which = which0 + blockIdx.z;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int C = H * d;
     const float* mu = (which == 0 ? mean_c : mean_s) + static_cast<size_t>(b) * C + h * d;
@@ -181,29 +183,37 @@ static int make_x_map(CUtensorMap* tm, const void* x, int B, int N, int C) {
     return make_tmap_bf16(tm, x, 3, dims, str, box);
 }
 
-int launch_proj_bf16(const void* fc, const void* fs, const float* mean_c, const float* rstd_c, const float* mean_s,
-                     const float* rstd_s, const float* w, const float* bias, int B, int Nc, int Ns, int H, int d,
-                     void* q, void* k, void* v, float* mu_v, void* ws, cudaStream_t s) {
+int launch_proj_bf16(int parts, const void* fc, const void* fs, const float* mean_c, const float* rstd_c,
+                     const float* mean_s, const float* rstd_s, const float* w, const float* bias, int B, int Bs, int Nc,
+                     int Ns, int H, int d, void* q, void* k, void* v, float* mu_v, void* ws, cudaStream_t s) {
+    // parts: 1 = Q from fc (batch B), 2 = K and V' from fs (batch Bs).  Bw = batch stride of the folded weights.
+    const int Bw = B > Bs ? B : Bs;
     __nv_bfloat16* wf = static_cast<__nv_bfloat16*>(ws);
-    float* bf = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + fold_w_bytes(B, H, d));
-    fold_kernel<<<dim3(H, B, 3), 256, 0, s>>>(w, bias, mean_c, rstd_c, mean_s, rstd_s, B, H, d, wf, bf, mu_v);
-    count_launch();
-
+    float* bf = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + fold_w_bytes(Bw, H, d));
     const int C = H * d;
-    CUtensorMap tmC, tmS, tmW;
-    if (int e = make_x_map(&tmC, fc, B, Nc, C)) return e;
-    if (int e = make_x_map(&tmS, fs, B, Ns, C)) return e;
-    uint64_t dimsW[2] = {static_cast<uint64_t>(d), static_cast<uint64_t>(3) * B * H * d};
+    CUtensorMap tmW;
+    uint64_t dimsW[2] = {static_cast<uint64_t>(d), static_cast<uint64_t>(3) * Bw * H * d};
     uint64_t strW[1] = {static_cast<uint64_t>(d) * 2};
     uint32_t boxW[2] = {PRJ_D, PRJ_D};
     if (int e = make_tmap_bf16(&tmW, wf, 2, dimsW, strW, boxW)) return e;
-
-    proj_tc_kernel<1><<<dim3((Nc + PRJ_BM - 1) / PRJ_BM, H, B), PRJ_THREADS, 0, s>>>(
-        tmC, tmW, bf, 0, B, H, Nc, static_cast<__nv_bfloat16*>(q), nullptr);
-    count_launch();
-    proj_tc_kernel<2><<<dim3((Ns + PRJ_BM - 1) / PRJ_BM, H, B), PRJ_THREADS, 0, s>>>(
-        tmS, tmW, bf, 1, B, H, Ns, static_cast<__nv_bfloat16*>(k), static_cast<__nv_bfloat16*>(v));
-    count_launch();
+    if (parts & 1) {
+        fold_kernel<<<dim3(H, B, 1), 256, 0, s>>>(w, bias, mean_c, rstd_c, mean_s, rstd_s, 0, Bw, H, d, wf, bf, mu_v);
+        count_launch();
+        CUtensorMap tmC;
+        if (int e = make_x_map(&tmC, fc, B, Nc, C)) return e;
+        proj_tc_kernel<1><<<dim3((Nc + PRJ_BM - 1) / PRJ_BM, H, B), PRJ_THREADS, 0, s>>>(
+            tmC, tmW, bf, 0, Bw, H, Nc, static_cast<__nv_bfloat16*>(q), nullptr);
+        count_launch();
+    }
+    if (parts & 2) {
+        fold_kernel<<<dim3(H, Bs, 2), 256, 0, s>>>(w, bias, mean_c, rstd_c, mean_s, rstd_s, 1, Bw, H, d, wf, bf, mu_v);
+        count_launch();
+        CUtensorMap tmS;
+        if (int e = make_x_map(&tmS, fs, Bs, Ns, C)) return e;
+        proj_tc_kernel<2><<<dim3((Ns + PRJ_BM - 1) / PRJ_BM, H, Bs), PRJ_THREADS, 0, s>>>(
+            tmS, tmW, bf, 1, Bw, H, Ns, static_cast<__nv_bfloat16*>(k), static_cast<__nv_bfloat16*>(v));
+        count_launch();
+    }
     return check_cuda(cudaGetLastError(), "proj_tc launch");
 }
 

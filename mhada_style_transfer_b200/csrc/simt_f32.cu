@@ -127,20 +127,25 @@ __global__ void muv_kernel(const float* __restrict__ wh, const float* __restrict
     mu_v[i] = a + bh[g * d + o];
 }
 
-int launch_proj_f32(const float* fc, const float* fs, const float* mean_c, const float* rstd_c,
-                    const float* mean_s, const float* rstd_s, const float* w, const float* bias, int B, int Nc,
+int launch_proj_f32(int parts, const float* fc, const float* fs, const float* mean_c, const float* rstd_c,
+                    const float* mean_s, const float* rstd_s, const float* w, const float* bias, int B, int Bs, int Nc,
                     int Ns, int H, int d, float* q, float* k, float* v, float* mu_v, cudaStream_t s) {
     const int C = H * d;
     const size_t wsz = static_cast<size_t>(H) * d * d, bsz = static_cast<size_t>(H) * d;
-    dim3 gq((B * Nc + TILE - 1) / TILE, (d + TILE - 1) / TILE, H), gk((B * Ns + TILE - 1) / TILE, (d + TILE - 1) / TILE, H);
-    grouped_linear_f32_kernel<<<gq, 256, 0, s>>>(fc, C, w, bias, mean_c, rstd_c, 1, B * Nc, Nc, d, d, q, C);
-    count_launch();
-    grouped_linear_f32_kernel<<<gk, 256, 0, s>>>(fs, C, w + wsz, bias + bsz, mean_s, rstd_s, 1, B * Ns, Ns, d, d, k, C);
-    count_launch();
-    grouped_linear_f32_kernel<<<gk, 256, 0, s>>>(fs, C, w + 2 * wsz, nullptr, mean_s, nullptr, 2, B * Ns, Ns, d, d, v, C);
-    count_launch();
-    muv_kernel<<<(B * C + 255) / 256, 256, 0, s>>>(w + 2 * wsz, bias + 2 * bsz, mean_s, B, H, d, mu_v);
-    count_launch();
+    if (parts & 1) {
+        dim3 gq((B * Nc + TILE - 1) / TILE, (d + TILE - 1) / TILE, H);
+        grouped_linear_f32_kernel<<<gq, 256, 0, s>>>(fc, C, w, bias, mean_c, rstd_c, 1, B * Nc, Nc, d, d, q, C);
+        count_launch();
+    }
+    if (parts & 2) {
+        dim3 gk((Bs * Ns + TILE - 1) / TILE, (d + TILE - 1) / TILE, H);
+        grouped_linear_f32_kernel<<<gk, 256, 0, s>>>(fs, C, w + wsz, bias + bsz, mean_s, rstd_s, 1, Bs * Ns, Ns, d, d, k, C);
+        count_launch();
+        grouped_linear_f32_kernel<<<gk, 256, 0, s>>>(fs, C, w + 2 * wsz, nullptr, mean_s, nullptr, 2, Bs * Ns, Ns, d, d, v, C);
+        count_launch();
+        muv_kernel<<<(Bs * C + 255) / 256, 256, 0, s>>>(w + 2 * wsz, bias + 2 * bsz, mean_s, Bs, H, d, mu_v);
+        count_launch();
+    }
     return check_cuda(cudaGetLastError(), "proj_f32 launch");
 }
 
@@ -161,6 +166,7 @@ struct AttnF32Params {
     float* out;
     const float *x_mean, *x_rstd, *mu_v, *q_mean, *q_rstd, *k_mean, *k_rstd;
     int H, Nc, Ns, dqk, dv, ldq, ldk, ldv, ldx, ldo;
+    int kv_shared;   // 1: one K / V / mu_v set (style) serves every image of the batch
 };
 
 __global__ void __launch_bounds__(256) attn_f32_kernel(const AttnF32Params p) {
@@ -177,12 +183,13 @@ __global__ void __launch_bounds__(256) attn_f32_kernel(const AttnF32Params p) {
     const int q0 = blockIdx.x * TILE, c0 = blockIdx.y * TILE;
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const float* qb = p.q + static_cast<size_t>(b) * p.Nc * p.ldq + h * p.dqk;
-    const float* kb = p.k + static_cast<size_t>(b) * p.Ns * p.ldk + h * p.dqk;
-    const float* vb = p.v + static_cast<size_t>(b) * p.Ns * p.ldv + h * p.dv;
+    const int bkv = p.kv_shared ? 0 : b;
+    const float* kb = p.k + static_cast<size_t>(bkv) * p.Ns * p.ldk + h * p.dqk;
+    const float* vb = p.v + static_cast<size_t>(bkv) * p.Ns * p.ldv + h * p.dv;
     const float* qmu = p.q_mean ? p.q_mean + static_cast<size_t>(b) * p.H * p.dqk + h * p.dqk : nullptr;
     const float* qrs = p.q_mean ? p.q_rstd + static_cast<size_t>(b) * p.H * p.dqk + h * p.dqk : nullptr;
-    const float* kmu = p.k_mean ? p.k_mean + static_cast<size_t>(b) * p.H * p.dqk + h * p.dqk : nullptr;
-    const float* krs = p.k_mean ? p.k_rstd + static_cast<size_t>(b) * p.H * p.dqk + h * p.dqk : nullptr;
+    const float* kmu = p.k_mean ? p.k_mean + static_cast<size_t>(bkv) * p.H * p.dqk + h * p.dqk : nullptr;
+    const float* krs = p.k_mean ? p.k_rstd + static_cast<size_t>(bkv) * p.H * p.dqk + h * p.dqk : nullptr;
 
     // running (unnormalised) A.V and A.V^2 with their Kahan compensation terms: a plain fp32 chain over
     // Ns = 4096..32400 keys drifts by ~sqrt(Ns) ulp, which alone would eat the 1e-3 max-abs budget
@@ -334,7 +341,7 @@ __global__ void __launch_bounds__(256) attn_f32_kernel(const AttnF32Params p) {
             size_t sidx = static_cast<size_t>(b) * p.H * p.dv + ch;
             float xn = (__ldg(p.x + (static_cast<size_t>(b) * p.Nc + n) * p.ldx + ch) - __ldg(p.x_mean + sidx)) *
                        __ldg(p.x_rstd + sidx);
-            float mu = p.mu_v ? __ldg(p.mu_v + sidx) : 0.f;
+            float mu = p.mu_v ? __ldg(p.mu_v + static_cast<size_t>(bkv) * p.H * p.dv + ch) : 0.f;
             p.out[(static_cast<size_t>(b) * p.Nc + n) * p.ldo + ch] = fmaf(sd, xn, m + mu);
         }
     }
@@ -349,6 +356,7 @@ int launch_attn_f32(const mhada_attn_args& a, cudaStream_t s) {
     p.q_mean = a.q_mean; p.q_rstd = a.q_rstd; p.k_mean = a.k_mean; p.k_rstd = a.k_rstd;
     p.H = a.H; p.Nc = a.Nc; p.Ns = a.Ns; p.dqk = a.dqk; p.dv = a.dv;
     p.ldq = a.ldq; p.ldk = a.ldk; p.ldv = a.ldv; p.ldx = a.ldx; p.ldo = a.ldo;
+    p.kv_shared = (a.kv_batch == 1 && a.B > 1) ? 1 : 0;
     dim3 grid((a.Nc + TILE - 1) / TILE, (a.dv + TILE - 1) / TILE, a.B * a.H);
     attn_f32_kernel<<<grid, 256, 0, s>>>(p);
     count_launch();

@@ -25,7 +25,7 @@ from torch.nn import functional as F
 from . import _lib
 
 __all__ = ["Softmax", "CosineSimilarity", "AdaAttnForLoss", "AdaAttN", "AdaAttnMultiHead", "AdaAttnTransformer",
-           "AdaAttnTransformerMultiHead", "Decoder", "set_precision"]
+           "AdaAttnTransformerMultiHead", "Decoder", "StyleCache", "set_precision"]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -118,6 +118,52 @@ def _layer_forward(dt: torch.dtype, tfc, tfs, tfcs, w_fgh, b_fgh, w_out, b_out, 
                                    _ptr(b_out), B, Nc, Ns, C, num_heads, flags, _ptr(out), _ptr(ws), ws.numel(),
                                    _stream())
     _lib.check("mhada_layer_forward", rc)
+    return out
+
+
+class StyleCache:
+    """Style side of the MHAda layers, computed once per style: per layer the K, V (V') and mu_v
+    that `mhada_style_precompute` wrote.  They depend on the style features and the layer's g / h weights only,
+    so one cache serves every content image / video frame; a style batch of 1 is broadcast over any content batch
+    (the reference needs equal batches, adaDecoder.py:177-183, and recomputes all of this per frame,
+    infer_video.py:91-92)."""
+
+    def __init__(self, dtype: torch.dtype, style_batch: int, tokens: int, channels: int, buffers, weight_keys):
+        self.dtype, self.style_batch, self.tokens, self.channels = dtype, style_batch, tokens, channels
+        self.buffers = buffers            # one uint8 device tensor per layer
+        self.weight_keys = weight_keys    # parameter versions the buffers were computed from
+
+    def __len__(self):
+        return len(self.buffers)
+
+
+def _style_precompute(dt: torch.dtype, tfs: torch.Tensor, w_fgh, b_fgh, num_heads: int) -> torch.Tensor:
+    L = _lib.lib()
+    Bs, hs, ws_, C = tfs.shape
+    Ns = hs * ws_
+    code = _code(dt)
+    cache = torch.empty(L.mhada_style_cache_bytes(code, Bs, Ns, C, num_heads), dtype=torch.uint8, device=tfs.device)
+    ws = _workspace(tfs.device, L.mhada_layer_workspace(code, Bs, Ns, Ns, C, num_heads))
+    with torch.cuda.device(tfs.device):
+        rc = L.mhada_style_precompute(code, _ptr(tfs), _ptr(w_fgh), _ptr(b_fgh), Bs, Ns, C, num_heads, _ptr(cache),
+                                      cache.numel(), _ptr(ws), ws.numel(), _stream())
+    _lib.check("mhada_style_precompute", rc)
+    return cache
+
+
+def _layer_forward_cached(dt, tfc, tfcs, cache: torch.Tensor, Bs: int, Ns: int, w_fgh, b_fgh, w_out, b_out,
+                          num_heads: int):
+    L = _lib.lib()
+    B, h, w, C = tfc.shape
+    Nc = h * w
+    out = torch.empty((B, h, w, C), dtype=dt, device=tfc.device)
+    code = _code(dt)
+    ws = _workspace(tfc.device, L.mhada_layer_workspace(code, B, Nc, Ns, C, num_heads))
+    with torch.cuda.device(tfc.device):
+        rc = L.mhada_layer_forward_cached(code, _ptr(tfc), _ptr(tfcs), _ptr(cache), Bs, _ptr(w_fgh), _ptr(b_fgh),
+                                          _ptr(w_out), _ptr(b_out), B, Nc, Ns, C, num_heads, _ptr(out), _ptr(ws),
+                                          ws.numel(), _stream())
+    _lib.check("mhada_layer_forward_cached", rc)
     return out
 
 
@@ -304,6 +350,15 @@ class AdaAttnMultiHead(nn.Module):
         return _layer_forward(dt, tfc, tfs, tfcs, w, b, wo, bo, self.num_heads, out,
                               _lib.REUSE_FS_STATS if reuse_fs_stats else 0)
 
+    def precompute_style_tokens(self, dt, tfs) -> torch.Tensor:
+        """K, V', mu_v of this layer for token-major style features (one uint8 cache buffer)."""
+        w, b, _, _ = self.packed_weights()
+        return _style_precompute(dt, tfs, w, b, self.num_heads)
+
+    def forward_tokens_cached(self, dt, tfc, tfcs, cache: torch.Tensor, style_batch: int, style_tokens: int):
+        w, b, wo, bo = self.packed_weights()
+        return _layer_forward_cached(dt, tfc, tfcs, cache, style_batch, style_tokens, w, b, wo, bo, self.num_heads)
+
     def forward(self, fc: torch.Tensor, fs: torch.Tensor, fcs: torch.Tensor):
         self._check_shapes(fc, fs, fcs)
         _require_cuda(fc, fs, fcs)
@@ -461,12 +516,61 @@ class AdaAttnTransformerMultiHead(nn.Module):
         self.decoder = Decoder()
         self.precision = "auto"
 
+    def _weight_keys(self):
+        return tuple(p._version for m in self.adaAttnHead for p in m.parameters())
+
+    def precompute_style(self, fs, precision: str = None) -> StyleCache:
+        """Extension: run the style side of all 2*num_layers layers once.  `fs` is the list of
+        style feature maps `vit_s(s)` (batch 1 or the content batch).  Pass the result instead of `fs`:
+            cache = adaFormer.precompute_style(fs);  fcs, cs = adaFormer(fc, cache)      # every frame"""
+        _require_cuda(*fs)
+        _no_autograd(self, *fs)
+        L0 = self.adaAttnHead[0]
+        _check_activation(L0.activation)
+        dt = _resolve_precision(precision or self.precision, L0.head_dim, *fs[: self.num_layers])
+        bufs = []
+        Bs, C, hs, ws_ = fs[0].shape
+        for i in range(self.num_layers):
+            if fs[i].shape != fs[0].shape:
+                raise RuntimeError("all style feature maps must have the same shape")
+            tfs = _token_major(fs[i], dt)
+            bufs.append(self.adaAttnHead[2 * i].precompute_style_tokens(dt, tfs))
+            bufs.append(self.adaAttnHead[2 * i + 1].precompute_style_tokens(dt, tfs))
+        return StyleCache(dt, Bs, hs * ws_, C, bufs, self._weight_keys())
+
+    def _forward_cached(self, fc, cache: StyleCache):
+        L0 = self.adaAttnHead[0]
+        if len(cache) != 2 * self.num_layers or cache.channels != L0.num_heads * L0.head_dim:
+            raise RuntimeError("StyleCache was built for a different model")
+        if cache.weight_keys != self._weight_keys():
+            raise RuntimeError("StyleCache is stale: the model parameters changed since precompute_style()")
+        _require_cuda(*fc)
+        _no_autograd(self, *fc)
+        B = fc[0].shape[0]
+        if cache.style_batch not in (1, B):
+            raise RuntimeError(f"style batch {cache.style_batch} must be 1 or the content batch {B}")
+        in_dtype, dt = fc[0].dtype, cache.dtype
+        tfc = [_token_major(t, dt) for t in fc[: self.num_layers]]
+        fcs = tfc[0]
+        for i in range(self.num_layers):
+            fcs = self.adaAttnHead[2 * i].forward_tokens_cached(dt, tfc[i], fcs, cache.buffers[2 * i], cache.style_batch,
+                                                                cache.tokens)
+            fcs = self.adaAttnHead[2 * i + 1].forward_tokens_cached(dt, fcs, fcs, cache.buffers[2 * i + 1],
+                                                                    cache.style_batch, cache.tokens)
+        fcs = fcs.permute(0, 3, 1, 2)
+        cs = self.decoder(fcs)
+        if dt != in_dtype:
+            fcs, cs = fcs.to(in_dtype), cs.to(in_dtype)
+        return fcs, cs
+
     def forward(self, *args):
         # model(fc_list, fs_list) or model((fc_list, fs_list)) -- adaDecoder.py:253-260
         if len(args) == 1:
             fc, fs = args[0]
         else:
             fc, fs = args
+        if isinstance(fs, StyleCache):
+            return self._forward_cached(fc, fs)
         L0 = self.adaAttnHead[0]
         for i in range(self.num_layers):
             L0._check_shapes(fc[i], fs[i], fc[0])

@@ -240,6 +240,35 @@ def _check_constant_style(m, tfcs, const_fs, rows, oc, oc32):
     assert ec32["max_abs"] <= FP32_MAX_ABS, ec32
 
 
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_style_cache_matches_uncached(precision):
+    """the style side computed once (precompute_style) gives bit-identical results to the plain call,
+    and one style (batch 1) serves a batch of frames -- the infer_video.py situation (one style, many frames)."""
+    case = dict(B=3, hw=(12, 20), hsws=(8, 8), seed=91)           # cross sizes like infer_video.py (Nc != Ns)
+    fc, fs, sd = cases.transformer_inputs(case)
+    m = build_transformer(sd, precision)
+    dfc = [dev(x) for x in fc]
+    dfs_all = [dev(x) for x in fs]
+    with torch.no_grad():
+        ref_fcs, ref_cs = m(dfc, dfs_all)
+        cache = m.precompute_style(dfs_all)
+        got_fcs, got_cs = m(dfc, cache)
+    assert torch.equal(ref_fcs, got_fcs) and torch.equal(ref_cs, got_cs)
+    # one style for all frames: equals the plain call with that style repeated per frame
+    dfs_one = [t[:1] for t in dfs_all]
+    with torch.no_grad():
+        cache1 = m.precompute_style(dfs_one)
+        b_fcs, b_cs = m(dfc, cache1)
+        rep_fcs, rep_cs = m(dfc, [t.expand(3, -1, -1, -1).contiguous() for t in dfs_one])
+    assert cache1.style_batch == 1
+    assert torch.equal(b_fcs, rep_fcs) and torch.equal(b_cs, rep_cs)
+    # a stale cache (weights changed) is refused
+    with torch.no_grad():
+        m.adaAttnHead[0].out_conv.bias.add_(1.0)
+    with torch.no_grad(), pytest.raises(RuntimeError, match="stale"):
+        m(dfc, cache1)
+
+
 def test_errors_on_device():
     m = M.AdaAttnMultiHead(512, 8, activation="cosine").to(DEV)
     x = torch.zeros(1, 512, 4, 4, device=DEV)

@@ -83,8 +83,8 @@ def _proj_case(code, B, H, hw, hsws, seed=3):
     v = torch.empty(B, Ns, C * (2 if code == BF16 else 1), dtype=dt, device=G.DEV)
     muv = torch.empty(B, C, dtype=torch.float32, device=G.DEV)
     wsb = G.ws(L.mhada_proj_workspace(B, H, d))
-    _lib.check("mhada_proj", L.mhada_proj(code, G.ptr(tfc), G.ptr(tfs), G.ptr(mc), G.ptr(rc), G.ptr(ms), G.ptr(rs),
-                                          G.ptr(w), G.ptr(b), B, Nc, Ns, H, d, G.ptr(q), G.ptr(k), G.ptr(v),
+    _lib.check("mhada_proj", L.mhada_proj(code, 3, G.ptr(tfc), G.ptr(tfs), G.ptr(mc), G.ptr(rc), G.ptr(ms), G.ptr(rs),
+                                          G.ptr(w), G.ptr(b), B, B, Nc, Ns, H, d, G.ptr(q), G.ptr(k), G.ptr(v),
                                           G.ptr(muv), G.ptr(wsb), wsb.numel(), G.stream()))
     # oracle on the tensors the kernels saw
     eq = np.zeros((B, C) + tuple(hw)); ek = np.zeros((B, C) + tuple(hsws)); ev = np.zeros_like(ek)

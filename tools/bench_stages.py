@@ -65,8 +65,8 @@ def main():
         _lib.check("stats", L.mhada_in_stats(P(fcs), code, B, Nc, C, C, P(mean[4]), P(mean[5]), P(sws), sws.numel(), st))
 
     def proj():
-        _lib.check("proj", L.mhada_proj(code, P(fc), P(fs), P(mean[0]), P(mean[1]), P(mean[2]), P(mean[3]), P(w), P(b),
-                                        B, Nc, Ns, H, d, P(q), P(k), P(v), P(muv), P(pws), pws.numel(), st))
+        _lib.check("proj", L.mhada_proj(code, 3, P(fc), P(fs), P(mean[0]), P(mean[1]), P(mean[2]), P(mean[3]), P(w), P(b),
+                                        B, B, Nc, Ns, H, d, P(q), P(k), P(v), P(muv), P(pws), pws.numel(), st))
 
     args = _lib.AttnArgs()
     args.dtype = code
