@@ -12,6 +12,11 @@ Precision (`module.precision`, default "auto"):
   "bf16"  tcgen05 tensor-core kernels, bf16 storage / fp32 accumulate (head_dim 64)
   "auto"  bf16 path when the inputs are bf16/fp16 and head_dim == 64, else fp32 path
 There is no CPU path: CPU tensors raise.
+
+Training (train_image.py:105-144): the FORWARD always runs the CUDA kernels.  When gradients are required the
+layers become autograd Functions whose BACKWARD recomputes the layer with PyTorch ops in fp32 and differentiates
+that (cuBLAS through torch; own backward kernels are SURVEY N4), and the decoder takes the plain differentiable
+PyTorch path.  Gradients are checked against the reference's float64 autograd (tests/golden/grad_*).
 """
 from __future__ import annotations
 
@@ -61,11 +66,71 @@ def _require_cuda(*tensors):
                                "(there is no CPU fallback; use the reference package on CPU)")
 
 
+def _needs_grad(module: nn.Module, *tensors) -> bool:
+    return torch.is_grad_enabled() and (any(t.requires_grad for t in tensors) or
+                                        any(p.requires_grad for p in module.parameters()))
+
+
 def _no_autograd(module: nn.Module, *tensors):
-    if torch.is_grad_enabled() and (any(t.requires_grad for t in tensors) or
-                                    any(p.requires_grad for p in module.parameters())):
-        raise RuntimeError("the B200 MHAda path is forward-only in this round: call it under torch.no_grad() "
+    if _needs_grad(module, *tensors):
+        raise RuntimeError("this entry point of the B200 MHAda path is forward-only: call it under torch.no_grad() "
                            "(the reference inference scripts do, e.g. infer_image.py:82)")
+
+
+def _instance_norm_torch(x):                       # x [..., N]: per-row statistics over the last axis
+    mu = x.mean(-1, keepdim=True)
+    var = x.var(-1, unbiased=False, keepdim=True)
+    return (x - mu) * torch.rsqrt(var + 1e-5)
+
+
+def _layer_math_torch(fc, fs, fcs, wf, bf, wg, bg, wh, bh, wo, bo, num_heads: int):
+    """Differentiable fp32 PyTorch restatement of one layer (adaDecoder.py:162-206), used ONLY by the backward of
+    _MhadaLayerFn (recompute-and-differentiate).  matmul / einsum only: no TF32 on the default settings."""
+    B, C, h, w = fc.shape
+    d = C // num_heads
+    xc = fc.reshape(B, num_heads, d, -1)
+    xs = fs.reshape(B, num_heads, d, -1)
+    xx = fcs.reshape(B, num_heads, d, -1)
+    heads = []
+    for i in range(num_heads):                     # head by head: the Nc x Ns map of one head at a time
+        q = torch.matmul(wf[i], _instance_norm_torch(xc[:, i])) + bf[i][None, :, None]        # [B,d,Nc]
+        k = torch.matmul(wg[i], _instance_norm_torch(xs[:, i])) + bg[i][None, :, None]        # [B,d,Ns]
+        v = (torch.matmul(wh[i], xs[:, i]) + bh[i][None, :, None]).transpose(1, 2)            # [B,Ns,d]
+        a = torch.softmax(torch.matmul(q.transpose(1, 2), k), dim=-1)                         # [B,Nc,Ns]
+        m = torch.matmul(a, v)
+        var = torch.matmul(a, v * v) - m * m
+        sd = torch.sqrt(var.clamp(min=1e-6))
+        heads.append((sd * _instance_norm_torch(xx[:, i]).transpose(1, 2) + m).transpose(1, 2))   # [B,d,Nc]
+    cat = torch.cat(heads, dim=1)                                                             # [B,C,Nc]
+    if wo is not None:
+        cat = torch.matmul(wo, cat) + bo[None, :, None]
+    return cat.reshape(B, C, h, w)
+
+
+class _MhadaLayerFn(torch.autograd.Function):
+    """Forward: the CUDA kernels.  Backward: recompute with _layer_math_torch in fp32 and differentiate."""
+
+    @staticmethod
+    def forward(ctx, run_forward, num_heads, has_out, fc, fs, fcs, wf, bf, wg, bg, wh, bh, wo, bo):
+        ctx.num_heads, ctx.has_out = num_heads, has_out
+        ctx.save_for_backward(fc, fs, fcs, wf, bf, wg, bg, wh, bh, wo, bo)
+        with torch.no_grad():
+            return run_forward(fc, fs, fcs)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        saved = ctx.saved_tensors
+        with torch.enable_grad():
+            leaves = [t.detach().float().requires_grad_(True) for t in saved]
+            fc, fs, fcs, wf, bf, wg, bg, wh, bh, wo, bo = leaves
+            out = _layer_math_torch(fc, fs, fcs, wf, bf, wg, bg, wh, bh, wo if ctx.has_out else None,
+                                    bo if ctx.has_out else None, ctx.num_heads)
+            need = [i for i, ng in enumerate(ctx.needs_input_grad[3:]) if ng and (ctx.has_out or i < 9)]
+            grads = torch.autograd.grad(out, [leaves[i] for i in need], grad_out.float(), allow_unused=True)
+        full = [None] * len(leaves)
+        for i, g in zip(need, grads):
+            full[i] = None if g is None else g.to(saved[i].dtype)
+        return (None, None, None, *full)
 
 
 def _token_major(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
@@ -359,11 +424,25 @@ class AdaAttnMultiHead(nn.Module):
         w, b, wo, bo = self.packed_weights()
         return _layer_forward_cached(dt, tfc, tfcs, cache, style_batch, style_tokens, w, b, wo, bo, self.num_heads)
 
+    def _stacked_params(self):
+        d = self.head_dim
+        st = lambda lst, attr, shape: torch.stack([getattr(m, attr).reshape(shape) for m in lst])
+        return (st(self.f_list, "weight", (d, d)), st(self.f_list, "bias", (d,)),
+                st(self.g_list, "weight", (d, d)), st(self.g_list, "bias", (d,)),
+                st(self.h_list, "weight", (d, d)), st(self.h_list, "bias", (d,)),
+                self.out_conv.weight.reshape(self.out_conv.weight.shape[0], -1), self.out_conv.bias)
+
     def forward(self, fc: torch.Tensor, fs: torch.Tensor, fcs: torch.Tensor):
         self._check_shapes(fc, fs, fcs)
         _require_cuda(fc, fs, fcs)
-        _no_autograd(self, fc, fs, fcs)
         _check_activation(self.activation)
+        if _needs_grad(self, fc, fs, fcs):
+            # kernels forward, PyTorch recompute backward (module docstring); torch.stack keeps the graph to the
+            # per-head Conv2d parameters
+            return _MhadaLayerFn.apply(self._forward_nograd, self.num_heads, True, fc, fs, fcs, *self._stacked_params())
+        return self._forward_nograd(fc, fs, fcs)
+
+    def _forward_nograd(self, fc, fs, fcs):
         dt = _resolve_precision(self.precision, self.head_dim, fc, fs, fcs)
         tfc, tfs = _token_major(fc, dt), _token_major(fs, dt)
         tfcs = tfc if _same_tensor(fc, fcs) else _token_major(fcs, dt)
@@ -461,7 +540,8 @@ class Decoder(nn.Module):
         return [*self.conv1, *self.conv2, *self.conv3]
 
     def forward(self, fcs: torch.Tensor):
-        if not fcs.is_cuda:
+        if not fcs.is_cuda or _needs_grad(self, fcs):
+            # CPU, or training: the plain (differentiable) PyTorch ops of conv.py:96-100
             return self.conv3(self.conv2(self.conv1(fcs)))
         if fcs.dtype not in (torch.float32, torch.bfloat16):
             fcs = fcs.to(torch.bfloat16)
@@ -575,8 +655,13 @@ class AdaAttnTransformerMultiHead(nn.Module):
         for i in range(self.num_layers):
             L0._check_shapes(fc[i], fs[i], fc[0])
         _require_cuda(*fc, *fs)
-        _no_autograd(self, *fc, *fs)
         _check_activation(L0.activation)
+        if _needs_grad(self, *fc, *fs):
+            fcs = fc[0]                                                          # adaDecoder.py:262-267, layer by layer
+            for i in range(self.num_layers):
+                fcs = self.adaAttnHead[2 * i](fc[i], fs[i], fcs)
+                fcs = self.adaAttnHead[2 * i + 1](fcs, fs[i], fcs)
+            return fcs, self.decoder(fcs)
         in_dtype = fc[0].dtype
         dt = _resolve_precision(self.precision, L0.head_dim, *fc[: self.num_layers], *fs[: self.num_layers])
         tfc = [_token_major(t, dt) for t in fc[: self.num_layers]]

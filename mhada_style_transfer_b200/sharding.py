@@ -66,3 +66,33 @@ def run_sharded(model: Callable, fc: Sequence[torch.Tensor], fs: Sequence[torch.
             _, probe = model([t[:1] for t in fc], [t[:1] for t in fs])
         cs = probe[:0]
     return gather_batches(cs, n, dst=dst, group=group)
+
+
+def allreduce_gradients(module: torch.nn.Module, group=None, bucket_bytes: int = 32 << 20) -> None:
+    """Average the gradients of `module` over the ranks (the data-parallel step train_image.py never had: it is
+    single-GPU, train_image.py:139-144).  Gradients are flattened into ~32 MB buckets so the 25 M parameters of the
+    three networks take a handful of collectives; over NVLink 5 the bucket size is chosen for launch latency and
+    overlap, not for link count."""
+    world = dist.get_world_size(group)
+    grads = [p.grad for p in module.parameters() if p.grad is not None]
+    bucket, size = [], 0
+
+    def flush():
+        nonlocal bucket, size
+        if not bucket:
+            return
+        flat = torch.cat([g.reshape(-1) for g in bucket])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        flat.div_(world)
+        off = 0
+        for g in bucket:
+            g.copy_(flat[off: off + g.numel()].view_as(g))
+            off += g.numel()
+        bucket, size = [], 0
+
+    for g in grads:
+        bucket.append(g)
+        size += g.numel() * g.element_size()
+        if size >= bucket_bytes:
+            flush()
+    flush()

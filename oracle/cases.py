@@ -54,7 +54,23 @@ DECODER_CASES = [
     dict(name="decoder_5x7", kind="decoder", B=1, hw=(5, 7), seed=61),
 ]
 
-ALL_CASES = LAYER_CASES + ADAATTN_CASES + FORLOSS_CASES + TRANSFORMER_CASES + DECODER_CASES
+GRAD_CASES = [
+    # d(loss)/d(inputs, weights) of one AdaAttnMultiHead layer, loss = sum(out * G); reference autograd in float64
+    dict(name="grad_layer_c128_h2", kind="grad", B=2, C=128, H=2, hw=(10, 10), hsws=(8, 9), gain=1.0, seed=71),
+]
+
+ALL_CASES = LAYER_CASES + ADAATTN_CASES + FORLOSS_CASES + TRANSFORMER_CASES + DECODER_CASES + GRAD_CASES
+
+GRAD_KEYS = ("fc", "fs", "fcs", "f_list.0.weight", "f_list.1.bias", "g_list.1.weight", "g_list.0.bias",
+             "h_list.0.weight", "h_list.1.bias", "out_conv.weight", "out_conv.bias")
+
+
+def grad_inputs(case: dict):
+    fc, fs, fcs, sd = layer_inputs(case)
+    B, C = case["B"], case["C"]
+    h, w = case["hw"]
+    G = synth.bellish(case["seed"] * 10 + 9, (B, C, h, w), 0.0, 1.0)
+    return fc, fs, fcs, sd, G
 
 
 def by_name(name: str) -> dict:

@@ -95,6 +95,22 @@ def main(prefix: str = ""):
             arrays["cs"] = cases.pixel_sublattice(cs64, case["img_sub"]).astype(np.float32)
             meta["fcs"] = summarize(fcs64); meta["cs"] = summarize(cs64)
             meta["fcs_ref32_vs_ref64"] = errors(fcs32, fcs64); meta["cs_ref32_vs_ref64"] = errors(cs32, cs64)
+        elif kind == "grad":
+            fc, fs, fcs, sd, G = cases.grad_inputs(case)
+            m = AdaAttnMultiHead(case["C"], case["H"]).to(torch.float64)
+            m.load_state_dict(synth.to_torch(sd, torch.float64), strict=True)
+            tin = [T(a, torch.float64).requires_grad_(True) for a in (fc, fs, fcs)]
+            out = m(*tin)
+            loss = (out * T(G, torch.float64)).sum()
+            loss.backward()
+            named = dict(m.named_parameters())
+            grads = {"fc": tin[0].grad, "fs": tin[1].grad, "fcs": tin[2].grad}
+            for k in cases.GRAD_KEYS[3:]:
+                grads[k] = named[k].grad
+            for k, g in grads.items():
+                arrays[k.replace(".", "__")] = g.numpy().astype(np.float32)
+                meta[k] = summarize(g.numpy())
+            meta["loss"] = float(loss)
         elif kind == "decoder":
             x, sd = cases.decoder_inputs(case)
             sd_local = {k[len("decoder."):]: v for k, v in sd.items()}

@@ -135,3 +135,36 @@ def test_torch_port_matches_reference(golden_index):
     ec = O.errors(cases.pixel_sublattice(cs.numpy(), case["img_sub"]), g["cs"])
     assert ef["max_abs"] <= 5 * meta["fcs_ref32_vs_ref64"]["max_abs"] + 1e-4, ef
     assert ec["max_abs_rel"] <= 1e-4, ec
+
+
+@pytest.mark.parametrize("case", cases.GRAD_CASES, ids=lambda c: c["name"])
+def test_reference_gradients_agree_with_oracle_finite_differences(case, golden_index):
+    """The golden gradients (reference autograd, float64) against directional finite differences of the numpy
+    oracle: pins the gradient fixtures independently of any autograd."""
+    fc, fs, fcs, sd, G = cases.grad_inputs(case)
+    g = load_golden(case["name"])
+    meta = golden_index[case["name"]]
+
+    def loss(fc_, fs_, fcs_, sd_):
+        return float((O.ada_attn_multi_head(fc_, fs_, fcs_, sd_, case["H"]) * G).sum())
+
+    assert loss(fc, fs, fcs, sd) == pytest.approx(meta["loss"], rel=1e-10)
+    rng = np.random.default_rng(0)
+    eps = 1e-5
+    for key, arr in (("fc", fc), ("fs", fs), ("fcs", fcs), ("g_list.1.weight", sd["g_list.1.weight"]),
+                     ("out_conv.bias", sd["out_conv.bias"])):
+        v = rng.standard_normal(arr.shape)
+        args = dict(fc=fc, fs=fs, fcs=fcs)
+
+        def at(sign):
+            if key in args:
+                a = dict(args)
+                a[key] = arr + sign * eps * v
+                return loss(a["fc"], a["fs"], a["fcs"], sd)
+            sd2 = dict(sd)
+            sd2[key] = arr + sign * eps * v
+            return loss(fc, fs, fcs, sd2)
+
+        fd = (at(+1) - at(-1)) / (2 * eps)
+        an = float((g[key.replace(".", "__")].astype(np.float64) * v).sum())
+        assert fd == pytest.approx(an, rel=2e-4, abs=1e-6 * abs(an) + 1e-6), key
