@@ -9,20 +9,24 @@
 //
 // CTA = 2 query tiles of 128 rows x 1 head, key tiles of 64, 12 warps:
 //   warp 0       TMA producer: Q (once), K ring (4 x 8 KB), V' ring (4 x 16 KB), 128B swizzle
-//   warp 1       tcgen05.mma issuer (one elected lane)
-//   warp 2       TMEM allocator (512 columns; per query tile t: S buffers at t*256 + {0, 64}, O at t*256 + 128)
-//   warp 3       stages the epilogue constants (mean/rstd of fcs, mu_v) into shared memory
+//   warp 1, 2    tcgen05.mma issuers, one elected lane each: warp 1 for query tile 0, warp 2 for query tile 1
+//                (warp 2 also allocates the 512 TMEM columns; per query tile t: S buffers at t*256 + {0, 64},
+//                O at t*256 + 128)
+//   warp 3       idle after set-up
 //   warps 4-7    softmax + epilogue for query tile 0 (thread = row; TMEM lane = row, no shuffles)
 //   warps 8-11   same for query tile 1
 // Pipeline (measured motivation in DESIGN.md, attention section): S is DOUBLE-BUFFERED in TMEM, so
 // S(j+1), S(j+2) are computed while the softmax warps still work on tile j -- they do not wait for the
 // tensor core in steady state, and the exp2 (MUFU) units, which bound this head_dim-64 problem, stay busy.
-// MMA issue order per key tile j and query tile t:  [P_t(j) ready]  PV_t(j)  S_t(j+2).
-// Rescaling of O is lazy (only when a row max grows by more than 2^8) and done in place in TMEM by the
-// softmax warps after waiting for the last PV into that accumulator.
+// MMA issue order per key tile j of query tile t:  [P_t(j) ready]  PV_t(j)  S_t(j+2).
+// The softmax reference (row maximum) LAGS: exact for the first key tile of a work item, afterwards it only
+// moves when a tile maximum exceeds it by 2^64 (checked before P leaves the registers; then O is rescaled in
+// place in TMEM and the tile redone).  The per-tile maximum therefore is off the critical path.
 //
 // Tensor-bound: algorithmic FLOPs = 6 * B * Nc * Ns * C per layer (2 QK^T + 2 AV + 2 AV^2).
 #include <math.h>
+
+#include <type_traits>
 
 #include "common.h"
 #include "ptx.cuh"
@@ -34,16 +38,39 @@ constexpr int AT_BN = 64;        // keys per tile
 constexpr int AT_D = 64;         // head dim (dqk = dv)
 constexpr int AT_DV2 = 128;      // [V~ | V~^2]
 constexpr int AT_KST = 4, AT_VST = 4;
-constexpr int AT_THREADS = 384;
+// Which of every 8 consecutive column PAIRS of an S tile take exp2 on the FMA pipes (Cody-Waite split + degree-3
+// polynomial + exponent insertion) instead of MUFU.EX2: bit i set = pair i.  The MUFU issues one warp-wide EX2
+// per 8 cycles per sub-partition -- 1024 cycles per key tile for the two query tiles against 768 tensor-core
+// cycles -- which is what the FlashAttention-4 trick attacks.  MEASURED ON B200 (tools/microbench/mufu_bench.cu,
+// DESIGN.md): the packed FFMA2 / FADD2 cost two issue cycles each, the polynomial path comes to ~12 issue cycles
+// per element against 8 MUFU cycles, and with two softmax warps per sub-partition no mask beats 0 (0x88: +3 %
+// before the row sums moved to FHADD, 0 % after; 0xAA: -1 %).  Kept (parity-tested) for sm_103, whose MUFU is
+// the same width but whose clocks / ratios differ; default off.
+#ifndef MHADA_AT_POLY
+#define MHADA_AT_POLY 0
+#endif
+constexpr int AT_TILE_THREADS = 128;             // softmax threads per query tile (thread = row)
+constexpr int AT_THREADS = 128 + 2 * AT_TILE_THREADS;
+constexpr unsigned AT_POLY = MHADA_AT_POLY;
+#ifndef MHADA_AT_TRACE_QUARTER
+#define MHADA_AT_TRACE_QUARTER 0
+#endif
+constexpr int AT_TRACE_QUARTER = MHADA_AT_TRACE_QUARTER;   // which softmax warp of a tile writes the trace stamps
+// 2^f on [-0.5, 0.5], minimax in relative error (7.5e-5 = 2^-13.7, far below the bf16 rounding of P that follows)
+constexpr float AT_EX2_C0 = 0.9999281168f, AT_EX2_C1 = 0.6932609677f, AT_EX2_C2 = 0.2426107526f, AT_EX2_C3 = 0.0551714078f;
 constexpr uint32_t AT_Q_BYTES = AT_BM * AT_D * 2;          // 16 KB per query tile
 constexpr uint32_t AT_K_BYTES = AT_BN * AT_D * 2;          // 8 KB
 constexpr uint32_t AT_V_BYTES = AT_BN * AT_DV2 * 2;        // 16 KB (two 64-column boxes)
 constexpr uint32_t AT_SMEM_DATA = 2 * AT_Q_BYTES + AT_KST * AT_K_BYTES + AT_VST * AT_V_BYTES;
-constexpr float AT_RESCALE_THRESHOLD = 8.0f;               // log2 units: P <= 2^8
+constexpr float AT_RESCALE_THRESHOLD = 64.0f;              // log2 units: weights of a tile may reach 2^64 before the reference moves
+// 0: the two query tiles' softmax warps run free (default since the row maximum left the critical path: with one
+//    MMA issuer per tile the streams de-phase on their own; cfg2 0.422 ms / cfg3 0.857 ms);
+// 2: half-section hand-off through named barriers every key tile (was the default while each tile had a max phase
+//    to hide; now 0.437 / 0.891 ms).
 #ifndef MHADA_AT_PINGPONG
-#define MHADA_AT_PINGPONG 2
+#define MHADA_AT_PINGPONG 0
 #endif
-constexpr int AT_PINGPONG = MHADA_AT_PINGPONG;   // 0 free-running, 1 one-time half-tile offset, 2 half-section hand-off every tile
+constexpr int AT_PINGPONG = MHADA_AT_PINGPONG;
 
 // Trace slots (development aid, attn_tc_kernel<true> only): clock64() stamps of CTA (0,0,0).
 //   softmax WG t, iteration j: trace[(t*64 + j)*8 + e], e = 0 S ready, 1 S in registers, 2 max/rescale done,
@@ -69,7 +96,7 @@ struct AttnBars {
     uint64_t pv_done[2];      // one phase per key tile: PV_t(j) retired (O_t quiescent until P_t(j+1) arrives)
     uint64_t o_full[2];       // one phase per work item: its last PV_t retired
     uint32_t tmem_slot;
-    float cst[2][3][AT_D];    // per warpgroup: x_mean, x_rstd, mu_v of the current (image, head)
+    float cst[2][3][AT_D];    // per query tile: x_mean, x_rstd, mu_v of the current (image, head)
 };
 
 template <bool TRACE>
@@ -109,9 +136,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     }
     if (warp == 1 && lane == 0) {
         mbar_init(&bars->q_full, 1);
-        mbar_init(&bars->q_empty, 1);
-        for (int s = 0; s < AT_KST; ++s) { mbar_init(&bars->k_full[s], 1); mbar_init(&bars->k_empty[s], 1); }
-        for (int s = 0; s < AT_VST; ++s) { mbar_init(&bars->v_full[s], 1); mbar_init(&bars->v_empty[s], 1); }
+        mbar_init(&bars->q_empty, 2);                   // "empty" barriers: one commit per MMA issuer
+        for (int s = 0; s < AT_KST; ++s) { mbar_init(&bars->k_full[s], 1); mbar_init(&bars->k_empty[s], 2); }
+        for (int s = 0; s < AT_VST; ++s) { mbar_init(&bars->v_full[s], 1); mbar_init(&bars->v_empty[s], 2); }
         for (int t = 0; t < 2; ++t) {
             for (int u = 0; u < 2; ++u) {
                 mbar_init(&bars->s_full[t][u], 1);
@@ -169,31 +196,38 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 }
             }
         }
-      } else if (warp == 1) {
-        // ===================================================================== MMA issuer
+      } else if (warp == 1 || warp == 2) {
+        // ===================================================================== MMA issuers
+        // One issuing thread PER QUERY TILE (warp 1: tile 0, warp 2: tile 1), on two different SM sub-partitions:
+        // an issuer runs ~120 instructions per key tile in the issue slots it shares with two softmax warps
+        // (one thread issuing for both tiles cost its sub-partition's softmax warps ~220 cycles per key tile, and
+        // the whole CTA waits for the slowest sub-partition), and the two tiles' chains no longer wait for each
+        // other's P.  K / V' / Q slots are released when BOTH issuers' MMAs have read them (empty barriers count 2;
+        // tcgen05.commit tracks the MMAs of the committing thread).
         if (elect_one()) {
+            const int t = warp - 1;
             constexpr uint32_t idesc_s = make_idesc_bf16(AT_BM, AT_BN, 0, 0);     // S = Q K^T, both K-major
             constexpr uint32_t idesc_o = make_idesc_bf16(AT_BM, AT_DV2, 0, 1);    // O += P V', V' MN-major
-            const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV);
-            auto issue_s = [&](int t, int g) {         // S_t(g) -> S buffer g&1 of query tile t
-                const int ks = g % AT_KST;
-                const uint64_t da = make_smem_desc(q_addr + t * AT_Q_BYTES, 16, 1024);
-                const uint64_t db = make_smem_desc(k_addr + ks * AT_K_BYTES, 16, 1024);
-                const uint32_t d_tm = tmem + t * 256 + (g & 1) * 64;
+            // descriptors differ in the 14-bit start-address field only: keep the high words constant
+            const uint64_t q_desc = make_smem_desc(smem_u32(sQ) + t * AT_Q_BYTES, 16, 1024);
+            const uint64_t k_desc = make_smem_desc(smem_u32(sK), 16, 1024);
+            const uint64_t v_desc = make_smem_desc(smem_u32(sV), AT_V_BYTES / 2, 1024);   // LBO = box stride, SBO = 8 key rows
+            const uint32_t s_tm0 = tmem + t * 256, o_tm0 = tmem + t * 256 + 128;
+            auto issue_s = [&](int g) {                // S_t(g) -> S buffer g&1
+                const uint64_t db = desc_advance(k_desc, (g % AT_KST) * AT_K_BYTES);
+                const uint32_t d_tm = s_tm0 + (g & 1) * 64;
 #pragma unroll
                 for (int k = 0; k < AT_D / 16; ++k)
-                    umma_ss(d_tm, desc_advance(da, k * 32), desc_advance(db, k * 32), idesc_s, k != 0);
+                    umma_ss(d_tm, desc_advance(q_desc, k * 32), desc_advance(db, k * 32), idesc_s, k != 0);
                 umma_commit(&bars->s_full[t][g & 1]);
             };
-            auto issue_pv = [&](int t, int g, bool first, bool last) {
-                // B = V' tile [64 keys][128 cols] as two [64][64] boxes: LBO = box stride, SBO = 8 key rows
-                const int vs = g % AT_VST;
-                const uint64_t db = make_smem_desc(v_addr + vs * AT_V_BYTES, AT_V_BYTES / 2, 1024);
-                const uint32_t a_tm = tmem + t * 256 + (g & 1) * 64;      // P_t(g) aliases S buffer g&1
+            auto issue_pv = [&](int g, bool first, bool last) {
+                const uint64_t db = desc_advance(v_desc, (g % AT_VST) * AT_V_BYTES);
+                const uint32_t a_tm = s_tm0 + (g & 1) * 64;          // P_t(g) aliases S buffer g&1
 #pragma unroll
-                for (int k = 0; k < AT_BN / 16; ++k)
-                    umma_ts(tmem + t * 256 + 128, a_tm + k * 8, desc_advance(db, k * 2048), idesc_o,
-                            (!first || k != 0) ? 1u : 0u);
+                for (int k = 0; k < AT_BN / 16; ++k) {
+                    umma_ts(o_tm0, a_tm + k * 8, desc_advance(db, k * 2048), idesc_o, (!first || k != 0) ? 1u : 0u);
+                }
                 umma_commit(&bars->pv_done[t]);
                 if (last) umma_commit(&bars->o_full[t]);
             };
@@ -205,36 +239,27 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                     const int g = g0 + j;
                     mbar_wait(&bars->k_full[g % AT_KST], (g / AT_KST) & 1);
                     tc_fence_after();
-                    issue_s(0, g);
-                    issue_s(1, g);
+                    issue_s(g);
                     umma_commit(&bars->k_empty[g % AT_KST]);
                 }
                 if (T <= 2) umma_commit(&bars->q_empty);
                 for (int j = 0; j < T; ++j) {
                     const int g = g0 + j, vs = g % AT_VST;
-                    const bool more = (j + 2 < T);
                     mbar_wait(&bars->v_full[vs], (g / AT_VST) & 1);
-                    if (n == 0) stamp(2, j, 4);
-#pragma unroll
-                    for (int t = 0; t < 2; ++t) {
-                        mbar_wait(&bars->p_ready[t][g & 1], (g >> 1) & 1);
+                    if (n == 0 && t == 0) stamp(2, j, 4);
+                    mbar_wait(&bars->p_ready[t][g & 1], (g >> 1) & 1);
+                    tc_fence_after();
+                    if (n == 0) stamp(2, j, 2 * t);
+                    issue_pv(g, j == 0, j == T - 1);
+                    umma_commit(&bars->v_empty[vs]);
+                    if (j + 2 < T) {
+                        mbar_wait(&bars->k_full[(g + 2) % AT_KST], ((g + 2) / AT_KST) & 1);
                         tc_fence_after();
-                        if (n == 0) stamp(2, j, 2 * t);
-                        issue_pv(t, g, j == 0, j == T - 1);
-                        if (t == 1) umma_commit(&bars->v_empty[vs]);
-                        if (more) {
-                            if (t == 0) {
-                                mbar_wait(&bars->k_full[(g + 2) % AT_KST], ((g + 2) / AT_KST) & 1);
-                                tc_fence_after();
-                            }
-                            issue_s(t, g + 2);
-                            if (t == 1) {
-                                umma_commit(&bars->k_empty[(g + 2) % AT_KST]);
-                                if (j + 3 == T) umma_commit(&bars->q_empty);   // that was the last S of this item
-                            }
-                        }
-                        if (n == 0) stamp(2, j, 2 * t + 1);
+                        issue_s(g + 2);
+                        umma_commit(&bars->k_empty[(g + 2) % AT_KST]);
+                        if (j + 3 == T) umma_commit(&bars->q_empty);   // that was the last S of this item
                     }
+                    if (n == 0) stamp(2, j, 2 * t + 1);
                 }
             }
         }
@@ -242,19 +267,18 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     } else {
         setmaxnreg_inc<216>();
         // ===================================================================== softmax + epilogue
-        const int t = (warp - 4) >> 2;           // query tile of this warpgroup
-        const int quarter = warp & 3;            // TMEM lane quarter this warp may touch
+        const int t = (warp - 4) >> 2;           // query tile of this warp
+        const int quarter = warp & 3;            // TMEM lane quarter this warp may touch (= its SM sub-partition)
         const int row = quarter * 32 + lane;
-        const int wg_tid = threadIdx.x - 128 - t * 128;
-        const uint32_t s_tm = tmem_addr(tmem, quarter * 32, t * 256);
+        const int tile_tid = threadIdx.x - 128 - t * AT_TILE_THREADS;
+        const uint32_t s_tm = tmem_addr(tmem, quarter * 32, t * 256);        // P(j) overwrites the first 32 columns of S(j)
         const uint32_t o_tm = tmem_addr(tmem, quarter * 32, t * 256 + 128);
-        const bool tr0 = TRACE && quarter == 0 && lane == 0;
+        const bool tr0 = TRACE && quarter == AT_TRACE_QUARTER && lane == 0;
 
-        // De-phasing of the two warpgroups (named barriers 1, 2; 256 threads each): warpgroup t may start the
-        // exp2 stream of a tile once the OTHER one is half way through its own, so one group's TMEM loads / row
-        // max / P stores run while the other keeps the MUFU busy, and the two streams overlap by half (a lone
-        // warp per SMSP cannot saturate the MUFU, two can).
-        if (AT_PINGPONG == 2 && t == 1) named_bar_arrive(1, 256);
+        // De-phasing of the two query tiles (named barriers 1, 2): the warps of tile t may start the exp2 stream
+        // of a key tile once the OTHER tile's warps are half way through theirs, so one group's TMEM loads / row
+        // max / P stores run while the other keeps the MUFU busy.
+        if (AT_PINGPONG == 2 && t == 1) named_bar_arrive(1, 2 * AT_TILE_THREADS);
 
         int n = 0;
         for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++n) {
@@ -264,13 +288,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             // epilogue operands that do not depend on the attention: issue their loads now
             {
                 const size_t sidx = (static_cast<size_t>(b) * p.H + h) * AT_D;
-                named_bar_sync(3 + t, 128);          // previous item's epilogue of this warpgroup is done with cst
-                if (wg_tid < AT_D) {
-                    bars->cst[t][0][wg_tid] = p.x_mean[sidx + wg_tid];
-                    bars->cst[t][1][wg_tid] = p.x_rstd[sidx + wg_tid];
-                } else {
+                named_bar_sync(3 + t, AT_TILE_THREADS);   // previous item's epilogue of this tile is done with cst
+                if (tile_tid < AT_D) {
+                    bars->cst[t][0][tile_tid] = p.x_mean[sidx + tile_tid];
+                    bars->cst[t][1][tile_tid] = p.x_rstd[sidx + tile_tid];
+                } else if (tile_tid < 2 * AT_D) {
                     const size_t vidx = (static_cast<size_t>(p.kv_shared ? 0 : b) * p.H + h) * AT_D;
-                    bars->cst[t][2][wg_tid - AT_D] = p.mu_v ? p.mu_v[vidx + wg_tid - AT_D] : 0.f;
+                    bars->cst[t][2][tile_tid - AT_D] = p.mu_v ? p.mu_v[vidx + tile_tid - AT_D] : 0.f;
                 }
             }
             const int nrow = q0 + t * AT_BM + row;
@@ -279,40 +303,109 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             const __nv_bfloat16* xrow = p.x + tok * p.ldx + h * AT_D;
             __nv_bfloat16* orow = p.out + tok * p.ldo + h * AT_D;
 
-            float m_used = -INFINITY, l = 0.f;
-            for (int j = 0; j < T; ++j) {
+            // Online softmax with a LAGGING reference: the weights of key tile j are 2^(s - m) with m the (integer)
+            // reference fixed by the tiles before it; the exact maximum is taken up front for the first tile of an
+            // item only.  For every later tile the row maximum is computed in the shadow of the exp2 stream -- the
+            // MUFU, not the issue port, paces that stream -- and checked BEFORE the weights leave the registers:
+            // only if a row's tile maximum exceeds its reference by more than 2^AT_RESCALE_THRESHOLD does the warp
+            // take the slow path (rescale its part of O, recompute the tile with the new reference).  bf16 / fp32
+            // are floating point, so weights up to 2^64 lose nothing; the threshold only guards the exponent range
+            // (2^64 * |V~|^2 * Ns stays far below 2^127).
+            float m_used = 0.f, l = 0.f;
+            // FIRST is a compile-time tag: the first tile's copy of the code has the maximum in front of the weights,
+            // every other tile has no data dependence between the two (a run-time select would create one)
+            auto key_tile = [&](const int j, auto first_tag) {
+                constexpr bool FIRST = decltype(first_tag)::value;
                 const int g = g0 + j;
-                const uint32_t sb_tm = s_tm + (g & 1) * 64;
                 mbar_wait(&bars->s_full[t][g & 1], (g >> 1) & 1);
                 tc_fence_after();
                 const bool tr = tr0 && n == 0;
                 if (tr) stamp(t, j, 0);
-                uint32_t s[64];
-                tmem_ld_x32(sb_tm, s);
-                tmem_ld_x32(sb_tm + 32, s + 32);
-                tmem_wait_ld();
+                uint32_t s[AT_BN];
+                const int valid = p.Ns - j * AT_BN;               // keys in this tile (tail tile: < 64)
+                auto load_s = [&]() {
+                    tmem_ld_x32(s_tm + (g & 1) * 64, s);
+                    tmem_ld_x32(s_tm + (g & 1) * 64 + 32, s + 32);
+                    tmem_wait_ld();
+                    if (valid < AT_BN) {
+#pragma unroll
+                        for (int i = 0; i < AT_BN; ++i)
+                            if (i >= valid) s[i] = 0xff800000u;   // -inf
+                    }
+                };
+                load_s();
                 if (tr) stamp(t, j, 1);
-                const int valid = p.Ns - j * AT_BN;       // keys in this tile (tail tile: < 64)
-                if (valid < AT_BN) {
+                // row maximum of the tile: 8 independent chains (a single deep FMNMX chain costs ~4 cycles per link)
+                auto tile_max = [&]() {
+                    float mxa[8];
 #pragma unroll
-                    for (int i = 0; i < 64; ++i)
-                        if (i >= valid) s[i] = 0xff800000u;   // -inf
-                }
-                // row max: 8 independent chains (a single deep FMNMX chain costs ~4 cycles per link)
-                float mxa[8];
+                    for (int i = 0; i < 8; ++i) mxa[i] = __uint_as_float(s[i]);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) mxa[i] = __uint_as_float(s[i]);
+                    for (int i = 8; i < AT_BN; ++i) mxa[i & 7] = fmaxf(mxa[i & 7], __uint_as_float(s[i]));
+                    return fmaxf(fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])),
+                                 fmaxf(fmaxf(mxa[4], mxa[5]), fmaxf(mxa[6], mxa[7])));
+                };
+                // The reference is kept INTEGER-valued: rescale factors are exact powers of two and
+                // frac(s - m) = frac(s), which the polynomial path uses.
+                if (FIRST) m_used = ceilf(tile_max());
+                if (AT_PINGPONG == 2) named_bar_sync(1 + t, 2 * AT_TILE_THREADS);
+                if (tr) stamp(t, j, 2);
+
+                // P = exp2(S - m), packed bf16x2.  Packed f32x2 adds (FADD2) for the subtraction and for the row sum.
+                // The row sum uses the ROUNDED weights the MMA sees: with l = sum(p) but M, E built from bf16(p),
+                // Var = E - M^2 picks up eps * M^2 (eps ~ 2^-9) and sqrt() of that is percent-level when the
+                // attention is peaked.
+                uint32_t pk[AT_BN / 2];
+                float l_tile;
+                float mxl[4];                         // this thread's running maxima of the tile, filled by weights()
+                auto weights = [&](bool hand_off) {
+                    const float2 neg_m = make_float2(-m_used, -m_used);
+                    // polynomial path: t = s + (1.5 * 2^23 - m) rounds s to the nearest integer j (m is an integer, so
+                    // the constant is exact) and leaves j - m in the low mantissa bits; f = s - j in [-0.5, 0.5];
+                    // 2^(s - m) = poly(f) with (j - m) added to the exponent field.  s is clamped to m - 125 first so
+                    // the exponent cannot wrap (also turns the -inf of masked tail columns into ~2^-125).
+                    const float magic = 12582912.f - m_used;
+                    const float2 k2 = make_float2(magic, magic), nk2 = make_float2(-magic, -magic);
+                    const float s_min = m_used - 125.f;
+                    float la[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                for (int i = 8; i < 64; ++i) mxa[i & 7] = fmaxf(mxa[i & 7], __uint_as_float(s[i]));
-                const float mx = fmaxf(fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])),
-                                       fmaxf(fmaxf(mxa[4], mxa[5]), fmaxf(mxa[6], mxa[7])));
-                if (j == 0) {
-                    m_used = mx;
-                } else {
+                    for (int i = 0; i < 4; ++i) mxl[i] = -INFINITY;
+#pragma unroll
+                    for (int i = 0; i < AT_BN / 2; ++i) {
+                        float2 sv = make_float2(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1]));
+                        // the tile maximum rides along in the issue slots the MUFU leaves free (FMNMX3)
+                        mxl[i & 3] = fmaxf(fmaxf(mxl[i & 3], sv.x), sv.y);
+                        if ((AT_POLY >> (i & 7)) & 1u) {
+                            sv.x = fmaxf(sv.x, s_min);
+                            sv.y = fmaxf(sv.y, s_min);
+                            const float2 tt = __fadd2_rn(sv, k2);
+                            const float2 f = __ffma2_rn(__fadd2_rn(tt, nk2), make_float2(-1.f, -1.f), sv);
+                            float2 pp = __ffma2_rn(make_float2(AT_EX2_C3, AT_EX2_C3), f, make_float2(AT_EX2_C2, AT_EX2_C2));
+                            pp = __ffma2_rn(pp, f, make_float2(AT_EX2_C1, AT_EX2_C1));
+                            pp = __ffma2_rn(pp, f, make_float2(AT_EX2_C0, AT_EX2_C0));
+                            pk[i] = pack_bf16x2(__int_as_float(__float_as_int(pp.x) + (__float_as_int(tt.x) << 23)),
+                                                __int_as_float(__float_as_int(pp.y) + (__float_as_int(tt.y) << 23)));
+                        } else {
+                            const float2 x = __fadd2_rn(sv, neg_m);
+                            pk[i] = pack_bf16x2(ex2_approx(x.x), ex2_approx(x.y));
+                        }
+                        // row sum of the ROUNDED weights: FHADD.BF16 adds one bf16 half of the packed word to an f32
+                        la[(2 * i) & 3] = add_f32_bf16_lo(la[(2 * i) & 3], pk[i]);
+                        la[(2 * i + 1) & 3] = add_f32_bf16_hi(la[(2 * i + 1) & 3], pk[i]);
+                        // half way: let the other tile's warps start their stream (not after the very last tile of the CTA)
+                        if (AT_PINGPONG == 2 && hand_off && i == AT_BN / 4 - 1 && !(t == 1 && last_item && j == T - 1))
+                            named_bar_arrive(2 - t, 2 * AT_TILE_THREADS);
+                    }
+                    l_tile = (la[0] + la[1]) + (la[2] + la[3]);
+                };
+                weights(true);
+                if (!FIRST) {
+                    const float mx = fmaxf(fmaxf(mxl[0], mxl[1]), fmaxf(mxl[2], mxl[3]));
                     const bool grow = mx > m_used + AT_RESCALE_THRESHOLD;
                     if (__any_sync(0xffffffffu, grow)) {
-                        const float m_new = grow ? mx : m_used;
-                        const float sc = ex2_approx(m_used - m_new);    // 1 for rows that keep their max
+                        // slow path (rare): new reference for the rows that grew, O and l brought to it, weights redone
+                        const float m_new = grow ? ceilf(mx) : m_used;
+                        const float sc = ex2_approx(m_used - m_new);    // 1 for rows that keep their reference
                         l *= sc;
                         m_used = m_new;
                         // O_t may only be touched once PV_t(g-1) has retired; PV_t(g) cannot start before our P arrives
@@ -327,49 +420,31 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                             for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * sc);
                             tmem_st_x32(o_tm + c, o);
                         }
+                        load_s();                       // S is still intact in TMEM: P has not been stored yet
+                        weights(false);
                     }
                 }
-                if (AT_PINGPONG == 2) named_bar_sync(1 + t, 256);
-                if (tr) stamp(t, j, 2);
-                // P = exp2(S - m), packed bf16x2, written over the first 32 columns of this S buffer.
-                // Packed f32x2 adds (FADD2) for the subtraction and for the row sum; four independent sum chains.
-                // The row sum uses the ROUNDED weights the MMA sees: with l = sum(p) but M, E built from bf16(p),
-                // Var = E - M^2 picks up eps * M^2 (eps ~ 2^-9) and sqrt() of that is percent-level when the
-                // attention is peaked.
-                const float2 neg_m = make_float2(-m_used, -m_used);
-                float2 la = make_float2(0.f, 0.f), lb = make_float2(0.f, 0.f);
+                l += l_tile;
 #pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    uint32_t pk[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const float2 x = __fadd2_rn(make_float2(__uint_as_float(s[c * 32 + 2 * i]),
-                                                                __uint_as_float(s[c * 32 + 2 * i + 1])), neg_m);
-                        pk[i] = pack_bf16x2(ex2_approx(x.x), ex2_approx(x.y));
-                        const float2 r = make_float2(bf16_lo(pk[i]), bf16_hi(pk[i]));
-                        if (i & 1) la = __fadd2_rn(la, r); else lb = __fadd2_rn(lb, r);
-                    }
-                    tmem_st_x16(sb_tm + c * 16, pk);
-                    // half way: let the other warpgroup start its stream (not after the very last tile of the CTA)
-                    if (AT_PINGPONG == 2 && c == 0 && !(t == 1 && last_item && j == T - 1)) named_bar_arrive(2 - t, 256);
-                }
-                l += (la.x + la.y) + (lb.x + lb.y);
+                for (int c = 0; c < AT_BN / 2; c += 16) tmem_st_x16(s_tm + (g & 1) * 64 + c, pk + c);
                 if (tr) stamp(t, j, 3);
                 tmem_wait_st();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bars->p_ready[t][g & 1]);
                 if (tr) stamp(t, j, 4);
-            }
+            };
+            key_tile(0, std::true_type{});
+            for (int j = 1; j < T; ++j) key_tile(j, std::false_type{});
 
             // ---- epilogue: O/l -> (M~, E~) -> sqrt(max(E~ - M~^2, 1e-6)) * IN(fcs) + M~ + mu_v
             // The fcs row is fetched before waiting for the last PV, so its latency hides behind the MMA tail.
-            uint4 xv[8];
+            uint4 xv[AT_D / 8];
             if (row_ok) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) xv[i] = __ldg(reinterpret_cast<const uint4*>(xrow) + i);
+                for (int i = 0; i < AT_D / 8; ++i) xv[i] = __ldg(reinterpret_cast<const uint4*>(xrow) + i);
             }
-            named_bar_sync(3 + t, 128);              // cst[t] of this item is complete
+            named_bar_sync(3 + t, AT_TILE_THREADS);  // cst[t] of this item is complete
             // (pv_done cannot be used here: a parity wait is only meaningful while the barrier is at most one
             // phase ahead, and a late warp may find both PV(T-2) and PV(T-1) retired -- o_full has one phase per item)
             mbar_wait(&bars->o_full[t], n & 1);

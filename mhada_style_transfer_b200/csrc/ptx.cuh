@@ -18,6 +18,12 @@ namespace mh {
 #define MHADA_WAIT_TIMEOUT_NS 4000000000ull   // an mbarrier wait that lasts 4 s traps (never hang a box)
 #endif
 
+// suspend-time hint of mbarrier.try_wait: the waiting thread is parked by the hardware until the phase completes
+// (or the hint expires) instead of spinning in the issue slots its sub-partition shares with the softmax warps
+#ifndef MHADA_TRY_WAIT_HINT
+#define MHADA_TRY_WAIT_HINT 1000000u
+#endif
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
@@ -56,10 +62,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred P;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
         "selp.b32 %0, 1, 0, P;\n\t}"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(MHADA_TRY_WAIT_HINT)
         : "memory");
     return ok != 0;
 }
@@ -235,6 +241,21 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     uint32_t r;
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
     return r;
+}
+// f32 + one bf16 half of a packed word in ONE instruction (FHADD.BF16 with an .H0 / .H1 operand selector)
+__device__ __forceinline__ float add_f32_bf16_lo(float acc, uint32_t packed) {
+    asm("{\n\t.reg .b16 lo, hi;\n\t"
+        "mov.b32 {lo, hi}, %1;\n\t"
+        "add.rn.f32.bf16 %0, lo, %0;\n\t}"
+        : "+f"(acc) : "r"(packed));
+    return acc;
+}
+__device__ __forceinline__ float add_f32_bf16_hi(float acc, uint32_t packed) {
+    asm("{\n\t.reg .b16 lo, hi;\n\t"
+        "mov.b32 {lo, hi}, %1;\n\t"
+        "add.rn.f32.bf16 %0, hi, %0;\n\t}"
+        : "+f"(acc) : "r"(packed));
+    return acc;
 }
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }

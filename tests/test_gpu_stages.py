@@ -176,18 +176,23 @@ def test_attn_f32(B, H, Nc, Ns, dqk, dv):
     assert e["max_abs_rel"] < 2e-5, e
 
 
-@pytest.mark.parametrize("B,H,Nc,Ns,gain", [(1, 1, 128, 128, 0.5), (1, 1, 256, 128, 0.5), (1, 1, 128, 384, 0.5),
-                                            (2, 8, 256, 256, 0.6), (1, 8, 135, 143, 0.6), (1, 2, 300, 1000, 0.6),
-                                            (1, 2, 512, 700, 2.0), (1, 8, 4096, 4096, 0.6), (1, 1, 70, 1, 0.6)])
-def test_attn_bf16(B, H, Nc, Ns, gain):
+@pytest.mark.parametrize("B,H,Nc,Ns,gain,ramp", [(1, 1, 128, 128, 0.5, 0), (1, 1, 256, 128, 0.5, 0), (1, 1, 128, 384, 0.5, 0),
+                                                 (2, 8, 256, 256, 0.6, 0), (1, 8, 135, 143, 0.6, 0), (1, 2, 300, 1000, 0.6, 0),
+                                                 (1, 2, 512, 700, 2.0, 0), (1, 8, 4096, 4096, 0.6, 0), (1, 1, 70, 1, 0.6, 0),
+                                                 (1, 2, 300, 700, 0.6, 4.0), (2, 2, 256, 1000, 1.0, 1.0)])
+def test_attn_bf16(B, H, Nc, Ns, gain, ramp):
     """tcgen05 kernel against a float64 evaluation on the SAME bf16-rounded operands: what is left is
-    the bf16 rounding of P, fp32 accumulation and the bf16 output rounding."""
+    the bf16 rounding of P, fp32 accumulation and the bf16 output rounding.  ramp > 0: keys of later tiles are
+    scaled up (x(1 + ramp) per 64 keys), so row maxima jump by hundreds of log2 units from one key tile to the
+    next -- the kernel's reference-update (rescale + redo) path."""
     L = _lib.lib()
     d = 64
     C = H * d
     bf = lambda a: torch.from_numpy(a).float().to(G.DEV).to(torch.bfloat16).contiguous()
     q = synth.bellish(11, (B, Nc, C), 0, gain)          # log2 units: logits std ~ gain^2 * 8
     k = synth.bellish(12, (B, Ns, C), 0, gain)
+    if ramp:
+        k = k * (1.0 + ramp * (np.arange(Ns) // 64))[None, :, None]
     vt = synth.bellish(13, (B, Ns, H, d), 0, 40.0)
     x = synth.bellish(14, (B, Nc, C), 2.0, 30.0)
     muv = synth.uniform(15, (B, C), -3, 3)
