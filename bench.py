@@ -236,10 +236,24 @@ def main():
             style = model.precompute_style(fs_d)        # once per style, outside the per-frame steps
         fs_h = []                                       # the style does not travel per step
 
+    # The only collective on the path is the gather of the decoded images to rank 0.  It runs on a side stream so
+    # that step i's gather (NCCL over NVLink) overlaps step i+1's kernels; the timed region ends only after the
+    # last gather has completed (the compute stream waits for the side stream before the closing event).
+    comm_stream = torch.cuda.Stream(device) if world > 1 else None
+
+    def gather_async(cs):
+        ready = torch.cuda.Event()
+        ready.record()
+        with torch.cuda.stream(comm_stream):
+            comm_stream.wait_event(ready)
+            c = cs.contiguous()
+            cs.record_stream(comm_stream)
+            dist.gather(c, gather_buf, dst=0)
+
     def step_device():
         fcs, cs = model(fc_d, style if style is not None else fs_d)
         if world > 1:
-            dist.gather(cs.contiguous(), gather_buf, dst=0)     # the only collective: final gather over NVLink
+            gather_async(cs)
         return cs
 
     out_shape = (B, 3, 8 * wl["hw"][0], 8 * wl["hw"][1])
@@ -273,7 +287,7 @@ def main():
         fcs, cs = model([t.permute(0, 3, 1, 2) for t in fc],
                         style if style is not None else [t.permute(0, 3, 1, 2) for t in fs])
         if world > 1:
-            dist.gather(cs.contiguous(), gather_buf, dst=0)
+            gather_async(cs)
         cs_host[i & 1].copy_(cs, non_blocking=True)        # D2H of the decoded images
         e2e_state["i"] = i + 1
         return cs
@@ -292,6 +306,8 @@ def main():
             e0.record()
             for _ in range(steps):
                 fn()
+            if comm_stream is not None:
+                torch.cuda.current_stream().wait_stream(comm_stream)
             e1.record()
             torch.cuda.synchronize()
             if world > 1:
@@ -363,7 +379,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": wl["dtype"], "data": "synthetic",
             "config": {"workload": wl["desc"], "images_per_gpu_per_step": B, "tokens": [Nc, Ns], "heads": H,
-                       "channels": C, "layers": 2 * LAYERS, "sharding": "by image, one process per GPU, final gather",
+                       "channels": C, "layers": 2 * LAYERS, "sharding": "by image, one process per GPU, gather of the decoded images to rank 0 (side stream, overlapped)",
                        "l2": f"inputs {h2d / 1e6:.0f} MB/step + {L.mhada_layer_workspace(_lib.BF16 if esz == 2 else _lib.F32, B, Nc, Ns, C, H) / 1e6:.0f} MB workspace exceed the 126 MB L2"},
             "e2e": {"value": round(e2e_value, 2), "unit": "images/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": round(ms_e2e / args.steps, 4)},
