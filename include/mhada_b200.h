@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define MHADA_ABI_VERSION 3
+#define MHADA_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define MHADA_API __attribute__((visibility("default")))
@@ -44,6 +44,7 @@ extern "C" {
 typedef void* mhada_stream_t; /* cudaStream_t */
 
 enum mhada_dtype { MHADA_F32 = 0, MHADA_BF16 = 1 };
+enum mhada_activation { MHADA_ACT_SOFTMAX = 0, MHADA_ACT_COSINE = 1 };
 
 enum mhada_status {
     MHADA_OK = 0,
@@ -122,6 +123,8 @@ typedef struct mhada_attn_args {
     int kv_batch;        /* batch of k / v / mu_v (/ k_mean, k_rstd): 0 or B = one per image; 1 = one style shared by
                             all B images (the reference cannot do this, adaDecoder.py:177-183; infer_video.py uses one
                             style for every frame) */
+    int activation;      /* MHADA_ACT_SOFTMAX (Softmax, adaDecoder.py:11-17) or MHADA_ACT_COSINE (CosineSimilarity,
+                            adaDecoder.py:20-34: a = (cos(q, k) + 1) / sum_k (cos(q, k) + 1)); cosine is f32-path only */
 } mhada_attn_args;
 MHADA_API int mhada_attn(const mhada_attn_args* args, mhada_stream_t stream);
 
@@ -146,6 +149,7 @@ MHADA_API int mhada_linear(int dtype, const void* x, int ldx, const float* w, co
  *     (the two layers of a level share fs, adaDecoder.py:264-265): its statistics are not recomputed.
  * ---------------------------------------------------------------------------------------------- */
 #define MHADA_REUSE_FS_STATS 1
+#define MHADA_LAYER_COSINE 2   /* activation = "cosine" (adaDecoder.py:155-160); MHADA_F32 only */
 MHADA_API size_t mhada_layer_workspace(int dtype, int B, int Nc, int Ns, int C, int H);
 MHADA_API int mhada_layer_forward(int dtype, const void* fc, const void* fs, const void* fcs, const float* w_fgh,
                         const float* b_fgh, const float* w_out, const float* b_out, int B, int Nc, int Ns, int C,
@@ -166,8 +170,8 @@ MHADA_API int mhada_style_precompute(int dtype, const void* fs, const float* w_f
                                      mhada_stream_t stream);
 MHADA_API int mhada_layer_forward_cached(int dtype, const void* fc, const void* fcs, const void* cache, int Bs,
                                          const float* w_fgh, const float* b_fgh, const float* w_out,
-                                         const float* b_out, int B, int Nc, int Ns, int C, int H, void* out, void* ws,
-                                         size_t ws_bytes, mhada_stream_t stream);
+                                         const float* b_out, int B, int Nc, int Ns, int C, int H, int flags, void* out,
+                                         void* ws, size_t ws_bytes, mhada_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * (5b) Decoder glue -- replaces nn.ReflectionPad2d(1) (MHAdaSTr/network/conv.py:26-27) and, when

@@ -13,9 +13,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libmhada_b200.so")
 
 F32, BF16 = 0, 1
-ABI_VERSION = 3
+ABI_VERSION = 4
 PROJ_Q, PROJ_KV = 1, 2
 REUSE_FS_STATS = 1
+LAYER_COSINE = 2
+ACT_SOFTMAX, ACT_COSINE = 0, 1
 
 
 class AttnArgs(ctypes.Structure):
@@ -28,6 +30,7 @@ class AttnArgs(ctypes.Structure):
         ("x_mean", c_void_p), ("x_rstd", c_void_p), ("mu_v", c_void_p),
         ("q_mean", c_void_p), ("q_rstd", c_void_p), ("k_mean", c_void_p), ("k_rstd", c_void_p),
         ("kv_batch", c_int),
+        ("activation", c_int),
     ]
 
 
@@ -56,8 +59,8 @@ SIGNATURES = {
     "mhada_style_precompute": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_size_t,
                                        c_void_p, c_size_t, c_void_p]),
     "mhada_layer_forward_cached": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
-                                           c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t,
-                                           c_void_p]),
+                                           c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                           c_size_t, c_void_p]),
     "mhada_pad_reflect": (c_int, [c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "mhada_layer_workspace": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "mhada_layer_forward": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -128,6 +128,8 @@ int layer_impl(const char* who, int dtype, const void* fc, const void* fs, const
     if (dtype == MHADA_BF16)
         REQUIRE(d == 64, MHADA_ERR_UNSUPPORTED,
                 "%s: the bf16 tensor-core path implements head_dim 64 (C/H = %d); use MHADA_F32", who, d);
+    REQUIRE(!(flags & MHADA_LAYER_COSINE) || dtype == MHADA_F32, MHADA_ERR_UNSUPPORTED,
+            "%s: the cosine activation (adaDecoder.py:20-34) runs on the MHADA_F32 path only", who);
     REQUIRE(aligned16(fc) && (!fs || aligned16(fs)) && aligned16(fcs) && aligned32(out) && aligned32(ws), MHADA_ERR_ARG,
             "%s: inputs must be 16-byte aligned, out and ws 32-byte aligned", who);
     if (dtype == MHADA_BF16) REQUIRE(C % 16 == 0, MHADA_ERR_ARG, "%s: bf16 path needs C %% 16 == 0", who);
@@ -179,6 +181,7 @@ int layer_impl(const char* who, int dtype, const void* fc, const void* fs, const
     a.ldq = C; a.ldk = C; a.ldv = dtype == MHADA_BF16 ? 2 * C : C; a.ldx = C; a.ldo = C;
     a.x_mean = mean_x; a.x_rstd = rstd_x; a.mu_v = cache ? cv.mu_v : w.mu_v;
     a.kv_batch = cache ? Bs : B;
+    a.activation = (flags & MHADA_LAYER_COSINE) ? MHADA_ACT_COSINE : MHADA_ACT_SOFTMAX;
     if (int e = attn_dispatch(a, s)) return e;
     // (4) out_conv                                                           adaDecoder.py:202-205
     if (w_out) {
@@ -284,6 +287,10 @@ int mhada_attn(const mhada_attn_args* a, mhada_stream_t stream) {
     REQUIRE(a->q && a->k && a->v && a->x && a->out && a->x_mean && a->x_rstd, MHADA_ERR_ARG, "mhada_attn: null pointer");
     REQUIRE(a->B > 0 && a->H > 0 && a->Nc > 0 && a->Ns > 0 && a->dqk > 0 && a->dv > 0, MHADA_ERR_ARG,
             "mhada_attn: bad sizes");
+    REQUIRE(a->activation == MHADA_ACT_SOFTMAX || a->activation == MHADA_ACT_COSINE, MHADA_ERR_ARG,
+            "mhada_attn: unknown activation %d", a->activation);
+    REQUIRE(a->activation == MHADA_ACT_SOFTMAX || a->dtype == MHADA_F32, MHADA_ERR_UNSUPPORTED,
+            "mhada_attn: the cosine activation runs on the MHADA_F32 path only");
     REQUIRE(a->kv_batch == 0 || a->kv_batch == 1 || a->kv_batch == a->B, MHADA_ERR_ARG,
             "mhada_attn: kv_batch must be 0, 1 or B");
     REQUIRE((a->q_mean == nullptr) == (a->q_rstd == nullptr) && (a->k_mean == nullptr) == (a->k_rstd == nullptr),
@@ -375,12 +382,12 @@ int mhada_layer_forward(int dtype, const void* fc, const void* fs, const void* f
 
 int mhada_layer_forward_cached(int dtype, const void* fc, const void* fcs, const void* cache, int Bs,
                                const float* w_fgh, const float* b_fgh, const float* w_out, const float* b_out, int B,
-                               int Nc, int Ns, int C, int H, void* out, void* ws, size_t ws_bytes,
+                               int Nc, int Ns, int C, int H, int flags, void* out, void* ws, size_t ws_bytes,
                                mhada_stream_t stream) {
     REQUIRE(cache && aligned32(cache), MHADA_ERR_ARG, "mhada_layer_forward_cached: cache must be a 32-byte aligned pointer");
     REQUIRE(Bs == 1 || Bs == B, MHADA_ERR_ARG, "mhada_layer_forward_cached: style batch %d must be 1 or the content batch %d", Bs, B);
     return layer_impl("mhada_layer_forward_cached", dtype, fc, nullptr, fcs, cache, Bs, w_fgh, b_fgh, w_out, b_out, B, Nc, Ns,
-                      C, H, 0, out, ws, ws_bytes, stream);
+                      C, H, flags & ~MHADA_REUSE_FS_STATS, out, ws, ws_bytes, stream);
 }
 
 int mhada_style_precompute(int dtype, const void* fs, const float* w_fgh, const float* b_fgh, int Bs, int Ns, int C,

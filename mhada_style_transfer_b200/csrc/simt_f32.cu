@@ -169,6 +169,10 @@ struct AttnF32Params {
     int kv_shared;   // 1: one K / V / mu_v set (style) serves every image of the batch
 };
 
+// COSINE = false: A = softmax(Q K^T)                                   (Softmax, adaDecoder.py:11-17)
+// COSINE = true : A = (cos(q_i, k_j) + 1) / sum_j (cos(q_i, k_j) + 1)   (CosineSimilarity, adaDecoder.py:20-34);
+//                 |q_i|^2 and |k_j|^2 are accumulated next to the dot products, no running maximum is needed.
+template <bool COSINE>
 __global__ void __launch_bounds__(256) attn_f32_kernel(const AttnF32Params p) {
     __shared__ float Ps[TILE][TILE + 1];
     __shared__ union {
@@ -205,6 +209,7 @@ __global__ void __launch_bounds__(256) attn_f32_kernel(const AttnF32Params p) {
     for (int k0 = 0; k0 < p.Ns; k0 += TILE) {
         // ---- S = Q K^T for this key tile
         float s[4][4], sc[4][4];
+        float qq[4] = {0.f, 0.f, 0.f, 0.f}, kk2[4] = {0.f, 0.f, 0.f, 0.f};      // squared norms (COSINE)
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -245,6 +250,13 @@ __global__ void __launch_bounds__(256) attn_f32_kernel(const AttnF32Params p) {
                     for (int i = 0; i < 4; ++i)
 #pragma unroll
                         for (int j = 0; j < 4; ++j) part[i][j] = fmaf(a[i], bb[j], part[i][j]);
+                    if (COSINE) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            qq[i] = fmaf(a[i], a[i], qq[i]);
+                            kk2[i] = fmaf(bb[i], bb[i], kk2[i]);
+                        }
+                    }
                 }
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
@@ -253,9 +265,25 @@ __global__ void __launch_bounds__(256) attn_f32_kernel(const AttnF32Params p) {
             }
             __syncthreads();
         }
+        if (COSINE) {
+            // ---- weights cos + 1 (>= 0): plain running sums, nothing to rescale
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float rs = 0.f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float e = k0 + tx + 16 * j < p.Ns ? s[i][j] / (sqrtf(qq[i]) * sqrtf(kk2[j])) + 1.f : 0.f;
+                    rs += e;
+                    Ps[ty + 16 * i][tx + 16 * j] = e;
+                }
+#pragma unroll
+                for (int o = 8; o >= 1; o >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, o);
+                lrow[i] += rs;
+            }
+        }
         // ---- online softmax (rows are shared by the 16 threads with equal ty = one half warp)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < 4 && !COSINE; ++i) {
             float mx = -INFINITY;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -358,7 +386,10 @@ int launch_attn_f32(const mhada_attn_args& a, cudaStream_t s) {
     p.ldq = a.ldq; p.ldk = a.ldk; p.ldv = a.ldv; p.ldx = a.ldx; p.ldo = a.ldo;
     p.kv_shared = (a.kv_batch == 1 && a.B > 1) ? 1 : 0;
     dim3 grid((a.Nc + TILE - 1) / TILE, (a.dv + TILE - 1) / TILE, a.B * a.H);
-    attn_f32_kernel<<<grid, 256, 0, s>>>(p);
+    if (a.activation == MHADA_ACT_COSINE)
+        attn_f32_kernel<true><<<grid, 256, 0, s>>>(p);
+    else
+        attn_f32_kernel<false><<<grid, 256, 0, s>>>(p);
     count_launch();
     return check_cuda(cudaGetLastError(), "attn_f32 launch");
 }

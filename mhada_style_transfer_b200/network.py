@@ -83,7 +83,7 @@ def _instance_norm_torch(x):                       # x [..., N]: per-row statist
     return (x - mu) * torch.rsqrt(var + 1e-5)
 
 
-def _layer_math_torch(fc, fs, fcs, wf, bf, wg, bg, wh, bh, wo, bo, num_heads: int):
+def _layer_math_torch(fc, fs, fcs, wf, bf, wg, bg, wh, bh, wo, bo, num_heads: int, cosine: bool = False):
     """Differentiable fp32 PyTorch restatement of one layer (adaDecoder.py:162-206), used ONLY by the backward of
     _MhadaLayerFn (recompute-and-differentiate).  matmul / einsum only: no TF32 on the default settings."""
     B, C, h, w = fc.shape
@@ -96,7 +96,12 @@ def _layer_math_torch(fc, fs, fcs, wf, bf, wg, bg, wh, bh, wo, bo, num_heads: in
         q = torch.matmul(wf[i], _instance_norm_torch(xc[:, i])) + bf[i][None, :, None]        # [B,d,Nc]
         k = torch.matmul(wg[i], _instance_norm_torch(xs[:, i])) + bg[i][None, :, None]        # [B,d,Ns]
         v = (torch.matmul(wh[i], xs[:, i]) + bh[i][None, :, None]).transpose(1, 2)            # [B,Ns,d]
-        a = torch.softmax(torch.matmul(q.transpose(1, 2), k), dim=-1)                         # [B,Nc,Ns]
+        logits = torch.matmul(q.transpose(1, 2), k)                                           # [B,Nc,Ns]
+        if cosine:                                                                            # adaDecoder.py:29-33
+            sim = logits / (q.norm(dim=1).unsqueeze(2) * k.norm(dim=1).unsqueeze(1)) + 1
+            a = sim / sim.sum(dim=-1, keepdim=True)
+        else:
+            a = torch.softmax(logits, dim=-1)
         m = torch.matmul(a, v)
         var = torch.matmul(a, v * v) - m * m
         sd = torch.sqrt(var.clamp(min=1e-6))
@@ -111,8 +116,8 @@ class _MhadaLayerFn(torch.autograd.Function):
     """Forward: the CUDA kernels.  Backward: recompute with _layer_math_torch in fp32 and differentiate."""
 
     @staticmethod
-    def forward(ctx, run_forward, num_heads, has_out, fc, fs, fcs, wf, bf, wg, bg, wh, bh, wo, bo):
-        ctx.num_heads, ctx.has_out = num_heads, has_out
+    def forward(ctx, run_forward, num_heads, has_out, cosine, fc, fs, fcs, wf, bf, wg, bg, wh, bh, wo, bo):
+        ctx.num_heads, ctx.has_out, ctx.cosine = num_heads, has_out, cosine
         ctx.save_for_backward(fc, fs, fcs, wf, bf, wg, bg, wh, bh, wo, bo)
         with torch.no_grad():
             return run_forward(fc, fs, fcs)
@@ -124,13 +129,13 @@ class _MhadaLayerFn(torch.autograd.Function):
             leaves = [t.detach().float().requires_grad_(True) for t in saved]
             fc, fs, fcs, wf, bf, wg, bg, wh, bh, wo, bo = leaves
             out = _layer_math_torch(fc, fs, fcs, wf, bf, wg, bg, wh, bh, wo if ctx.has_out else None,
-                                    bo if ctx.has_out else None, ctx.num_heads)
-            need = [i for i, ng in enumerate(ctx.needs_input_grad[3:]) if ng and (ctx.has_out or i < 9)]
+                                    bo if ctx.has_out else None, ctx.num_heads, ctx.cosine)
+            need = [i for i, ng in enumerate(ctx.needs_input_grad[4:]) if ng and (ctx.has_out or i < 9)]
             grads = torch.autograd.grad(out, [leaves[i] for i in need], grad_out.float(), allow_unused=True)
         full = [None] * len(leaves)
         for i, g in zip(need, grads):
             full[i] = None if g is None else g.to(saved[i].dtype)
-        return (None, None, None, *full)
+        return (None, None, None, None, *full)
 
 
 def _token_major(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
@@ -153,7 +158,19 @@ def _code(dtype: torch.dtype) -> int:
     return _lib.BF16 if dtype == torch.bfloat16 else _lib.F32
 
 
-def _resolve_precision(precision: str, head_dim: int, *inputs) -> torch.dtype:
+def _is_cosine(activation) -> bool:
+    return isinstance(activation, CosineSimilarity)
+
+
+def _resolve_precision(precision: str, head_dim: int, *inputs, activation=None) -> torch.dtype:
+    if activation is not None and _is_cosine(activation):
+        if precision == "bf16":
+            raise NotImplementedError("activation='cosine' runs on the fp32 kernels only; use precision 'auto' or 'fp32'")
+        return torch.float32
+    return _resolve_precision_softmax(precision, head_dim, *inputs)
+
+
+def _resolve_precision_softmax(precision: str, head_dim: int, *inputs) -> torch.dtype:
     if precision not in ("auto", "fp32", "bf16"):
         raise ValueError(f"Unknown precision: {precision}")
     if precision == "fp32":
@@ -217,7 +234,7 @@ def _style_precompute(dt: torch.dtype, tfs: torch.Tensor, w_fgh, b_fgh, num_head
 
 
 def _layer_forward_cached(dt, tfc, tfcs, cache: torch.Tensor, Bs: int, Ns: int, w_fgh, b_fgh, w_out, b_out,
-                          num_heads: int):
+                          num_heads: int, flags: int = 0):
     L = _lib.lib()
     B, h, w, C = tfc.shape
     Nc = h * w
@@ -226,8 +243,8 @@ def _layer_forward_cached(dt, tfc, tfcs, cache: torch.Tensor, Bs: int, Ns: int, 
     ws = _workspace(tfc.device, L.mhada_layer_workspace(code, B, Nc, Ns, C, num_heads))
     with torch.cuda.device(tfc.device):
         rc = L.mhada_layer_forward_cached(code, _ptr(tfc), _ptr(tfcs), _ptr(cache), Bs, _ptr(w_fgh), _ptr(b_fgh),
-                                          _ptr(w_out), _ptr(b_out), B, Nc, Ns, C, num_heads, _ptr(out), _ptr(ws),
-                                          ws.numel(), _stream())
+                                          _ptr(w_out), _ptr(b_out), B, Nc, Ns, C, num_heads, flags, _ptr(out),
+                                          _ptr(ws), ws.numel(), _stream())
     _lib.check("mhada_layer_forward_cached", rc)
     return out
 
@@ -270,11 +287,12 @@ class Softmax(nn.Module):
 
 
 class CosineSimilarity(nn.Module):
-    """Marker for the 'cosine' activation (adaDecoder.py:20-34); accepted by the constructors like the
-    reference, not implemented by the kernels yet (no reference script uses it)."""
+    """Marker for the 'cosine' activation (adaDecoder.py:20-34): a = (cos(q, k) + 1) / sum_k (cos(q, k) + 1).
+    Runs on the fp32 kernels (attn_f32_kernel<COSINE>); no reference script uses it, so there is no
+    tensor-core variant."""
 
-    def forward(self, q, k):  # pragma: no cover
-        raise NotImplementedError("activation='cosine' is not implemented on the B200 path yet")
+    def forward(self, q, k):  # pragma: no cover - the attention map is never materialised on this path
+        raise RuntimeError("the N x N attention map is never materialised on the B200 path")
 
 
 def _make_activation(activation: str) -> nn.Module:
@@ -286,8 +304,12 @@ def _make_activation(activation: str) -> nn.Module:
 
 
 def _check_activation(m: nn.Module):
-    if isinstance(m, CosineSimilarity):
-        raise NotImplementedError("activation='cosine' is not implemented on the B200 path yet")
+    if not isinstance(m, (Softmax, CosineSimilarity)):
+        raise ValueError(f"Unknown activation module: {type(m).__name__}")
+
+
+def _act_flags(m: nn.Module) -> int:
+    return _lib.LAYER_COSINE if _is_cosine(m) else 0
 
 
 # ------------------------------------------------------------------------------------------------
@@ -335,6 +357,7 @@ class AdaAttnForLoss(nn.Module):
             a.k_mean, a.k_rstd = stats[2].data_ptr(), stats[3].data_ptr()
             a.x_mean, a.x_rstd = stats[4].data_ptr(), stats[5].data_ptr()
             a.mu_v = None
+            a.activation = _lib.ACT_COSINE if _is_cosine(self.activation) else _lib.ACT_SOFTMAX
             _lib.check("mhada_attn", L.mhada_attn(ctypes.byref(a), st))
         res = out.permute(0, 3, 1, 2)
         return res if res.dtype == c_x.dtype else res.to(c_x.dtype)
@@ -361,11 +384,11 @@ class AdaAttN(nn.Module):
         _require_cuda(fc, fs, fcs)
         _no_autograd(self, fc, fs, fcs)
         _check_activation(self.activation)
-        dt = _resolve_precision(self.precision, fc.shape[1], fc, fs, fcs)
+        dt = _resolve_precision(self.precision, fc.shape[1], fc, fs, fcs, activation=self.activation)
         w, b, _, _ = self._packed.get([[self.f], [self.g], [self.h]], None)
         tfc, tfs = _token_major(fc, dt), _token_major(fs, dt)
         tfcs = tfc if _same_tensor(fc, fcs) else _token_major(fcs, dt)
-        out = _layer_forward(dt, tfc, tfs, tfcs, w, b, None, None, 1).permute(0, 3, 1, 2)
+        out = _layer_forward(dt, tfc, tfs, tfcs, w, b, None, None, 1, flags=_act_flags(self.activation)).permute(0, 3, 1, 2)
         return out if out.dtype == fc.dtype else out.to(fc.dtype)
 
 
@@ -413,7 +436,7 @@ class AdaAttnMultiHead(nn.Module):
         reuse_fs_stats: `tfs` is the tensor the previous layer call on this stream used (same workspace)."""
         w, b, wo, bo = self.packed_weights()
         return _layer_forward(dt, tfc, tfs, tfcs, w, b, wo, bo, self.num_heads, out,
-                              _lib.REUSE_FS_STATS if reuse_fs_stats else 0)
+                              (_lib.REUSE_FS_STATS if reuse_fs_stats else 0) | _act_flags(self.activation))
 
     def precompute_style_tokens(self, dt, tfs) -> torch.Tensor:
         """K, V', mu_v of this layer for token-major style features (one uint8 cache buffer)."""
@@ -422,7 +445,8 @@ class AdaAttnMultiHead(nn.Module):
 
     def forward_tokens_cached(self, dt, tfc, tfcs, cache: torch.Tensor, style_batch: int, style_tokens: int):
         w, b, wo, bo = self.packed_weights()
-        return _layer_forward_cached(dt, tfc, tfcs, cache, style_batch, style_tokens, w, b, wo, bo, self.num_heads)
+        return _layer_forward_cached(dt, tfc, tfcs, cache, style_batch, style_tokens, w, b, wo, bo, self.num_heads,
+                                     _act_flags(self.activation))
 
     def _stacked_params(self):
         d = self.head_dim
@@ -439,11 +463,12 @@ class AdaAttnMultiHead(nn.Module):
         if _needs_grad(self, fc, fs, fcs):
             # kernels forward, PyTorch recompute backward (module docstring); torch.stack keeps the graph to the
             # per-head Conv2d parameters
-            return _MhadaLayerFn.apply(self._forward_nograd, self.num_heads, True, fc, fs, fcs, *self._stacked_params())
+            return _MhadaLayerFn.apply(self._forward_nograd, self.num_heads, True, _is_cosine(self.activation), fc, fs, fcs,
+                                       *self._stacked_params())
         return self._forward_nograd(fc, fs, fcs)
 
     def _forward_nograd(self, fc, fs, fcs):
-        dt = _resolve_precision(self.precision, self.head_dim, fc, fs, fcs)
+        dt = _resolve_precision(self.precision, self.head_dim, fc, fs, fcs, activation=self.activation)
         tfc, tfs = _token_major(fc, dt), _token_major(fs, dt)
         tfcs = tfc if _same_tensor(fc, fcs) else _token_major(fcs, dt)
         out = self.forward_tokens(dt, tfc, tfs, tfcs).permute(0, 3, 1, 2)
@@ -607,7 +632,7 @@ class AdaAttnTransformerMultiHead(nn.Module):
         _no_autograd(self, *fs)
         L0 = self.adaAttnHead[0]
         _check_activation(L0.activation)
-        dt = _resolve_precision(precision or self.precision, L0.head_dim, *fs[: self.num_layers])
+        dt = _resolve_precision(precision or self.precision, L0.head_dim, *fs[: self.num_layers], activation=L0.activation)
         bufs = []
         Bs, C, hs, ws_ = fs[0].shape
         for i in range(self.num_layers):
@@ -663,7 +688,8 @@ class AdaAttnTransformerMultiHead(nn.Module):
                 fcs = self.adaAttnHead[2 * i + 1](fcs, fs[i], fcs)
             return fcs, self.decoder(fcs)
         in_dtype = fc[0].dtype
-        dt = _resolve_precision(self.precision, L0.head_dim, *fc[: self.num_layers], *fs[: self.num_layers])
+        dt = _resolve_precision(self.precision, L0.head_dim, *fc[: self.num_layers], *fs[: self.num_layers],
+                                activation=L0.activation)
         tfc = [_token_major(t, dt) for t in fc[: self.num_layers]]
         tfs = [_token_major(t, dt) for t in fs[: self.num_layers]]
         fcs = tfc[0]                                                         # :262

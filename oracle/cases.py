@@ -29,10 +29,16 @@ LAYER_CASES = [
     dict(name="layer_c64_h1_2keys", kind="layer", B=1, C=64, H=1, hw=(6, 6), hsws=(1, 2), gain=1.0, seed=18),
     dict(name="layer_c512_h8_selffcs", kind="layer", B=1, C=512, H=8, hw=(12, 12), hsws=(12, 12), gain=1.0, seed=19,
          fcs_is_fc=True),
+    # activation="cosine" (CosineSimilarity, adaDecoder.py:20-34): a = (cos + 1) / sum(cos + 1)
+    dict(name="layer_c512_h8_cosine", kind="layer", B=1, C=512, H=8, hw=(12, 12), hsws=(10, 14), gain=1.0, seed=20,
+         activation="cosine"),
+    dict(name="layer_c128_h2_cosine", kind="layer", B=2, C=128, H=2, hw=(9, 7), hsws=(20, 12), gain=1.0, seed=21,
+         activation="cosine"),
 ]
 
 ADAATTN_CASES = [
     dict(name="adaattn_c64_10x10", kind="adaattn", B=2, C=64, hw=(10, 10), hsws=(7, 9), seed=31),
+    dict(name="adaattn_c64_cosine", kind="adaattn", B=1, C=64, hw=(8, 8), hsws=(9, 9), seed=32, activation="cosine"),
 ]
 
 FORLOSS_CASES = [
@@ -40,6 +46,8 @@ FORLOSS_CASES = [
     dict(name="forloss_relu3_1", kind="forloss", B=1, v=256, qk=448, hw=(12, 12), hsws=(12, 12), seed=41),
     dict(name="forloss_relu4_1", kind="forloss", B=2, v=512, qk=960, hw=(6, 6), hsws=(6, 6), seed=42),
     dict(name="forloss_relu5_1", kind="forloss", B=1, v=512, qk=1472, hw=(3, 3), hsws=(3, 3), seed=43),
+    dict(name="forloss_relu3_1_cosine", kind="forloss", B=1, v=256, qk=448, hw=(8, 8), hsws=(8, 10), seed=44,
+         activation="cosine"),
 ]
 
 TRANSFORMER_CASES = [

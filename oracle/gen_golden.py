@@ -70,19 +70,19 @@ def main(prefix: str = ""):
         arrays, meta = {}, {"kind": kind}
         if kind == "layer":
             fc, fs, fcs, sd = cases.layer_inputs(case)
-            o = run_both(lambda: AdaAttnMultiHead(case["C"], case["H"]), sd, (fc, fs, fcs))
+            o = run_both(lambda: AdaAttnMultiHead(case["C"], case["H"], case.get("activation", "softmax")), sd, (fc, fs, fcs))
             o64, o32 = o["f64"].numpy(), o["f32"].numpy()
             arrays["out"] = o64.astype(np.float32)
             meta["out"] = summarize(o64); meta["ref32_vs_ref64"] = errors(o32, o64)
         elif kind == "adaattn":
             fc, fs, fcs, sd = cases.adaattn_inputs(case)
-            o = run_both(lambda: AdaAttN(case["C"]), sd, (fc, fs, fcs))
+            o = run_both(lambda: AdaAttN(case["C"], case.get("activation", "softmax")), sd, (fc, fs, fcs))
             o64, o32 = o["f64"].numpy(), o["f32"].numpy()
             arrays["out"] = o64.astype(np.float32)
             meta["out"] = summarize(o64); meta["ref32_vs_ref64"] = errors(o32, o64)
         elif kind == "forloss":
             args = cases.forloss_inputs(case)
-            o = run_both(lambda: AdaAttnForLoss(case["v"], case["qk"]), None, args)
+            o = run_both(lambda: AdaAttnForLoss(case["v"], case["qk"], case.get("activation", "softmax")), None, args)
             o64, o32 = o["f64"].numpy(), o["f32"].numpy()
             arrays["out"] = o64.astype(np.float32)
             meta["out"] = summarize(o64); meta["ref32_vs_ref64"] = errors(o32, o64)

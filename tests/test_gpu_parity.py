@@ -42,7 +42,7 @@ def bf16_tol(case):
 
 
 def build_layer(case, sd):
-    m = M.AdaAttnMultiHead(case["C"], case["H"])
+    m = M.AdaAttnMultiHead(case["C"], case["H"], case.get("activation", "softmax"))
     m.load_state_dict(synth.to_torch(sd, torch.float32), strict=True)
     return m.to(DEV).eval()
 
@@ -60,7 +60,8 @@ def test_layer_fp32_vs_reference_golden(case, golden_index):
     assert e["max_abs"] <= fp32_tol(golden_index[case["name"]]["ref32_vs_ref64"]), e
 
 
-@pytest.mark.parametrize("case", [c for c in cases.LAYER_CASES if c["C"] // c["H"] == 64], ids=lambda c: c["name"])
+@pytest.mark.parametrize("case", [c for c in cases.LAYER_CASES if c["C"] // c["H"] == 64 and "activation" not in c],
+                         ids=lambda c: c["name"])
 def test_layer_bf16_vs_reference_golden(case, golden_index):
     fc, fs, fcs, sd = cases.layer_inputs(case)
     m = build_layer(case, sd)
@@ -96,7 +97,7 @@ def test_layer_accepts_nchw_and_channels_last():
 @pytest.mark.parametrize("case", cases.ADAATTN_CASES, ids=lambda c: c["name"])
 def test_adaattn_fp32(case, golden_index):
     fc, fs, fcs, sd = cases.adaattn_inputs(case)
-    m = M.AdaAttN(case["C"])
+    m = M.AdaAttN(case["C"], case.get("activation", "softmax"))
     m.load_state_dict(synth.to_torch(sd, torch.float32), strict=True)
     m = m.to(DEV).eval()
     with torch.no_grad():
@@ -108,7 +109,7 @@ def test_adaattn_fp32(case, golden_index):
 @pytest.mark.parametrize("case", cases.FORLOSS_CASES, ids=lambda c: c["name"])
 def test_forloss_fp32(case, golden_index):
     args = [dev(a) for a in cases.forloss_inputs(case)]
-    m = M.AdaAttnForLoss(case["v"], case["qk"]).to(DEV).eval()
+    m = M.AdaAttnForLoss(case["v"], case["qk"], case.get("activation", "softmax")).to(DEV).eval()
     with torch.no_grad():
         out = m(*args)
     e = O.errors(out.cpu().numpy(), load_golden(case["name"])["out"])
@@ -271,6 +272,7 @@ def test_style_cache_matches_uncached(precision):
 
 def test_errors_on_device():
     m = M.AdaAttnMultiHead(512, 8, activation="cosine").to(DEV)
+    m.precision = "bf16"                # the cosine activation exists on the fp32 kernels only
     x = torch.zeros(1, 512, 4, 4, device=DEV)
     with torch.no_grad(), pytest.raises(NotImplementedError):
         m(x, x, x)
@@ -327,6 +329,30 @@ def test_layer_gradients_bf16_forward():
     g = load_golden(case["name"])
     assert O.errors(tin[0].grad.cpu().numpy(), g["fc"])["max_abs_rel"] <= 2e-4
     assert O.errors(m.out_conv.weight.grad.cpu().numpy(), g["out_conv__weight"])["max_abs_rel"] <= 2e-4
+
+
+def test_cosine_layer_gradient_matches_oracle_finite_difference():
+    """activation="cosine" under autograd: CUDA forward (fp32 kernels), recompute backward; d(loss)/d(fc) and
+    d(loss)/d(fs) against directional finite differences of the float64 oracle."""
+    case = cases.by_name("layer_c128_h2_cosine")
+    fc, fs, fcs, sd = cases.layer_inputs(case)
+    m = build_layer(case, sd)
+    G = synth.bellish(991, fc.shape, 0.0, 1.0)
+    tin = [dev(a).requires_grad_(True) for a in (fc, fs, fcs)]
+    out = m(*tin)
+    assert O.errors(out.detach().cpu().numpy(), load_golden(case["name"])["out"])["max_abs"] <= FP32_MAX_ABS
+    (out * dev(G)).sum().backward()
+    rng = np.random.default_rng(1)
+    loss = lambda a, b: float((O.ada_attn_multi_head(a, b, fcs, sd, case["H"], activation="cosine") * G).sum())
+    eps = 1e-5
+    for idx, base in ((0, fc), (1, fs)):
+        v = rng.standard_normal(base.shape)
+        plus = [fc, fs]; minus = [fc, fs]
+        plus[idx] = base + eps * v
+        minus[idx] = base - eps * v
+        fd = (loss(*plus) - loss(*minus)) / (2 * eps)
+        an = float((tin[idx].grad.double().cpu().numpy() * v).sum())
+        assert an == pytest.approx(fd, rel=2e-3, abs=1e-4 * abs(fd) + 1e-5), (idx, an, fd)
 
 
 def test_transformer_train_step_runs():

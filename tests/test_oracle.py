@@ -27,7 +27,7 @@ def _check_sums(got64, meta, key="out"):
 @pytest.mark.parametrize("case", cases.LAYER_CASES, ids=lambda c: c["name"])
 def test_layer_matches_reference(case, golden_index):
     fc, fs, fcs, sd = cases.layer_inputs(case)
-    got = O.ada_attn_multi_head(fc, fs, fcs, sd, case["H"])
+    got = O.ada_attn_multi_head(fc, fs, fcs, sd, case["H"], activation=case.get("activation", "softmax"))
     meta = golden_index[case["name"]]
     _check(got, load_golden(case["name"])["out"], meta)
     _check_sums(got, meta)
@@ -36,7 +36,7 @@ def test_layer_matches_reference(case, golden_index):
 @pytest.mark.parametrize("case", cases.ADAATTN_CASES, ids=lambda c: c["name"])
 def test_adaattn_matches_reference(case, golden_index):
     fc, fs, fcs, sd = cases.adaattn_inputs(case)
-    got = O.ada_attn(fc, fs, fcs, sd)
+    got = O.ada_attn(fc, fs, fcs, sd, activation=case.get("activation", "softmax"))
     meta = golden_index[case["name"]]
     _check(got, load_golden(case["name"])["out"], meta)
     _check_sums(got, meta)
@@ -44,7 +44,7 @@ def test_adaattn_matches_reference(case, golden_index):
 
 @pytest.mark.parametrize("case", cases.FORLOSS_CASES, ids=lambda c: c["name"])
 def test_forloss_matches_reference(case, golden_index):
-    got = O.ada_attn_for_loss(*cases.forloss_inputs(case))
+    got = O.ada_attn_for_loss(*cases.forloss_inputs(case), activation=case.get("activation", "softmax"))
     meta = golden_index[case["name"]]
     _check(got, load_golden(case["name"])["out"], meta)
     _check_sums(got, meta)
