@@ -166,6 +166,29 @@ def cpu_port_run(wl, images: int, steps: int, warmup: int, budget_s: float):
     return times
 
 
+def gpu_eager_port_run(wl, device, steps: int = 3, warmup: int = 1):
+    """The reference's eager PyTorch path on THIS GPU (oracle/torch_port.py = the reference's ATen op sequence, fp32,
+    PyTorch's default TF32 settings, Nc x Ns map materialised per head): the like-for-like bar SURVEY.md 8(d) asks
+    for next to the CPU baseline.  Part of the baseline leg; device-resident inputs, CUDA events."""
+    from oracle import synth, torch_port
+    sd = {k: v.to(device) for k, v in torch_port.prepare(synth.transformer_state(1234)).items()}
+    g = torch.Generator().manual_seed(0)
+    hw, hs, B = wl["hw"], wl["hsws"], wl["B"]
+    fc = [(torch.randn(B, C, hw[0], hw[1], generator=g) * 85 + 1.3).to(device) for _ in range(LAYERS)]
+    fs = [(torch.randn(B, C, hs[0], hs[1], generator=g) * 85 + 1.3).to(device) for _ in range(LAYERS)]
+    with torch.no_grad():
+        for _ in range(warmup):
+            torch_port.transformer(fc, fs, sd)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            torch_port.transformer(fc, fs, sd)
+        e1.record()
+        torch.cuda.synchronize()
+    return B * steps / (e0.elapsed_time(e1) * 1e-3)
+
+
 def run_reference(args, wl, rank):
     if rank != 0:
         return
@@ -292,6 +315,8 @@ def main():
         e2e_state["i"] = i + 1
         return cs
 
+    stage_ms = {}
+
     def timed(fn, steps, warmup, profile=False):
         with torch.no_grad():
             for _ in range(warmup):
@@ -317,6 +342,10 @@ def main():
             attn_ms, attn_n = ctypes.c_float(0), ctypes.c_int(0)
             if profile:
                 _lib.check("mhada_profile_end", L.mhada_profile_end(ctypes.byref(attn_ms), ctypes.byref(attn_n)))
+                for name, code in (("stats", 0), ("proj", 1), ("linear", 3)):
+                    sm, sn = ctypes.c_float(0), ctypes.c_int(0)
+                    _lib.check("mhada_profile_stage", L.mhada_profile_stage(code, ctypes.byref(sm), ctypes.byref(sn)))
+                    stage_ms[name] = (sm.value, sn.value)
         if world > 1:
             t = torch.tensor([ms], device=device)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -372,6 +401,26 @@ def main():
                 "share_of_step": round(attn_ms / ms_total, 4), "traffic": None,
                 "note": "fp32 parity path (FFMA); the roofline claim is made on the bf16 workload"}
 
+    # HBM-bound stages of the six layers, timed by events inside the same steps: algorithmic bytes (every distinct
+    # input of a stage read once, every output written once) over the measured device time
+    esz_b = 2 if wl["dtype"] == "bf16" else 4
+    tc_, ts_ = esz_b * B * C * Nc, esz_b * (wl.get("style_batch", B)) * C * Ns
+    vmul = 2 if wl["dtype"] == "bf16" else 1                      # V' = [V~ | V~^2] on the bf16 path
+    # statistics: layer 2i scans fc[i], fs[i] and (i > 0) fcs; layer 2i+1 scans its fc (= fcs), fs statistics are reused
+    stats_bytes = (3 * LAYERS - 1) * tc_ + (LAYERS * ts_ if style is None else 0)
+    # projections: read fc (+ fs), write Q (+ K and V')
+    proj_bytes = 2 * LAYERS * (2 * tc_ + ((2 + vmul) * ts_ if style is None else 0))
+    linear_bytes = 2 * LAYERS * 2 * tc_
+    kernels = []
+    for name, nbytes in (("stats", stats_bytes), ("proj", proj_bytes), ("linear", linear_bytes)):
+        ms_s, n_s = stage_ms.get(name, (0.0, 0))
+        if n_s:
+            per_step_ms = ms_s / args.steps
+            gbs = nbytes / (per_step_ms * 1e-3) / 1e9
+            kernels.append({"stage": name, "bound": "hbm", "achieved": round(gbs, 1), "peak": pk["hbm_gbs"], "unit": "GB/s",
+                            "frac": round(gbs / pk["hbm_gbs"], 4), "ms_per_step": round(per_step_ms, 4),
+                            "algorithmic_bytes_per_step": nbytes, "brackets_per_step": n_s // args.steps})
+
     if rank == 0:
         line = {
             "metric": "images_per_sec", "value": round(value, 2), "unit": "images/s", "n_gpus": world,
@@ -385,7 +434,7 @@ def main():
                     "d2h_bytes_per_step": d2h, "ms_per_step": round(ms_e2e / args.steps, 4)},
             "gpu_launches": launches_per_step * args.steps,
             "gpu_launches_per_step": launches_per_step,
-            "roofline": roof, "clocks": clocks,
+            "roofline": roof, "kernels": kernels, "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
             times = cpu_port_run(wl, 1, steps=3, warmup=1, budget_s=25.0)
@@ -393,6 +442,14 @@ def main():
             line["cpu_baseline"] = {"value": round(1.0 / sec, 4), "unit": "images/s", "cores": torch.get_num_threads(),
                                     "kind": "port", "sample": f"{len(times)} x 1 image of the workload (fp32, "
                                     "oracle/torch_port.py = the reference's ATen op sequence) after 1 warm-up"}
+            try:
+                line["cpu_baseline"]["gpu_eager_port"] = {
+                    "value": round(gpu_eager_port_run(wl, device), 2), "unit": "images/s",
+                    "note": "same port run eagerly on this GPU in fp32 (PyTorch defaults), 3 steps after 1 warm-up: "
+                            "the reference's own GPU path restated, not a bench value"}
+            except RuntimeError as e:          # e.g. out of memory for the materialised maps at large sizes
+                line["cpu_baseline"]["gpu_eager_port"] = {"unavailable": str(e).splitlines()[0][:120]}
+            torch.cuda.empty_cache()
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

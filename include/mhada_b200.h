@@ -200,6 +200,11 @@ MHADA_API long long mhada_total_launch_count(void);
 MHADA_API int mhada_debug_attn_trace(const mhada_attn_args* args, long long* trace, mhada_stream_t stream);
 MHADA_API int mhada_profile_begin(void);
 MHADA_API int mhada_profile_end(float* attn_ms_total, int* attn_launches);
+/*     Per-stage totals of the last begin/end bracket (valid after mhada_profile_end): device time between the
+ *     events that surround the launches of one stage of mhada_layer_forward(_cached), and how many such brackets. */
+enum mhada_stage { MHADA_STAGE_STATS = 0, MHADA_STAGE_PROJ = 1, MHADA_STAGE_ATTN = 2, MHADA_STAGE_LINEAR = 3,
+                   MHADA_STAGE_COUNT = 4 };
+MHADA_API int mhada_profile_stage(int stage, float* ms_total, int* brackets);
 
 #ifdef __cplusplus
 }

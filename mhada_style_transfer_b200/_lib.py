@@ -37,6 +37,7 @@ class AttnArgs(ctypes.Structure):
 # name -> (restype, argtypes); kept in one table so tests can check the export list against the header
 SIGNATURES = {
     "mhada_abi_version": (c_int, []),
+    "mhada_profile_stage": (c_int, [c_int, POINTER(c_float), POINTER(c_int)]),
     "mhada_last_error": (c_char_p, []),
     "mhada_device_check": (c_int, []),
     "mhada_last_launch_count": (c_int, []),

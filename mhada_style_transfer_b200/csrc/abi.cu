@@ -60,32 +60,42 @@ LayerWs carve(int dtype, int B, int Nc, int Ns, int C, int H, uint8_t* base) {
     return w;
 }
 
-// ---- optional event bracketing of the attention launches (mhada_profile_*)
+// ---- optional event bracketing of the stages of a layer (mhada_profile_*): statistics, projections, attention,
+//      out_conv, each between a pair of events recorded on the launching stream
 struct Profiler {
     bool on = false;
     std::vector<cudaEvent_t> ev;   // pairs: start, stop
-    size_t used = 0;
+    std::vector<int> stage;        // stage of pair i
+    size_t used = 0;               // events in use
+    float ms[MHADA_STAGE_COUNT] = {0.f, 0.f, 0.f, 0.f};
+    int n[MHADA_STAGE_COUNT] = {0, 0, 0, 0};
 };
 thread_local Profiler g_prof;
 
-int attn_dispatch(const mhada_attn_args& a, cudaStream_t s) {
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    if (g_prof.on) {
-        if (g_prof.used + 2 > g_prof.ev.size()) {
-            for (int i = 0; i < 2; ++i) {
-                cudaEvent_t e;
-                if (int err = check_cuda(cudaEventCreate(&e), "cudaEventCreate")) return err;
-                g_prof.ev.push_back(e);
-            }
+struct StageTimer {
+    cudaEvent_t e1 = nullptr;
+    cudaStream_t s;
+    StageTimer(int stage, cudaStream_t stream) : s(stream) {
+        if (!g_prof.on) return;
+        while (g_prof.used + 2 > g_prof.ev.size()) {
+            cudaEvent_t e;
+            if (cudaEventCreate(&e) != cudaSuccess) return;
+            g_prof.ev.push_back(e);
         }
-        e0 = g_prof.ev[g_prof.used];
+        if (g_prof.stage.size() < g_prof.ev.size() / 2) g_prof.stage.resize(g_prof.ev.size() / 2);
+        g_prof.stage[g_prof.used / 2] = stage;
+        cudaEventRecord(g_prof.ev[g_prof.used], s);
         e1 = g_prof.ev[g_prof.used + 1];
         g_prof.used += 2;
-        cudaEventRecord(e0, s);
     }
-    int rc = a.dtype == MHADA_BF16 ? launch_attn_bf16(a, s) : launch_attn_f32(a, s);
-    if (e1) cudaEventRecord(e1, s);
-    return rc;
+    ~StageTimer() {
+        if (e1) cudaEventRecord(e1, s);
+    }
+};
+
+int attn_dispatch(const mhada_attn_args& a, cudaStream_t s) {
+    StageTimer timer(MHADA_STAGE_ATTN, s);
+    return a.dtype == MHADA_BF16 ? launch_attn_bf16(a, s) : launch_attn_f32(a, s);
 }
 
 struct StyleCacheView {
@@ -159,11 +169,12 @@ int layer_impl(const char* who, int dtype, const void* fc, const void* fs, const
             mean_x = w.mean_x;
             rstd_x = w.rstd_x;
         }
+        StageTimer timer(MHADA_STAGE_STATS, s);
         if (int e = launch_stats_multi(n, xs, ns, ms, rs, dtype, B, C, C, static_cast<float*>(w.stats_ws), s)) return e;
     }
     // (2) projections                                                        adaDecoder.py:173-183
     const int parts = cache ? MHADA_PROJ_Q : (MHADA_PROJ_Q | MHADA_PROJ_KV);
-    if (dtype == MHADA_BF16) {
+    if (StageTimer timer(MHADA_STAGE_PROJ, s); dtype == MHADA_BF16) {
         if (int e = launch_proj_bf16(parts, fc, fs, w.mean_c, w.rstd_c, w.mean_s, w.rstd_s, w_fgh, b_fgh, B, cache ? 0 : B, Nc, Ns,
                                      H, d, w.q, w.k, w.v, w.mu_v, w.proj_ws, s))
             return e;
@@ -185,6 +196,7 @@ int layer_impl(const char* who, int dtype, const void* fc, const void* fs, const
     if (int e = attn_dispatch(a, s)) return e;
     // (4) out_conv                                                           adaDecoder.py:202-205
     if (w_out) {
+        StageTimer timer(MHADA_STAGE_LINEAR, s);
         if (dtype == MHADA_BF16) {
             if (int e = launch_linear_bf16(w.heads, C, w_out, b_out, B * Nc, C, C, out, C, w.lin_ws, s)) return e;
         } else {
@@ -208,18 +220,25 @@ int mhada_profile_begin(void) {
 
 int mhada_profile_end(float* attn_ms_total, int* attn_launches) {
     g_prof.on = false;
-    float total = 0.f;
-    int n = 0;
+    for (int st = 0; st < MHADA_STAGE_COUNT; ++st) g_prof.ms[st] = 0.f, g_prof.n[st] = 0;
     for (size_t i = 0; i + 1 < g_prof.used; i += 2) {
         if (int e = check_cuda(cudaEventSynchronize(g_prof.ev[i + 1]), "cudaEventSynchronize")) return e;
         float ms = 0.f;
         if (int e = check_cuda(cudaEventElapsedTime(&ms, g_prof.ev[i], g_prof.ev[i + 1]), "cudaEventElapsedTime")) return e;
-        total += ms;
-        ++n;
+        const int st = g_prof.stage[i / 2];
+        g_prof.ms[st] += ms;
+        ++g_prof.n[st];
     }
     g_prof.used = 0;
-    if (attn_ms_total) *attn_ms_total = total;
-    if (attn_launches) *attn_launches = n;
+    if (attn_ms_total) *attn_ms_total = g_prof.ms[MHADA_STAGE_ATTN];
+    if (attn_launches) *attn_launches = g_prof.n[MHADA_STAGE_ATTN];
+    return 0;
+}
+
+int mhada_profile_stage(int stage, float* ms_total, int* brackets) {
+    REQUIRE(stage >= 0 && stage < MHADA_STAGE_COUNT, MHADA_ERR_ARG, "mhada_profile_stage: bad stage %d", stage);
+    if (ms_total) *ms_total = g_prof.ms[stage];
+    if (brackets) *brackets = g_prof.n[stage];
     return 0;
 }
 

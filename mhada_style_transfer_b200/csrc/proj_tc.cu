@@ -66,43 +66,66 @@ __global__ void __launch_bounds__(256) fold_kernel(const float* __restrict__ w, 
     }
 }
 
-// NOUT = 1: Q from fc.   NOUT = 2: K and V' from the same fs tile.
-// grid (ceil(N/128), H, B)
-template <int NOUT>
-__global__ void __launch_bounds__(PRJ_THREADS)
-proj_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
-               const float* __restrict__ bfold, int which0, int B, int H, int N,
-               __nv_bfloat16* __restrict__ out0, __nv_bfloat16* __restrict__ out1) {
-    constexpr uint32_t A_BYTES = PRJ_BM * PRJ_D * 2, W_BYTES = PRJ_D * PRJ_D * 2;
-    constexpr uint32_t TM_COLS = NOUT * 64;
-    __shared__ __align__(1024) uint8_t smem[A_BYTES + NOUT * W_BYTES];
-    __shared__ uint64_t full, accum;
+// Persistent projection kernel: one launch covers the content side (Q from fc) and the style side (K and V' from
+// the same fs tile).  A work item is one (128-token tile, head); heads are the fastest index, so the CTAs that run
+// side by side read and write the eight 128-byte head slices of the same token rows (whole 1 KB rows in DRAM).
+// Style items (three output tiles) come first, content items (one) after, dealt round-robin to the CTAs.
+//   warp 0      TMA producer: X tile [128 x 64] + one or two folded 64 x 64 weight tiles per item, 3-stage ring
+//   warp 1      tcgen05.mma issuer; accumulators double-buffered in TMEM (2 x 128 columns), so the MMAs of item
+//               n+1 run while the epilogue warps drain item n
+//   warps 2-5   epilogue: TMEM -> registers, + folded bias, bf16, 256-bit stores (V' also stores the squares)
+// Two CTAs per SM (96 KB of shared memory, 256 TMEM columns each).
+constexpr int PRJ_STAGES = 3;
+constexpr uint32_t PRJ_A_BYTES = PRJ_BM * PRJ_D * 2, PRJ_W_BYTES = PRJ_D * PRJ_D * 2;
+constexpr uint32_t PRJ_STAGE_BYTES = PRJ_A_BYTES + 2 * PRJ_W_BYTES;
+
+struct ProjParams {
+    const float* bfold;              // [3][Bw][H][64] folded biases
+    __nv_bfloat16 *q, *k, *v;
+    int Bw, H, Bc, Nc, Bs, Ns;       // Bc / Bs = 0 when that side is not projected
+    int tiles_c, tiles_s, items_s, items;
+};
+
+struct ProjItem {
+    int side, b, h, n0;              // side 0 = content (Q), 1 = style (K, V')
+};
+
+__device__ __forceinline__ ProjItem proj_item(const ProjParams& p, int idx) {
+    ProjItem it;
+    it.side = idx < p.items_s ? 1 : 0;
+    const int r = it.side ? idx : idx - p.items_s;
+    const int tiles = it.side ? p.tiles_s : p.tiles_c;
+    it.h = r % p.H;
+    it.n0 = ((r / p.H) % tiles) * PRJ_BM;
+    it.b = r / (p.H * tiles);
+    return it;
+}
+
+__global__ void __launch_bounds__(PRJ_THREADS, 2)
+proj_tc_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmS,
+               const __grid_constant__ CUtensorMap tmW, const ProjParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ uint64_t full[PRJ_STAGES], empty[PRJ_STAGES], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_slot;
-    __shared__ float bias_s[NOUT][PRJ_D];
+    __shared__ float bias_s[2][2][PRJ_D];        // [accumulator buffer][output][channel]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n0 = blockIdx.x * PRJ_BM, h = blockIdx.y, b = blockIdx.z;
-    const int C = H * PRJ_D;
 
     if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmX);
+        tma_prefetch_desc(&tmC);
+        tma_prefetch_desc(&tmS);
         tma_prefetch_desc(&tmW);
     }
     if (warp == 1) {
         if (lane == 0) {
-            mbar_init(&full, 1);
-            mbar_init(&accum, 1);
+            for (int s = 0; s < PRJ_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+            for (int u = 0; u < 2; ++u) { mbar_init(&acc_full[u], 1); mbar_init(&acc_empty[u], 4); }
             fence_mbar_init();
         }
         __syncwarp();
-        tmem_alloc(&tmem_slot, TM_COLS);
+        tmem_alloc(&tmem_slot, 256);
         tmem_relinquish();
-    }
-    if (warp >= 2) {
-        for (int i = threadIdx.x - 64; i < NOUT * PRJ_D; i += 128) {
-            int t = i / PRJ_D, o = i % PRJ_D;
-            bias_s[t][o] = bfold[((static_cast<size_t>(which0 + t) * B + b) * H + h) * PRJ_D + o];
-        }
     }
     tc_fence_before();
     __syncthreads();
@@ -111,69 +134,99 @@ proj_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 
     if (warp == 0) {
         if (elect_one()) {
-            mbar_arrive_expect_tx(&full, A_BYTES + NOUT * W_BYTES);
-            tma_load_3d(smem, &tmX, &full, h * PRJ_D, n0, b);
-#pragma unroll
-            for (int t = 0; t < NOUT; ++t)
-                tma_load_2d(smem + A_BYTES + t * W_BYTES, &tmW, &full, 0,
-                            (((which0 + t) * B + b) * H + h) * PRJ_D);
+            int n = 0;
+            for (int idx = blockIdx.x; idx < p.items; idx += gridDim.x, ++n) {
+                const ProjItem it = proj_item(p, idx);
+                const int s = n % PRJ_STAGES;
+                mbar_wait(&empty[s], ((n / PRJ_STAGES) & 1) ^ 1);
+                uint8_t* st = smem + s * PRJ_STAGE_BYTES;
+                mbar_arrive_expect_tx(&full[s], PRJ_A_BYTES + (it.side ? 2 : 1) * PRJ_W_BYTES);
+                tma_load_3d(st, it.side ? &tmS : &tmC, &full[s], it.h * PRJ_D, it.n0, it.b);
+                const int which0 = it.side ? 1 : 0;
+                tma_load_2d(st + PRJ_A_BYTES, &tmW, &full[s], 0, ((which0 * p.Bw + it.b) * p.H + it.h) * PRJ_D);
+                if (it.side)
+                    tma_load_2d(st + PRJ_A_BYTES + PRJ_W_BYTES, &tmW, &full[s], 0, ((2 * p.Bw + it.b) * p.H + it.h) * PRJ_D);
+            }
         }
     } else if (warp == 1) {
         if (elect_one()) {
             constexpr uint32_t idesc = make_idesc_bf16(PRJ_BM, PRJ_D, 0, 0);
-            mbar_wait(&full, 0);
-            tc_fence_after();
-            const uint32_t a_addr = smem_u32(smem);
-            const uint64_t da = make_smem_desc(a_addr, 16, 1024);
+            int n = 0;
+            for (int idx = blockIdx.x; idx < p.items; idx += gridDim.x, ++n) {
+                const int side = idx < p.items_s ? 1 : 0;
+                const int s = n % PRJ_STAGES, u = n & 1;
+                mbar_wait(&full[s], (n / PRJ_STAGES) & 1);
+                mbar_wait(&acc_empty[u], ((n >> 1) & 1) ^ 1);       // epilogue has drained this accumulator buffer
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(smem + s * PRJ_STAGE_BYTES);
+                const uint64_t da = make_smem_desc(a_addr, 16, 1024);
+                for (int t = 0; t <= side; ++t) {
+                    const uint64_t db = make_smem_desc(a_addr + PRJ_A_BYTES + t * PRJ_W_BYTES, 16, 1024);
 #pragma unroll
-            for (int t = 0; t < NOUT; ++t) {
-                const uint64_t db = make_smem_desc(a_addr + A_BYTES + t * W_BYTES, 16, 1024);
-#pragma unroll
-                for (int k = 0; k < PRJ_D / 16; ++k)
-                    umma_ss(tmem + t * 64, desc_advance(da, k * 32), desc_advance(db, k * 32), idesc, k != 0);
+                    for (int k = 0; k < PRJ_D / 16; ++k)
+                        umma_ss(tmem + u * 128 + t * 64, desc_advance(da, k * 32), desc_advance(db, k * 32), idesc, k != 0);
+                }
+                umma_commit(&empty[s]);         // the stage may be refilled once these MMAs have read it
+                umma_commit(&acc_full[u]);
             }
-            umma_commit(&accum);
         }
     } else {
         const int quarter = warp & 3;
-        const int n = n0 + quarter * 32 + lane;
-        mbar_wait(&accum, 0);
-        tc_fence_after();
+        const int et = threadIdx.x - 64;            // 0 .. 127 among the epilogue threads
+        const int C = p.H * PRJ_D;
+        int n = 0;
+        for (int idx = blockIdx.x; idx < p.items; idx += gridDim.x, ++n) {
+            const ProjItem it = proj_item(p, idx);
+            const int u = n & 1;
+            const int nout = it.side ? 2 : 1;
+            const int N = it.side ? p.Ns : p.Nc;
+            // bias_s[u] was last read two items ago; every epilogue thread has passed the barrier of item n-1 since
+            if (et < nout * PRJ_D) {
+                const int t = et / PRJ_D, o = et % PRJ_D;
+                bias_s[u][t][o] = p.bfold[((static_cast<size_t>(it.side ? 1 + t : 0) * p.Bw + it.b) * p.H + it.h) * PRJ_D + o];
+            }
+            named_bar_sync(1, 128);
+            mbar_wait(&acc_full[u], (n >> 1) & 1);
+            tc_fence_after();
+            const int row = it.n0 + quarter * 32 + lane;
+            for (int t = 0; t < nout; ++t) {
+                const bool is_v = it.side && t == 1;
 #pragma unroll
-        for (int t = 0; t < NOUT; ++t) {
-            const bool is_v = (NOUT == 2 && t == 1);
+                for (int c = 0; c < PRJ_D; c += 32) {
+                    uint32_t r[32];
+                    tmem_ld_x32(tmem_addr(tmem, quarter * 32, u * 128 + t * 64 + c), r);
+                    tmem_wait_ld();
+                    if (row < N) {
+                        uint32_t lo[16], sq[16];
 #pragma unroll
-            for (int c = 0; c < PRJ_D; c += 32) {
-                uint32_t r[32];
-                tmem_ld_x32(tmem_addr(tmem, quarter * 32, t * 64 + c), r);
-                tmem_wait_ld();
-                if (n < N) {
-                    uint32_t lo[16], sq[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        float v0 = __uint_as_float(r[2 * i]) + bias_s[t][c + 2 * i];
-                        float v1 = __uint_as_float(r[2 * i + 1]) + bias_s[t][c + 2 * i + 1];
-                        lo[i] = pack_bf16x2(v0, v1);
-                        sq[i] = pack_bf16x2(v0 * v0, v1 * v1);
-                    }
-                    if (!is_v) {
-                        __nv_bfloat16* o = (t == 0 ? out0 : out1) + (static_cast<size_t>(b) * N + n) * C + h * PRJ_D + c;
-                        st_global_256(o, lo);
-                        st_global_256(o + 16, lo + 8);
-                    } else {
-                        __nv_bfloat16* o = out1 + (static_cast<size_t>(b) * N + n) * (2 * C) + h * (2 * PRJ_D) + c;
-                        st_global_256(o, lo);
-                        st_global_256(o + 16, lo + 8);
-                        st_global_256(o + PRJ_D, sq);
-                        st_global_256(o + PRJ_D + 16, sq + 8);
+                        for (int i = 0; i < 16; ++i) {
+                            float v0 = __uint_as_float(r[2 * i]) + bias_s[u][t][c + 2 * i];
+                            float v1 = __uint_as_float(r[2 * i + 1]) + bias_s[u][t][c + 2 * i + 1];
+                            lo[i] = pack_bf16x2(v0, v1);
+                            sq[i] = pack_bf16x2(v0 * v0, v1 * v1);
+                        }
+                        if (!is_v) {
+                            __nv_bfloat16* o = (it.side ? p.k : p.q) + (static_cast<size_t>(it.b) * N + row) * C + it.h * PRJ_D + c;
+                            st_global_256(o, lo);
+                            st_global_256(o + 16, lo + 8);
+                        } else {
+                            __nv_bfloat16* o = p.v + (static_cast<size_t>(it.b) * N + row) * (2 * C) + it.h * (2 * PRJ_D) + c;
+                            st_global_256(o, lo);
+                            st_global_256(o + 16, lo + 8);
+                            st_global_256(o + PRJ_D, sq);
+                            st_global_256(o + PRJ_D + 16, sq + 8);
+                        }
                     }
                 }
             }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[u]);
         }
-        tc_fence_before();
     }
+    tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem, TM_COLS);
+    if (warp == 1) tmem_dealloc(tmem, 256);
 }
 
 static int make_x_map(CUtensorMap* tm, const void* x, int B, int N, int C) {
@@ -196,24 +249,50 @@ int launch_proj_bf16(int parts, const void* fc, const void* fs, const float* mea
     uint64_t strW[1] = {static_cast<uint64_t>(d) * 2};
     uint32_t boxW[2] = {PRJ_D, PRJ_D};
     if (int e = make_tmap_bf16(&tmW, wf, 2, dimsW, strW, boxW)) return e;
-    if (parts & 1) {
-        fold_kernel<<<dim3(H, B, 1), 256, 0, s>>>(w, bias, mean_c, rstd_c, mean_s, rstd_s, 0, Bw, H, d, wf, bf, mu_v);
+    const bool do_c = parts & 1, do_s = parts & 2;
+    // fold the instance norm into the per-image weights: one launch when both sides have the same batch
+    if (do_c && do_s && B == Bs) {
+        fold_kernel<<<dim3(H, B, 3), 256, 0, s>>>(w, bias, mean_c, rstd_c, mean_s, rstd_s, 0, Bw, H, d, wf, bf, mu_v);
         count_launch();
-        CUtensorMap tmC;
-        if (int e = make_x_map(&tmC, fc, B, Nc, C)) return e;
-        proj_tc_kernel<1><<<dim3((Nc + PRJ_BM - 1) / PRJ_BM, H, B), PRJ_THREADS, 0, s>>>(
-            tmC, tmW, bf, 0, Bw, H, Nc, static_cast<__nv_bfloat16*>(q), nullptr);
-        count_launch();
+    } else {
+        if (do_c) {
+            fold_kernel<<<dim3(H, B, 1), 256, 0, s>>>(w, bias, mean_c, rstd_c, mean_s, rstd_s, 0, Bw, H, d, wf, bf, mu_v);
+            count_launch();
+        }
+        if (do_s) {
+            fold_kernel<<<dim3(H, Bs, 2), 256, 0, s>>>(w, bias, mean_c, rstd_c, mean_s, rstd_s, 1, Bw, H, d, wf, bf, mu_v);
+            count_launch();
+        }
     }
-    if (parts & 2) {
-        fold_kernel<<<dim3(H, Bs, 2), 256, 0, s>>>(w, bias, mean_c, rstd_c, mean_s, rstd_s, 1, Bw, H, d, wf, bf, mu_v);
-        count_launch();
-        CUtensorMap tmS;
-        if (int e = make_x_map(&tmS, fs, Bs, Ns, C)) return e;
-        proj_tc_kernel<2><<<dim3((Ns + PRJ_BM - 1) / PRJ_BM, H, Bs), PRJ_THREADS, 0, s>>>(
-            tmS, tmW, bf, 1, Bw, H, Ns, static_cast<__nv_bfloat16*>(k), static_cast<__nv_bfloat16*>(v));
-        count_launch();
+    CUtensorMap tmC, tmS;
+    if (int e = make_x_map(&tmC, do_c ? fc : fs, do_c ? B : Bs, do_c ? Nc : Ns, C)) return e;
+    if (int e = make_x_map(&tmS, do_s ? fs : fc, do_s ? Bs : B, do_s ? Ns : Nc, C)) return e;
+    ProjParams p;
+    p.bfold = bf;
+    p.q = static_cast<__nv_bfloat16*>(q); p.k = static_cast<__nv_bfloat16*>(k); p.v = static_cast<__nv_bfloat16*>(v);
+    p.Bw = Bw; p.H = H;
+    p.Bc = do_c ? B : 0; p.Nc = Nc; p.Bs = do_s ? Bs : 0; p.Ns = Ns;
+    p.tiles_c = (Nc + PRJ_BM - 1) / PRJ_BM;
+    p.tiles_s = (Ns + PRJ_BM - 1) / PRJ_BM;
+    p.items_s = p.Bs * H * p.tiles_s;
+    p.items = p.items_s + p.Bc * H * p.tiles_c;
+    constexpr size_t smem = PRJ_STAGES * PRJ_STAGE_BYTES + 1024;
+    static bool attr_done = false;
+    if (!attr_done) {
+        if (int e = check_cuda(cudaFuncSetAttribute(proj_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                    static_cast<int>(smem)), "proj smem attr"))
+            return e;
+        attr_done = true;
     }
+    static int n_sm = 0;
+    if (n_sm == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
+    }
+    const int grid = p.items < 2 * n_sm ? p.items : 2 * n_sm;
+    proj_tc_kernel<<<grid, PRJ_THREADS, smem, s>>>(tmC, tmS, tmW, p);
+    count_launch();
     return check_cuda(cudaGetLastError(), "proj_tc launch");
 }
 
