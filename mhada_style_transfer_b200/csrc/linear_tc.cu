@@ -3,22 +3,20 @@
 // Replaces torch.cat + nn.Conv2d(C, C, 1) at MHAdaSTr/network/adaDecoder.py:202-205 (the concat is
 // free: every head's attention epilogue already wrote its 64-channel slice of the same [M, C] buffer).
 //
-// Structure (one 128 x BN output tile per CTA, 6 warps):
-//   warp 0      TMA producer : x and W tiles -> 128B-swizzled shared memory, 4-stage mbarrier ring
-//   warp 1      tcgen05.mma issuer (one elected lane), accumulator in TMEM (BN columns)
-//   warps 2..5  epilogue     : tcgen05.ld (lane = row) -> + bias -> bf16 -> global
+// Structure (persistent CTAs, two per SM, 6 warps; a work item is one 128 x BN output tile, the BN tiles of the
+// same 128 rows are consecutive items so that x is read from HBM once and from L2 by the other column tiles):
+//   warp 0      TMA producer : x and W tiles -> 128B-swizzled shared memory, 3-stage mbarrier ring that runs
+//               straight across work items (the loads of item n+1 start while item n is still in the MMAs)
+//   warp 1      tcgen05.mma issuer (one elected lane); accumulators DOUBLE-BUFFERED in TMEM (2 x BN columns):
+//               the MMAs of item n+1 overlap the epilogue of item n
+//   warps 2..5  epilogue     : tcgen05.ld (lane = row) -> + bias -> bf16 -> 256-bit global stores
 // HBM-bound at C = 512: algorithmic bytes = M*Cin*2 (read) + M*Cout*2 (write) (+ 0.5 MB weights).
 #include "common.h"
 #include "ptx.cuh"
 
 namespace mh {
 
-// 2 stages on purpose: 64 KB of shared memory per CTA lets three CTAs share an SM, so one CTA's pipeline fill and
-// epilogue overlap the others' main loops (r1: 4 stages = 1 CTA/SM = 52 us on cfg2, 7 serial waves)
-#ifndef MHADA_LIN_STAGES
-#define MHADA_LIN_STAGES 2
-#endif
-constexpr int LIN_BM = 128, LIN_BK = 64, LIN_STAGES = MHADA_LIN_STAGES, LIN_THREADS = 192;
+constexpr int LIN_BM = 128, LIN_BK = 64, LIN_STAGES = 3, LIN_THREADS = 192;
 
 __global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) {
     size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
@@ -26,19 +24,17 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16*
 }
 
 template <int BN>
-__global__ void __launch_bounds__(LIN_THREADS)
+__global__ void __launch_bounds__(LIN_THREADS, 2)
 linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const float* __restrict__ bias, __nv_bfloat16* __restrict__ y, int ldy, int M, int ktiles) {
+                 const float* __restrict__ bias, __nv_bfloat16* __restrict__ y, int ldy, int M, int ktiles, int ntiles,
+                 int items) {
     constexpr uint32_t A_BYTES = LIN_BM * LIN_BK * 2, B_BYTES = BN * LIN_BK * 2, STAGE = A_BYTES + B_BYTES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + LIN_STAGES * STAGE);
-    uint64_t* empty = full + LIN_STAGES;
-    uint64_t* accum = empty + LIN_STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 1);
+    __shared__ uint64_t full[LIN_STAGES], empty[LIN_STAGES], acc_full[2], acc_empty[2];
+    __shared__ uint32_t tmem_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * LIN_BM, n0 = blockIdx.y * BN;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -50,75 +46,95 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 mbar_init(&full[s], 1);
                 mbar_init(&empty[s], 1);
             }
-            mbar_init(accum, 1);
+            for (int u = 0; u < 2; ++u) {
+                mbar_init(&acc_full[u], 1);
+                mbar_init(&acc_empty[u], 4);      // one arrive per epilogue warp
+            }
             fence_mbar_init();
         }
         __syncwarp();
-        tmem_alloc(tmem_slot, BN);
+        tmem_alloc(&tmem_slot, 2 * BN);
         tmem_relinquish();
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
+    const uint32_t tmem = tmem_slot;
 
     if (warp == 0) {
         if (elect_one()) {
-            for (int kt = 0; kt < ktiles; ++kt) {
-                const int s = kt % LIN_STAGES;
-                mbar_wait(&empty[s], ((kt / LIN_STAGES) & 1) ^ 1);
-                mbar_arrive_expect_tx(&full[s], STAGE);
-                uint8_t* a = smem + s * STAGE;
-                tma_load_2d(a, &tmA, &full[s], kt * LIN_BK, m0);
-                tma_load_2d(a + A_BYTES, &tmB, &full[s], kt * LIN_BK, n0);
+            int g = 0;                                            // running k-tile counter of this CTA
+            for (int it = blockIdx.x; it < items; it += gridDim.x) {
+                const int m0 = (it / ntiles) * LIN_BM, n0 = (it % ntiles) * BN;
+                for (int kt = 0; kt < ktiles; ++kt, ++g) {
+                    const int s = g % LIN_STAGES;
+                    mbar_wait(&empty[s], ((g / LIN_STAGES) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&full[s], STAGE);
+                    uint8_t* a = smem + s * STAGE;
+                    tma_load_2d(a, &tmA, &full[s], kt * LIN_BK, m0);
+                    tma_load_2d(a + A_BYTES, &tmB, &full[s], kt * LIN_BK, n0);
+                }
             }
         }
     } else if (warp == 1) {
         if (elect_one()) {
             constexpr uint32_t idesc = make_idesc_bf16(LIN_BM, BN, 0, 0);
-            for (int kt = 0; kt < ktiles; ++kt) {
-                const int s = kt % LIN_STAGES;
-                mbar_wait(&full[s], (kt / LIN_STAGES) & 1);
+            int g = 0, n = 0;
+            for (int it = blockIdx.x; it < items; it += gridDim.x, ++n) {
+                const int u = n & 1;
+                mbar_wait(&acc_empty[u], ((n >> 1) & 1) ^ 1);     // the epilogue has drained this accumulator buffer
                 tc_fence_after();
-                const uint32_t a_addr = smem_u32(smem + s * STAGE);
-                const uint64_t da = make_smem_desc(a_addr, 16, 1024);
-                const uint64_t db = make_smem_desc(a_addr + A_BYTES, 16, 1024);
+                for (int kt = 0; kt < ktiles; ++kt, ++g) {
+                    const int s = g % LIN_STAGES;
+                    mbar_wait(&full[s], (g / LIN_STAGES) & 1);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + s * STAGE);
+                    const uint64_t da = make_smem_desc(a_addr, 16, 1024);
+                    const uint64_t db = make_smem_desc(a_addr + A_BYTES, 16, 1024);
 #pragma unroll
-                for (int k = 0; k < LIN_BK / 16; ++k)
-                    umma_ss(tmem, desc_advance(da, k * 32), desc_advance(db, k * 32), idesc, (kt | k) != 0);
-                umma_commit(&empty[s]);
+                    for (int k = 0; k < LIN_BK / 16; ++k)
+                        umma_ss(tmem + u * BN, desc_advance(da, k * 32), desc_advance(db, k * 32), idesc, (kt | k) != 0);
+                    umma_commit(&empty[s]);
+                }
+                umma_commit(&acc_full[u]);
             }
-            umma_commit(accum);
         }
     } else {
         // epilogue warps 2..5 -> TMEM lane quarters 2,3,0,1
         const int quarter = warp & 3;
         const int row = quarter * 32 + lane;
-        const int m = m0 + row;
-        mbar_wait(accum, 0);
-        tc_fence_after();
+        int n = 0;
+        for (int it = blockIdx.x; it < items; it += gridDim.x, ++n) {
+            const int m = (it / ntiles) * LIN_BM + row, n0 = (it % ntiles) * BN;
+            const int u = n & 1;
+            mbar_wait(&acc_full[u], (n >> 1) & 1);
+            tc_fence_after();
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
-            uint32_t r[32];
-            tmem_ld_x32(tmem_addr(tmem, quarter * 32, c), r);
-            tmem_wait_ld();
-            if (m < M) {
-                uint32_t o[16];
+            for (int c = 0; c < BN; c += 32) {
+                uint32_t r[32];
+                tmem_ld_x32(tmem_addr(tmem, quarter * 32, u * BN + c), r);
+                tmem_wait_ld();
+                if (m < M) {
+                    uint32_t o[16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    float v0 = __uint_as_float(r[2 * i]) + __ldg(bias + n0 + c + 2 * i);
-                    float v1 = __uint_as_float(r[2 * i + 1]) + __ldg(bias + n0 + c + 2 * i + 1);
-                    o[i] = pack_bf16x2(v0, v1);
+                    for (int i = 0; i < 16; ++i) {
+                        float v0 = __uint_as_float(r[2 * i]) + __ldg(bias + n0 + c + 2 * i);
+                        float v1 = __uint_as_float(r[2 * i + 1]) + __ldg(bias + n0 + c + 2 * i + 1);
+                        o[i] = pack_bf16x2(v0, v1);
+                    }
+                    __nv_bfloat16* dst = y + static_cast<size_t>(m) * ldy + n0 + c;
+                    st_global_256(dst, o);
+                    st_global_256(dst + 16, o + 8);
                 }
-                __nv_bfloat16* dst = y + static_cast<size_t>(m) * ldy + n0 + c;
-                st_global_256(dst, o);
-                st_global_256(dst + 16, o + 8);
             }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[u]);
         }
-        tc_fence_before();
     }
+    tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem, BN);
+    if (warp == 1) tmem_dealloc(tmem, 2 * BN);
 }
 
 size_t linear_bf16_workspace(int Cout, int Cin) { return align_up(static_cast<size_t>(Cout) * Cin * 2, 256); }
@@ -131,7 +147,7 @@ static int launch_linear_tc(const CUtensorMap& tmA, const void* wbf, const float
     uint64_t strB[1] = {static_cast<uint64_t>(Cin) * 2};
     uint32_t boxB[2] = {LIN_BK, BN};
     if (int e = make_tmap_bf16(&tmB, wbf, 2, dimsB, strB, boxB)) return e;
-    constexpr size_t smem = LIN_STAGES * (LIN_BM * LIN_BK * 2 + BN * LIN_BK * 2) + 1024 + 256;
+    constexpr size_t smem = LIN_STAGES * (LIN_BM * LIN_BK * 2 + BN * LIN_BK * 2) + 1024;
     static bool attr_done = false;   // idempotent; a benign race only repeats the call
     if (!attr_done) {
         if (int e = check_cuda(cudaFuncSetAttribute(linear_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -139,9 +155,16 @@ static int launch_linear_tc(const CUtensorMap& tmA, const void* wbf, const float
             return e;
         attr_done = true;
     }
-    dim3 grid((M + LIN_BM - 1) / LIN_BM, Cout / BN);
+    const int ntiles = Cout / BN, items = ((M + LIN_BM - 1) / LIN_BM) * ntiles;
+    static int n_sm = 0;
+    if (n_sm == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
+    }
+    const int grid = items < 2 * n_sm ? items : 2 * n_sm;
     linear_tc_kernel<BN><<<grid, LIN_THREADS, smem, s>>>(tmA, tmB, bias, static_cast<__nv_bfloat16*>(y), ldy, M,
-                                                         Cin / LIN_BK);
+                                                         Cin / LIN_BK, ntiles, items);
     count_launch();
     return check_cuda(cudaGetLastError(), "linear_tc launch");
 }
