@@ -156,29 +156,59 @@ int layer_impl(const char* who, int dtype, const void* fc, const void* fs, const
     //     MHADA_REUSE_FS_STATS: fs (and this workspace) are the ones of the previous call, so mean_s / rstd_s
     //     are still valid -- the two layers of a level share fs (adaDecoder.py:264-265)
     const float *mean_x = w.mean_c, *rstd_x = w.rstd_c;
-    {
-        const void* xs[3];
-        float* ms[3];
-        float* rs[3];
-        int ns[3];
-        int n = 0;
-        xs[n] = fc; ms[n] = w.mean_c; rs[n] = w.rstd_c; ns[n] = Nc; ++n;
-        if (!cache && !(flags & MHADA_REUSE_FS_STATS)) { xs[n] = fs; ms[n] = w.mean_s; rs[n] = w.rstd_s; ns[n] = Ns; ++n; }
-        if (fcs != fc) {
-            xs[n] = fcs; ms[n] = w.mean_x; rs[n] = w.rstd_x; ns[n] = Nc; ++n;
-            mean_x = w.mean_x;
-            rstd_x = w.rstd_x;
-        }
-        StageTimer timer(MHADA_STAGE_STATS, s);
-        if (int e = launch_stats_multi(n, xs, ns, ms, rs, dtype, B, C, C, static_cast<float*>(w.stats_ws), s)) return e;
+    if (fcs != fc) {
+        mean_x = w.mean_x;
+        rstd_x = w.rstd_x;
     }
-    // (2) projections                                                        adaDecoder.py:173-183
     const int parts = cache ? MHADA_PROJ_Q : (MHADA_PROJ_Q | MHADA_PROJ_KV);
-    if (StageTimer timer(MHADA_STAGE_PROJ, s); dtype == MHADA_BF16) {
-        if (int e = launch_proj_bf16(parts, fc, fs, w.mean_c, w.rstd_c, w.mean_s, w.rstd_s, w_fgh, b_fgh, B, cache ? 0 : B, Nc, Ns,
-                                     H, d, w.q, w.k, w.v, w.mu_v, w.proj_ws, s))
+    const bool fs_stats = !cache && !(flags & MHADA_REUSE_FS_STATS);
+    if (dtype == MHADA_BF16) {
+        // bf16 path: first pass of the statistics, then ONE kernel that finishes them and folds them into the
+        // projection weights (fold_stats_kernel), then the persistent projection kernel
+        const void* xs[3];
+        int ns[3];
+        int n = 0, ti_s = -1, ti_x = -1;
+        xs[n] = fc; ns[n] = Nc; ++n;
+        if (fs_stats) { ti_s = n; xs[n] = fs; ns[n] = Ns; ++n; }
+        if (fcs != fc) { ti_x = n; xs[n] = fcs; ns[n] = Nc; ++n; }
+        StatsPartialInfo info{};
+        {
+            StageTimer timer(MHADA_STAGE_STATS, s);
+            if (int e = launch_stats_partial(n, xs, ns, dtype, B, C, C, static_cast<float*>(w.stats_ws), &info, s)) return e;
+        }
+        StageTimer timer(MHADA_STAGE_PROJ, s);
+        FoldStatsJob job{};
+        job.max_splits = info.max_splits;
+        auto role = [&](int kind, int ti, const void* x, int N, float* mean, float* rstd) {
+            const int r = job.n_roles++;
+            job.kind[r] = kind; job.ti[r] = ti; job.x[r] = x; job.N[r] = N;
+            job.splits[r] = ti >= 0 ? info.splits[ti] : 0;
+            job.mean[r] = mean; job.rstd[r] = rstd;
+        };
+        role(0, 0, fc, Nc, w.mean_c, w.rstd_c);
+        if (!cache) {
+            role(1, ti_s, fs, Ns, w.mean_s, w.rstd_s);
+            role(2, ti_s, fs, Ns, w.mean_s, w.rstd_s);
+        }
+        if (fcs != fc) role(3, ti_x, fcs, Nc, w.mean_x, w.rstd_x);
+        if (int e = launch_fold_stats(job, static_cast<const float*>(w.stats_ws), w_fgh, b_fgh, B, H, d, w.mu_v, w.proj_ws, s))
+            return e;
+        if (int e = launch_proj_bf16_folded(parts, fc, fs, B, cache ? 0 : B, Nc, Ns, H, d, w.q, w.k, w.v, w.proj_ws, s))
             return e;
     } else {
+        {
+            const void* xs[3];
+            float* ms[3];
+            float* rs[3];
+            int ns[3];
+            int n = 0;
+            xs[n] = fc; ms[n] = w.mean_c; rs[n] = w.rstd_c; ns[n] = Nc; ++n;
+            if (fs_stats) { xs[n] = fs; ms[n] = w.mean_s; rs[n] = w.rstd_s; ns[n] = Ns; ++n; }
+            if (fcs != fc) { xs[n] = fcs; ms[n] = w.mean_x; rs[n] = w.rstd_x; ns[n] = Nc; ++n; }
+            StageTimer timer(MHADA_STAGE_STATS, s);
+            if (int e = launch_stats_multi(n, xs, ns, ms, rs, dtype, B, C, C, static_cast<float*>(w.stats_ws), s)) return e;
+        }
+        StageTimer timer(MHADA_STAGE_PROJ, s);
         if (int e = launch_proj_f32(parts, static_cast<const float*>(fc), static_cast<const float*>(fs), w.mean_c, w.rstd_c,
                                     w.mean_s, w.rstd_s, w_fgh, b_fgh, B, cache ? 0 : B, Nc, Ns, H, d, static_cast<float*>(w.q),
                                     static_cast<float*>(w.k), static_cast<float*>(w.v), w.mu_v, s))

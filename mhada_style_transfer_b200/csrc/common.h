@@ -34,6 +34,14 @@ int launch_stats(const void* x, int dtype, int B, int N, int C, int ld, float* m
 int launch_stats_multi(int n, const void* const* x, const int* N, float* const* mean, float* const* rstd, int dtype,
                        int B, int C, int ld, float* ws, cudaStream_t s);
 
+// first pass of the statistics only (bf16 layer path: fold_stats_kernel finishes them)
+struct StatsPartialInfo {
+    int max_splits;
+    int splits[3];
+};
+int launch_stats_partial(int n, const void* const* x, const int* N, int dtype, int B, int C, int ld, float* ws,
+                         StatsPartialInfo* info, cudaStream_t s);
+
 // f32 SIMT path
 // parts: 1 = Q (content batch B), 2 = K, V (style batch Bs)
 int launch_proj_f32(int parts, const float* fc, const float* fs, const float* mean_c, const float* rstd_c,
@@ -48,6 +56,19 @@ size_t proj_bf16_workspace(int B, int H, int d);
 int launch_proj_bf16(int parts, const void* fc, const void* fs, const float* mean_c, const float* rstd_c,
                      const float* mean_s, const float* rstd_s, const float* w, const float* bias, int B, int Bs, int Nc,
                      int Ns, int H, int d, void* q, void* k, void* v, float* mu_v, void* ws, cudaStream_t s);
+// Roles of fold_stats_kernel: finish the statistics of one tensor from the partial sums (ti >= 0) or take them from
+// mean / rstd (ti < 0), write them, and fold them into one projection's weights (kind 0 f, 1 g, 2 h; 3 = none).
+struct FoldStatsJob {
+    int n_roles;
+    int kind[4], ti[4], N[4], splits[4];
+    const void* x[4];
+    float *mean[4], *rstd[4];
+    int max_splits;
+};
+int launch_fold_stats(const FoldStatsJob& job, const float* partial, const float* w, const float* bias, int B, int H,
+                      int d, float* mu_v, void* proj_ws, cudaStream_t s);
+int launch_proj_bf16_folded(int parts, const void* fc, const void* fs, int B, int Bs, int Nc, int Ns, int H, int d, void* q,
+                            void* k, void* v, void* ws, cudaStream_t s);
 int launch_attn_bf16(const mhada_attn_args& a, cudaStream_t s);
 int launch_attn_bf16_impl(const mhada_attn_args& a, long long* trace, cudaStream_t s);   // trace: 3*64*8 slots or null
 size_t linear_bf16_workspace(int Cout, int Cin);

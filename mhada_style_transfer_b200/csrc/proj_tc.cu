@@ -29,16 +29,15 @@ size_t proj_bf16_workspace(int B, int H, int d) {
 // lanes walk the input channels, so every global read / write is a contiguous row segment.
 // which = which0 + blockIdx.z: 0 = f (content side, batch B), 1 = g, 2 = h (style side, batch Bs).  B here is the
 // batch STRIDE of the folded-weight workspace ([3][B][H][d][d]), the same for both sides.
-__global__ void __launch_bounds__(256) fold_kernel(const float* __restrict__ w, const float* __restrict__ bias,
-                                                   const float* __restrict__ mean_c, const float* __restrict__ rstd_c,
-                                                   const float* __restrict__ mean_s, const float* __restrict__ rstd_s,
-                                                   int which0, int B, int H, int d, __nv_bfloat16* __restrict__ wf,
-                                                   float* __restrict__ bf, float* __restrict__ mu_v) {
-    const int h = blockIdx.x, b = blockIdx.y, which = which0 + blockIdx.z;
+// Folds the statistics (mu, rs: 64 channels of one head, global or shared memory) into the weights of projection
+// `which` of image b, head h.  256 threads = 8 warps: warp w folds output rows w, w+8, ...; lanes walk the input
+// channels, so every global read / write is a contiguous row segment.
+__device__ __forceinline__ void fold_head(const float* __restrict__ w, const float* __restrict__ bias, const float* mu,
+                                          const float* rs, int which, int b, int h, int B, int H, int d,
+                                          __nv_bfloat16* __restrict__ wf, float* __restrict__ bf,
+                                          float* __restrict__ mu_v) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int C = H * d;
-    const float* mu = (which == 0 ? mean_c : mean_s) + static_cast<size_t>(b) * C + h * d;
-    const float* rs = (which == 0 ? rstd_c : rstd_s) + static_cast<size_t>(b) * C + h * d;
     const float gain = which == 0 ? kLog2e : 1.f;
     for (int o = warp; o < d; o += 8) {
         const float* wr = w + ((static_cast<size_t>(which) * H + h) * d + o) * d;
@@ -64,6 +63,69 @@ __global__ void __launch_bounds__(256) fold_kernel(const float* __restrict__ w, 
             }
         }
     }
+}
+
+// grid (H, batch of this part, number of projections).
+// which = which0 + blockIdx.z: 0 = f (content side, batch B), 1 = g, 2 = h (style side, batch Bs).  B here is the
+// batch STRIDE of the folded-weight workspace ([3][B][H][d][d]), the same for both sides.
+__global__ void __launch_bounds__(256) fold_kernel(const float* __restrict__ w, const float* __restrict__ bias,
+                                                   const float* __restrict__ mean_c, const float* __restrict__ rstd_c,
+                                                   const float* __restrict__ mean_s, const float* __restrict__ rstd_s,
+                                                   int which0, int B, int H, int d, __nv_bfloat16* __restrict__ wf,
+                                                   float* __restrict__ bf, float* __restrict__ mu_v) {
+    const int h = blockIdx.x, b = blockIdx.y, which = which0 + blockIdx.z;
+    const int C = H * d;
+    const float* mu = (which == 0 ? mean_c : mean_s) + static_cast<size_t>(b) * C + h * d;
+    const float* rs = (which == 0 ? rstd_c : rstd_s) + static_cast<size_t>(b) * C + h * d;
+    fold_head(w, bias, mu, rs, which, b, h, B, H, d, wf, bf, mu_v);
+}
+
+// Second pass of the instance-norm statistics FUSED with the fold (the layer path; saves a launch and a round trip
+// per layer): block (h, b, role) finishes mean / rstd of its head's 64 channels from the per-split partial sums of
+// stats_partial_kernel -- same arithmetic as stats_final_kernel (double, pivot = first token) -- publishes them, and
+// folds them into its projection.  Roles g and h both finish the fs statistics (64 channels x <= 32 splits: cheaper
+// than a hand-over); role kind 3 only publishes (fcs: consumed by the attention epilogue).  ti < 0: the statistics
+// are already in mean / rstd (MHADA_REUSE_FS_STATS).
+__global__ void __launch_bounds__(256) fold_stats_kernel(const FoldStatsJob job, const float* __restrict__ partial,
+                                                         const float* __restrict__ w, const float* __restrict__ bias, int B,
+                                                         int H, __nv_bfloat16* __restrict__ wf, float* __restrict__ bf,
+                                                         float* __restrict__ mu_v) {
+    constexpr int d = PRJ_D;
+    __shared__ float mu_s[d], rs_s[d];
+    const int h = blockIdx.x, b = blockIdx.y, role = blockIdx.z;
+    const int C = H * d;
+    const int kind = job.kind[role], ti = job.ti[role];
+    if (threadIdx.x < d) {
+        const int c = h * d + threadIdx.x;
+        const size_t r = static_cast<size_t>(b) * C + c;
+        float m, rs;
+        if (ti >= 0) {
+            const int N = job.N[role], nsplit = job.splits[role];
+            double a = 0.0, q = 0.0;
+            for (int sp = 0; sp < nsplit; ++sp) {
+                const float* p = partial + (((static_cast<size_t>(ti) * B + b) * job.max_splits + sp) * C + c) * 2;
+                a += p[0];
+                q += p[1];
+            }
+            const double piv = __bfloat162float(static_cast<const __nv_bfloat16*>(job.x[role])[static_cast<size_t>(b) * N * C + c]);
+            const double mm = a / N;
+            double var = q / N - mm * mm;
+            if (var < 0.0) var = 0.0;
+            m = static_cast<float>(piv + mm);
+            rs = static_cast<float>(1.0 / sqrt(var + static_cast<double>(1e-5f)));   // nn.InstanceNorm2d eps, as stats.cu
+            if (kind != 2) {                       // roles g and h compute the same numbers: one of them writes
+                job.mean[role][r] = m;
+                job.rstd[role][r] = rs;
+            }
+        } else {
+            m = job.mean[role][r];
+            rs = job.rstd[role][r];
+        }
+        mu_s[threadIdx.x] = m;
+        rs_s[threadIdx.x] = rs;
+    }
+    __syncthreads();
+    if (kind < 3) fold_head(w, bias, mu_s, rs_s, kind, b, h, B, H, d, wf, bf, mu_v);
 }
 
 // Persistent projection kernel: one launch covers the content side (Q from fc) and the style side (K and V' from
@@ -236,9 +298,9 @@ static int make_x_map(CUtensorMap* tm, const void* x, int B, int N, int C) {
     return make_tmap_bf16(tm, x, 3, dims, str, box);
 }
 
-int launch_proj_bf16(int parts, const void* fc, const void* fs, const float* mean_c, const float* rstd_c,
-                     const float* mean_s, const float* rstd_s, const float* w, const float* bias, int B, int Bs, int Nc,
-                     int Ns, int H, int d, void* q, void* k, void* v, float* mu_v, void* ws, cudaStream_t s) {
+// the persistent projection kernel on weights that are already folded (in `ws`)
+int launch_proj_bf16_folded(int parts, const void* fc, const void* fs, int B, int Bs, int Nc, int Ns, int H, int d, void* q,
+                            void* k, void* v, void* ws, cudaStream_t s) {
     // parts: 1 = Q from fc (batch B), 2 = K and V' from fs (batch Bs).  Bw = batch stride of the folded weights.
     const int Bw = B > Bs ? B : Bs;
     __nv_bfloat16* wf = static_cast<__nv_bfloat16*>(ws);
@@ -250,20 +312,6 @@ int launch_proj_bf16(int parts, const void* fc, const void* fs, const float* mea
     uint32_t boxW[2] = {PRJ_D, PRJ_D};
     if (int e = make_tmap_bf16(&tmW, wf, 2, dimsW, strW, boxW)) return e;
     const bool do_c = parts & 1, do_s = parts & 2;
-    // fold the instance norm into the per-image weights: one launch when both sides have the same batch
-    if (do_c && do_s && B == Bs) {
-        fold_kernel<<<dim3(H, B, 3), 256, 0, s>>>(w, bias, mean_c, rstd_c, mean_s, rstd_s, 0, Bw, H, d, wf, bf, mu_v);
-        count_launch();
-    } else {
-        if (do_c) {
-            fold_kernel<<<dim3(H, B, 1), 256, 0, s>>>(w, bias, mean_c, rstd_c, mean_s, rstd_s, 0, Bw, H, d, wf, bf, mu_v);
-            count_launch();
-        }
-        if (do_s) {
-            fold_kernel<<<dim3(H, Bs, 2), 256, 0, s>>>(w, bias, mean_c, rstd_c, mean_s, rstd_s, 1, Bw, H, d, wf, bf, mu_v);
-            count_launch();
-        }
-    }
     CUtensorMap tmC, tmS;
     if (int e = make_x_map(&tmC, do_c ? fc : fs, do_c ? B : Bs, do_c ? Nc : Ns, C)) return e;
     if (int e = make_x_map(&tmS, do_s ? fs : fc, do_s ? Bs : B, do_s ? Ns : Nc, C)) return e;
@@ -294,6 +342,39 @@ int launch_proj_bf16(int parts, const void* fc, const void* fs, const float* mea
     proj_tc_kernel<<<grid, PRJ_THREADS, smem, s>>>(tmC, tmS, tmW, p);
     count_launch();
     return check_cuda(cudaGetLastError(), "proj_tc launch");
+}
+
+int launch_fold_stats(const FoldStatsJob& job, const float* partial, const float* w, const float* bias, int B, int H,
+                      int d, float* mu_v, void* proj_ws, cudaStream_t s) {
+    __nv_bfloat16* wf = static_cast<__nv_bfloat16*>(proj_ws);
+    float* bf = reinterpret_cast<float*>(static_cast<uint8_t*>(proj_ws) + fold_w_bytes(B, H, d));
+    fold_stats_kernel<<<dim3(H, B, job.n_roles), 256, 0, s>>>(job, partial, w, bias, B, H, wf, bf, mu_v);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "fold_stats launch");
+}
+
+int launch_proj_bf16(int parts, const void* fc, const void* fs, const float* mean_c, const float* rstd_c,
+                     const float* mean_s, const float* rstd_s, const float* w, const float* bias, int B, int Bs, int Nc,
+                     int Ns, int H, int d, void* q, void* k, void* v, float* mu_v, void* ws, cudaStream_t s) {
+    const int Bw = B > Bs ? B : Bs;
+    __nv_bfloat16* wf = static_cast<__nv_bfloat16*>(ws);
+    float* bf = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + fold_w_bytes(Bw, H, d));
+    const bool do_c = parts & 1, do_s = parts & 2;
+    // fold the instance norm into the per-image weights: one launch when both sides have the same batch
+    if (do_c && do_s && B == Bs) {
+        fold_kernel<<<dim3(H, B, 3), 256, 0, s>>>(w, bias, mean_c, rstd_c, mean_s, rstd_s, 0, Bw, H, d, wf, bf, mu_v);
+        count_launch();
+    } else {
+        if (do_c) {
+            fold_kernel<<<dim3(H, B, 1), 256, 0, s>>>(w, bias, mean_c, rstd_c, mean_s, rstd_s, 0, Bw, H, d, wf, bf, mu_v);
+            count_launch();
+        }
+        if (do_s) {
+            fold_kernel<<<dim3(H, Bs, 2), 256, 0, s>>>(w, bias, mean_c, rstd_c, mean_s, rstd_s, 1, Bw, H, d, wf, bf, mu_v);
+            count_launch();
+        }
+    }
+    return launch_proj_bf16_folded(parts, fc, fs, B, Bs, Nc, Ns, H, d, q, k, v, ws, s);
 }
 
 }  // namespace mh

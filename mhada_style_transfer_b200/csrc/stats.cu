@@ -169,32 +169,53 @@ size_t stats_workspace(int B, int N, int C) {
     return static_cast<size_t>(3) * B * 32 * C * 2 * sizeof(float);
 }
 
-int launch_stats_multi(int n, const void* const* x, const int* N, float* const* mean, float* const* rstd, int dtype,
-                       int B, int C, int ld, float* ws, cudaStream_t s) {
+static StatsJob make_job(int n, const void* const* x, const int* N, float* const* mean, float* const* rstd) {
     StatsJob job{};
     job.n = n;
     job.max_splits = 0;
     for (int i = 0; i < n; ++i) {
-        job.x[i] = x[i]; job.mean[i] = mean[i]; job.rstd[i] = rstd[i]; job.N[i] = N[i];
+        job.x[i] = x[i]; job.N[i] = N[i];
+        job.mean[i] = mean ? mean[i] : nullptr;
+        job.rstd[i] = rstd ? rstd[i] : nullptr;
         job.tps[i] = stats_tokens_per_split(N[i]);
         job.splits[i] = stats_splits(N[i]);
         if (job.splits[i] > job.max_splits) job.max_splits = job.splits[i];
     }
+    return job;
+}
+
+static void launch_partial(const StatsJob& job, int dtype, int B, int C, int ld, float* ws, cudaStream_t s) {
     const int vec = dtype == MHADA_BF16 ? 8 : 4;
-    dim3 grid((C + 32 * vec - 1) / (32 * vec), job.max_splits, B * n);
-    const int fin_blocks = (n * B * C + 255) / 256;
-    if (dtype == MHADA_BF16) {
+    dim3 grid((C + 32 * vec - 1) / (32 * vec), job.max_splits, B * job.n);
+    if (dtype == MHADA_BF16)
         stats_partial_kernel<__nv_bfloat16><<<grid, kStatsThreads, 0, s>>>(job, B, C, ld, ws);
-        count_launch();
-        stats_final_kernel<__nv_bfloat16><<<fin_blocks, 256, 0, s>>>(job, ws, B, C, ld);
-        count_launch();
-    } else {
+    else
         stats_partial_kernel<float><<<grid, kStatsThreads, 0, s>>>(job, B, C, ld, ws);
-        count_launch();
+    count_launch();
+}
+
+int launch_stats_multi(int n, const void* const* x, const int* N, float* const* mean, float* const* rstd, int dtype,
+                       int B, int C, int ld, float* ws, cudaStream_t s) {
+    const StatsJob job = make_job(n, x, N, mean, rstd);
+    launch_partial(job, dtype, B, C, ld, ws, s);
+    const int fin_blocks = (n * B * C + 255) / 256;
+    if (dtype == MHADA_BF16)
+        stats_final_kernel<__nv_bfloat16><<<fin_blocks, 256, 0, s>>>(job, ws, B, C, ld);
+    else
         stats_final_kernel<float><<<fin_blocks, 256, 0, s>>>(job, ws, B, C, ld);
-        count_launch();
-    }
+    count_launch();
     return check_cuda(cudaGetLastError(), "stats launch");
+}
+
+// First pass only: the per-split partial sums [n][B][max_splits][C][2] stay in `ws`; the caller's next kernel
+// (fold_stats_kernel, proj_tc.cu) finishes the statistics of the channels it needs.
+int launch_stats_partial(int n, const void* const* x, const int* N, int dtype, int B, int C, int ld, float* ws,
+                         StatsPartialInfo* info, cudaStream_t s) {
+    const StatsJob job = make_job(n, x, N, nullptr, nullptr);
+    launch_partial(job, dtype, B, C, ld, ws, s);
+    info->max_splits = job.max_splits;
+    for (int i = 0; i < 3; ++i) info->splits[i] = i < n ? job.splits[i] : 0;
+    return check_cuda(cudaGetLastError(), "stats partial launch");
 }
 
 int launch_stats(const void* x, int dtype, int B, int N, int C, int ld, float* mean, float* rstd, float* ws,
