@@ -180,6 +180,12 @@ MHADA_API int mhada_layer_forward_cached(int dtype, const void* fc, const void* 
  *         x [B, H, W, C]  ->  y [B, Ho + 2, Wo + 2, C],   Ho, Wo = H, W or 2H, 2W.
  *     C must be a multiple of 8 (bf16) / 4 (f32); pointers 16-byte aligned.
  * ---------------------------------------------------------------------------------------------- */
+/*     Last decoder block in one kernel -- replaces ReflectionPad2d(1) + Conv2d(64, Cout <= 8, 3) (+ ReLU) of
+ *     conv3[1] = ConvReLU(64, 3, 3, 1), conv.py:90-93: x [B, H, W, 64] bf16 channels_last, NOT padded (the
+ *     reflection is resolved in the kernel's load indices); w float [Cout][64][3][3]; y [B, Cout, H, W] bf16.
+ *     MHADA_BF16 only (the fp32 path keeps the library convolution). */
+MHADA_API int mhada_conv3x3_small(int dtype, const void* x, const float* w, const float* bias, int B, int H, int W, int Cin,
+                                  int Cout, int relu, void* y, mhada_stream_t stream);
 MHADA_API int mhada_pad_reflect(int dtype, const void* x, int B, int H, int W, int C, int upsample, void* y,
                                 mhada_stream_t stream);
 

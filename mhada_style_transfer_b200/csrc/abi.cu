@@ -399,6 +399,17 @@ int mhada_linear(int dtype, const void* x, int ldx, const float* w, const float*
     return launch_linear_bf16(x, ldx, w, bias, M, Cin, Cout, y, ldy, ws, s);
 }
 
+int mhada_conv3x3_small(int dtype, const void* x, const float* w, const float* bias, int B, int H, int W, int Cin, int Cout,
+                        int relu, void* y, mhada_stream_t stream) {
+    g_launches = 0;
+    REQUIRE(x && w && bias && y, MHADA_ERR_ARG, "mhada_conv3x3_small: null pointer");
+    REQUIRE(dtype == MHADA_BF16, MHADA_ERR_UNSUPPORTED, "mhada_conv3x3_small: MHADA_BF16 only");
+    REQUIRE(B > 0 && H >= 2 && W >= 2, MHADA_ERR_ARG, "mhada_conv3x3_small: bad sizes (ReflectionPad2d(1) needs H, W >= 2)");
+    REQUIRE(aligned16(x), MHADA_ERR_ARG, "mhada_conv3x3_small: x must be 16-byte aligned");
+    if (int e = device_check()) return e;
+    return launch_conv3x3_small(x, w, bias, B, H, W, Cin, Cout, relu, y, static_cast<cudaStream_t>(stream));
+}
+
 int mhada_pad_reflect(int dtype, const void* x, int B, int H, int W, int C, int upsample, void* y,
                       mhada_stream_t stream) {
     REQUIRE(x && y, MHADA_ERR_ARG, "mhada_pad_reflect: null pointer");

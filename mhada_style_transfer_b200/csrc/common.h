@@ -75,6 +75,9 @@ size_t linear_bf16_workspace(int Cout, int Cin);
 int launch_linear_bf16(const void* x, int ldx, const float* w, const float* bias, int M, int Cin, int Cout, void* y,
                        int ldy, void* ws, cudaStream_t s);
 
+// decoder: last block (reflect pad + 3x3 conv to <= 8 channels + ReLU) in one kernel
+int launch_conv3x3_small(const void* x, const float* w, const float* bias, int B, int H, int W, int Cin, int Cout, int relu,
+                         void* y, cudaStream_t s);
 // decoder glue
 int launch_pad_reflect(int dtype, const void* x, int B, int H, int W, int C, int upsample, void* y, cudaStream_t s);
 

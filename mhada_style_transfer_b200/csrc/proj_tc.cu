@@ -92,21 +92,37 @@ __global__ void __launch_bounds__(256) fold_stats_kernel(const FoldStatsJob job,
                                                          float* __restrict__ mu_v) {
     constexpr int d = PRJ_D;
     __shared__ float mu_s[d], rs_s[d];
+    __shared__ double part_a[4][d], part_q[4][d];
     const int h = blockIdx.x, b = blockIdx.y, role = blockIdx.z;
     const int C = H * d;
     const int kind = job.kind[role], ti = job.ti[role];
+    const int ch = threadIdx.x & (d - 1), grp = threadIdx.x >> 6;      // 4 groups of 64 threads share the splits
+    if (ti >= 0) {
+        // split s goes to group s % 4; the per-group sums are then added in group order 0..3.  (The order differs
+        // from stats_final_kernel's sequential loop only in double precision: the float results are the same
+        // unless a sum lands within 1e-16 relative of a rounding boundary.)
+        const int nsplit = job.splits[role];
+        const int c = h * d + ch;
+        double a = 0.0, q = 0.0;
+        const float* p0 = partial + ((static_cast<size_t>(ti) * B + b) * job.max_splits * C + c) * 2;
+#pragma unroll 8
+        for (int sp = grp; sp < nsplit; sp += 4) {
+            const float2 v = __ldg(reinterpret_cast<const float2*>(p0 + static_cast<size_t>(sp) * C * 2));
+            a += v.x;
+            q += v.y;
+        }
+        part_a[grp][ch] = a;
+        part_q[grp][ch] = q;
+    }
+    __syncthreads();
     if (threadIdx.x < d) {
         const int c = h * d + threadIdx.x;
         const size_t r = static_cast<size_t>(b) * C + c;
         float m, rs;
         if (ti >= 0) {
-            const int N = job.N[role], nsplit = job.splits[role];
-            double a = 0.0, q = 0.0;
-            for (int sp = 0; sp < nsplit; ++sp) {
-                const float* p = partial + (((static_cast<size_t>(ti) * B + b) * job.max_splits + sp) * C + c) * 2;
-                a += p[0];
-                q += p[1];
-            }
+            const int N = job.N[role];
+            const double a = ((part_a[0][ch] + part_a[1][ch]) + part_a[2][ch]) + part_a[3][ch];
+            const double q = ((part_q[0][ch] + part_q[1][ch]) + part_q[2][ch]) + part_q[3][ch];
             const double piv = __bfloat162float(static_cast<const __nv_bfloat16*>(job.x[role])[static_cast<size_t>(b) * N * C + c]);
             const double mm = a / N;
             double var = q / N - mm * mm;

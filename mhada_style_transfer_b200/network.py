@@ -531,6 +531,19 @@ def _pad_reflect(x_tok: torch.Tensor, upsample: bool) -> torch.Tensor:
     return y
 
 
+def _conv3x3_small_relu(x_tok: torch.Tensor, w: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """[B,H,W,64] bf16 -> [B,Cout,H,W] bf16: ReflectionPad2d(1) + 3x3 conv + bias + ReLU (mhada_conv3x3_small)."""
+    L = _lib.lib()
+    B, H, W, C = x_tok.shape
+    cout = w.shape[0]
+    wf, bf = w.detach().float().contiguous(), b.detach().float().contiguous()
+    y = torch.empty((B, cout, H, W), dtype=torch.bfloat16, device=x_tok.device)
+    with torch.cuda.device(x_tok.device):
+        rc = L.mhada_conv3x3_small(_lib.BF16, _ptr(x_tok), _ptr(wf), _ptr(bf), B, H, W, C, cout, 1, _ptr(y), _stream())
+    _lib.check("mhada_conv3x3_small", rc)
+    return y
+
+
 _CUDNN_RELU_OK = {}
 
 
@@ -577,6 +590,10 @@ class Decoder(nn.Module):
         ctx = torch.backends.cudnn.flags(enabled=True, allow_tf32=False) if x.dtype == torch.float32 else _NullCtx()
         with ctx:                                            # fp32 path: the reference's fp32 arithmetic, not TF32
             for blk in self._blocks():
+                cin, cout = blk.conv.conv.in_channels, blk.conv.conv.out_channels
+                if x.dtype == torch.bfloat16 and cin == 64 and cout <= 8 and not up and not blk.scale_factor:
+                    # last block (conv.py:90-93): pad + conv + ReLU in one own kernel, straight to NCHW planes
+                    return _conv3x3_small_relu(x, blk.conv.conv.weight, blk.conv.conv.bias)
                 xp = _pad_reflect(x, up)                     # conv.py:26-27 (+ :71 of the previous block)
                 w, b = blk.conv._weights(x.dtype)
                 y = _conv3x3_relu(xp.permute(0, 3, 1, 2), w, b)
