@@ -39,6 +39,43 @@ __device__ __forceinline__ void fold_head(const float* __restrict__ w, const flo
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int C = H * d;
     const float gain = which == 0 ? kLog2e : 1.f;
+    if (d == PRJ_D) {
+        // head_dim 64 (the only one the tensor-core path runs): all 16 weight loads of the warp's 8 rows are issued
+        // before the first use -- row by row, each row waited a full L2 round trip (14.6 us for 256 tiny blocks)
+        float wv[8][2];
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+                wv[r][k] = __ldg(w + ((static_cast<size_t>(which) * H + h) * PRJ_D + warp + 8 * r) * PRJ_D + lane + 32 * k);
+        const float mu0 = mu[lane], mu1 = mu[lane + 32];
+        const float rs0 = which != 2 ? rs[lane] : 1.f, rs1 = which != 2 ? rs[lane + 32] : 1.f;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int o = warp + 8 * r;
+            __nv_bfloat16* dst = wf + (((static_cast<size_t>(which) * B + b) * H + h) * PRJ_D + o) * PRJ_D;
+            float wa = wv[r][0] * gain, wb = wv[r][1] * gain;
+            if (which != 2) { wa *= rs0; wb *= rs1; }
+            const __nv_bfloat16 ba = __float2bfloat16_rn(wa), bb = __float2bfloat16_rn(wb);
+            dst[lane] = ba;
+            dst[lane + 32] = bb;
+            float acc = fmaf(__bfloat162float(ba), mu0, 0.f);      // same order as the generic loop below
+            acc = fmaf(__bfloat162float(bb), mu1, acc);
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+            if (lane == 0) {
+                const float bo = bias[(static_cast<size_t>(which) * H + h) * PRJ_D + o];
+                const size_t bi = ((static_cast<size_t>(which) * B + b) * H + h) * PRJ_D + o;
+                if (which == 2) {
+                    bf[bi] = -acc;
+                    mu_v[static_cast<size_t>(b) * C + h * PRJ_D + o] = acc + bo;
+                } else {
+                    bf[bi] = bo * gain - acc;
+                }
+            }
+        }
+        return;
+    }
     for (int o = warp; o < d; o += 8) {
         const float* wr = w + ((static_cast<size_t>(which) * H + h) * d + o) * d;
         __nv_bfloat16* dst = wf + (((static_cast<size_t>(which) * B + b) * H + h) * d + o) * d;
