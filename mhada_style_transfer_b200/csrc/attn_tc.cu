@@ -7,14 +7,15 @@
 // is consumed straight from TMEM by the second MMA, which multiplies by V' = [V~ | V~^2] (128 wide)
 // so the mean and the second moment come out of ONE pass (V~ = V - mu_v, added back at the end).
 //
-// CTA = 2 query tiles of 128 rows x 1 head, key tiles of 64, 12 warps:
+// CTA = 2 query tiles of 128 rows x 1 head, key tiles of 64, 16 warps:
 //   warp 0       TMA producer: Q (once), K ring (4 x 8 KB), V' ring (4 x 16 KB), 128B swizzle
 //   warp 1, 2    tcgen05.mma issuers, one elected lane each: warp 1 for query tile 0, warp 2 for query tile 1
 //                (warp 2 also allocates the 512 TMEM columns; per query tile t: S buffers at t*256 + {0, 64},
 //                O at t*256 + 128)
 //   warp 3       idle after set-up
-//   warps 4-7    softmax + epilogue for query tile 0 (thread = row; TMEM lane = row, no shuffles)
+//   warps 4-7    softmax for query tile 0 (thread = row; TMEM lane = row, no shuffles)
 //   warps 8-11   same for query tile 1
+//   warps 12-15  epilogue of both query tiles (reads O out of TMEM while the other warps are in the next work item)
 // Pipeline (measured motivation in DESIGN.md, attention section): S is DOUBLE-BUFFERED in TMEM, so
 // S(j+1), S(j+2) are computed while the softmax warps still work on tile j -- they do not wait for the
 // tensor core in steady state, and the exp2 (MUFU) units, which bound this head_dim-64 problem, stay busy.
@@ -50,7 +51,7 @@ constexpr int AT_KST = 4, AT_VST = 4;
 #define MHADA_AT_POLY 0
 #endif
 constexpr int AT_TILE_THREADS = 128;             // softmax threads per query tile (thread = row)
-constexpr int AT_THREADS = 128 + 2 * AT_TILE_THREADS;
+constexpr int AT_THREADS = 128 + 2 * AT_TILE_THREADS + 128;   // + one epilogue warpgroup
 constexpr unsigned AT_POLY = MHADA_AT_POLY;
 #ifndef MHADA_AT_TRACE_QUARTER
 #define MHADA_AT_TRACE_QUARTER 0
@@ -96,7 +97,10 @@ struct AttnBars {
     uint64_t pv_done[2];      // one phase per key tile: PV_t(j) retired (O_t quiescent until P_t(j+1) arrives)
     uint64_t o_full[2];       // one phase per work item: its last PV_t retired
     uint32_t tmem_slot;
-    float cst[2][3][AT_D];    // per query tile: x_mean, x_rstd, mu_v of the current (image, head)
+    uint64_t epi_ready[2];    // one phase per work item: the softmax warps of tile t are done, lsum[t] is written
+    uint64_t o_free[2];       // one phase per work item: the epilogue warps have read O_t out of TMEM
+    float cst[3][AT_D];       // x_mean, x_rstd, mu_v of the (image, head) the epilogue warps are working on
+    float lsum[2][AT_BM];     // row sums of the finished work item, per query tile
 };
 
 template <bool TRACE>
@@ -146,6 +150,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             }
             mbar_init(&bars->pv_done[t], 1);
             mbar_init(&bars->o_full[t], 1);
+            mbar_init(&bars->epi_ready[t], 4);      // one arrive per softmax warp
+            mbar_init(&bars->o_free[t], 4);         // one arrive per epilogue warp
         }
         fence_mbar_init();
     }
@@ -161,7 +167,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     // Register hand-over: the setmaxnreg calls sit INSIDE the role branches (no join before the role
     // code) so ptxas allocates each branch against its own budget.
     if (warp < 4) {
-      setmaxnreg_dec<64>();
+      setmaxnreg_dec<56>();
       if (warp == 0) {
         // ===================================================================== TMA producer
         if (elect_one()) {
@@ -248,6 +254,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                     mbar_wait(&bars->v_full[vs], (g / AT_VST) & 1);
                     if (n == 0 && t == 0) stamp(2, j, 4);
                     mbar_wait(&bars->p_ready[t][g & 1], (g >> 1) & 1);
+                    if (j == 0 && n > 0) mbar_wait(&bars->o_free[t], (n - 1) & 1);   // O_t of the previous item has been read
                     tc_fence_after();
                     if (n == 0) stamp(2, j, 2 * t);
                     issue_pv(g, j == 0, j == T - 1);
@@ -264,13 +271,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             }
         }
       }
-    } else {
-        setmaxnreg_inc<216>();
-        // ===================================================================== softmax + epilogue
+    } else if (warp < 12) {
+        setmaxnreg_inc<152>();
+        // ===================================================================== softmax
         const int t = (warp - 4) >> 2;           // query tile of this warp
         const int quarter = warp & 3;            // TMEM lane quarter this warp may touch (= its SM sub-partition)
         const int row = quarter * 32 + lane;
-        const int tile_tid = threadIdx.x - 128 - t * AT_TILE_THREADS;
         const uint32_t s_tm = tmem_addr(tmem, quarter * 32, t * 256);        // P(j) overwrites the first 32 columns of S(j)
         const uint32_t o_tm = tmem_addr(tmem, quarter * 32, t * 256 + 128);
         const bool tr0 = TRACE && quarter == AT_TRACE_QUARTER && lane == 0;
@@ -282,26 +288,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 
         int n = 0;
         for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++n) {
-            const int qx = it % XT, h = (it / XT) % p.H, b = it / (XT * p.H);
-            const int q0 = qx * (2 * AT_BM), g0 = n * T;
+            const int g0 = n * T;
             const bool last_item = it + static_cast<int>(gridDim.x) >= n_items;
-            // epilogue operands that do not depend on the attention: issue their loads now
-            {
-                const size_t sidx = (static_cast<size_t>(b) * p.H + h) * AT_D;
-                named_bar_sync(3 + t, AT_TILE_THREADS);   // previous item's epilogue of this tile is done with cst
-                if (tile_tid < AT_D) {
-                    bars->cst[t][0][tile_tid] = p.x_mean[sidx + tile_tid];
-                    bars->cst[t][1][tile_tid] = p.x_rstd[sidx + tile_tid];
-                } else if (tile_tid < 2 * AT_D) {
-                    const size_t vidx = (static_cast<size_t>(p.kv_shared ? 0 : b) * p.H + h) * AT_D;
-                    bars->cst[t][2][tile_tid - AT_D] = p.mu_v ? p.mu_v[vidx + tile_tid - AT_D] : 0.f;
-                }
-            }
-            const int nrow = q0 + t * AT_BM + row;
-            const bool row_ok = nrow < p.Nc;
-            const size_t tok = static_cast<size_t>(b) * p.Nc + (row_ok ? nrow : 0);
-            const __nv_bfloat16* xrow = p.x + tok * p.ldx + h * AT_D;
-            __nv_bfloat16* orow = p.out + tok * p.ldo + h * AT_D;
 
             // Online softmax with a LAGGING reference: the weights of key tile j are 2^(s - m) with m the (integer)
             // reference fixed by the tiles before it; the exact maximum is taken up front for the first tile of an
@@ -437,52 +425,99 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             key_tile(0, std::true_type{});
             for (int j = 1; j < T; ++j) key_tile(j, std::false_type{});
 
-            // ---- epilogue: O/l -> (M~, E~) -> sqrt(max(E~ - M~^2, 1e-6)) * IN(fcs) + M~ + mu_v
-            // The fcs row is fetched before waiting for the last PV, so its latency hides behind the MMA tail.
-            uint4 xv[AT_D / 8];
-            if (row_ok) {
-#pragma unroll
-                for (int i = 0; i < AT_D / 8; ++i) xv[i] = __ldg(reinterpret_cast<const uint4*>(xrow) + i);
-            }
-            named_bar_sync(3 + t, AT_TILE_THREADS);  // cst[t] of this item is complete
-            // (pv_done cannot be used here: a parity wait is only meaningful while the barrier is at most one
-            // phase ahead, and a late warp may find both PV(T-2) and PV(T-1) retired -- o_full has one phase per item)
-            mbar_wait(&bars->o_full[t], n & 1);
-            if (tr0 && n == 0) stamp(t, 63, 5);
-            tc_fence_after();
-            const float inv = 1.f / l;
-            const uint32_t* xw = reinterpret_cast<const uint32_t*>(xv);
-            // kept rolled on purpose: unrolling it costs the main loop registers (measured 0.472 -> 0.444 ms on cfg2)
-#pragma unroll 1
-            for (int c = 0; c < AT_D; c += 32) {
-                uint32_t mm[32], ee[32];
-                tmem_ld_x32(o_tm + c, mm);
-                tmem_ld_x32(o_tm + AT_D + c, ee);
-                tmem_wait_ld();
-                uint32_t ov[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    float r[2];
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int ch = c + 2 * i + e;
-                        const float m = __uint_as_float(mm[2 * i + e]) * inv;
-                        const float ex = __uint_as_float(ee[2 * i + e]) * inv;
-                        float sd;
-                        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sd) : "f"(fmaxf(fmaf(-m, m, ex), 1e-6f)));
-                        const float xf = e == 0 ? bf16_lo(xw[(c >> 1) + i]) : bf16_hi(xw[(c >> 1) + i]);
-                        const float xn = (xf - bars->cst[t][0][ch]) * bars->cst[t][1][ch];
-                        r[e] = fmaf(sd, xn, m + bars->cst[t][2][ch]);
-                    }
-                    ov[i] = pack_bf16x2(r[0], r[1]);
-                }
-                if (row_ok) {
-                    st_global_256(orow + c, ov);
-                    st_global_256(orow + c + 16, ov + 8);
-                }
-            }
+            // ---- hand the finished tile to the epilogue warps and go straight on to the next work item
+            // (lsum[t] / epi_ready[t] may only be reused once the epilogue of the PREVIOUS item has read them: it
+            // arrived on o_free[t] after doing so; in steady state that was ~a whole item ago)
+            if (n > 0) mbar_wait(&bars->o_free[t], (n - 1) & 1);
+            bars->lsum[t][row] = l;
             tc_fence_before();
-            if (tr0 && n == 0) stamp(t, 63, 6);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->epi_ready[t]);
+            if (tr0 && n == 0) stamp(t, 63, 5);
+        }
+    } else {
+        setmaxnreg_inc<152>();
+        // ===================================================================== epilogue warpgroup (warps 12-15)
+        // O/l -> (M~, E~) -> sqrt(max(E~ - M~^2, 1e-6)) * IN(fcs) + M~ + mu_v for both query tiles of a work item,
+        // while the softmax warps and the tensor core are already in the next item: per item the softmax warps used
+        // to spend ~3400 cycles here plus the wait for their slowest sibling (8 % of a cfg2 item).
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        const int et = threadIdx.x - (AT_THREADS - 128);          // 0 .. 127
+        const bool tr0 = TRACE && quarter == AT_TRACE_QUARTER && lane == 0;
+        int n = 0;
+        for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++n) {
+            const int qx = it % XT, h = (it / XT) % p.H, b = it / (XT * p.H);
+            const int q0 = qx * (2 * AT_BM);
+            {
+                const size_t sidx = (static_cast<size_t>(b) * p.H + h) * AT_D;
+                named_bar_sync(3, 128);                   // the previous item's epilogue is done with cst
+                if (et < AT_D) {
+                    bars->cst[0][et] = p.x_mean[sidx + et];
+                    bars->cst[1][et] = p.x_rstd[sidx + et];
+                } else {
+                    const size_t vidx = (static_cast<size_t>(p.kv_shared ? 0 : b) * p.H + h) * AT_D;
+                    bars->cst[2][et - AT_D] = p.mu_v ? p.mu_v[vidx + et - AT_D] : 0.f;
+                }
+                named_bar_sync(3, 128);
+            }
+#pragma unroll 1
+            for (int t = 0; t < 2; ++t) {
+                const uint32_t o_tm = tmem_addr(tmem, quarter * 32, t * 256 + 128);
+                const int nrow = q0 + t * AT_BM + row;
+                const bool row_ok = nrow < p.Nc;
+                const size_t tok = static_cast<size_t>(b) * p.Nc + (row_ok ? nrow : 0);
+                const __nv_bfloat16* xrow = p.x + tok * p.ldx + h * AT_D;
+                __nv_bfloat16* orow = p.out + tok * p.ldo + h * AT_D;
+                // The fcs row is fetched before waiting for the tile, so its latency hides behind the attention.
+                uint4 xv[AT_D / 8];
+                if (row_ok) {
+#pragma unroll
+                    for (int i = 0; i < AT_D / 8; ++i) xv[i] = __ldg(reinterpret_cast<const uint4*>(xrow) + i);
+                }
+                mbar_wait(&bars->epi_ready[t], n & 1);    // softmax warps done: lsum[t] is valid
+                // (pv_done cannot be used here: a parity wait is only meaningful while the barrier is at most one
+                // phase ahead -- o_full has one phase per item)
+                mbar_wait(&bars->o_full[t], n & 1);       // the last PV of the item has retired
+                tc_fence_after();
+                const float inv = 1.f / bars->lsum[t][row];
+                const uint32_t* xw = reinterpret_cast<const uint32_t*>(xv);
+#pragma unroll 1
+                for (int c = 0; c < AT_D; c += 32) {
+                    uint32_t mm[32], ee[32];
+                    tmem_ld_x32(o_tm + c, mm);
+                    tmem_ld_x32(o_tm + AT_D + c, ee);
+                    tmem_wait_ld();
+                    if (c + 32 == AT_D) {
+                        // O_t and lsum[t] are in registers: the next item's first PV may overwrite the accumulator
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&bars->o_free[t]);
+                    }
+                    uint32_t ov[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        float r[2];
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int ch = c + 2 * i + e;
+                            const float m = __uint_as_float(mm[2 * i + e]) * inv;
+                            const float ex = __uint_as_float(ee[2 * i + e]) * inv;
+                            float sd;
+                            asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sd) : "f"(fmaxf(fmaf(-m, m, ex), 1e-6f)));
+                            const float xf = e == 0 ? bf16_lo(xw[(c >> 1) + i]) : bf16_hi(xw[(c >> 1) + i]);
+                            const float xn = (xf - bars->cst[0][ch]) * bars->cst[1][ch];
+                            r[e] = fmaf(sd, xn, m + bars->cst[2][ch]);
+                        }
+                        ov[i] = pack_bf16x2(r[0], r[1]);
+                    }
+                    if (row_ok) {
+                        st_global_256(orow + c, ov);
+                        st_global_256(orow + c + 16, ov + 8);
+                    }
+                }
+                if (tr0 && n == 0) stamp(t, 63, 6);
+            }
         }
     }
     __syncthreads();
