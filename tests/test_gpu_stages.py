@@ -247,3 +247,54 @@ def test_pad_reflect(code, B, H, W, C, up):
     got = y.float().cpu().numpy().astype(np.float64).transpose(0, 3, 1, 2)
     e = O.errors(got, want)
     assert e["max_abs_rel"] <= (4e-3 if (code == BF16 and up) else 1e-6), e
+
+
+@pytest.mark.parametrize("B,H,W,cout", [(1, 40, 56, 3), (2, 33, 17, 3), (1, 64, 64, 8), (1, 2, 2, 1)])
+def test_conv3x3_small(B, H, W, cout):
+    """mhada_conv3x3_small (reflect pad + 3x3 conv from 64 channels + ReLU, one kernel) against float64 on the same
+    bf16-rounded operands: what is left is the fp32 accumulation order and the bf16 output rounding."""
+    L = _lib.lib()
+    x = synth.bellish(71, (B, H, W, 64), 0.3, 1.0)
+    w = synth.bellish(72, (cout, 64, 3, 3), 0.0, 0.05)
+    b = synth.uniform(73, (cout,), -0.5, 0.5)
+    tx = torch.from_numpy(x).float().to(G.DEV).to(torch.bfloat16).contiguous()
+    tw, tb = G.f32(w), G.f32(b)
+    y = torch.empty(B, cout, H, W, dtype=torch.bfloat16, device=G.DEV)
+    _lib.check("mhada_conv3x3_small", L.mhada_conv3x3_small(BF16, tx.data_ptr(), tw.data_ptr(), tb.data_ptr(), B, H, W, 64, cout,
+                                                            1, y.data_ptr(), G.stream()))
+    torch.cuda.synchronize()
+    xr = tx.double().permute(0, 3, 1, 2)
+    wr = tw.to(torch.bfloat16).double()
+    want = torch.relu(torch.nn.functional.conv2d(torch.nn.functional.pad(xr, (1, 1, 1, 1), mode="reflect"), wr, tb.double()))
+    e = O.errors(y.double().cpu().numpy(), want.cpu().numpy())
+    assert e["max_abs_rel"] < 6e-3, e                   # bf16 output rounding: 2^-9 of the value
+
+
+def test_profile_stage_brackets():
+    """mhada_profile_stage: one bracket per stage per layer call, times are positive and attention dominates."""
+    L = _lib.lib()
+    B, H, d, N = 2, 8, 64, 4096
+    C = H * d
+    g = torch.Generator(device=G.DEV).manual_seed(0)
+    fc, fs = ((torch.randn(B, N, C, device=G.DEV, generator=g) * 10).bfloat16() for _ in range(2))
+    w = (torch.rand(3, H, d, d, device=G.DEV, generator=g) - 0.5) / 4
+    b = (torch.rand(3, H, d, device=G.DEV, generator=g) - 0.5) / 4
+    wo = (torch.rand(C, C, device=G.DEV, generator=g) - 0.5) / 11
+    bo = (torch.rand(C, device=G.DEV, generator=g) - 0.5) / 11
+    out = torch.empty_like(fc)
+    ws = torch.empty(L.mhada_layer_workspace(BF16, B, N, N, C, H), dtype=torch.uint8, device=G.DEV)
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    L.mhada_profile_begin()
+    for _ in range(3):
+        _lib.check("layer", L.mhada_layer_forward(BF16, P(fc), P(fs), P(fc), P(w), P(b), P(wo), P(bo), B, N, N, C, H, 0, P(out), P(ws),
+                                                  ws.numel(), G.stream()))
+    ms, n = ctypes.c_float(0), ctypes.c_int(0)
+    _lib.check("end", L.mhada_profile_end(ctypes.byref(ms), ctypes.byref(n)))
+    assert n.value == 3 and ms.value > 0
+    total = {}
+    for name, code in (("stats", 0), ("proj", 1), ("attn", 2), ("linear", 3)):
+        _lib.check("stage", L.mhada_profile_stage(code, ctypes.byref(ms), ctypes.byref(n)))
+        assert n.value == 3 and ms.value > 0, name
+        total[name] = ms.value
+    assert total["attn"] == max(total.values()), total
+    assert L.mhada_profile_stage(7, ctypes.byref(ms), ctypes.byref(n)) != 0
