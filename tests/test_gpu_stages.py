@@ -179,7 +179,10 @@ def test_attn_f32(B, H, Nc, Ns, dqk, dv):
 @pytest.mark.parametrize("B,H,Nc,Ns,gain,ramp", [(1, 1, 128, 128, 0.5, 0), (1, 1, 256, 128, 0.5, 0), (1, 1, 128, 384, 0.5, 0),
                                                  (2, 8, 256, 256, 0.6, 0), (1, 8, 135, 143, 0.6, 0), (1, 2, 300, 1000, 0.6, 0),
                                                  (1, 2, 512, 700, 2.0, 0), (1, 8, 4096, 4096, 0.6, 0), (1, 1, 70, 1, 0.6, 0),
-                                                 (1, 2, 300, 700, 0.6, 4.0), (2, 2, 256, 1000, 1.0, 1.0)])
+                                                 (1, 2, 300, 700, 0.6, 4.0), (2, 2, 256, 1000, 1.0, 1.0),
+                                                 # persistent CTAs (288 work items) with 1 / 3 key tiles per item: the softmax
+                                                 # warps can run a whole item ahead of the epilogue warps (flow control)
+                                                 (36, 8, 256, 64, 0.6, 0), (36, 8, 200, 130, 0.6, 0), (74, 4, 256, 1, 0.6, 0)])
 def test_attn_bf16(B, H, Nc, Ns, gain, ramp):
     """tcgen05 kernel against a float64 evaluation on the SAME bf16-rounded operands: what is left is
     the bf16 rounding of P, fp32 accumulation and the bf16 output rounding.  ramp > 0: keys of later tiles are
