@@ -136,8 +136,8 @@ int layer_impl(const char* who, int dtype, const void* fc, const void* fs, const
     REQUIRE(out != fc && out != fs && out != fcs, MHADA_ERR_ARG, "%s: out must not alias an input", who);
     const int d = C / H;
     if (dtype == MHADA_BF16)
-        REQUIRE(d == 64, MHADA_ERR_UNSUPPORTED,
-                "%s: the bf16 tensor-core path implements head_dim 64 (C/H = %d); use MHADA_F32", who, d);
+        REQUIRE(d == 64 || d == 128, MHADA_ERR_UNSUPPORTED,
+                "%s: the bf16 tensor-core path implements head_dim 64 and 128 (C/H = %d); use MHADA_F32", who, d);
     REQUIRE(!(flags & MHADA_LAYER_COSINE) || dtype == MHADA_F32, MHADA_ERR_UNSUPPORTED,
             "%s: the cosine activation (adaDecoder.py:20-34) runs on the MHADA_F32 path only", who);
     REQUIRE(aligned16(fc) && (!fs || aligned16(fs)) && aligned16(fcs) && aligned32(out) && aligned32(ws), MHADA_ERR_ARG,
@@ -322,7 +322,8 @@ int mhada_proj(int dtype, int parts, const void* fc, const void* fs, const float
                                static_cast<float*>(v), mu_v, s);
     }
     REQUIRE(dtype == MHADA_BF16, MHADA_ERR_ARG, "mhada_proj: bad dtype %d", dtype);
-    REQUIRE(d == 64, MHADA_ERR_UNSUPPORTED, "mhada_proj: the bf16 tensor-core path implements head_dim 64, got %d", d);
+    REQUIRE(d == 64 || d == 128, MHADA_ERR_UNSUPPORTED,
+            "mhada_proj: the bf16 tensor-core path implements head_dim 64 and 128, got %d", d);
     REQUIRE(ws && ws_bytes >= proj_bf16_workspace(B > Bs ? B : Bs, H, d), MHADA_ERR_WORKSPACE, "mhada_proj: workspace too small");
     REQUIRE((!(parts & 1) || (aligned16(fc) && aligned32(q))) && (!(parts & 2) || (aligned16(fs) && aligned32(k) && aligned32(v))) &&
                 aligned16(ws),
@@ -353,10 +354,10 @@ int mhada_attn(const mhada_attn_args* a, mhada_stream_t stream) {
         return attn_dispatch(*a, s);
     }
     REQUIRE(a->dtype == MHADA_BF16, MHADA_ERR_ARG, "mhada_attn: bad dtype %d", a->dtype);
-    REQUIRE(a->dqk == 64 && a->dv == 64, MHADA_ERR_UNSUPPORTED,
-            "mhada_attn: the bf16 tensor-core path implements dqk = dv = 64, got %d / %d", a->dqk, a->dv);
+    REQUIRE(a->dqk == a->dv && (a->dqk == 64 || a->dqk == 128), MHADA_ERR_UNSUPPORTED,
+            "mhada_attn: the bf16 tensor-core path implements dqk = dv = 64 or 128, got %d / %d", a->dqk, a->dv);
     REQUIRE(!a->q_mean && !a->k_mean, MHADA_ERR_UNSUPPORTED, "mhada_attn: normalise-on-load is f32-path only");
-    const int C = a->H * 64;
+    const int C = a->H * a->dqk;
     REQUIRE(a->ldq >= C && a->ldk >= C && a->ldv >= 2 * C && a->ldx >= C && a->ldo >= C, MHADA_ERR_ARG,
             "mhada_attn: pitch smaller than the row");
     REQUIRE(a->ldq % 8 == 0 && a->ldk % 8 == 0 && a->ldv % 8 == 0 && a->ldx % 8 == 0 && a->ldo % 16 == 0 &&
@@ -458,8 +459,8 @@ int mhada_style_precompute(int dtype, const void* fs, const float* w_fgh, const 
     REQUIRE(dtype == MHADA_F32 || dtype == MHADA_BF16, MHADA_ERR_ARG, "mhada_style_precompute: bad dtype %d", dtype);
     const int d = C / H;
     if (dtype == MHADA_BF16)
-        REQUIRE(d == 64 && C % 16 == 0, MHADA_ERR_UNSUPPORTED,
-                "mhada_style_precompute: the bf16 tensor-core path implements head_dim 64 (C/H = %d)", d);
+        REQUIRE((d == 64 || d == 128) && C % 16 == 0, MHADA_ERR_UNSUPPORTED,
+                "mhada_style_precompute: the bf16 tensor-core path implements head_dim 64 and 128 (C/H = %d)", d);
     REQUIRE(aligned16(fs) && aligned32(cache) && aligned32(ws), MHADA_ERR_ARG, "mhada_style_precompute: misaligned pointer");
     StyleCacheView cv = carve_cache(dtype, Bs, Ns, C, static_cast<uint8_t*>(cache));
     REQUIRE(cache_bytes >= cv.total, MHADA_ERR_WORKSPACE, "mhada_style_precompute: cache %zu < %zu", cache_bytes, cv.total);

@@ -59,10 +59,17 @@ constexpr unsigned AT_POLY = MHADA_AT_POLY;
 constexpr int AT_TRACE_QUARTER = MHADA_AT_TRACE_QUARTER;   // which softmax warp of a tile writes the trace stamps
 // 2^f on [-0.5, 0.5], minimax in relative error (7.5e-5 = 2^-13.7, far below the bf16 rounding of P that follows)
 constexpr float AT_EX2_C0 = 0.9999281168f, AT_EX2_C1 = 0.6932609677f, AT_EX2_C2 = 0.2426107526f, AT_EX2_C3 = 0.0551714078f;
-constexpr uint32_t AT_Q_BYTES = AT_BM * AT_D * 2;          // 16 KB per query tile
-constexpr uint32_t AT_K_BYTES = AT_BN * AT_D * 2;          // 8 KB
+constexpr uint32_t AT_QC_BYTES = AT_BM * AT_D * 2;         // 16 KB per query tile and 64-channel chunk of the head
+constexpr uint32_t AT_KC_BYTES = AT_BN * AT_D * 2;         // 8 KB per key tile and chunk
 constexpr uint32_t AT_V_BYTES = AT_BN * AT_DV2 * 2;        // 16 KB (two 64-column boxes)
-constexpr uint32_t AT_SMEM_DATA = 2 * AT_Q_BYTES + AT_KST * AT_K_BYTES + AT_VST * AT_V_BYTES;
+// KCH = head_dim / 64.  The kernel's "head" index runs over VALUE SLICES of 64 channels (p.H = heads * KCH): slice
+// hv belongs to head hv / KCH, whose full-width Q and K (KCH chunks) it contracts for the logits, and owns value
+// columns [hv * 64, +64) and their squares.  With KCH = 2 (4 heads at C = 512) each head's logits and weights are
+// computed once per slice, i.e. twice: the accumulator [V~ | V~^2] of a whole 128-wide head would need 256 TMEM
+// columns per query tile and leave room for one tile per CTA.
+template <int KCH> constexpr uint32_t at_smem_data() {
+    return 2 * KCH * AT_QC_BYTES + AT_KST * KCH * AT_KC_BYTES + AT_VST * AT_V_BYTES;
+}
 constexpr float AT_RESCALE_THRESHOLD = 64.0f;              // log2 units: weights of a tile may reach 2^64 before the reference moves
 // 0: the two query tiles' softmax warps run free (default since the row maximum left the critical path: with one
 //    MMA issuer per tile the streams de-phase on their own; cfg2 0.422 ms / cfg3 0.857 ms);
@@ -103,13 +110,14 @@ struct AttnBars {
     float lsum[2][AT_BM];     // row sums of the finished work item, per query tile
 };
 
-template <bool TRACE>
+template <bool TRACE, int KCH>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const AttnTcParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sQ = smem;
+    constexpr uint32_t AT_Q_BYTES = KCH * AT_QC_BYTES, AT_K_BYTES = KCH * AT_KC_BYTES;   // per query tile / key tile
     uint8_t* sK = sQ + 2 * AT_Q_BYTES;
     uint8_t* sV = sK + AT_KST * AT_K_BYTES;
     AttnBars* bars = reinterpret_cast<AttnBars*>(sV + AT_VST * AT_V_BYTES);
@@ -180,12 +188,19 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                     const int g = g0 + j, ks = g % AT_KST;
                     mbar_wait(&bars->k_empty[ks], ((g / AT_KST) & 1) ^ 1);
                     mbar_arrive_expect_tx(&bars->k_full[ks], AT_K_BYTES);
-                    tma_load_3d(sK + ks * AT_K_BYTES, &tmK, &bars->k_full[ks], h * AT_D, j * AT_BN, bkv);
+#pragma unroll
+                    for (int c = 0; c < KCH; ++c)
+                        tma_load_3d(sK + ks * AT_K_BYTES + c * AT_KC_BYTES, &tmK, &bars->k_full[ks],
+                                    ((h / KCH) * KCH + c) * AT_D, j * AT_BN, bkv);
                 };
                 mbar_wait(&bars->q_empty, (n & 1) ^ 1);      // all S MMAs of the previous item have read Q
                 mbar_arrive_expect_tx(&bars->q_full, 2 * AT_Q_BYTES);
-                tma_load_3d(sQ, &tmQ, &bars->q_full, h * AT_D, q0, b);
-                tma_load_3d(sQ + AT_Q_BYTES, &tmQ, &bars->q_full, h * AT_D, q0 + AT_BM, b);
+#pragma unroll
+                for (int c = 0; c < KCH; ++c) {
+                    tma_load_3d(sQ + c * AT_QC_BYTES, &tmQ, &bars->q_full, ((h / KCH) * KCH + c) * AT_D, q0, b);
+                    tma_load_3d(sQ + AT_Q_BYTES + c * AT_QC_BYTES, &tmQ, &bars->q_full, ((h / KCH) * KCH + c) * AT_D,
+                                q0 + AT_BM, b);
+                }
                 load_k(0);
                 if (T > 1) load_k(1);
                 for (int j = 0; j < T; ++j) {
@@ -223,8 +238,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 const uint64_t db = desc_advance(k_desc, (g % AT_KST) * AT_K_BYTES);
                 const uint32_t d_tm = s_tm0 + (g & 1) * 64;
 #pragma unroll
-                for (int k = 0; k < AT_D / 16; ++k)
-                    umma_ss(d_tm, desc_advance(q_desc, k * 32), desc_advance(db, k * 32), idesc_s, k != 0);
+                for (int c = 0; c < KCH; ++c)
+#pragma unroll
+                    for (int k = 0; k < AT_D / 16; ++k)
+                        umma_ss(d_tm, desc_advance(q_desc, c * AT_QC_BYTES + k * 32), desc_advance(db, c * AT_KC_BYTES + k * 32),
+                                idesc_s, (c | k) != 0);
                 umma_commit(&bars->s_full[t][g & 1]);
             };
             auto issue_pv = [&](int g, bool first, bool last) {
@@ -529,8 +547,17 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 
 int launch_attn_bf16(const mhada_attn_args& a, cudaStream_t s) { return launch_attn_bf16_impl(a, nullptr, s); }
 
+template <int KCH>
+static int launch_attn_bf16_kch(const mhada_attn_args& a, long long* trace, cudaStream_t s);
+
 int launch_attn_bf16_impl(const mhada_attn_args& a, long long* trace, cudaStream_t s) {
-    const int C = a.H * AT_D;
+    if (a.dqk == 2 * AT_D) return launch_attn_bf16_kch<2>(a, trace, s);
+    return launch_attn_bf16_kch<1>(a, trace, s);
+}
+
+template <int KCH>
+static int launch_attn_bf16_kch(const mhada_attn_args& a, long long* trace, cudaStream_t s) {
+    const int C = a.H * KCH * AT_D;
     const int kvB = a.kv_batch == 1 ? 1 : a.B;       // style batch: 1 = shared by all images
     CUtensorMap tmQ, tmK, tmV;
     {
@@ -555,21 +582,21 @@ int launch_attn_bf16_impl(const mhada_attn_args& a, long long* trace, cudaStream
     p.x = static_cast<const __nv_bfloat16*>(a.x);
     p.out = static_cast<__nv_bfloat16*>(a.out);
     p.x_mean = a.x_mean; p.x_rstd = a.x_rstd; p.mu_v = a.mu_v;
-    p.B = a.B; p.H = a.H; p.Nc = a.Nc; p.Ns = a.Ns; p.ldx = a.ldx; p.ldo = a.ldo;
+    p.B = a.B; p.H = a.H * KCH; p.Nc = a.Nc; p.Ns = a.Ns; p.ldx = a.ldx; p.ldo = a.ldo;     // p.H: value slices
     p.kv_shared = (a.kv_batch == 1 && a.B > 1) ? 1 : 0;
     p.trace = trace;
-    constexpr size_t smem = AT_SMEM_DATA + sizeof(AttnBars) + 1024;
+    constexpr size_t smem = at_smem_data<KCH>() + sizeof(AttnBars) + 1024;
     static bool attr_done = false;
     if (!attr_done) {
-        if (int e = check_cuda(cudaFuncSetAttribute(attn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        if (int e = check_cuda(cudaFuncSetAttribute(attn_tc_kernel<false, KCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                     static_cast<int>(smem)), "attn smem attr"))
             return e;
-        if (int e = check_cuda(cudaFuncSetAttribute(attn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        if (int e = check_cuda(cudaFuncSetAttribute(attn_tc_kernel<true, KCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                     static_cast<int>(smem)), "attn smem attr"))
             return e;
         attr_done = true;
     }
-    const int n_items = ((a.Nc + 2 * AT_BM - 1) / (2 * AT_BM)) * a.H * a.B;
+    const int n_items = ((a.Nc + 2 * AT_BM - 1) / (2 * AT_BM)) * p.H * a.B;
     static int n_sm = 0;
     if (n_sm == 0) {
         int dev = 0;
@@ -587,9 +614,9 @@ int launch_attn_bf16_impl(const mhada_attn_args& a, long long* trace, cudaStream
 #endif
     dim3 grid(persistent ? n_sm : n_items);
     if (trace)
-        attn_tc_kernel<true><<<grid, AT_THREADS, smem, s>>>(tmQ, tmK, tmV, p);
+        attn_tc_kernel<true, KCH><<<grid, AT_THREADS, smem, s>>>(tmQ, tmK, tmV, p);
     else
-        attn_tc_kernel<false><<<grid, AT_THREADS, smem, s>>>(tmQ, tmK, tmV, p);
+        attn_tc_kernel<false, KCH><<<grid, AT_THREADS, smem, s>>>(tmQ, tmK, tmV, p);
     count_launch();
     return check_cuda(cudaGetLastError(), "attn_tc launch");
 }

@@ -125,15 +125,15 @@ __global__ void __launch_bounds__(256) fold_kernel(const float* __restrict__ w, 
 // are already in mean / rstd (MHADA_REUSE_FS_STATS).
 __global__ void __launch_bounds__(256) fold_stats_kernel(const FoldStatsJob job, const float* __restrict__ partial,
                                                          const float* __restrict__ w, const float* __restrict__ bias, int B,
-                                                         int H, __nv_bfloat16* __restrict__ wf, float* __restrict__ bf,
+                                                         int H, int d, __nv_bfloat16* __restrict__ wf, float* __restrict__ bf,
                                                          float* __restrict__ mu_v) {
-    constexpr int d = PRJ_D;
-    __shared__ float mu_s[d], rs_s[d];
-    __shared__ double part_a[4][d], part_q[4][d];
+    // d = head_dim: 64 or 128 (a power of two <= 256 in general); 256 / d groups of d threads share the splits
+    __shared__ float mu_s[256], rs_s[256];
+    __shared__ double part_a[256], part_q[256];                        // [group][channel], group-major
     const int h = blockIdx.x, b = blockIdx.y, role = blockIdx.z;
     const int C = H * d;
     const int kind = job.kind[role], ti = job.ti[role];
-    const int ch = threadIdx.x & (d - 1), grp = threadIdx.x >> 6;      // 4 groups of 64 threads share the splits
+    const int ch = threadIdx.x & (d - 1), grp = threadIdx.x / d, ngrp = 256 / d;
     if (ti >= 0) {
         // split s goes to group s % 4; the per-group sums are then added in group order 0..3.  (The order differs
         // from stats_final_kernel's sequential loop only in double precision: the float results are the same
@@ -143,13 +143,13 @@ __global__ void __launch_bounds__(256) fold_stats_kernel(const FoldStatsJob job,
         double a = 0.0, q = 0.0;
         const float* p0 = partial + ((static_cast<size_t>(ti) * B + b) * job.max_splits * C + c) * 2;
 #pragma unroll 8
-        for (int sp = grp; sp < nsplit; sp += 4) {
+        for (int sp = grp; sp < nsplit; sp += ngrp) {
             const float2 v = __ldg(reinterpret_cast<const float2*>(p0 + static_cast<size_t>(sp) * C * 2));
             a += v.x;
             q += v.y;
         }
-        part_a[grp][ch] = a;
-        part_q[grp][ch] = q;
+        part_a[grp * d + ch] = a;
+        part_q[grp * d + ch] = q;
     }
     __syncthreads();
     if (threadIdx.x < d) {
@@ -158,8 +158,11 @@ __global__ void __launch_bounds__(256) fold_stats_kernel(const FoldStatsJob job,
         float m, rs;
         if (ti >= 0) {
             const int N = job.N[role];
-            const double a = ((part_a[0][ch] + part_a[1][ch]) + part_a[2][ch]) + part_a[3][ch];
-            const double q = ((part_q[0][ch] + part_q[1][ch]) + part_q[2][ch]) + part_q[3][ch];
+            double a = part_a[ch], q = part_q[ch];
+            for (int gI = 1; gI < ngrp; ++gI) {
+                a += part_a[gI * d + ch];
+                q += part_q[gI * d + ch];
+            }
             const double piv = __bfloat162float(static_cast<const __nv_bfloat16*>(job.x[role])[static_cast<size_t>(b) * N * C + c]);
             const double mm = a / N;
             double var = q / N - mm * mm;
@@ -190,9 +193,11 @@ __global__ void __launch_bounds__(256) fold_stats_kernel(const FoldStatsJob job,
 //               n+1 run while the epilogue warps drain item n
 //   warps 2-5   epilogue: TMEM -> registers, + folded bias, bf16, 256-bit stores (V' also stores the squares)
 // Two CTAs per SM (96 KB of shared memory, 256 TMEM columns each).
+// KCH = head_dim / 64: a head's d x d projection is done as KCH output blocks of 64 channels (one per work item),
+// each contracting the KCH input chunks of the token tile with KCH 64 x 64 weight blocks.
 constexpr int PRJ_STAGES = 3;
 constexpr uint32_t PRJ_A_BYTES = PRJ_BM * PRJ_D * 2, PRJ_W_BYTES = PRJ_D * PRJ_D * 2;
-constexpr uint32_t PRJ_STAGE_BYTES = PRJ_A_BYTES + 2 * PRJ_W_BYTES;
+template <int KCH> constexpr uint32_t prj_stage_bytes() { return KCH * (PRJ_A_BYTES + 2 * PRJ_W_BYTES); }
 
 struct ProjParams {
     const float* bfold;              // [3][Bw][H][64] folded biases
@@ -202,11 +207,11 @@ struct ProjParams {
 };
 
 struct ProjItem {
-    int side, b, h, n0;              // side 0 = content (Q), 1 = style (K, V')
+    int side, b, h, n0;              // side 0 = content (Q), 1 = style (K, V'); h = output block = head * KCH + block
 };
 
 __device__ __forceinline__ ProjItem proj_item(const ProjParams& p, int idx) {
-    ProjItem it;
+    ProjItem it;                     // p.H counts 64-channel output blocks (heads * KCH)
     it.side = idx < p.items_s ? 1 : 0;
     const int r = it.side ? idx : idx - p.items_s;
     const int tiles = it.side ? p.tiles_s : p.tiles_c;
@@ -216,7 +221,8 @@ __device__ __forceinline__ ProjItem proj_item(const ProjParams& p, int idx) {
     return it;
 }
 
-__global__ void __launch_bounds__(PRJ_THREADS, 2)
+template <int KCH>
+__global__ void __launch_bounds__(PRJ_THREADS, KCH == 1 ? 2 : 1)
 proj_tc_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmS,
                const __grid_constant__ CUtensorMap tmW, const ProjParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -226,6 +232,8 @@ proj_tc_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_constant__ 
     __shared__ float bias_s[2][2][PRJ_D];        // [accumulator buffer][output][channel]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr uint32_t PRJ_STAGE_BYTES = prj_stage_bytes<KCH>();
+    constexpr uint32_t X_BYTES = KCH * PRJ_A_BYTES, W_BYTES = KCH * PRJ_W_BYTES;   // per stage: X | W(out 0) | W(out 1)
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmC);
@@ -255,12 +263,20 @@ proj_tc_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_constant__ 
                 const int s = n % PRJ_STAGES;
                 mbar_wait(&empty[s], ((n / PRJ_STAGES) & 1) ^ 1);
                 uint8_t* st = smem + s * PRJ_STAGE_BYTES;
-                mbar_arrive_expect_tx(&full[s], PRJ_A_BYTES + (it.side ? 2 : 1) * PRJ_W_BYTES);
-                tma_load_3d(st, it.side ? &tmS : &tmC, &full[s], it.h * PRJ_D, it.n0, it.b);
+                mbar_arrive_expect_tx(&full[s], X_BYTES + (it.side ? 2 : 1) * W_BYTES);
+                const int head = it.h / KCH;
                 const int which0 = it.side ? 1 : 0;
-                tma_load_2d(st + PRJ_A_BYTES, &tmW, &full[s], 0, ((which0 * p.Bw + it.b) * p.H + it.h) * PRJ_D);
-                if (it.side)
-                    tma_load_2d(st + PRJ_A_BYTES + PRJ_W_BYTES, &tmW, &full[s], 0, ((2 * p.Bw + it.b) * p.H + it.h) * PRJ_D);
+#pragma unroll
+                for (int c = 0; c < KCH; ++c) {
+                    // input chunk c of the head; weight block (output block it.h, input chunk c): rows of W' are output
+                    // channels ([3][Bw][heads * KCH * 64] rows in all), columns input channels of the head
+                    tma_load_3d(st + c * PRJ_A_BYTES, it.side ? &tmS : &tmC, &full[s], (head * KCH + c) * PRJ_D, it.n0, it.b);
+                    tma_load_2d(st + X_BYTES + c * PRJ_W_BYTES, &tmW, &full[s], c * PRJ_D,
+                                ((which0 * p.Bw + it.b) * p.H + it.h) * PRJ_D);
+                    if (it.side)
+                        tma_load_2d(st + X_BYTES + W_BYTES + c * PRJ_W_BYTES, &tmW, &full[s], c * PRJ_D,
+                                    ((2 * p.Bw + it.b) * p.H + it.h) * PRJ_D);
+                }
             }
         }
     } else if (warp == 1) {
@@ -276,10 +292,13 @@ proj_tc_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_constant__ 
                 const uint32_t a_addr = smem_u32(smem + s * PRJ_STAGE_BYTES);
                 const uint64_t da = make_smem_desc(a_addr, 16, 1024);
                 for (int t = 0; t <= side; ++t) {
-                    const uint64_t db = make_smem_desc(a_addr + PRJ_A_BYTES + t * PRJ_W_BYTES, 16, 1024);
+                    const uint64_t db = make_smem_desc(a_addr + X_BYTES + t * W_BYTES, 16, 1024);
 #pragma unroll
-                    for (int k = 0; k < PRJ_D / 16; ++k)
-                        umma_ss(tmem + u * 128 + t * 64, desc_advance(da, k * 32), desc_advance(db, k * 32), idesc, k != 0);
+                    for (int c = 0; c < KCH; ++c)
+#pragma unroll
+                        for (int k = 0; k < PRJ_D / 16; ++k)
+                            umma_ss(tmem + u * 128 + t * 64, desc_advance(da, c * PRJ_A_BYTES + k * 32),
+                                    desc_advance(db, c * PRJ_W_BYTES + k * 32), idesc, (c | k) != 0);
                 }
                 umma_commit(&empty[s]);         // the stage may be refilled once these MMAs have read it
                 umma_commit(&acc_full[u]);
@@ -359,6 +378,7 @@ int launch_proj_bf16_folded(int parts, const void* fc, const void* fs, int B, in
     __nv_bfloat16* wf = static_cast<__nv_bfloat16*>(ws);
     float* bf = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + fold_w_bytes(Bw, H, d));
     const int C = H * d;
+    const int kch = d / PRJ_D;
     CUtensorMap tmW;
     uint64_t dimsW[2] = {static_cast<uint64_t>(d), static_cast<uint64_t>(3) * Bw * H * d};
     uint64_t strW[1] = {static_cast<uint64_t>(d) * 2};
@@ -371,17 +391,20 @@ int launch_proj_bf16_folded(int parts, const void* fc, const void* fs, int B, in
     ProjParams p;
     p.bfold = bf;
     p.q = static_cast<__nv_bfloat16*>(q); p.k = static_cast<__nv_bfloat16*>(k); p.v = static_cast<__nv_bfloat16*>(v);
-    p.Bw = Bw; p.H = H;
+    p.Bw = Bw; p.H = H * kch;                      // 64-channel output blocks
     p.Bc = do_c ? B : 0; p.Nc = Nc; p.Bs = do_s ? Bs : 0; p.Ns = Ns;
     p.tiles_c = (Nc + PRJ_BM - 1) / PRJ_BM;
     p.tiles_s = (Ns + PRJ_BM - 1) / PRJ_BM;
-    p.items_s = p.Bs * H * p.tiles_s;
-    p.items = p.items_s + p.Bc * H * p.tiles_c;
-    constexpr size_t smem = PRJ_STAGES * PRJ_STAGE_BYTES + 1024;
+    p.items_s = p.Bs * p.H * p.tiles_s;
+    p.items = p.items_s + p.Bc * p.H * p.tiles_c;
+    const size_t smem = PRJ_STAGES * (kch == 1 ? prj_stage_bytes<1>() : prj_stage_bytes<2>()) + 1024;
     static bool attr_done = false;
     if (!attr_done) {
-        if (int e = check_cuda(cudaFuncSetAttribute(proj_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                    static_cast<int>(smem)), "proj smem attr"))
+        if (int e = check_cuda(cudaFuncSetAttribute(proj_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                    static_cast<int>(PRJ_STAGES * prj_stage_bytes<1>() + 1024)), "proj smem attr"))
+            return e;
+        if (int e = check_cuda(cudaFuncSetAttribute(proj_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                    static_cast<int>(PRJ_STAGES * prj_stage_bytes<2>() + 1024)), "proj smem attr"))
             return e;
         attr_done = true;
     }
@@ -391,8 +414,12 @@ int launch_proj_bf16_folded(int parts, const void* fc, const void* fs, int B, in
         cudaGetDevice(&dev);
         if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
     }
-    const int grid = p.items < 2 * n_sm ? p.items : 2 * n_sm;
-    proj_tc_kernel<<<grid, PRJ_THREADS, smem, s>>>(tmC, tmS, tmW, p);
+    const int ctas = (kch == 1 ? 2 : 1) * n_sm;
+    const int grid = p.items < ctas ? p.items : ctas;
+    if (kch == 1)
+        proj_tc_kernel<1><<<grid, PRJ_THREADS, smem, s>>>(tmC, tmS, tmW, p);
+    else
+        proj_tc_kernel<2><<<grid, PRJ_THREADS, smem, s>>>(tmC, tmS, tmW, p);
     count_launch();
     return check_cuda(cudaGetLastError(), "proj_tc launch");
 }
@@ -401,7 +428,7 @@ int launch_fold_stats(const FoldStatsJob& job, const float* partial, const float
                       int d, float* mu_v, void* proj_ws, cudaStream_t s) {
     __nv_bfloat16* wf = static_cast<__nv_bfloat16*>(proj_ws);
     float* bf = reinterpret_cast<float*>(static_cast<uint8_t*>(proj_ws) + fold_w_bytes(B, H, d));
-    fold_stats_kernel<<<dim3(H, B, job.n_roles), 256, 0, s>>>(job, partial, w, bias, B, H, wf, bf, mu_v);
+    fold_stats_kernel<<<dim3(H, B, job.n_roles), 256, 0, s>>>(job, partial, w, bias, B, H, d, wf, bf, mu_v);
     count_launch();
     return check_cuda(cudaGetLastError(), "fold_stats launch");
 }

@@ -9,8 +9,8 @@ CUDA stream.  PyTorch is used for memory, streams and the decoder convolutions o
 
 Precision (`module.precision`, default "auto"):
   "fp32"  true-fp32 SIMT kernels (the reference's arithmetic; any head_dim)
-  "bf16"  tcgen05 tensor-core kernels, bf16 storage / fp32 accumulate (head_dim 64)
-  "auto"  bf16 path when the inputs are bf16/fp16 and head_dim == 64, else fp32 path
+  "bf16"  tcgen05 tensor-core kernels, bf16 storage / fp32 accumulate (head_dim 64 or 128)
+  "auto"  bf16 path when the inputs are bf16/fp16 and head_dim is 64 or 128, else fp32 path
 There is no CPU path: CPU tensors raise.
 
 Training (train_image.py:105-144): the FORWARD always runs the CUDA kernels.  When gradients are required the
@@ -158,6 +158,9 @@ def _code(dtype: torch.dtype) -> int:
     return _lib.BF16 if dtype == torch.bfloat16 else _lib.F32
 
 
+_TC_HEAD_DIMS = (64, 128)      # head dims the tcgen05 kernels implement (128: value columns in two slices of 64)
+
+
 def _is_cosine(activation) -> bool:
     return isinstance(activation, CosineSimilarity)
 
@@ -176,12 +179,12 @@ def _resolve_precision_softmax(precision: str, head_dim: int, *inputs) -> torch.
     if precision == "fp32":
         return torch.float32
     if precision == "bf16":
-        if head_dim != 64:
-            raise NotImplementedError(f"the bf16 tensor-core path implements head_dim 64, got {head_dim}; "
+        if head_dim not in _TC_HEAD_DIMS:
+            raise NotImplementedError(f"the bf16 tensor-core path implements head_dim 64 and 128, got {head_dim}; "
                                       "use precision='fp32'")
         return torch.bfloat16
     low = all(t.dtype in (torch.bfloat16, torch.float16) for t in inputs)
-    return torch.bfloat16 if (low and head_dim == 64) else torch.float32
+    return torch.bfloat16 if (low and head_dim in _TC_HEAD_DIMS) else torch.float32
 
 
 def _layer_forward(dt: torch.dtype, tfc, tfs, tfcs, w_fgh, b_fgh, w_out, b_out, num_heads: int, out=None,

@@ -184,12 +184,22 @@ def test_attn_f32(B, H, Nc, Ns, dqk, dv):
                                                  # warps can run a whole item ahead of the epilogue warps (flow control)
                                                  (36, 8, 256, 64, 0.6, 0), (36, 8, 200, 130, 0.6, 0), (74, 4, 256, 1, 0.6, 0)])
 def test_attn_bf16(B, H, Nc, Ns, gain, ramp):
+    _attn_bf16_case(B, H, Nc, Ns, gain, ramp, 64)
+
+
+@pytest.mark.parametrize("B,H,Nc,Ns,gain,ramp", [(1, 1, 128, 128, 0.4, 0), (2, 4, 300, 700, 0.45, 0), (1, 2, 135, 143, 0.45, 2.0),
+                                                 (1, 4, 1024, 1024, 0.45, 0)])
+def test_attn_bf16_head_dim_128(B, H, Nc, Ns, gain, ramp):
+    """head_dim 128: logits contract two 64-channel chunks, value columns are processed in two slices."""
+    _attn_bf16_case(B, H, Nc, Ns, gain, ramp, 128)
+
+
+def _attn_bf16_case(B, H, Nc, Ns, gain, ramp, d):
     """tcgen05 kernel against a float64 evaluation on the SAME bf16-rounded operands: what is left is
     the bf16 rounding of P, fp32 accumulation and the bf16 output rounding.  ramp > 0: keys of later tiles are
     scaled up (x(1 + ramp) per 64 keys), so row maxima jump by hundreds of log2 units from one key tile to the
     next -- the kernel's reference-update (rescale + redo) path."""
     L = _lib.lib()
-    d = 64
     C = H * d
     bf = lambda a: torch.from_numpy(a).float().to(G.DEV).to(torch.bfloat16).contiguous()
     q = synth.bellish(11, (B, Nc, C), 0, gain)          # log2 units: logits std ~ gain^2 * 8
@@ -201,7 +211,9 @@ def test_attn_bf16(B, H, Nc, Ns, gain, ramp):
     muv = synth.uniform(15, (B, C), -3, 3)
     tq, tk, tx = bf(q), bf(k), bf(x)
     tvt = bf(vt)
-    tv = torch.cat([tvt, (tvt.float() ** 2).to(torch.bfloat16)], dim=3).reshape(B, Ns, 2 * C).contiguous()
+    # V' layout: per 64-channel value slice [V~ | V~^2] (for head_dim 64 a slice is a head)
+    tvs = tvt.reshape(B, Ns, C // 64, 64)
+    tv = torch.cat([tvs, (tvs.float() ** 2).to(torch.bfloat16)], dim=3).reshape(B, Ns, 2 * C).contiguous()
     xm, xr = G.stats(tx, BF16)
     tmu = G.f32(muv)
     out = torch.empty(B, Nc, C, dtype=torch.bfloat16, device=G.DEV)
@@ -216,7 +228,7 @@ def test_attn_bf16(B, H, Nc, Ns, gain, ramp):
     n = lambda t: t.float().cpu().numpy().astype(np.float64)
     # the kernel's second moment uses the bf16-rounded squares; mirror that in the expectation
     vv = n(tvt).reshape(B, Ns, C)
-    v2 = n(tv).reshape(B, Ns, H, 2, d)[:, :, :, 1].reshape(B, Ns, C)
+    v2 = n((tvt.float() ** 2).to(torch.bfloat16)).reshape(B, Ns, C)
     want = np.zeros((B, Nc, C))
     for h in range(H):
         sl = slice(h * d, (h + 1) * d)
