@@ -153,10 +153,12 @@ __global__ void stats_final_kernel(const StatsJob job, const float* __restrict__
 }
 
 // Tokens per split depend on N only (never on B), so the statistics of an image -- and with them the
-// whole layer -- are bit-identical whatever batch the image is part of.  At most 32 splits: each CTA
-// streams >= 64 tokens with eight 16-byte loads in flight per lane.
+// whole layer -- are bit-identical whatever batch the image is part of.  At most 128 splits: each CTA
+// streams >= 64 tokens with eight 16-byte loads in flight per lane (with 32 splits a single-tensor launch was
+// 512 CTAs on cfg2 and 64 on cfg3: 2.9 TB/s and 1.5 TB/s).
+constexpr int kStatsMaxSplits = 128;
 static int stats_tokens_per_split(int N) {
-    int t = (N + 31) / 32;
+    int t = (N + kStatsMaxSplits - 1) / kStatsMaxSplits;
     return t < 64 ? 64 : t;
 }
 static int stats_splits(int N) {
@@ -166,7 +168,7 @@ static int stats_splits(int N) {
 
 size_t stats_workspace(int B, int N, int C) {
     // room for three tensors of up to N tokens (one launch serves fc, fs and fcs of a layer)
-    return static_cast<size_t>(3) * B * 32 * C * 2 * sizeof(float);
+    return static_cast<size_t>(3) * B * kStatsMaxSplits * C * 2 * sizeof(float);
 }
 
 static StatsJob make_job(int n, const void* const* x, const int* N, float* const* mean, float* const* rstd) {
