@@ -94,4 +94,4 @@ def test_workspace_formula_matches_design(lib):
     # bf16, cfg2: Q,K,heads [8,4096,512] bf16 + V' [8,4096,1024] bf16 dominate
     n = lib.mhada_layer_workspace(_lib.BF16, 8, 4096, 4096, 512, 8)
     tensors = 8 * 4096 * 512 * 2 * 5
-    assert tensors <= n <= tensors + (8 << 20)
+    assert tensors <= n <= tensors + (16 << 20)          # + statistics partial sums (12.6 MB), folded weights, stats
