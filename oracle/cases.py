@@ -58,6 +58,11 @@ TRANSFORMER_CASES = [
          img_sub=8),
 ]
 
+SINGLE_HEAD_TRANSFORMER_CASES = [
+    # AdaAttnTransformer (adaDecoder.py:209-232): three single-head AdaAttN layers + decoder, returns cs only
+    dict(name="single_head_transformer_6x8", kind="single_head_transformer", B=1, hw=(6, 8), hsws=(7, 5), seed=55, img_sub=1),
+]
+
 DECODER_CASES = [
     dict(name="decoder_5x7", kind="decoder", B=1, hw=(5, 7), seed=61),
 ]
@@ -67,7 +72,8 @@ GRAD_CASES = [
     dict(name="grad_layer_c128_h2", kind="grad", B=2, C=128, H=2, hw=(10, 10), hsws=(8, 9), gain=1.0, seed=71),
 ]
 
-ALL_CASES = LAYER_CASES + ADAATTN_CASES + FORLOSS_CASES + TRANSFORMER_CASES + DECODER_CASES + GRAD_CASES
+ALL_CASES = (LAYER_CASES + ADAATTN_CASES + FORLOSS_CASES + TRANSFORMER_CASES + SINGLE_HEAD_TRANSFORMER_CASES +
+             DECODER_CASES + GRAD_CASES)
 
 GRAD_KEYS = ("fc", "fs", "fcs", "f_list.0.weight", "f_list.1.bias", "g_list.1.weight", "g_list.0.bias",
              "h_list.0.weight", "h_list.1.bias", "out_conv.weight", "out_conv.bias")
@@ -137,6 +143,11 @@ def transformer_inputs(case: dict, num_layers: int = 3):
     fs = [synth.features(s * 100 + 10 + i, B, 512, hs, ws) for i in range(num_layers)]
     sd = synth.transformer_state(s)
     return fc, fs, sd
+
+
+def single_head_transformer_inputs(case: dict, num_layers: int = 3):
+    fc, fs, _ = transformer_inputs(case, num_layers)
+    return fc, fs, synth.single_head_transformer_state(case["seed"], num_layers)
 
 
 def decoder_inputs(case: dict):

@@ -24,7 +24,7 @@ import torch
 REF = os.environ.get("MHADA_REFERENCE", "/root/reference/MHAdaSTr")
 sys.path.insert(0, REF)
 from network.adaDecoder import (AdaAttN, AdaAttnForLoss, AdaAttnMultiHead,  # noqa: E402
-                                AdaAttnTransformerMultiHead)
+                                AdaAttnTransformer, AdaAttnTransformerMultiHead)
 from network.conv import Decoder  # noqa: E402
 
 from . import cases, synth  # noqa: E402
@@ -95,6 +95,12 @@ def main(prefix: str = ""):
             arrays["cs"] = cases.pixel_sublattice(cs64, case["img_sub"]).astype(np.float32)
             meta["fcs"] = summarize(fcs64); meta["cs"] = summarize(cs64)
             meta["fcs_ref32_vs_ref64"] = errors(fcs32, fcs64); meta["cs_ref32_vs_ref64"] = errors(cs32, cs64)
+        elif kind == "single_head_transformer":
+            fc, fs, sd = cases.single_head_transformer_inputs(case)
+            o = run_both(lambda: AdaAttnTransformer(), sd, (fc, fs))
+            cs64, cs32 = o["f64"].numpy(), o["f32"].numpy()
+            arrays["cs"] = cases.pixel_sublattice(cs64, case["img_sub"]).astype(np.float32)
+            meta["cs"] = summarize(cs64); meta["cs_ref32_vs_ref64"] = errors(cs32, cs64)
         elif kind == "grad":
             fc, fs, fcs, sd, G = cases.grad_inputs(case)
             m = AdaAttnMultiHead(case["C"], case["H"]).to(torch.float64)

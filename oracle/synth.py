@@ -145,6 +145,15 @@ def transformer_state(seed: int, num_layers: int = 3, qkv_dim: int = 512, num_he
     return sd
 
 
+def single_head_transformer_state(seed: int, num_layers: int = 3, qkv_dim: int = 512) -> dict:
+    """Keys of AdaAttnTransformer (MHAdaSTr/network/adaDecoder.py:209-225): adaAttNs.{i}.{f,g,h} + decoder."""
+    sd = {}
+    for l in range(num_layers):
+        sd.update(adaattn_state(seed + 29 * l, qkv_dim, prefix=f"adaAttNs.{l}."))
+    sd.update(decoder_state(seed))
+    return sd
+
+
 def to_torch(sd: dict, dtype=None):
     import torch
     out = {}

@@ -106,6 +106,20 @@ def test_adaattn_fp32(case, golden_index):
     assert e["max_abs"] <= fp32_tol(golden_index[case["name"]]["ref32_vs_ref64"]), e
 
 
+@pytest.mark.parametrize("case", cases.SINGLE_HEAD_TRANSFORMER_CASES, ids=lambda c: c["name"])
+def test_single_head_transformer_fp32(case, golden_index):
+    """AdaAttnTransformer (adaDecoder.py:209-232): head_dim 512 runs on the fp32 kernels; decoded image vs reference."""
+    fc, fs, sd = cases.single_head_transformer_inputs(case)
+    m = M.AdaAttnTransformer()
+    m.load_state_dict(synth.to_torch(sd, torch.float32), strict=True)
+    m = m.to(DEV).eval()
+    with torch.no_grad():
+        cs = m([dev(x) for x in fc], [dev(x) for x in fs])
+    meta = golden_index[case["name"]]
+    e = O.errors(cases.pixel_sublattice(cs.cpu().numpy(), case["img_sub"]), load_golden(case["name"])["cs"])
+    assert e["max_abs_rel"] <= max(1e-4, 5 * meta["cs_ref32_vs_ref64"]["max_abs_rel"]), e
+
+
 @pytest.mark.parametrize("case", cases.FORLOSS_CASES, ids=lambda c: c["name"])
 def test_forloss_fp32(case, golden_index):
     args = [dev(a) for a in cases.forloss_inputs(case)]

@@ -50,6 +50,17 @@ def test_forloss_matches_reference(case, golden_index):
     _check_sums(got, meta)
 
 
+@pytest.mark.parametrize("case", cases.SINGLE_HEAD_TRANSFORMER_CASES, ids=lambda c: c["name"])
+def test_single_head_transformer_matches_reference(case, golden_index):
+    fc, fs, sd = cases.single_head_transformer_inputs(case)
+    got = O.transformer_single_head(fc, fs, sd)
+    meta = golden_index[case["name"]]
+    g = load_golden(case["name"])
+    e = O.errors(cases.pixel_sublattice(got, case["img_sub"]), g["cs"])
+    assert e["max_abs_rel"] <= 2e-6, e
+    _check_sums(got, meta, key="cs")
+
+
 @pytest.mark.parametrize("case", cases.DECODER_CASES, ids=lambda c: c["name"])
 def test_decoder_matches_reference(case, golden_index):
     x, sd = cases.decoder_inputs(case)
