@@ -138,6 +138,49 @@ class _MhadaLayerFn(torch.autograd.Function):
         return (None, None, None, None, *full)
 
 
+def _forloss_math_torch(c_x, s_x, c_1x, s_1x, cosine: bool):
+    """Differentiable fp32 PyTorch restatement of AdaAttnForLoss.forward (adaDecoder.py:53-81), used ONLY by the
+    backward of _ForLossFn."""
+    B, dv, h, w = c_x.shape
+    q = _instance_norm_torch(c_1x.reshape(B, c_1x.shape[1], -1)).transpose(1, 2)          # [B,Nc,dqk]
+    k = _instance_norm_torch(s_1x.reshape(B, s_1x.shape[1], -1))                          # [B,dqk,Ns]
+    v = s_x.reshape(B, dv, -1).transpose(1, 2)                                            # [B,Ns,dv]
+    logits = torch.matmul(q, k)
+    if cosine:
+        sim = logits / (q.norm(dim=2, keepdim=True) * k.norm(dim=1, keepdim=True)) + 1
+        a = sim / sim.sum(dim=-1, keepdim=True)
+    else:
+        a = torch.softmax(logits, dim=-1)
+    m = torch.matmul(a, v)
+    sd = torch.sqrt((torch.matmul(a, v * v) - m * m).clamp(min=1e-6))
+    out = sd * _instance_norm_torch(c_x.reshape(B, dv, -1)).transpose(1, 2) + m
+    return out.transpose(1, 2).reshape(B, dv, h, w)
+
+
+class _ForLossFn(torch.autograd.Function):
+    """Forward: the CUDA kernels.  Backward: recompute with _forloss_math_torch in fp32 and differentiate."""
+
+    @staticmethod
+    def forward(ctx, run_forward, cosine, c_x, s_x, c_1x, s_1x):
+        ctx.cosine = cosine
+        ctx.save_for_backward(c_x, s_x, c_1x, s_1x)
+        with torch.no_grad():
+            return run_forward(c_x, s_x, c_1x, s_1x)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        saved = ctx.saved_tensors
+        with torch.enable_grad():
+            leaves = [t.detach().float().requires_grad_(True) for t in saved]
+            out = _forloss_math_torch(*leaves, ctx.cosine)
+            need = [i for i, ng in enumerate(ctx.needs_input_grad[2:]) if ng]
+            grads = torch.autograd.grad(out, [leaves[i] for i in need], grad_out.float(), allow_unused=True)
+        full = [None] * 4
+        for i, g in zip(need, grads):
+            full[i] = None if g is None else g.to(saved[i].dtype)
+        return (None, None, *full)
+
+
 def _token_major(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     """(B,C,h,w) with any strides -> contiguous (B,h,w,C) of `dtype` (one fused copy, or none when the
     tensor already is channels_last in that dtype, which is what the reference ViT emits)."""
@@ -329,8 +372,14 @@ class AdaAttnForLoss(nn.Module):
 
     def forward(self, c_x, s_x, c_1x, s_1x):
         _require_cuda(c_x, s_x, c_1x, s_1x)
-        _no_autograd(self, c_x, s_x, c_1x, s_1x)
         _check_activation(self.activation)
+        if _needs_grad(self, c_x, s_x, c_1x, s_1x):
+            # train_image.py / lossfn.py:26-34 call this on VGG features that may carry gradients: kernels forward,
+            # PyTorch recompute backward (like the layers)
+            return _ForLossFn.apply(self._forward_nograd, _is_cosine(self.activation), c_x, s_x, c_1x, s_1x)
+        return self._forward_nograd(c_x, s_x, c_1x, s_1x)
+
+    def _forward_nograd(self, c_x, s_x, c_1x, s_1x):
         L = _lib.lib()
         dt = torch.float32
         tq, tk, tv, tx = (_token_major(t, dt) for t in (c_1x, s_1x, s_x, c_x))
@@ -385,8 +434,17 @@ class AdaAttN(nn.Module):
 
     def forward(self, fc: torch.Tensor, fs: torch.Tensor, fcs: torch.Tensor):
         _require_cuda(fc, fs, fcs)
-        _no_autograd(self, fc, fs, fcs)
         _check_activation(self.activation)
+        if _needs_grad(self, fc, fs, fcs):
+            d = fc.shape[1]
+            params = [t.reshape(1, *shape) for m in (self.f, self.g, self.h)
+                      for t, shape in ((m.weight, (d, d)), (m.bias, (d,)))]
+            none = fc.new_zeros(0)
+            return _MhadaLayerFn.apply(self._forward_nograd, 1, False, _is_cosine(self.activation), fc, fs, fcs, *params,
+                                       none, none)
+        return self._forward_nograd(fc, fs, fcs)
+
+    def _forward_nograd(self, fc, fs, fcs):
         dt = _resolve_precision(self.precision, fc.shape[1], fc, fs, fcs, activation=self.activation)
         w, b, _, _ = self._packed.get([[self.f], [self.g], [self.h]], None)
         tfc, tfs = _token_major(fc, dt), _token_major(fs, dt)

@@ -321,10 +321,6 @@ def test_errors_on_device():
     x = torch.zeros(1, 512, 4, 4, device=DEV)
     with torch.no_grad(), pytest.raises(NotImplementedError):
         m(x, x, x)
-    fl = M.AdaAttnForLoss(64, 64).to(DEV)
-    xg = torch.zeros(1, 64, 4, 4, device=DEV, requires_grad=True)
-    with pytest.raises(RuntimeError, match="forward-only"):
-        fl(xg, xg, xg, xg)              # the loss-side variant has no backward yet
     m2 = M.AdaAttnMultiHead(512, 2).to(DEV)       # head_dim 256: fp32 kernels only
     m2.precision = "bf16"
     with torch.no_grad(), pytest.raises(NotImplementedError):
@@ -398,6 +394,41 @@ def test_cosine_layer_gradient_matches_oracle_finite_difference():
         fd = (loss(*plus) - loss(*minus)) / (2 * eps)
         an = float((tin[idx].grad.double().cpu().numpy() * v).sum())
         assert an == pytest.approx(fd, rel=2e-3, abs=1e-4 * abs(fd) + 1e-5), (idx, an, fd)
+
+
+def test_forloss_gradient_matches_oracle_finite_difference():
+    """AdaAttnForLoss under autograd (lossfn.py:26-34 feeds it VGG features): CUDA forward, recompute backward;
+    gradients w.r.t. all four inputs against directional finite differences of the float64 oracle."""
+    case = cases.by_name("forloss_relu5_1")
+    args = cases.forloss_inputs(case)
+    m = M.AdaAttnForLoss(case["v"], case["qk"]).to(DEV)
+    tin = [dev(a).requires_grad_(True) for a in args]
+    out = m(*tin)
+    G = synth.bellish(993, out.shape, 0.0, 1.0)
+    (out * dev(G)).sum().backward()
+    rng = np.random.default_rng(2)
+    loss = lambda *a: float((O.ada_attn_for_loss(*a) * G).sum())
+    eps = 1e-5
+    for idx in range(4):
+        v = rng.standard_normal(args[idx].shape)
+        plus, minus = list(args), list(args)
+        plus[idx] = args[idx] + eps * v
+        minus[idx] = args[idx] - eps * v
+        fd = (loss(*plus) - loss(*minus)) / (2 * eps)
+        an = float((tin[idx].grad.double().cpu().numpy() * v).sum())
+        assert an == pytest.approx(fd, rel=2e-3, abs=1e-4 * abs(fd) + 1e-5), (idx, an, fd)
+
+
+def test_single_head_transformer_trains():
+    """AdaAttnTransformer under autograd: every parameter receives a finite gradient."""
+    case = cases.SINGLE_HEAD_TRANSFORMER_CASES[0]
+    fc, fs, sd = cases.single_head_transformer_inputs(case)
+    m = M.AdaAttnTransformer()
+    m.load_state_dict(synth.to_torch(sd, torch.float32), strict=True)
+    m = m.to(DEV).train()
+    cs = m([dev(x) for x in fc], [dev(x) for x in fs])
+    cs.float().mean().backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all().item() for p in m.parameters())
 
 
 def test_transformer_train_step_runs():
