@@ -95,3 +95,38 @@ def test_workspace_formula_matches_design(lib):
     n = lib.mhada_layer_workspace(_lib.BF16, 8, 4096, 4096, 512, 8)
     tensors = 8 * 4096 * 512 * 2 * 5
     assert tensors <= n <= tensors + (16 << 20)          # + statistics partial sums (12.6 MB), folded weights, stats
+
+
+def test_abi_argument_checks_of_the_newer_entry_points(lib):
+    """Validation that happens before any CUDA call (so it runs on a CPU box): cosine / head-dim rules, the decoder
+    block kernel, the stage profiler."""
+    buf = (ctypes.c_float * 4096)()
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    aligned = ctypes.c_void_p((p.value + 63) & ~63)
+    other = ctypes.c_void_p(aligned.value + 2048)
+    # cosine is an fp32-path activation
+    rc = lib.mhada_layer_forward(_lib.BF16, aligned, aligned, aligned, aligned, aligned, None, None, 1, 4, 4, 512, 8,
+                                 _lib.LAYER_COSINE, other, other, 1 << 30, None)
+    assert rc == -2 and b"cosine" in lib.mhada_last_error()
+    # tensor-core path: head_dim 64 and 128 only
+    rc = lib.mhada_layer_forward(_lib.BF16, aligned, aligned, aligned, aligned, aligned, None, None, 1, 4, 4, 512, 2, 0,
+                                 other, other, 1 << 30, None)
+    assert rc == -2 and b"head_dim" in lib.mhada_last_error()
+    a = _lib.AttnArgs()
+    a.dtype = _lib.F32
+    a.B, a.H, a.Nc, a.Ns, a.dqk, a.dv = 1, 1, 4, 4, 64, 64
+    for f in ("q", "k", "v", "x", "out", "x_mean", "x_rstd"):
+        setattr(a, f, aligned.value)
+    a.ldq = a.ldk = a.ldv = a.ldx = a.ldo = 64
+    a.activation = 7
+    assert lib.mhada_attn(ctypes.byref(a), None) == -1 and b"activation" in lib.mhada_last_error()
+    a.dtype, a.activation = _lib.BF16, _lib.ACT_COSINE
+    assert lib.mhada_attn(ctypes.byref(a), None) == -2
+    # decoder block kernel
+    assert lib.mhada_conv3x3_small(_lib.BF16, None, aligned, aligned, 1, 8, 8, 64, 3, 1, other, None) == -1
+    assert lib.mhada_conv3x3_small(_lib.F32, aligned, aligned, aligned, 1, 8, 8, 64, 3, 1, other, None) == -2
+    assert lib.mhada_conv3x3_small(_lib.BF16, aligned, aligned, aligned, 1, 1, 8, 64, 3, 1, other, None) == -1
+    # stage profiler
+    ms, n = ctypes.c_float(0), ctypes.c_int(0)
+    assert lib.mhada_profile_stage(9, ctypes.byref(ms), ctypes.byref(n)) == -1
+    assert lib.mhada_profile_stage(0, ctypes.byref(ms), ctypes.byref(n)) == 0
