@@ -92,8 +92,35 @@ struct AttnTcParams {
     const float *x_mean, *x_rstd, *mu_v;   // [B, H*64]
     int B, H, Nc, Ns, ldx, ldo;
     int kv_shared;            // 1: one K / V' / mu_v set (style) serves every image of the batch
+    int n_full;               // work items 0 .. n_full-1 are query-tile PAIRS; the items after them are single query
+    int n_single;             // tiles (the two halves of the remaining pairs), each CTA's LAST item -- see attn_item()
     long long* trace;         // AT_TRACE_WORDS entries or nullptr
 };
+
+// Work item decode.  Items [0, n_full) are query-tile pairs of (image, value slice); query pairs are the fastest index so
+// CTAs that run side by side share the K / V' tiles of one (image, head) in L2.  Items [n_full, n_full + n_single) are
+// the pairs that do not fill a whole round of the persistent CTAs, cut into their two 128-row tiles: a single-tile item
+// keeps one softmax warpgroup and one issuer busy and takes ~60 % of a pair's time (its MUFU is uncontended), so the
+// last round of a single 1024 x 1024 image (512 pairs on 148 SMs: 3 rounds + 68 pairs) costs 0.6 instead of 1 round.
+// A single item is always the LAST item of its CTA: the idle tile's barriers are simply never touched again.
+struct AttnItem {
+    int h, b, q0;
+    bool single;
+};
+__device__ __forceinline__ AttnItem attn_item(const AttnTcParams& p, int it, int XT) {
+    AttnItem a;
+    int pair = it, tile = 0;
+    a.single = it >= p.n_full;
+    if (a.single) {
+        const int u = it - p.n_full;
+        pair = p.n_full + (u >> 1);
+        tile = u & 1;
+    }
+    a.h = (pair / XT) % p.H;
+    a.b = pair / (XT * p.H);
+    a.q0 = (pair % XT) * (2 * AT_BM) + tile * AT_BM;
+    return a;
+}
 
 struct AttnBars {
     uint64_t q_full, q_empty;
@@ -125,7 +152,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int T = (p.Ns + AT_BN - 1) / AT_BN;                 // key tiles per work item
     const int XT = (p.Nc + 2 * AT_BM - 1) / (2 * AT_BM);      // query-tile pairs per (image, head)
-    const int n_items = XT * p.H * p.B;
+    const int n_items = p.n_full + p.n_single;
     // PERSISTENT: this CTA handles work items blockIdx.x, blockIdx.x + gridDim.x, ... (query-tile pair fastest,
     // so CTAs that run side by side share K / V' of the same (image, head) in L2).  All pipeline counters run
     // on across items: g = (local item number) * T + j is the global key-tile index of this CTA.
@@ -181,8 +208,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         if (elect_one()) {
             int n = 0;
             for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++n) {
-                const int qx = it % XT, h = (it / XT) % p.H, b = it / (XT * p.H);
-                const int q0 = qx * (2 * AT_BM), g0 = n * T;
+                const AttnItem wi = attn_item(p, it, XT);
+                const int h = wi.h, b = wi.b, q0 = wi.q0, g0 = n * T;
                 const int bkv = p.kv_shared ? 0 : b;
                 auto load_k = [&](int j) {
                     const int g = g0 + j, ks = g % AT_KST;
@@ -194,12 +221,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                                     ((h / KCH) * KCH + c) * AT_D, j * AT_BN, bkv);
                 };
                 mbar_wait(&bars->q_empty, (n & 1) ^ 1);      // all S MMAs of the previous item have read Q
-                mbar_arrive_expect_tx(&bars->q_full, 2 * AT_Q_BYTES);
+                mbar_arrive_expect_tx(&bars->q_full, (wi.single ? 1 : 2) * AT_Q_BYTES);
 #pragma unroll
                 for (int c = 0; c < KCH; ++c) {
                     tma_load_3d(sQ + c * AT_QC_BYTES, &tmQ, &bars->q_full, ((h / KCH) * KCH + c) * AT_D, q0, b);
-                    tma_load_3d(sQ + AT_Q_BYTES + c * AT_QC_BYTES, &tmQ, &bars->q_full, ((h / KCH) * KCH + c) * AT_D,
-                                q0 + AT_BM, b);
+                    if (!wi.single)
+                        tma_load_3d(sQ + AT_Q_BYTES + c * AT_QC_BYTES, &tmQ, &bars->q_full, ((h / KCH) * KCH + c) * AT_D,
+                                    q0 + AT_BM, b);
                 }
                 load_k(0);
                 if (T > 1) load_k(1);
@@ -259,6 +287,27 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++n) {
                 const int g0 = n * T;
                 mbar_wait(&bars->q_full, n & 1);
+                if (t == 1 && it >= p.n_full) {
+                    // single-tile item: tile 1 is idle, but the K / V' / Q slots are released by TWO arrivals -- keep
+                    // pace with the loads and give this issuer's share
+                    for (int j = 0; j < 2 && j < T; ++j) {
+                        const int g = g0 + j;
+                        mbar_wait(&bars->k_full[g % AT_KST], (g / AT_KST) & 1);
+                        mbar_arrive(&bars->k_empty[g % AT_KST]);
+                    }
+                    if (T <= 2) mbar_arrive(&bars->q_empty);
+                    for (int j = 0; j < T; ++j) {
+                        const int g = g0 + j, vs = g % AT_VST;
+                        mbar_wait(&bars->v_full[vs], (g / AT_VST) & 1);
+                        mbar_arrive(&bars->v_empty[vs]);
+                        if (j + 2 < T) {
+                            mbar_wait(&bars->k_full[(g + 2) % AT_KST], ((g + 2) / AT_KST) & 1);
+                            mbar_arrive(&bars->k_empty[(g + 2) % AT_KST]);
+                            if (j + 3 == T) mbar_arrive(&bars->q_empty);
+                        }
+                    }
+                    continue;
+                }
                 for (int j = 0; j < 2 && j < T; ++j) {
                     const int g = g0 + j;
                     mbar_wait(&bars->k_full[g % AT_KST], (g / AT_KST) & 1);
@@ -308,6 +357,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++n) {
             const int g0 = n * T;
             const bool last_item = it + static_cast<int>(gridDim.x) >= n_items;
+            if (t == 1 && it >= p.n_full) continue;       // single-tile item (always the CTA's last): tile 1 idles
 
             // Online softmax with a LAGGING reference: the weights of key tile j are 2^(s - m) with m the (integer)
             // reference fixed by the tiles before it; the exact maximum is taken up front for the first tile of an
@@ -465,8 +515,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         const bool tr0 = TRACE && quarter == AT_TRACE_QUARTER && lane == 0;
         int n = 0;
         for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++n) {
-            const int qx = it % XT, h = (it / XT) % p.H, b = it / (XT * p.H);
-            const int q0 = qx * (2 * AT_BM);
+            const AttnItem wi = attn_item(p, it, XT);
+            const int h = wi.h, b = wi.b, q0 = wi.q0;
             {
                 const size_t sidx = (static_cast<size_t>(b) * p.H + h) * AT_D;
                 named_bar_sync(3, 128);                   // the previous item's epilogue is done with cst
@@ -480,7 +530,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 named_bar_sync(3, 128);
             }
 #pragma unroll 1
-            for (int t = 0; t < 2; ++t) {
+            for (int t = 0; t < (wi.single ? 1 : 2); ++t) {
                 const uint32_t o_tm = tmem_addr(tmem, quarter * 32, t * 256 + 128);
                 const int nrow = q0 + t * AT_BM + row;
                 const bool row_ok = nrow < p.Nc;
@@ -596,7 +646,10 @@ static int launch_attn_bf16_kch(const mhada_attn_args& a, long long* trace, cuda
             return e;
         attr_done = true;
     }
-    const int n_items = ((a.Nc + 2 * AT_BM - 1) / (2 * AT_BM)) * p.H * a.B;
+    const int n_pairs = ((a.Nc + 2 * AT_BM - 1) / (2 * AT_BM)) * p.H * a.B;
+    int n_items = n_pairs;
+    p.n_full = n_pairs;
+    p.n_single = 0;
     static int n_sm = 0;
     if (n_sm == 0) {
         int dev = 0;
@@ -608,9 +661,20 @@ static int launch_attn_bf16_kch(const mhada_attn_args& a, long long* trace, cuda
     // (measured r1: cfg3 = 512 items -> 0.93 ms dynamic vs 0.99 ms static; cfg2 = 1024 items -> 0.465 vs 0.479).
     const int rounds = (n_items + n_sm - 1) / n_sm;
 #ifdef MHADA_AT_FORCE_PERSISTENT
-    const bool persistent = MHADA_AT_FORCE_PERSISTENT != 0;
+    bool persistent = MHADA_AT_FORCE_PERSISTENT != 0;
 #else
-    const bool persistent = n_items > n_sm && static_cast<double>(n_items) / (static_cast<double>(rounds) * n_sm) >= 0.9;
+    bool persistent = n_items > n_sm && static_cast<double>(n_items) / (static_cast<double>(rounds) * n_sm) >= 0.9;
+#endif
+#ifndef MHADA_AT_NO_SINGLE_TAIL
+    // A remainder of at most n_sm / 2 pairs after whole rounds: run it as single-tile items in the last round
+    // (cfg3: 512 pairs = 3 x 148 + 68 -> 444 pairs + 136 single tiles on 148 persistent CTAs).
+    const int rem = n_pairs % n_sm;
+    if (!trace && n_pairs > n_sm && rem > 0 && 2 * rem <= n_sm) {
+        p.n_full = n_pairs - rem;
+        p.n_single = 2 * rem;
+        n_items = p.n_full + p.n_single;
+        persistent = true;
+    }
 #endif
     dim3 grid(persistent ? n_sm : n_items);
     if (trace)

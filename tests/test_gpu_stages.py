@@ -182,7 +182,10 @@ def test_attn_f32(B, H, Nc, Ns, dqk, dv):
                                                  (1, 2, 300, 700, 0.6, 4.0), (2, 2, 256, 1000, 1.0, 1.0),
                                                  # persistent CTAs (288 work items) with 1 / 3 key tiles per item: the softmax
                                                  # warps can run a whole item ahead of the epilogue warps (flow control)
-                                                 (36, 8, 256, 64, 0.6, 0), (36, 8, 200, 130, 0.6, 0), (74, 4, 256, 1, 0.6, 0)])
+                                                 (36, 8, 256, 64, 0.6, 0), (36, 8, 200, 130, 0.6, 0), (74, 4, 256, 1, 0.6, 0),
+                                                 # 160 query pairs = one round of 148 + 12: the remainder runs as 24
+                                                 # single-tile items (second case: their second tiles are ragged)
+                                                 (20, 8, 256, 200, 0.6, 0), (20, 8, 200, 130, 0.6, 1.0)])
 def test_attn_bf16(B, H, Nc, Ns, gain, ramp):
     _attn_bf16_case(B, H, Nc, Ns, gain, ramp, 64)
 
