@@ -191,7 +191,7 @@ def test_attn_bf16(B, H, Nc, Ns, gain, ramp):
 
 
 @pytest.mark.parametrize("B,H,Nc,Ns,gain,ramp", [(1, 1, 128, 128, 0.4, 0), (2, 4, 300, 700, 0.45, 0), (1, 2, 135, 143, 0.45, 2.0),
-                                                 (1, 4, 1024, 1024, 0.45, 0)])
+                                                 (1, 4, 1024, 1024, 0.45, 0), (20, 4, 256, 200, 0.45, 0)])
 def test_attn_bf16_head_dim_128(B, H, Nc, Ns, gain, ramp):
     """head_dim 128: logits contract two 64-channel chunks, value columns are processed in two slices."""
     _attn_bf16_case(B, H, Nc, Ns, gain, ramp, 128)
