@@ -173,7 +173,7 @@ struct AttnF32Params {
 // COSINE = true : A = (cos(q_i, k_j) + 1) / sum_j (cos(q_i, k_j) + 1)   (CosineSimilarity, adaDecoder.py:20-34);
 //                 |q_i|^2 and |k_j|^2 are accumulated next to the dot products, no running maximum is needed.
 template <bool COSINE>
-__global__ void __launch_bounds__(256) attn_f32_kernel(const AttnF32Params p) {
+__global__ void __launch_bounds__(256, 2) attn_f32_kernel(const AttnF32Params p) {
     __shared__ float Ps[TILE][TILE + 1];
     __shared__ union {
         struct {
