@@ -48,7 +48,16 @@ want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__cycles_elapsed.avg", "sm__cycles_elapsed.avg.per_second", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "lts__t_bytes.sum", "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
         "smsp__inst_executed.sum", "launch__shared_mem_per_block_dynamic"]
-with open(os.path.join(out_dir, f"{tag}_attn_tc_ncu.md"), "w") as f:
+# sections appended by hand to the attention summary (other workloads) survive a regeneration
+_attn_md = os.path.join(out_dir, f"{tag}_attn_tc_ncu.md")
+_kept = ""
+if os.path.exists(_attn_md):
+    _old = open(_attn_md).read()
+    _i = _old.find("\n## cfg3 layer")
+    _kept = _old[_i:] if _i >= 0 else ""
+import atexit
+atexit.register(lambda: open(_attn_md, "a").write(_kept) if _kept else None)
+with open(_attn_md, "w") as f:
     f.write(f"# {tag}: `mh::attn_tc_kernel` under `ncu --set full --clock-control none` (B200)\n\n")
     f.write("Workload: cfg2 layer (B=8, H=8, Nc=Ns=4096, d=64): grid 1024 CTAs x 384 threads. "
             "Algorithmic FLOPs per launch = 6*B*Nc*Ns*C = 412.3 GFLOP; algorithmic HBM bytes = Q 33.5 + K 33.5 + V' 67.1 + fcs 33.5 MB read, 33.5 MB written.\n\n")
