@@ -636,26 +636,15 @@ static int launch_attn_bf16_kch(const mhada_attn_args& a, long long* trace, cuda
     p.kv_shared = (a.kv_batch == 1 && a.B > 1) ? 1 : 0;
     p.trace = trace;
     constexpr size_t smem = at_smem_data<KCH>() + sizeof(AttnBars) + 1024;
-    static bool attr_done = false;
-    if (!attr_done) {
-        if (int e = check_cuda(cudaFuncSetAttribute(attn_tc_kernel<false, KCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                    static_cast<int>(smem)), "attn smem attr"))
-            return e;
-        if (int e = check_cuda(cudaFuncSetAttribute(attn_tc_kernel<true, KCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                    static_cast<int>(smem)), "attn smem attr"))
-            return e;
-        attr_done = true;
-    }
+    static DeviceOnce once_plain, once_trace;          // per (kernel instantiation, device)
+    if (int e = smem_attr_once(once_plain, reinterpret_cast<const void*>(attn_tc_kernel<false, KCH>), smem, "attn smem attr")) return e;
+    if (trace)
+        if (int e = smem_attr_once(once_trace, reinterpret_cast<const void*>(attn_tc_kernel<true, KCH>), smem, "attn smem attr")) return e;
     const int n_pairs = ((a.Nc + 2 * AT_BM - 1) / (2 * AT_BM)) * p.H * a.B;
     int n_items = n_pairs;
     p.n_full = n_pairs;
     p.n_single = 0;
-    static int n_sm = 0;
-    if (n_sm == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
-    }
+    const int n_sm = sm_count();
     // Persistent (one CTA per SM, static round-robin over equal-cost items) when the last round is well filled;
     // otherwise one item per CTA so the hardware scheduler hands the tail to whichever SM is free first
     // (measured r1: cfg3 = 512 items -> 0.93 ms dynamic vs 0.99 ms static; cfg2 = 1024 items -> 0.465 vs 0.479).

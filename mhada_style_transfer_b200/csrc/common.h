@@ -17,6 +17,16 @@ const char* last_error();
 int check_cuda(cudaError_t e, const char* what);   // 0 or the error (message recorded)
 int device_check();
 
+// Per-device one-time set-up (SURVEY.md 8b "keyed by device"): cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a
+// PER-DEVICE property of a kernel, so a process that drives several GPUs must set it once on each; the SM count that
+// sizes persistent grids is per device too.  DeviceOnce holds one done-bit per device ordinal (thread safe; a race
+// only repeats the idempotent call).
+struct DeviceOnce {
+    unsigned long long done[4] = {0, 0, 0, 0};   // 256 device ordinals
+};
+int smem_attr_once(DeviceOnce& once, const void* kernel, size_t smem_bytes, const char* what);
+int sm_count();   // multiprocessors of the CURRENT device (cached per device)
+
 extern thread_local int g_launches;
 extern thread_local long long g_launches_total;
 inline void count_launch() { ++g_launches; ++g_launches_total; }

@@ -162,13 +162,9 @@ conv3x3_c64_small_kernel(const __nv_bfloat16* __restrict__ x, const float* __res
 template <int NT>
 static int launch_conv_small_nt(const void* x, const float* w, const float* bias, int B, int H, int W, int Cout, int relu,
                                 void* y, cudaStream_t s) {
-    static bool attr_done = false;
-    if (!attr_done) {
-        if (int e = check_cuda(cudaFuncSetAttribute(conv3x3_c64_small_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                    static_cast<int>(cs_smem_bytes(NT))), "conv_small smem attr"))
-            return e;
-        attr_done = true;
-    }
+    static DeviceOnce once;
+    if (int e = smem_attr_once(once, reinterpret_cast<const void*>(conv3x3_c64_small_kernel<NT>), cs_smem_bytes(NT), "conv_small smem attr"))
+        return e;
     dim3 grid((W + CS_TW - 1) / CS_TW, (H + CS_TH - 1) / CS_TH, B);
     conv3x3_c64_small_kernel<NT><<<grid, CS_THREADS, cs_smem_bytes(NT), s>>>(
         static_cast<const __nv_bfloat16*>(x), w, bias, static_cast<__nv_bfloat16*>(y), B, H, W, Cout, relu);

@@ -35,12 +35,43 @@ int device_check() {
     }
     int major = 0;
     e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
-    if (e != cudaSuccess || major != 10) {
-        set_error("libmhada_b200 needs an sm_100 (B200) device, found compute capability major %d", major);
+    int minor = -1;
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+    // built with -gencode arch=compute_100a,code=sm_100a only: arch-specific ("a") code is not forward compatible,
+    // so sm_103 (B300) would pass a major-only check and then fail with "no kernel image" at the first launch
+    if (e != cudaSuccess || major != 10 || minor != 0) {
+        set_error("libmhada_b200 is built for sm_100a (B200, compute capability 10.0) only; found %d.%d", major, minor);
         (void)cudaGetLastError();
         return MHADA_ERR_DEVICE;
     }
     return 0;
+}
+
+int smem_attr_once(DeviceOnce& once, const void* kernel, size_t smem_bytes, const char* what) {
+    int dev = 0;
+    if (int e = check_cuda(cudaGetDevice(&dev), "cudaGetDevice")) return e;
+    const bool tracked = dev >= 0 && dev < 256;
+    if (tracked && (__atomic_load_n(&once.done[dev >> 6], __ATOMIC_ACQUIRE) >> (dev & 63)) & 1ull) return 0;
+    if (int e = check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes)),
+                           what))
+        return e;
+    if (tracked) __atomic_fetch_or(&once.done[dev >> 6], 1ull << (dev & 63), __ATOMIC_RELEASE);
+    return 0;
+}
+
+int sm_count() {
+    static int cache[256];   // 0 = unknown
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    const bool tracked = dev >= 0 && dev < 256;
+    if (tracked) {
+        const int c = __atomic_load_n(&cache[dev], __ATOMIC_RELAXED);
+        if (c > 0) return c;
+    }
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    if (tracked) __atomic_store_n(&cache[dev], n, __ATOMIC_RELAXED);
+    return n;
 }
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

@@ -148,20 +148,10 @@ static int launch_linear_tc(const CUtensorMap& tmA, const void* wbf, const float
     uint32_t boxB[2] = {LIN_BK, BN};
     if (int e = make_tmap_bf16(&tmB, wbf, 2, dimsB, strB, boxB)) return e;
     constexpr size_t smem = LIN_STAGES * (LIN_BM * LIN_BK * 2 + BN * LIN_BK * 2) + 1024;
-    static bool attr_done = false;   // idempotent; a benign race only repeats the call
-    if (!attr_done) {
-        if (int e = check_cuda(cudaFuncSetAttribute(linear_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                    static_cast<int>(smem)), "linear smem attr"))
-            return e;
-        attr_done = true;
-    }
+    static DeviceOnce once;
+    if (int e = smem_attr_once(once, reinterpret_cast<const void*>(linear_tc_kernel<BN>), smem, "linear smem attr")) return e;
     const int ntiles = Cout / BN, items = ((M + LIN_BM - 1) / LIN_BM) * ntiles;
-    static int n_sm = 0;
-    if (n_sm == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
-    }
+    const int n_sm = sm_count();
     const int grid = items < 2 * n_sm ? items : 2 * n_sm;
     linear_tc_kernel<BN><<<grid, LIN_THREADS, smem, s>>>(tmA, tmB, bias, static_cast<__nv_bfloat16*>(y), ldy, M,
                                                          Cin / LIN_BK, ntiles, items);

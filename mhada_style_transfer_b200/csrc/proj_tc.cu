@@ -398,22 +398,13 @@ int launch_proj_bf16_folded(int parts, const void* fc, const void* fs, int B, in
     p.items_s = p.Bs * p.H * p.tiles_s;
     p.items = p.items_s + p.Bc * p.H * p.tiles_c;
     const size_t smem = PRJ_STAGES * (kch == 1 ? prj_stage_bytes<1>() : prj_stage_bytes<2>()) + 1024;
-    static bool attr_done = false;
-    if (!attr_done) {
-        if (int e = check_cuda(cudaFuncSetAttribute(proj_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                    static_cast<int>(PRJ_STAGES * prj_stage_bytes<1>() + 1024)), "proj smem attr"))
-            return e;
-        if (int e = check_cuda(cudaFuncSetAttribute(proj_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                    static_cast<int>(PRJ_STAGES * prj_stage_bytes<2>() + 1024)), "proj smem attr"))
-            return e;
-        attr_done = true;
+    static DeviceOnce once1, once2;
+    if (kch == 1) {
+        if (int e = smem_attr_once(once1, reinterpret_cast<const void*>(proj_tc_kernel<1>), smem, "proj smem attr")) return e;
+    } else {
+        if (int e = smem_attr_once(once2, reinterpret_cast<const void*>(proj_tc_kernel<2>), smem, "proj smem attr")) return e;
     }
-    static int n_sm = 0;
-    if (n_sm == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
-    }
+    const int n_sm = sm_count();
     const int ctas = (kch == 1 ? 2 : 1) * n_sm;
     const int grid = p.items < ctas ? p.items : ctas;
     if (kch == 1)

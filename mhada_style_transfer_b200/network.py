@@ -66,6 +66,22 @@ def _require_cuda(*tensors):
                                "(there is no CPU fallback; use the reference package on CPU)")
 
 
+def _check_layer_shapes(C: int, fc, fs, fcs):
+    """What the reference's view / bmm calls would reject (adaDecoder.py:105-131, :168-198), checked before any
+    pointer reaches the C ABI."""
+    if fc.dim() != 4 or fs.dim() != 4 or fcs.dim() != 4:
+        raise RuntimeError("fc, fs and fcs must be (b, qkv_dim, h, w)")
+    if fc.shape[1] != C or fs.shape[1] != C or fcs.shape[1] != C:
+        raise RuntimeError(f"expected {C} channels, got {fc.shape[1]}, {fs.shape[1]}, {fcs.shape[1]}")
+    if fs.shape[0] != fc.shape[0]:
+        # the reference reshapes K/V with the content batch (adaDecoder.py:177-183) and fails the same way
+        raise RuntimeError(f"style batch {fs.shape[0]} must equal content batch {fc.shape[0]}")
+    if fcs.shape != fc.shape:
+        raise RuntimeError("fcs must have the shape of fc")
+    if fc.device != fs.device or fc.device != fcs.device:
+        raise RuntimeError("fc, fs and fcs must be on the same device")
+
+
 def _needs_grad(module: nn.Module, *tensors) -> bool:
     return torch.is_grad_enabled() and (any(t.requires_grad for t in tensors) or
                                         any(p.requires_grad for p in module.parameters()))
@@ -300,15 +316,19 @@ class _PackedWeights:
     only when a parameter was modified (version counter) or moved."""
 
     def __init__(self):
-        self.key = None
-        self.tensors = None
+        self.cache = {}          # device -> (key, tensors): nn.DataParallel replicas share this object (shallow
+                                 # __dict__ copy) but each has its own parameters on its own device
 
     def get(self, groups: Sequence[Sequence[nn.Conv2d]], out_conv):
         params = [p for g in groups for m in g for p in (m.weight, m.bias)]
         if out_conv is not None:
             params += [out_conv.weight, out_conv.bias]
-        key = tuple((p.data_ptr(), p._version, p.device) for p in params)
-        if key != self.key:
+        dev = params[0].device
+        key = tuple((p.data_ptr(), p._version, p.dtype) for p in params)
+        hit = self.cache.get(dev)
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        if True:
             with torch.no_grad():
                 w = torch.stack([torch.stack([m.weight.reshape(m.weight.shape[0], -1) for m in g]) for g in groups])
                 b = torch.stack([torch.stack([m.bias for m in g]) for g in groups])
@@ -316,9 +336,8 @@ class _PackedWeights:
                 b = b.float().contiguous()
                 wo = out_conv.weight.reshape(out_conv.weight.shape[0], -1).float().contiguous() if out_conv is not None else None
                 bo = out_conv.bias.float().contiguous() if out_conv is not None else None
-            self.tensors = (w, b, wo, bo)
-            self.key = key
-        return self.tensors
+            self.cache[dev] = (key, (w, b, wo, bo))
+        return self.cache[dev][1]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -380,6 +399,8 @@ class AdaAttnForLoss(nn.Module):
         return self._forward_nograd(c_x, s_x, c_1x, s_1x)
 
     def _forward_nograd(self, c_x, s_x, c_1x, s_1x):
+        if any(t.dim() != 4 for t in (c_x, s_x, c_1x, s_1x)):
+            raise RuntimeError("AdaAttnForLoss: inputs must be (b, c, h, w)")
         L = _lib.lib()
         dt = torch.float32
         tq, tk, tv, tx = (_token_major(t, dt) for t in (c_1x, s_1x, s_x, c_x))
@@ -388,6 +409,10 @@ class AdaAttnForLoss(nn.Module):
         Nc, Ns = tq.shape[1] * tq.shape[2], tk.shape[1] * tk.shape[2]
         if tv.shape[1] * tv.shape[2] != Ns or h * w != Nc or tk.shape[3] != dqk or tv.shape[3] != dv:
             raise RuntimeError("AdaAttnForLoss: inconsistent shapes")
+        if not (tq.shape[0] == tk.shape[0] == tv.shape[0] == B):
+            # the reference's bmm / view calls (adaDecoder.py:55-79) need one batch size for all four inputs
+            raise RuntimeError(f"AdaAttnForLoss: batch sizes differ: c_x {B}, s_x {tv.shape[0]}, c_1x {tq.shape[0]}, "
+                               f"s_1x {tk.shape[0]}")
         dev = tx.device
         stats = torch.empty((6, B, max(dqk, dv)), dtype=torch.float32, device=dev)
         st = _stream()
@@ -433,6 +458,7 @@ class AdaAttN(nn.Module):
         self._packed = _PackedWeights()
 
     def forward(self, fc: torch.Tensor, fs: torch.Tensor, fcs: torch.Tensor):
+        _check_layer_shapes(self.f.in_channels, fc, fs, fcs)
         _require_cuda(fc, fs, fcs)
         _check_activation(self.activation)
         if _needs_grad(self, fc, fs, fcs):
@@ -481,16 +507,7 @@ class AdaAttnMultiHead(nn.Module):
         return self._packed.get([self.f_list, self.g_list, self.h_list], self.out_conv)
 
     def _check_shapes(self, fc, fs, fcs):
-        C = self.num_heads * self.head_dim
-        if fc.dim() != 4 or fs.dim() != 4 or fcs.dim() != 4:
-            raise RuntimeError("fc, fs and fcs must be (b, qkv_dim, h, w)")
-        if fc.shape[1] != C or fs.shape[1] != C or fcs.shape[1] != C:
-            raise RuntimeError(f"expected {C} channels, got {fc.shape[1]}, {fs.shape[1]}, {fcs.shape[1]}")
-        if fs.shape[0] != fc.shape[0]:
-            # the reference reshapes K/V with the content batch (adaDecoder.py:177-183) and fails the same way
-            raise RuntimeError(f"style batch {fs.shape[0]} must equal content batch {fc.shape[0]}")
-        if fcs.shape != fc.shape:
-            raise RuntimeError("fcs must have the shape of fc")
+        _check_layer_shapes(self.num_heads * self.head_dim, fc, fs, fcs)
 
     def forward_tokens(self, dt, tfc, tfs, tfcs, out=None, reuse_fs_stats: bool = False):
         """Token-major entry used by the transformer to chain layers without layout round trips.
@@ -605,28 +622,17 @@ def _conv3x3_small_relu(x_tok: torch.Tensor, w: torch.Tensor, b: torch.Tensor) -
     return y
 
 
-_CUDNN_RELU_OK = {}
-
-
 def _conv3x3_relu(xp_nchw: torch.Tensor, w: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
-    """3x3 conv (input already padded) + bias + ReLU.  cuDNN's fused conv-bias-relu when it accepts the
-    shape, else conv2d + relu_.  Library call: the decoder convolutions are the boundary neighbour."""
-    key = (xp_nchw.dtype, w.shape[0], w.shape[1])
-    if _CUDNN_RELU_OK.get(key, True):
-        try:
-            y = torch.cudnn_convolution_relu(xp_nchw, w, b, (1, 1), (0, 0), (1, 1), 1)
-            _CUDNN_RELU_OK[key] = True
-            return y
-        except RuntimeError:
-            _CUDNN_RELU_OK[key] = False
-    return F.conv2d(xp_nchw, w, b).relu_()
+    """3x3 conv (input already padded) + bias + ReLU as ONE cuDNN fused conv-bias-relu call (fp32 path of the decoder;
+    the bf16 path runs mhada_conv3x3).  No fallback: if cuDNN rejects the shape the error propagates."""
+    return torch.cudnn_convolution_relu(xp_nchw, w, b, (1, 1), (0, 0), (1, 1), 1)
 
 
 class Decoder(nn.Module):
     """Decoder.forward (conv.py:75-100).  On the GPU every block runs as
         [fused reflect-pad (+ x2 bilinear of the previous block)] -> cuDNN NHWC conv3x3 + bias + ReLU
     so activations stay channels_last and each one is written once and read once between convolutions.
-    CPU tensors take the plain PyTorch path (the decoder is not part of the no-fallback hot path)."""
+    CPU tensors raise (no CPU path); under autograd the plain differentiable PyTorch ops run on the GPU."""
 
     def __init__(self):
         super().__init__()
@@ -639,9 +645,11 @@ class Decoder(nn.Module):
         return [*self.conv1, *self.conv2, *self.conv3]
 
     def forward(self, fcs: torch.Tensor):
-        if not fcs.is_cuda or _needs_grad(self, fcs):
-            # CPU, or training: the plain (differentiable) PyTorch ops of conv.py:96-100
+        _require_cuda(fcs)                                   # no CPU path (use the reference package on CPU)
+        if _needs_grad(self, fcs):
+            # training (train_image.py:105-144): the plain differentiable PyTorch ops of conv.py:96-100 on the GPU
             return self.conv3(self.conv2(self.conv1(fcs)))
+        in_dtype = fcs.dtype
         if fcs.dtype not in (torch.float32, torch.bfloat16):
             fcs = fcs.to(torch.bfloat16)
         if fcs.shape[2] < 2 or fcs.shape[3] < 2:
@@ -654,13 +662,15 @@ class Decoder(nn.Module):
                 cin, cout = blk.conv.conv.in_channels, blk.conv.conv.out_channels
                 if x.dtype == torch.bfloat16 and cin == 64 and cout <= 8 and not up and not blk.scale_factor:
                     # last block (conv.py:90-93): pad + conv + ReLU in one own kernel, straight to NCHW planes
-                    return _conv3x3_small_relu(x, blk.conv.conv.weight, blk.conv.conv.bias)
+                    y = _conv3x3_small_relu(x, blk.conv.conv.weight, blk.conv.conv.bias)
+                    return y if y.dtype == in_dtype else y.to(in_dtype)
                 xp = _pad_reflect(x, up)                     # conv.py:26-27 (+ :71 of the previous block)
                 w, b = blk.conv._weights(x.dtype)
                 y = _conv3x3_relu(xp.permute(0, 3, 1, 2), w, b)
                 x = _token_major(y, y.dtype)                 # no copy when cuDNN answered in channels_last
                 up = bool(blk.scale_factor)
-        return x.permute(0, 3, 1, 2)
+        y = x.permute(0, 3, 1, 2)
+        return y if y.dtype == in_dtype else y.to(in_dtype)       # fp16 in -> fp16 out like the reference
 
 
 class _NullCtx:
@@ -700,7 +710,8 @@ class AdaAttnTransformerMultiHead(nn.Module):
         self.precision = "auto"
 
     def _weight_keys(self):
-        return tuple(p._version for m in self.adaAttnHead for p in m.parameters())
+        # version counter alone misses module.to() / .half() / load_state_dict(assign=True): those rebind storage
+        return tuple((p._version, p.data_ptr(), p.dtype, str(p.device)) for m in self.adaAttnHead for p in m.parameters())
 
     def precompute_style(self, fs, precision: str = None) -> StyleCache:
         """Extension: run the style side of all 2*num_layers layers once.  `fs` is the list of
@@ -732,6 +743,12 @@ class AdaAttnTransformerMultiHead(nn.Module):
         B = fc[0].shape[0]
         if cache.style_batch not in (1, B):
             raise RuntimeError(f"style batch {cache.style_batch} must be 1 or the content batch {B}")
+        for i in range(self.num_layers):
+            if fc[i].dim() != 4 or fc[i].shape != fc[0].shape or fc[i].shape[1] != cache.channels:
+                raise RuntimeError(f"fc[{i}] must be (b, {cache.channels}, h, w) with the shape of fc[0], got "
+                                   f"{tuple(fc[i].shape)}")
+            if fc[i].device != cache.buffers[0].device:
+                raise RuntimeError("content features and StyleCache are on different devices")
         in_dtype, dt = fc[0].dtype, cache.dtype
         tfc = [_token_major(t, dt) for t in fc[: self.num_layers]]
         fcs = tfc[0]

@@ -56,6 +56,18 @@ TRANSFORMER_CASES = [
     # cfg1-sized (512x512 image -> 64x64 tokens): outputs stored on a token / pixel sub-lattice
     dict(name="transformer_64x64_sub", kind="transformer", B=1, hw=(64, 64), hsws=(64, 64), seed=53, sub=37,
          img_sub=8),
+    # the sizes BASELINE.json states its targets on (r2): cfg2 batch (8 x 512^2), cfg3 (1024^2 -> 16384 tokens),
+    # cfg4 (1080p frame x 512^2 style: 32400 x 4096 tokens), and the 4-head six-layer chain of configs[4]
+    dict(name="transformer_b8_64x64_sub", kind="transformer", B=8, hw=(64, 64), hsws=(64, 64), seed=56, sub=149,
+         img_sub=16),
+    dict(name="transformer_128x128_sub", kind="transformer", B=1, hw=(128, 128), hsws=(128, 128), seed=57, sub=149,
+         img_sub=16),
+    dict(name="transformer_135x240_x_64x64_sub", kind="transformer", B=1, hw=(135, 240), hsws=(64, 64), seed=58,
+         sub=293, img_sub=24),
+    dict(name="transformer_h4_32x32_sub", kind="transformer", B=1, hw=(32, 32), hsws=(32, 32), seed=59, sub=7,
+         img_sub=4, heads=4),
+    dict(name="transformer_h4_64x64_sub", kind="transformer", B=2, hw=(64, 64), hsws=(48, 56), seed=60, sub=61,
+         img_sub=8, heads=4),
 ]
 
 SINGLE_HEAD_TRANSFORMER_CASES = [
@@ -141,7 +153,7 @@ def transformer_inputs(case: dict, num_layers: int = 3):
     s = case["seed"]
     fc = [synth.features(s * 100 + i, B, 512, h, w) for i in range(num_layers)]
     fs = [synth.features(s * 100 + 10 + i, B, 512, hs, ws) for i in range(num_layers)]
-    sd = synth.transformer_state(s)
+    sd = synth.transformer_state(s, num_heads=case.get("heads", 8))
     return fc, fs, sd
 
 

@@ -88,7 +88,7 @@ def main(prefix: str = ""):
             meta["out"] = summarize(o64); meta["ref32_vs_ref64"] = errors(o32, o64)
         elif kind == "transformer":
             fc, fs, sd = cases.transformer_inputs(case)
-            o = run_both(lambda: AdaAttnTransformerMultiHead(), sd, (fc, fs))
+            o = run_both(lambda: AdaAttnTransformerMultiHead(num_heads=case.get("heads", 8)), sd, (fc, fs))
             fcs64, cs64 = (t.numpy() for t in o["f64"])
             fcs32, cs32 = (t.numpy() for t in o["f32"])
             arrays["fcs"] = cases.token_sublattice(fcs64, case["sub"]).astype(np.float32)
