@@ -145,8 +145,8 @@ def test_decoder_vs_reference_golden(case, dtype, tol, golden_index):
     assert e["max_abs_rel"] <= tol, e
 
 
-def build_transformer(sd, precision="auto"):
-    m = M.AdaAttnTransformerMultiHead()
+def build_transformer(sd, precision="auto", heads=8):
+    m = M.AdaAttnTransformerMultiHead(num_heads=heads)
     m.load_state_dict(synth.to_torch(sd, torch.float32), strict=True)
     m = m.to(DEV).eval()
     return set_precision(m, precision)
@@ -155,10 +155,12 @@ def build_transformer(sd, precision="auto"):
 @pytest.mark.parametrize("case", cases.TRANSFORMER_CASES, ids=lambda c: c["name"])
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_transformer_vs_reference_golden(case, precision, golden_index):
-    """6 MHAda layers + decoder (adaDecoder.py:253-268); transformer_64x64_sub is BASELINE configs[0]'s
-    size (512x512 image -> 4096 tokens)."""
+    """6 MHAda layers + decoder (adaDecoder.py:253-268) against the UNMODIFIED reference's float64 output, at every
+    size BASELINE.json states a target on: transformer_64x64_sub = configs[0] (512x512 image -> 4096 tokens),
+    _b8_64x64 = configs[1] (batch 8), _128x128 = configs[2] (1024^2 -> 16384 tokens, streaming softmax),
+    _135x240_x_64x64 = configs[3] (1080p frame x 512^2 style), _h4_* = the 4-head chain of configs[4]."""
     fc, fs, sd = cases.transformer_inputs(case)
-    m = build_transformer(sd, precision)
+    m = build_transformer(sd, precision, case.get("heads", 8))
     with torch.no_grad():
         fcs, cs = m([dev(x) for x in fc], [dev(x) for x in fs])          # call form 1
         fcs2, cs2 = m(([dev(x) for x in fc], [dev(x) for x in fs]))      # call form 2 (ptflops style)
@@ -170,6 +172,12 @@ def test_transformer_vs_reference_golden(case, precision, golden_index):
     meta = golden_index[case["name"]]
     ef = O.errors(cases.token_sublattice(fcs.cpu().numpy(), case["sub"]), g["fcs"])
     ec = O.errors(cases.pixel_sublattice(cs.cpu().numpy(), case["img_sub"]), g["cs"])
+    print(case["name"], precision, "fcs", ef, "cs", ec)
+    if meta["cs"]["absmax"] == 0.0:
+        # the reference's decoded image is identically zero for this seed (the final ReLU clips everything):
+        # relative error is undefined, the image must be (near) zero too
+        assert float(cs.float().abs().max()) <= 1e-3, float(cs.float().abs().max())
+        ec = {"max_abs_rel": 0.0}
     if precision == "fp32":
         assert ef["max_abs"] <= fp32_tol(meta["fcs_ref32_vs_ref64"]), ef
         assert ec["max_abs_rel"] <= 1e-4, ec
@@ -332,10 +340,8 @@ def test_errors_on_device():
 # ---------------------------------------------------------------------------------------------------
 
 @pytest.mark.parametrize("case", cases.GRAD_CASES, ids=lambda c: c["name"])
-@pytest.mark.parametrize("precision,tol", [("fp32", 2e-4), ("bf16", None)])
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-4)])
 def test_layer_gradients_vs_reference_autograd(case, precision, tol, golden_index):
-    if precision == "bf16":
-        pytest.skip("head_dim 64 only on the tensor-core path; this fixture has head_dim 64 with C=128, H=2")  # pragma: no cover
     fc, fs, fcs, sd, G = cases.grad_inputs(case)
     m = build_layer(case, sd)
     m.precision = precision
