@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define MHADA_ABI_VERSION 4
+#define MHADA_ABI_VERSION 5
 
 #if defined(__GNUC__)
 #define MHADA_API __attribute__((visibility("default")))
@@ -43,7 +43,7 @@ extern "C" {
 
 typedef void* mhada_stream_t; /* cudaStream_t */
 
-enum mhada_dtype { MHADA_F32 = 0, MHADA_BF16 = 1 };
+enum mhada_dtype { MHADA_F32 = 0, MHADA_BF16 = 1, MHADA_U8 = 2 /* images only */ };
 enum mhada_activation { MHADA_ACT_SOFTMAX = 0, MHADA_ACT_COSINE = 1 };
 
 enum mhada_status {
@@ -189,6 +189,64 @@ MHADA_API int mhada_conv3x3_small(int dtype, const void* x, const float* w, cons
 MHADA_API int mhada_pad_reflect(int dtype, const void* x, int B, int H, int W, int C, int upsample, void* y,
                                 mhada_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * (7) ViT encoder -- replaces VisionTransformer.forward, MHAdaSTr/network/vit.py:148-169
+ *     (PatchEmbedding :105-117, PosEmbedding :67-102, EncoderBlock :45-64), so that the host boundary of the
+ *     pipeline is the IMAGE (infer_image.py:83-85: fc = vit_c(c); fs = vit_s(s); adaFormer(fc, fs)) and the
+ *     feature maps never leave HBM.  bf16 tensor-core path (tcgen05 GEMMs, f32 residual stream).
+ *
+ *     img: [B, 3, Himg, Wimg] planar (NCHW), MHADA_F32 or MHADA_U8 values 0..255 (utilities.py:11-16);
+ *          Himg, Wimg multiples of `patch`;  N = (Himg/patch) * (Wimg/patch) tokens, K0 = 3*patch*patch.
+ *     w_patch bf16 [D][K0] (conv_proj.weight flattened), b_patch f32 [D];
+ *     pos f32 [N][D] token-major positional table already resized to this N (vit.py:96-102), or NULL (vit_s).
+ *     Per layer l: LayerNorm(eps 1e-6) -> in_proj -> attention -> out_proj (+x) -> LayerNorm -> fc1 -> ReLU ->
+ *          fc2 (+x).  nn.MultiheadAttention is built WITHOUT batch_first (vit.py:48) and fed (B, N, D): it attends
+ *          ACROSS THE BATCH for every token position (sequence length = B) -- reproduced exactly:
+ *          for B = 1 the softmax is over one logit and the block reduces to out_proj(v_proj(LN(x))).
+ *     feat_f32[l] f32 [B, N, D]: the residual stream after layer l (required, they double as working buffers);
+ *     feat_bf16[l] bf16 [B, N, D] or NULL: the same values rounded, token-major = exactly the layout
+ *          mhada_layer_forward takes (the reference permutes to (B, D, h, w) views, vit.py:163-166).
+ *     ws: mhada_vit_workspace(B, N, D, F, K0) bytes.   D % 128 == 0, F % 128 == 0, K0 % 64 == 0, D / heads == 64,
+ *          B <= 32.
+ * ---------------------------------------------------------------------------------------------- */
+#define MHADA_VIT_MAX_LAYERS 8
+typedef struct mhada_vit_layer {
+    const void *w_in, *w_out, *w_fc1, *w_fc2;        /* bf16 [3D][D], [D][D], [F][D], [D][F] */
+    const float *b_in, *b_out, *b_fc1, *b_fc2;       /* f32  [3D],    [D],    [F],    [D]    */
+    const float *ln1_g, *ln1_b, *ln2_g, *ln2_b;      /* f32  [D] */
+} mhada_vit_layer;
+typedef struct mhada_vit_args {
+    int img_dtype;
+    const void* img;
+    int B, Himg, Wimg, patch;
+    int D, F, heads, n_layers;
+    const void* w_patch;
+    const float* b_patch;
+    const float* pos;
+    mhada_vit_layer layers[MHADA_VIT_MAX_LAYERS];
+    float* feat_f32[MHADA_VIT_MAX_LAYERS];
+    void* feat_bf16[MHADA_VIT_MAX_LAYERS];
+    void* ws;
+    size_t ws_bytes;
+} mhada_vit_args;
+MHADA_API size_t mhada_vit_workspace(int B, int N, int D, int F, int K0);
+MHADA_API int mhada_vit_forward(const mhada_vit_args* args, mhada_stream_t stream);
+/*     Stages of (7), exposed for the parity tests:
+ *     mhada_patch_im2col: img -> a0 bf16 [B*N][K0], column = c*patch*patch + dy*patch + dx (Conv2d weight order);
+ *     mhada_gemm_bf16:    y = act(x . W^T + bias (+ resid[m % resid_mod])), x bf16 [M, lda], W bf16 [N, ldw],
+ *                         results bf16 [M, ldo] and / or f32 [M, ldf]; K % 64 == 0, N % 128 == 0;
+ *     mhada_layernorm:    nn.LayerNorm(C, eps) over the last axis of f32 [M, C] -> bf16 [M, C]  (vit.py:54-55);
+ *     mhada_batch_attn:   the batch_first=False attention: qkv bf16 [B, N, 3*heads*hd] -> bf16 [B, N, heads*hd],
+ *                         softmax over the B images of a token position, scale 1/sqrt(hd). */
+MHADA_API int mhada_patch_im2col(int img_dtype, const void* img, int B, int Himg, int Wimg, int patch, void* a0,
+                                 mhada_stream_t stream);
+MHADA_API int mhada_gemm_bf16(const void* x, int lda, const void* w, int ldw, const float* bias, int M, int N, int K,
+                              void* out_bf16, int ldo, float* out_f32, int ldf, const float* resid, int ldr,
+                              int resid_mod, int relu, mhada_stream_t stream);
+MHADA_API int mhada_layernorm(const float* x, int M, int C, const float* gamma, const float* beta, float eps,
+                              void* y_bf16, mhada_stream_t stream);
+MHADA_API int mhada_batch_attn(const void* qkv, int B, int N, int heads, int hd, void* out, mhada_stream_t stream);
+
 /* Number of kernel launches the last mhada_layer_forward on this thread issued (bench bookkeeping). */
 MHADA_API int mhada_last_launch_count(void);
 /* Kernel launches issued by this library from this thread since it was loaded (monotonic). */
@@ -209,7 +267,7 @@ MHADA_API int mhada_profile_end(float* attn_ms_total, int* attn_launches);
 /*     Per-stage totals of the last begin/end bracket (valid after mhada_profile_end): device time between the
  *     events that surround the launches of one stage of mhada_layer_forward(_cached), and how many such brackets. */
 enum mhada_stage { MHADA_STAGE_STATS = 0, MHADA_STAGE_PROJ = 1, MHADA_STAGE_ATTN = 2, MHADA_STAGE_LINEAR = 3,
-                   MHADA_STAGE_COUNT = 4 };
+                   MHADA_STAGE_VIT = 4 /* one bracket per mhada_vit_forward */, MHADA_STAGE_COUNT = 5 };
 MHADA_API int mhada_profile_stage(int stage, float* ms_total, int* brackets);
 
 #ifdef __cplusplus

@@ -9,5 +9,7 @@ the forward runs hand-written sm_100a kernels through the C ABI in include/mhada
 from .network import (AdaAttN, AdaAttnForLoss, AdaAttnMultiHead, AdaAttnTransformer,  # noqa: F401
                       AdaAttnTransformerMultiHead, CosineSimilarity, Decoder, Softmax, StyleCache)
 
-__all__ = ["AdaAttnTransformer", "AdaAttnTransformerMultiHead", "AdaAttnForLoss", "AdaAttnMultiHead", "AdaAttN",
+from .vit import VisionTransformer  # noqa: F401,E402
+
+__all__ = ["VisionTransformer", "AdaAttnTransformer", "AdaAttnTransformerMultiHead", "AdaAttnForLoss", "AdaAttnMultiHead", "AdaAttN",
            "Decoder", "Softmax", "CosineSimilarity", "StyleCache"]

@@ -12,8 +12,9 @@ from ctypes import POINTER, c_char_p, c_float, c_int, c_size_t, c_void_p
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libmhada_b200.so")
 
-F32, BF16 = 0, 1
-ABI_VERSION = 4
+F32, BF16, U8 = 0, 1, 2
+ABI_VERSION = 5
+VIT_MAX_LAYERS = 8
 PROJ_Q, PROJ_KV = 1, 2
 REUSE_FS_STATS = 1
 LAYER_COSINE = 2
@@ -31,6 +32,25 @@ class AttnArgs(ctypes.Structure):
         ("q_mean", c_void_p), ("q_rstd", c_void_p), ("k_mean", c_void_p), ("k_rstd", c_void_p),
         ("kv_batch", c_int),
         ("activation", c_int),
+    ]
+
+
+class VitLayer(ctypes.Structure):
+    """mhada_vit_layer (include/mhada_b200.h)."""
+    _fields_ = [(n, c_void_p) for n in ("w_in", "w_out", "w_fc1", "w_fc2", "b_in", "b_out", "b_fc1", "b_fc2",
+                                        "ln1_g", "ln1_b", "ln2_g", "ln2_b")]
+
+
+class VitArgs(ctypes.Structure):
+    """mhada_vit_args (include/mhada_b200.h)."""
+    _fields_ = [
+        ("img_dtype", c_int), ("img", c_void_p),
+        ("B", c_int), ("Himg", c_int), ("Wimg", c_int), ("patch", c_int),
+        ("D", c_int), ("F", c_int), ("heads", c_int), ("n_layers", c_int),
+        ("w_patch", c_void_p), ("b_patch", c_void_p), ("pos", c_void_p),
+        ("layers", VitLayer * 8),
+        ("feat_f32", c_void_p * 8), ("feat_bf16", c_void_p * 8),
+        ("ws", c_void_p), ("ws_bytes", c_size_t),
     ]
 
 
@@ -56,6 +76,13 @@ SIGNATURES = {
     "mhada_linear_workspace": (c_size_t, [c_int, c_int, c_int]),
     "mhada_linear": (c_int, [c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int,
                              c_void_p, c_size_t, c_void_p]),
+    "mhada_vit_workspace": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    "mhada_vit_forward": (c_int, [POINTER(VitArgs), c_void_p]),
+    "mhada_patch_im2col": (c_int, [c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "mhada_gemm_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p,
+                                c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "mhada_layernorm": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p]),
+    "mhada_batch_attn": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "mhada_style_cache_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "mhada_style_precompute": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_size_t,
                                        c_void_p, c_size_t, c_void_p]),

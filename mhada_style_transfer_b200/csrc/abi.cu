@@ -67,8 +67,8 @@ struct Profiler {
     std::vector<cudaEvent_t> ev;   // pairs: start, stop
     std::vector<int> stage;        // stage of pair i
     size_t used = 0;               // events in use
-    float ms[MHADA_STAGE_COUNT] = {0.f, 0.f, 0.f, 0.f};
-    int n[MHADA_STAGE_COUNT] = {0, 0, 0, 0};
+    float ms[MHADA_STAGE_COUNT] = {};
+    int n[MHADA_STAGE_COUNT] = {};
 };
 thread_local Profiler g_prof;
 
@@ -398,6 +398,99 @@ int mhada_linear(int dtype, const void* x, int ldx, const float* w, const float*
     REQUIRE(ws && ws_bytes >= linear_bf16_workspace(Cout, Cin), MHADA_ERR_WORKSPACE, "mhada_linear: workspace too small");
     if (int e = device_check()) return e;
     return launch_linear_bf16(x, ldx, w, bias, M, Cin, Cout, y, ldy, ws, s);
+}
+
+size_t mhada_vit_workspace(int B, int N, int D, int F, int K0) {
+    if (B <= 0 || N <= 0 || D <= 0 || F <= 0 || K0 <= 0) return 0;
+    return vit_workspace(B, N, D, F, K0);
+}
+
+int mhada_vit_forward(const mhada_vit_args* a, mhada_stream_t stream) {
+    g_launches = 0;
+    REQUIRE(a, MHADA_ERR_ARG, "mhada_vit_forward: null args");
+    REQUIRE(a->img && a->w_patch && a->b_patch && a->ws, MHADA_ERR_ARG, "mhada_vit_forward: null pointer");
+    REQUIRE(a->img_dtype == MHADA_F32 || a->img_dtype == MHADA_U8, MHADA_ERR_ARG,
+            "mhada_vit_forward: images are MHADA_F32 or MHADA_U8 (0..255), got dtype %d", a->img_dtype);
+    REQUIRE(a->B > 0 && a->Himg > 0 && a->Wimg > 0 && a->patch > 0 && a->D > 0 && a->F > 0 && a->heads > 0 && a->n_layers > 0,
+            MHADA_ERR_ARG, "mhada_vit_forward: bad sizes");
+    REQUIRE(a->n_layers <= MHADA_VIT_MAX_LAYERS, MHADA_ERR_UNSUPPORTED, "mhada_vit_forward: at most %d layers", MHADA_VIT_MAX_LAYERS);
+    REQUIRE(a->Himg % a->patch == 0 && a->Wimg % a->patch == 0, MHADA_ERR_ARG,
+            "mhada_vit_forward: image %dx%d is not a multiple of the patch size %d", a->Himg, a->Wimg, a->patch);
+    REQUIRE(a->patch == 8 || a->patch == 16, MHADA_ERR_UNSUPPORTED, "mhada_vit_forward: patch size 8 or 16, got %d", a->patch);
+    REQUIRE(a->D % 128 == 0 && a->D <= 1024 && a->F % 128 == 0 && a->D % a->heads == 0 && a->D / a->heads == 64,
+            MHADA_ERR_UNSUPPORTED, "mhada_vit_forward: needs D %% 128 == 0, D <= 1024, F %% 128 == 0 and head_dim 64 (D=%d F=%d heads=%d)",
+            a->D, a->F, a->heads);
+    REQUIRE(a->B <= 32, MHADA_ERR_UNSUPPORTED,
+            "mhada_vit_forward: the batch-axis attention (vit.py:48,59) is implemented for batch <= 32, got %d", a->B);
+    const int N = (a->Himg / a->patch) * (a->Wimg / a->patch), K0 = 3 * a->patch * a->patch;
+    const int elem = a->img_dtype == MHADA_F32 ? 4 : 1;
+    REQUIRE((reinterpret_cast<uintptr_t>(a->img) % (8 * elem)) == 0 && (a->Wimg * elem) % (8 * elem) == 0, MHADA_ERR_ARG,
+            "mhada_vit_forward: image rows must be aligned to 8 pixels");
+    REQUIRE(aligned16(a->w_patch) && aligned16(a->ws) && (!a->pos || aligned16(a->pos)), MHADA_ERR_ARG,
+            "mhada_vit_forward: misaligned pointer");
+    for (int l = 0; l < a->n_layers; ++l) {
+        const mhada_vit_layer& L = a->layers[l];
+        REQUIRE(L.w_in && L.w_out && L.w_fc1 && L.w_fc2 && L.b_in && L.b_out && L.b_fc1 && L.b_fc2 && L.ln1_g && L.ln1_b &&
+                    L.ln2_g && L.ln2_b && a->feat_f32[l],
+                MHADA_ERR_ARG, "mhada_vit_forward: null pointer in layer %d", l);
+        REQUIRE(aligned16(L.w_in) && aligned16(L.w_out) && aligned16(L.w_fc1) && aligned16(L.w_fc2) && aligned16(L.ln1_g) &&
+                    aligned16(L.ln1_b) && aligned16(L.ln2_g) && aligned16(L.ln2_b) && aligned32(a->feat_f32[l]) &&
+                    (!a->feat_bf16[l] || aligned16(a->feat_bf16[l])),
+                MHADA_ERR_ARG, "mhada_vit_forward: misaligned pointer in layer %d", l);
+    }
+    REQUIRE(a->ws_bytes >= vit_workspace(a->B, N, a->D, a->F, K0), MHADA_ERR_WORKSPACE, "mhada_vit_forward: workspace %zu < %zu",
+            a->ws_bytes, vit_workspace(a->B, N, a->D, a->F, K0));
+    if (int e = device_check()) return e;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    StageTimer timer(MHADA_STAGE_VIT, s);
+    return vit_forward(*a, s);
+}
+
+int mhada_patch_im2col(int img_dtype, const void* img, int B, int Himg, int Wimg, int patch, void* a0, mhada_stream_t stream) {
+    REQUIRE(img && a0, MHADA_ERR_ARG, "mhada_patch_im2col: null pointer");
+    REQUIRE(img_dtype == MHADA_F32 || img_dtype == MHADA_U8, MHADA_ERR_ARG, "mhada_patch_im2col: bad image dtype %d", img_dtype);
+    REQUIRE(B > 0 && Himg > 0 && Wimg > 0 && patch > 0 && Himg % patch == 0 && Wimg % patch == 0, MHADA_ERR_ARG,
+            "mhada_patch_im2col: bad sizes");
+    const int elem = img_dtype == MHADA_F32 ? 4 : 1;
+    REQUIRE((reinterpret_cast<uintptr_t>(img) % (8 * elem)) == 0 && aligned16(a0), MHADA_ERR_ARG, "mhada_patch_im2col: misaligned pointer");
+    if (int e = device_check()) return e;
+    return launch_patch_im2col(img_dtype, img, B, Himg, Wimg, patch, a0, static_cast<cudaStream_t>(stream));
+}
+
+int mhada_gemm_bf16(const void* x, int lda, const void* w, int ldw, const float* bias, int M, int N, int K, void* out_bf16,
+                    int ldo, float* out_f32, int ldf, const float* resid, int ldr, int resid_mod, int relu,
+                    mhada_stream_t stream) {
+    REQUIRE(x && w && (out_bf16 || out_f32), MHADA_ERR_ARG, "mhada_gemm_bf16: null pointer");
+    REQUIRE(M > 0 && N > 0 && K > 0 && lda >= K && ldw >= K, MHADA_ERR_ARG, "mhada_gemm_bf16: bad sizes");
+    REQUIRE(K % 64 == 0 && N % 128 == 0, MHADA_ERR_UNSUPPORTED, "mhada_gemm_bf16: needs K %% 64 == 0 and N %% 128 == 0, got N=%d K=%d", N, K);
+    REQUIRE(lda % 8 == 0 && ldw % 8 == 0 && aligned16(x) && aligned16(w), MHADA_ERR_ARG,
+            "mhada_gemm_bf16: operands must be 16-byte aligned with pitches multiples of 8");
+    REQUIRE(!out_bf16 || (ldo >= N && ldo % 8 == 0 && aligned16(out_bf16)), MHADA_ERR_ARG, "mhada_gemm_bf16: bad bf16 output");
+    REQUIRE(!out_f32 || (ldf >= N && ldf % 8 == 0 && aligned32(out_f32)), MHADA_ERR_ARG, "mhada_gemm_bf16: bad f32 output");
+    REQUIRE(!resid || (ldr >= N && ldr % 4 == 0 && aligned16(resid) && resid_mod >= 0), MHADA_ERR_ARG, "mhada_gemm_bf16: bad residual");
+    if (int e = device_check()) return e;
+    GemmDesc g{};
+    g.a = x; g.lda = lda; g.w = w; g.ldw = ldw; g.bias = bias; g.M = M; g.N = N; g.K = K;
+    g.out_bf16 = out_bf16; g.ldo = ldo; g.out_f32 = out_f32; g.ldf = ldf; g.resid = resid; g.ldr = ldr; g.resid_mod = resid_mod;
+    g.relu = relu;
+    return launch_gemm_bf16(g, static_cast<cudaStream_t>(stream));
+}
+
+int mhada_layernorm(const float* x, int M, int C, const float* gamma, const float* beta, float eps, void* y_bf16,
+                    mhada_stream_t stream) {
+    REQUIRE(x && gamma && beta && y_bf16, MHADA_ERR_ARG, "mhada_layernorm: null pointer");
+    REQUIRE(M > 0 && C > 0, MHADA_ERR_ARG, "mhada_layernorm: bad sizes");
+    REQUIRE(aligned16(x) && aligned16(gamma) && aligned16(beta) && aligned16(y_bf16), MHADA_ERR_ARG, "mhada_layernorm: misaligned pointer");
+    if (int e = device_check()) return e;
+    return launch_layernorm(x, M, C, gamma, beta, eps, y_bf16, static_cast<cudaStream_t>(stream));
+}
+
+int mhada_batch_attn(const void* qkv, int B, int N, int heads, int hd, void* out, mhada_stream_t stream) {
+    REQUIRE(qkv && out, MHADA_ERR_ARG, "mhada_batch_attn: null pointer");
+    REQUIRE(B > 0 && N > 0 && heads > 0 && hd > 0, MHADA_ERR_ARG, "mhada_batch_attn: bad sizes");
+    REQUIRE(aligned16(qkv) && aligned16(out), MHADA_ERR_ARG, "mhada_batch_attn: misaligned pointer");
+    if (int e = device_check()) return e;
+    return launch_batch_attn(qkv, B, N, heads, hd, out, static_cast<cudaStream_t>(stream));
 }
 
 int mhada_conv3x3_small(int dtype, const void* x, const float* w, const float* bias, int B, int H, int W, int Cin, int Cout,

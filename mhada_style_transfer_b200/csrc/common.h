@@ -36,6 +36,10 @@ inline void count_launch() { ++g_launches; ++g_launches_total; }
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                    const uint64_t* strides_bytes, const uint32_t* box);
 
+// same for 2-byte (bf16) or 4-byte (f32) elements
+int make_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, const uint64_t* dims,
+              const uint64_t* strides_bytes, const uint32_t* box);
+
 // ---- launchers (one per kernel family); all return 0 / error code ------------------------------
 size_t stats_workspace(int B, int N, int C);
 int launch_stats(const void* x, int dtype, int B, int N, int C, int ld, float* mean, float* rstd, float* ws,
@@ -84,6 +88,26 @@ int launch_attn_bf16_impl(const mhada_attn_args& a, long long* trace, cudaStream
 size_t linear_bf16_workspace(int Cout, int Cin);
 int launch_linear_bf16(const void* x, int ldx, const float* w, const float* bias, int M, int Cin, int Cout, void* y,
                        int ldy, void* ws, cudaStream_t s);
+
+// ViT encoder: generic token GEMM with fused epilogue (gemm_tc.cu) and the small kernels (vit.cu)
+struct GemmDesc {
+    const void* a; int lda;          // bf16 [M, lda]
+    const void* w; int ldw;          // bf16 [N, ldw]  (nn.Linear / Conv2d weight layout: [out][in])
+    const float* bias;               // [N] or nullptr
+    int M, N, K;
+    void* out_bf16; int ldo;         // bf16 result or nullptr
+    float* out_f32; int ldf;         // f32 result or nullptr
+    const float* resid; int ldr;     // f32 residual or nullptr, row = m % resid_mod when resid_mod > 0
+    int resid_mod;
+    int relu;
+};
+int launch_gemm_bf16(const GemmDesc& d, cudaStream_t s);
+int launch_patch_im2col(int img_dtype, const void* img, int B, int Himg, int Wimg, int patch, void* a0, cudaStream_t s);
+int launch_layernorm(const float* x, int M, int C, const float* gamma, const float* beta, float eps, void* y_bf16,
+                     cudaStream_t s);
+int launch_batch_attn(const void* qkv, int B, int N, int heads, int hd, void* out, cudaStream_t s);
+size_t vit_workspace(int B, int N, int D, int F, int K0);
+int vit_forward(const mhada_vit_args& a, cudaStream_t s);
 
 // decoder: last block (reflect pad + 3x3 conv to <= 8 channels + ReLU) in one kernel
 int launch_conv3x3_small(const void* x, const float* w, const float* bias, int B, int H, int W, int Cin, int Cout, int relu,

@@ -1,0 +1,251 @@
+// Token GEMM on the tensor cores for the ViT encoder:
+//     y[M, N] = act( x[M, K] . W[N, K]^T + bias (+ resid[row(m), N]) )        bf16 operands, f32 accumulate
+//
+// Replaces, in MHAdaSTr/network/vit.py: PatchEmbedding.conv_proj as a GEMM over 8x8x3 patches (:105-117, + the
+// positional table :96-102 as a row-periodic residual), the in_proj / out_proj of nn.MultiheadAttention (:48,59),
+// the two nn.Linear of the MLP with the ReLU between them (:49-53,62-63) and both residual additions (:60,64).
+//
+// Structure: persistent CTAs (one per SM), 6 warps; a work item is one 128 x BN output tile, the BN tiles of the
+// same 128 rows are consecutive items (x comes from HBM once and from L2 for the other column tiles):
+//   warp 0      TMA producer: x and W tiles -> 128B-swizzled shared memory, STAGES-deep mbarrier ring that runs
+//               straight across work items
+//   warp 1      tcgen05.mma issuer (one elected lane), M = 128, N = BN, accumulators DOUBLE-BUFFERED in TMEM
+//               (2 x BN columns): the MMAs of item n+1 overlap the epilogue of item n
+//   warps 2..5  epilogue: tcgen05.ld (lane = row) -> + bias (+ residual) (ReLU) ->
+//                 bf16 result: packed into a 128B-swizzled staging slab (32 rows x 64 columns per warp, two slabs)
+//                              and written with ONE TMA STORE per slab (cp.async.bulk.tensor, rows past M clipped);
+//                 f32 result (the residual stream): 256-bit stores, 128 contiguous bytes per lane.
+// BN = 256 keeps the shared-memory operand traffic of the SS-mode MMAs at 96 B/clk (a 128 x 128 tile needs the
+// full 128 B/clk of the SM).  Compute-bound for K >= 512: 2*M*N*K FLOP; HBM bytes 2*M*K + 2*N*K + (2|4|6)*M*N.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace mh {
+
+constexpr int GM_BM = 128, GM_BK = 64, GM_THREADS = 192;
+constexpr uint32_t GM_STG_WARP = 2 * 32 * 128;   // two staging slabs (32 rows x 128 B) per epilogue warp
+
+struct GemmParams {
+    const float* bias;     // [N] or nullptr
+    const float* resid;    // f32 [*, ldr] or nullptr
+    float* out_f32;        // f32 [M, ldf] or nullptr
+    int ldr, resid_mod;    // residual row = m % resid_mod when resid_mod > 0 (positional table), else m
+    int ldf;
+    int has_bf16;          // bf16 result through the tensor map tmC
+    int relu;
+    int M, ktiles, ntiles, items;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(GM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
+    constexpr uint32_t A_BYTES = GM_BM * GM_BK * 2, B_BYTES = BN * GM_BK * 2, STAGE = A_BYTES + B_BYTES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ uint64_t full[STAGES], empty[STAGES], acc_full[2], acc_empty[2];
+    __shared__ uint32_t tmem_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        if (p.has_bf16) tma_prefetch_desc(&tmC);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < STAGES; ++s) {
+                mbar_init(&full[s], 1);
+                mbar_init(&empty[s], 1);
+            }
+            for (int u = 0; u < 2; ++u) {
+                mbar_init(&acc_full[u], 1);
+                mbar_init(&acc_empty[u], 4);      // one arrive per epilogue warp
+            }
+            fence_mbar_init();
+        }
+        __syncwarp();
+        tmem_alloc(&tmem_slot, 2 * BN);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            int g = 0;                                            // running k-tile counter of this CTA
+            for (int it = blockIdx.x; it < p.items; it += gridDim.x) {
+                const int m0 = (it / p.ntiles) * GM_BM, n0 = (it % p.ntiles) * BN;
+                for (int kt = 0; kt < p.ktiles; ++kt, ++g) {
+                    const int s = g % STAGES;
+                    mbar_wait(&empty[s], ((g / STAGES) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&full[s], STAGE);
+                    uint8_t* a = smem + s * STAGE;
+                    tma_load_2d(a, &tmA, &full[s], kt * GM_BK, m0);
+                    tma_load_2d(a + A_BYTES, &tmB, &full[s], kt * GM_BK, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            constexpr uint32_t idesc = make_idesc_bf16(GM_BM, BN, 0, 0);
+            int g = 0, n = 0;
+            for (int it = blockIdx.x; it < p.items; it += gridDim.x, ++n) {
+                const int u = n & 1;
+                mbar_wait(&acc_empty[u], ((n >> 1) & 1) ^ 1);     // the epilogue has drained this accumulator buffer
+                tc_fence_after();
+                for (int kt = 0; kt < p.ktiles; ++kt, ++g) {
+                    const int s = g % STAGES;
+                    mbar_wait(&full[s], (g / STAGES) & 1);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + s * STAGE);
+                    const uint64_t da = make_smem_desc(a_addr, 16, 1024);
+                    const uint64_t db = make_smem_desc(a_addr + A_BYTES, 16, 1024);
+#pragma unroll
+                    for (int k = 0; k < GM_BK / 16; ++k)
+                        umma_ss(tmem + u * BN, desc_advance(da, k * 32), desc_advance(db, k * 32), idesc, (kt | k) != 0);
+                    umma_commit(&empty[s]);
+                }
+                umma_commit(&acc_full[u]);
+            }
+        }
+    } else {
+        // epilogue warps 2..5 -> TMEM lane quarters 2, 3, 0, 1
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        uint8_t* stg = smem + STAGES * STAGE + (warp - 2) * GM_STG_WARP;      // 1024-byte aligned slabs
+        const uint32_t swz = static_cast<uint32_t>(lane & 7);
+        int nstore = 0;                                                        // TMA stores issued by this warp
+        int n = 0;
+        for (int it = blockIdx.x; it < p.items; it += gridDim.x, ++n) {
+            const int m0 = (it / p.ntiles) * GM_BM, n0 = (it % p.ntiles) * BN;
+            const int m = m0 + row;
+            const bool row_ok = m < p.M;
+            const int u = n & 1;
+            const float* rrow = nullptr;
+            if (p.resid && row_ok)
+                rrow = p.resid + static_cast<size_t>(p.resid_mod > 0 ? m % p.resid_mod : m) * p.ldr + n0;
+            float* frow = (p.out_f32 && row_ok) ? p.out_f32 + static_cast<size_t>(m) * p.ldf + n0 : nullptr;
+            mbar_wait(&acc_full[u], (n >> 1) & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < BN; c += 32) {
+                float4 rv[8];
+                if (rrow) {                                   // residual row segment: 128 contiguous bytes per lane
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) rv[i] = __ldg(reinterpret_cast<const float4*>(rrow + c) + i);
+                }
+                uint32_t r[32];
+                tmem_ld_x32(tmem_addr(tmem, quarter * 32, u * BN + c), r);
+                tmem_wait_ld();
+                if (c + 32 == BN) {                           // accumulator drained: the next-but-one item may start
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&acc_empty[u]);
+                }
+                float v[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) + (p.bias ? __ldg(p.bias + n0 + c + i) : 0.f);
+                if (rrow) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        v[4 * i] += rv[i].x; v[4 * i + 1] += rv[i].y; v[4 * i + 2] += rv[i].z; v[4 * i + 3] += rv[i].w;
+                    }
+                }
+                if (p.relu) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+                }
+                if (frow) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) st_global_256(frow + c + 8 * i, reinterpret_cast<const uint32_t*>(v + 8 * i));
+                }
+                if (p.has_bf16) {
+                    const int half = (c >> 5) & 1;            // which 32-column half of the 64-column slab
+                    uint8_t* slab = stg + (nstore & 1) * (32 * 128);
+                    if (half == 0) {
+                        // the slab was the source of the store issued two stores ago: wait until it has been read
+                        if (lane == 0) tma_store_wait_read<1>();
+                        __syncwarp();
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        uint4 w;
+                        w.x = pack_bf16x2(v[8 * q], v[8 * q + 1]);
+                        w.y = pack_bf16x2(v[8 * q + 2], v[8 * q + 3]);
+                        w.z = pack_bf16x2(v[8 * q + 4], v[8 * q + 5]);
+                        w.w = pack_bf16x2(v[8 * q + 6], v[8 * q + 7]);
+                        const uint32_t chunk = static_cast<uint32_t>(half * 4 + q) ^ swz;     // 128B swizzle
+                        *reinterpret_cast<uint4*>(slab + lane * 128 + chunk * 16) = w;
+                    }
+                    if (half == 1) {
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_2d(&tmC, slab, n0 + c - 32, m0 + quarter * 32);
+                            tma_store_commit();
+                        }
+                        ++nstore;
+                    }
+                }
+            }
+        }
+        if (lane == 0) tma_store_wait<0>();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, 2 * BN);
+}
+
+template <int BN, int STAGES>
+static int launch_gemm_bn(const GemmDesc& d, cudaStream_t s) {
+    CUtensorMap tmA, tmB, tmC;
+    {
+        uint64_t dims[2] = {static_cast<uint64_t>(d.K), static_cast<uint64_t>(d.M)};
+        uint64_t str[1] = {static_cast<uint64_t>(d.lda) * 2};
+        uint32_t box[2] = {GM_BK, GM_BM};
+        if (int e = make_tmap_bf16(&tmA, d.a, 2, dims, str, box)) return e;
+    }
+    {
+        uint64_t dims[2] = {static_cast<uint64_t>(d.K), static_cast<uint64_t>(d.N)};
+        uint64_t str[1] = {static_cast<uint64_t>(d.ldw) * 2};
+        uint32_t box[2] = {GM_BK, BN};
+        if (int e = make_tmap_bf16(&tmB, d.w, 2, dims, str, box)) return e;
+    }
+    if (d.out_bf16) {
+        uint64_t dims[2] = {static_cast<uint64_t>(d.N), static_cast<uint64_t>(d.M)};
+        uint64_t str[1] = {static_cast<uint64_t>(d.ldo) * 2};
+        uint32_t box[2] = {64, 32};
+        if (int e = make_tmap_bf16(&tmC, d.out_bf16, 2, dims, str, box)) return e;
+    } else {
+        tmC = tmA;      // never dereferenced
+    }
+    GemmParams p;
+    p.bias = d.bias; p.resid = d.resid; p.out_f32 = d.out_f32;
+    p.ldr = d.ldr; p.resid_mod = d.resid_mod; p.ldf = d.ldf;
+    p.has_bf16 = d.out_bf16 ? 1 : 0; p.relu = d.relu;
+    p.M = d.M; p.ktiles = d.K / GM_BK; p.ntiles = d.N / BN;
+    p.items = ((d.M + GM_BM - 1) / GM_BM) * p.ntiles;
+    constexpr size_t smem = STAGES * (GM_BM * GM_BK * 2 + BN * GM_BK * 2) + 4 * GM_STG_WARP + 1024;
+    static DeviceOnce once;
+    if (int e = smem_attr_once(once, reinterpret_cast<const void*>(gemm_tc_kernel<BN, STAGES>), smem, "gemm smem attr")) return e;
+    const int n_sm = sm_count();
+    const int grid = p.items < n_sm ? p.items : n_sm;
+    gemm_tc_kernel<BN, STAGES><<<grid, GM_THREADS, smem, s>>>(tmA, tmB, tmC, p);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "gemm_tc launch");
+}
+
+int launch_gemm_bf16(const GemmDesc& d, cudaStream_t s) {
+    if (d.M <= 0 || d.N <= 0 || d.K <= 0 || d.K % GM_BK != 0 || d.N % 128 != 0) {
+        set_error("gemm_tc: needs K %% 64 == 0 and N %% 128 == 0, got M=%d N=%d K=%d", d.M, d.N, d.K);
+        return MHADA_ERR_UNSUPPORTED;
+    }
+    if (d.N % 256 == 0) return launch_gemm_bn<256, 4>(d, s);
+    return launch_gemm_bn<128, 4>(d, s);
+}
+
+}  // namespace mh

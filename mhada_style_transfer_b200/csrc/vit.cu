@@ -1,0 +1,277 @@
+// ViT encoder around the token GEMM (gemm_tc.cu): the small HBM-bound kernels and the per-layer launch sequence.
+//
+// Replaces VisionTransformer.forward, MHAdaSTr/network/vit.py:148-169:
+//   patch_im2col_kernel   the gather half of PatchEmbedding.conv_proj (Conv2d k = stride = patch, :105-117): image
+//                         pixels -> bf16 rows [B*N, 3*patch*patch] in Conv2d weight order, so the convolution is a GEMM
+//   layernorm_kernel      nn.LayerNorm(hidden, eps=1e-6) (:54-55, used :58, :62): f32 residual stream -> bf16 GEMM operand
+//   batch_attn_kernel     nn.MultiheadAttention built without batch_first and fed (B, N, D) (:48, :59): the sequence
+//                         axis is the BATCH -- for every token position and head, softmax(q k^T / sqrt(hd)) over the B
+//                         images.  Reproduced as is: the reference's features of image k depend on the
+//                         other images of its batch.
+// All three are bandwidth-bound passes between the GEMMs; the residual stream stays f32 (the per-channel DC of the
+// patch embedding is ~20x the spatial signal the MHAda instance norm later extracts; bf16 would round it away).
+#include "common.h"
+#include "ptx.cuh"
+
+namespace mh {
+
+// ------------------------------------------------------------------------------------------------ patch gather
+// thread = (b, c, image row, patch column): reads `P` contiguous pixels, writes `P` contiguous bf16
+template <typename T, int P>
+__global__ void __launch_bounds__(256) patch_im2col_kernel(const T* __restrict__ img, __nv_bfloat16* __restrict__ a0,
+                                                           int B, int Himg, int Wimg) {
+    const int wp = Wimg / P, hp = Himg / P;
+    const size_t total = static_cast<size_t>(B) * 3 * Himg * wp;
+    const size_t t = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    if (t >= total) return;
+    const int xp = static_cast<int>(t % wp);
+    const int row = static_cast<int>((t / wp) % Himg);
+    const int c = static_cast<int>((t / (static_cast<size_t>(wp) * Himg)) % 3);
+    const int b = static_cast<int>(t / (static_cast<size_t>(wp) * Himg * 3));
+    const T* src = img + ((static_cast<size_t>(b) * 3 + c) * Himg + row) * Wimg + static_cast<size_t>(xp) * P;
+    const int y = row / P, dy = row % P;
+    const size_t n = static_cast<size_t>(b) * hp * wp + static_cast<size_t>(y) * wp + xp;
+    __nv_bfloat16* dst = a0 + n * (3 * P * P) + c * P * P + dy * P;
+    float v[P];
+    if constexpr (P == 8 && sizeof(T) == 4) {
+        const float4 lo = __ldg(reinterpret_cast<const float4*>(src)), hi = __ldg(reinterpret_cast<const float4*>(src) + 1);
+        v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+    } else if constexpr (P == 8 && sizeof(T) == 1) {
+        const uint2 w = __ldg(reinterpret_cast<const uint2*>(src));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            v[i] = static_cast<float>((w.x >> (8 * i)) & 0xffu);
+            v[4 + i] = static_cast<float>((w.y >> (8 * i)) & 0xffu);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < P; ++i) v[i] = static_cast<float>(src[i]);
+    }
+    if constexpr (P == 8) {
+        uint4 o;
+        o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]); o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+        *reinterpret_cast<uint4*>(dst) = o;
+    } else {
+#pragma unroll
+        for (int i = 0; i < P; ++i) dst[i] = __float2bfloat16_rn(v[i]);
+    }
+}
+
+int launch_patch_im2col(int img_dtype, const void* img, int B, int Himg, int Wimg, int patch, void* a0, cudaStream_t s) {
+    if (patch != 8 && patch != 16) {
+        set_error("patch_im2col: patch sizes 8 and 16 are implemented (3*patch^2 must be a multiple of 64), got %d", patch);
+        return MHADA_ERR_UNSUPPORTED;
+    }
+    const size_t total = static_cast<size_t>(B) * 3 * Himg * (Wimg / patch);
+    const unsigned grid = static_cast<unsigned>((total + 255) / 256);
+    __nv_bfloat16* out = static_cast<__nv_bfloat16*>(a0);
+    if (img_dtype == MHADA_F32) {
+        if (patch == 8) patch_im2col_kernel<float, 8><<<grid, 256, 0, s>>>(static_cast<const float*>(img), out, B, Himg, Wimg);
+        else patch_im2col_kernel<float, 16><<<grid, 256, 0, s>>>(static_cast<const float*>(img), out, B, Himg, Wimg);
+    } else {
+        if (patch == 8) patch_im2col_kernel<uint8_t, 8><<<grid, 256, 0, s>>>(static_cast<const uint8_t*>(img), out, B, Himg, Wimg);
+        else patch_im2col_kernel<uint8_t, 16><<<grid, 256, 0, s>>>(static_cast<const uint8_t*>(img), out, B, Himg, Wimg);
+    }
+    count_launch();
+    return check_cuda(cudaGetLastError(), "patch_im2col launch");
+}
+
+// ------------------------------------------------------------------------------------------------ LayerNorm
+// warp = token row; lane owns 4 consecutive channels of every 128-channel group (128-bit loads, 64-bit stores)
+constexpr int LN_MAXV = 8;      // C <= 1024
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, int M, int C,
+                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                        float eps, __nv_bfloat16* __restrict__ y) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const int nv = C >> 7;
+    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * C);
+    float4 v[LN_MAXV];
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < LN_MAXV; ++j)
+        if (j < nv) {
+            v[j] = __ldg(xr + j * 32 + lane);
+            sum += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+        }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / static_cast<float>(C);
+    float sq = 0.f;
+#pragma unroll
+    for (int j = 0; j < LN_MAXV; ++j)
+        if (j < nv) {
+            const float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
+            sq += (a * a + b * b) + (c * c + d * d);
+        }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq / static_cast<float>(C) + eps);      // biased variance, eps inside the root
+    uint2* yr = reinterpret_cast<uint2*>(y + static_cast<size_t>(row) * C);
+#pragma unroll
+    for (int j = 0; j < LN_MAXV; ++j)
+        if (j < nv) {
+            const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + j * 32 + lane);
+            const float4 be = __ldg(reinterpret_cast<const float4*>(beta) + j * 32 + lane);
+            uint2 o;
+            o.x = pack_bf16x2(fmaf((v[j].x - mean) * rstd, g.x, be.x), fmaf((v[j].y - mean) * rstd, g.y, be.y));
+            o.y = pack_bf16x2(fmaf((v[j].z - mean) * rstd, g.z, be.z), fmaf((v[j].w - mean) * rstd, g.w, be.w));
+            yr[j * 32 + lane] = o;
+        }
+}
+
+int launch_layernorm(const float* x, int M, int C, const float* gamma, const float* beta, float eps, void* y_bf16,
+                     cudaStream_t s) {
+    if (C % 128 != 0 || C > 128 * LN_MAXV) {
+        set_error("layernorm: C must be a multiple of 128 and at most %d, got %d", 128 * LN_MAXV, C);
+        return MHADA_ERR_UNSUPPORTED;
+    }
+    layernorm_kernel<<<(M + 7) / 8, 256, 0, s>>>(x, M, C, gamma, beta, eps, static_cast<__nv_bfloat16*>(y_bf16));
+    count_launch();
+    return check_cuda(cudaGetLastError(), "layernorm launch");
+}
+
+// ------------------------------------------------------------------------------------------------ batch-axis attention
+// warp = (token position n, head); the "sequence" is the B images.  q, k, v of the B images staged in shared memory
+// (f32), lane j < B owns key j for the logits, lane owns value columns 2*lane, 2*lane + 1 for the output.
+constexpr int BA_HD = 64;
+constexpr int BA_WARPS = 8;
+constexpr int BA_PITCH = BA_HD + 1;
+__global__ void __launch_bounds__(BA_WARPS * 32) batch_attn_kernel(const __nv_bfloat16* __restrict__ qkv, int B, int N,
+                                                                   int heads, __nv_bfloat16* __restrict__ out) {
+    extern __shared__ float ba_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long item = static_cast<long long>(blockIdx.x) * BA_WARPS + warp;     // n * heads + h
+    if (item >= static_cast<long long>(N) * heads) return;
+    const int n = static_cast<int>(item / heads), h = static_cast<int>(item % heads);
+    const int D = heads * BA_HD;
+    float* q = ba_smem + static_cast<size_t>(warp) * 3 * B * BA_PITCH;
+    float* k = q + B * BA_PITCH;
+    float* v = k + B * BA_PITCH;
+    for (int b = 0; b < B; ++b) {
+        const uint32_t* base = reinterpret_cast<const uint32_t*>(qkv + (static_cast<size_t>(b) * N + n) * 3 * D + h * BA_HD);
+        const uint32_t wq = __ldg(base + lane), wk = __ldg(base + D / 2 + lane), wv = __ldg(base + D + lane);
+        q[b * BA_PITCH + 2 * lane] = bf16_lo(wq); q[b * BA_PITCH + 2 * lane + 1] = bf16_hi(wq);
+        k[b * BA_PITCH + 2 * lane] = bf16_lo(wk); k[b * BA_PITCH + 2 * lane + 1] = bf16_hi(wk);
+        v[b * BA_PITCH + 2 * lane] = bf16_lo(wv); v[b * BA_PITCH + 2 * lane + 1] = bf16_hi(wv);
+    }
+    __syncwarp();
+    const float scale = 0.125f;                       // 1 / sqrt(64)
+    for (int i = 0; i < B; ++i) {
+        float sc = -INFINITY;
+        if (lane < B) {
+            float acc = 0.f;
+#pragma unroll 16
+            for (int d = 0; d < BA_HD; ++d) acc = fmaf(q[i * BA_PITCH + d], k[lane * BA_PITCH + d], acc);
+            sc = acc * scale;
+        }
+        float mx = sc;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float pj = lane < B ? __expf(sc - mx) : 0.f;
+        float sum = pj;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        pj /= sum;
+        float o0 = 0.f, o1 = 0.f;
+        for (int j = 0; j < B; ++j) {
+            const float pw = __shfl_sync(0xffffffffu, pj, j);
+            o0 = fmaf(pw, v[j * BA_PITCH + 2 * lane], o0);
+            o1 = fmaf(pw, v[j * BA_PITCH + 2 * lane + 1], o1);
+        }
+        reinterpret_cast<uint32_t*>(out + (static_cast<size_t>(i) * N + n) * D + h * BA_HD)[lane] = pack_bf16x2(o0, o1);
+    }
+}
+
+int launch_batch_attn(const void* qkv, int B, int N, int heads, int hd, void* out, cudaStream_t s) {
+    if (hd != BA_HD || B < 1 || B > 32) {
+        set_error("batch_attn: head_dim 64 and batch 1..32 are implemented, got head_dim %d, batch %d", hd, B);
+        return MHADA_ERR_UNSUPPORTED;
+    }
+    const size_t smem = static_cast<size_t>(BA_WARPS) * 3 * B * BA_PITCH * sizeof(float);
+    static DeviceOnce once;
+    if (int e = smem_attr_once(once, reinterpret_cast<const void*>(batch_attn_kernel), static_cast<size_t>(BA_WARPS) * 3 * 32 * BA_PITCH * sizeof(float),
+                               "batch_attn smem attr"))
+        return e;
+    const long long items = static_cast<long long>(N) * heads;
+    batch_attn_kernel<<<static_cast<unsigned>((items + BA_WARPS - 1) / BA_WARPS), BA_WARPS * 32, smem, s>>>(
+        static_cast<const __nv_bfloat16*>(qkv), B, N, heads, static_cast<__nv_bfloat16*>(out));
+    count_launch();
+    return check_cuda(cudaGetLastError(), "batch_attn launch");
+}
+
+// ------------------------------------------------------------------------------------------------ the encoder
+struct VitWs {
+    void *a0, *y, *qkv, *att, *hbuf;
+    float *x0, *x1;
+    size_t total;
+};
+static VitWs vit_carve(int B, int N, int D, int F, int K0, uint8_t* base) {
+    VitWs w;
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        void* p = base ? base + off : nullptr;
+        off += align_up(bytes, 1024);
+        return p;
+    };
+    const size_t M = static_cast<size_t>(B) * N;
+    w.a0 = take(M * K0 * 2);
+    w.y = take(M * D * 2);
+    w.qkv = take(M * (B == 1 ? D : 3 * D) * 2);
+    w.att = take(M * D * 2);
+    w.hbuf = take(M * F * 2);
+    w.x0 = static_cast<float*>(take(M * D * 4));
+    w.x1 = static_cast<float*>(take(M * D * 4));
+    w.total = off;
+    return w;
+}
+size_t vit_workspace(int B, int N, int D, int F, int K0) { return vit_carve(B, N, D, F, K0, nullptr).total; }
+
+int vit_forward(const mhada_vit_args& a, cudaStream_t s) {
+    const int P = a.patch, hp = a.Himg / P, wp = a.Wimg / P, N = hp * wp, K0 = 3 * P * P, D = a.D, F = a.F;
+    const int M = a.B * N;
+    VitWs w = vit_carve(a.B, N, D, F, K0, static_cast<uint8_t*>(a.ws));
+    // PatchEmbedding (+ PosEmbedding): vit.py:153-158
+    if (int e = launch_patch_im2col(a.img_dtype, a.img, a.B, a.Himg, a.Wimg, P, w.a0, s)) return e;
+    GemmDesc g{};
+    g.a = w.a0; g.lda = K0; g.w = a.w_patch; g.ldw = K0; g.bias = a.b_patch; g.M = M; g.N = D; g.K = K0;
+    g.out_f32 = w.x0; g.ldf = D; g.resid = a.pos; g.ldr = D; g.resid_mod = a.pos ? N : 0;
+    if (int e = launch_gemm_bf16(g, s)) return e;
+    const float* x = w.x0;
+    for (int l = 0; l < a.n_layers; ++l) {                                        // EncoderBlock.forward, vit.py:57-64
+        const mhada_vit_layer& L = a.layers[l];
+        if (int e = launch_layernorm(x, M, D, L.ln1_g, L.ln1_b, 1e-6f, w.y, s)) return e;               // :58
+        if (a.B == 1) {
+            // sequence length 1: softmax over a single logit is exactly 1, the attention output IS v (:59)
+            g = GemmDesc{};
+            g.a = w.y; g.lda = D; g.w = static_cast<const __nv_bfloat16*>(L.w_in) + static_cast<size_t>(2 * D) * D; g.ldw = D;
+            g.bias = L.b_in + 2 * D; g.M = M; g.N = D; g.K = D; g.out_bf16 = w.att; g.ldo = D;
+            if (int e = launch_gemm_bf16(g, s)) return e;
+        } else {
+            g = GemmDesc{};
+            g.a = w.y; g.lda = D; g.w = L.w_in; g.ldw = D; g.bias = L.b_in; g.M = M; g.N = 3 * D; g.K = D;
+            g.out_bf16 = w.qkv; g.ldo = 3 * D;
+            if (int e = launch_gemm_bf16(g, s)) return e;
+            if (int e = launch_batch_attn(w.qkv, a.B, N, a.heads, D / a.heads, w.att, s)) return e;
+        }
+        g = GemmDesc{};                                                                                 // out_proj + residual :60
+        g.a = w.att; g.lda = D; g.w = L.w_out; g.ldw = D; g.bias = L.b_out; g.M = M; g.N = D; g.K = D;
+        g.out_f32 = w.x1; g.ldf = D; g.resid = x; g.ldr = D;
+        if (int e = launch_gemm_bf16(g, s)) return e;
+        if (int e = launch_layernorm(w.x1, M, D, L.ln2_g, L.ln2_b, 1e-6f, w.y, s)) return e;             // :62
+        g = GemmDesc{};                                                                                 // mlp[0] + ReLU :63
+        g.a = w.y; g.lda = D; g.w = L.w_fc1; g.ldw = D; g.bias = L.b_fc1; g.M = M; g.N = F; g.K = D;
+        g.out_bf16 = w.hbuf; g.ldo = F; g.relu = 1;
+        if (int e = launch_gemm_bf16(g, s)) return e;
+        g = GemmDesc{};                                                                                 // mlp[2] + residual :64
+        g.a = w.hbuf; g.lda = F; g.w = L.w_fc2; g.ldw = F; g.bias = L.b_fc2; g.M = M; g.N = D; g.K = F;
+        g.out_f32 = a.feat_f32[l]; g.ldf = D; g.resid = w.x1; g.ldr = D;
+        g.out_bf16 = a.feat_bf16[l]; g.ldo = D;
+        if (int e = launch_gemm_bf16(g, s)) return e;
+        x = a.feat_f32[l];
+    }
+    return 0;
+}
+
+}  // namespace mh

@@ -1,0 +1,215 @@
+"""Host-side mirror of the reference's ViT encoder (MHAdaSTr/network/vit.py:45-169), SURVEY.md N3.
+
+Same class names, constructor signatures, attribute names and state_dict keys as the reference
+(`patch_embedding.conv_proj.*`, `pos_embedding.pos_embed`, `encoder.{i}.attention.in_proj_weight / in_proj_bias /
+out_proj.*`, `encoder.{i}.mlp.{0,2}.*`, `encoder.{i}.ln{1,2}.*`), so `vit_c.load_state_dict(torch.load(VITC_PATH),
+strict=True)` (infer_image.py:55) keeps working and, with the same torch seed, the random init is the reference's.
+
+The inference forward hands the image to `mhada_vit_forward` (include/mhada_b200.h): patch gather, tcgen05 GEMMs
+with fused bias / ReLU / residual / positional table, LayerNorm and the batch-axis attention as hand-written
+sm_100a kernels.  It returns the three feature maps as (B, hidden, h, w) views over TOKEN-MAJOR bf16 memory --
+exactly what `AdaAttnTransformerMultiHead` consumes without a copy -- so the pipeline's host boundary is the image
+(infer_image.py:83-85) and the features never leave HBM.
+
+Reference quirk kept on purpose: `nn.MultiheadAttention` is built without batch_first and fed
+(B, N, D), so it attends ACROSS THE BATCH for every token position.  The kernels reproduce that, so an image's
+features depend on the other images of its batch exactly as in the reference.
+
+There is no CPU path.  Under autograd (train_image.py:103-108) the forward runs the reference's own op sequence
+with PyTorch ops on the GPU (differentiable); own backward kernels are SURVEY N4.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List
+
+import torch
+import torch.nn as nn
+from torch.nn import functional as F
+
+from . import _lib
+from .network import _needs_grad, _require_cuda, _stream, _workspace
+
+__all__ = ["VisionTransformer", "EncoderBlock", "PatchEmbedding", "PosEmbedding"]
+
+
+class EncoderBlock(nn.Module):
+    """vit.py:45-64.  Parameters only; `forward` is the reference op sequence (used under autograd)."""
+
+    def __init__(self, num_heads: int, hidden_dim: int, mlp_dim: int):
+        super().__init__()
+        self.attention = nn.MultiheadAttention(embed_dim=hidden_dim, num_heads=num_heads)    # batch_first=False, :48
+        self.mlp = nn.Sequential(nn.Linear(hidden_dim, mlp_dim), nn.ReLU(), nn.Linear(mlp_dim, hidden_dim))
+        self.ln1 = nn.LayerNorm(hidden_dim, eps=1e-6)
+        self.ln2 = nn.LayerNorm(hidden_dim, eps=1e-6)
+
+    def forward(self, input: torch.Tensor):
+        x = self.ln1(input)
+        x, _ = self.attention(x, x, x, need_weights=False)
+        x = x + input
+        return x + self.mlp(self.ln2(x))
+
+
+class PosEmbedding(nn.Module):
+    """vit.py:67-102: learned (1, D, 32, 32) table, bilinearly resized to the token grid."""
+
+    def __init__(self, patch_size: int = 8, embed_dim: int = 512, base_embed_size: int = 32):
+        super().__init__()
+        self.patch_size, self.embed_dim, self.base_embed_size = patch_size, embed_dim, base_embed_size
+        self.pos_embed = nn.Parameter(torch.empty(1, embed_dim, base_embed_size, base_embed_size).normal_(std=0.02))
+        self._table = {}
+
+    def grid(self, out_h: int, out_w: int) -> torch.Tensor:
+        """(1, D, out_h, out_w) table (vit.py:91-94)."""
+        if out_h != self.base_embed_size or out_w != self.base_embed_size:
+            return F.interpolate(self.pos_embed, size=(out_h, out_w), mode="bilinear", align_corners=False)
+        return self.pos_embed
+
+    def token_table(self, out_h: int, out_w: int) -> torch.Tensor:
+        """f32 [N, D] token-major table for the GEMM epilogue; cached per grid size and parameter version."""
+        p = self.pos_embed
+        key = (out_h, out_w, p._version, p.data_ptr(), p.dtype, str(p.device))
+        hit = self._table.get(str(p.device))
+        if hit is None or hit[0] != key:
+            with torch.no_grad():
+                t = self.grid(out_h, out_w).float().reshape(self.embed_dim, out_h * out_w).t().contiguous()
+            self._table[str(p.device)] = hit = (key, t)
+        return hit[1]
+
+    def forward(self, x_shape: torch.Size) -> torch.Tensor:
+        b, _, h, w = x_shape
+        out_h, out_w = h // self.patch_size, w // self.patch_size
+        pe = self.grid(out_h, out_w).expand(b, -1, -1, -1)
+        return pe.reshape(b, self.embed_dim, out_h * out_w).permute(0, 2, 1)
+
+
+class PatchEmbedding(nn.Module):
+    """vit.py:105-117."""
+
+    def __init__(self, in_channels: int, patch_size: int, hidden_dim: int):
+        super().__init__()
+        self.conv_proj = nn.Conv2d(in_channels=in_channels, out_channels=hidden_dim, kernel_size=patch_size, stride=patch_size)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        x = self.conv_proj(x)
+        b, c, h, w = x.shape
+        return x.reshape(b, c, h * w).permute(0, 2, 1)
+
+
+class _VitWeights:
+    """bf16 copies of the GEMM weights and f32 copies of everything else, per device; rebuilt when a parameter was
+    modified (version counter), moved or rebound."""
+
+    def __init__(self):
+        self.cache = {}
+
+    def get(self, vit: "VisionTransformer"):
+        params = list(vit.parameters())
+        dev = params[0].device
+        key = tuple((p._version, p.data_ptr(), p.dtype) for p in params)
+        hit = self.cache.get(dev)
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        with torch.no_grad():
+            bf = lambda t: t.detach().to(torch.bfloat16).contiguous()
+            f32 = lambda t: t.detach().float().contiguous()
+            cp = vit.patch_embedding.conv_proj
+            packed = {"w_patch": bf(cp.weight.reshape(cp.weight.shape[0], -1)), "b_patch": f32(cp.bias), "layers": []}
+            for blk in vit.encoder:
+                a = blk.attention
+                packed["layers"].append(dict(
+                    w_in=bf(a.in_proj_weight), b_in=f32(a.in_proj_bias), w_out=bf(a.out_proj.weight), b_out=f32(a.out_proj.bias),
+                    w_fc1=bf(blk.mlp[0].weight), b_fc1=f32(blk.mlp[0].bias), w_fc2=bf(blk.mlp[2].weight), b_fc2=f32(blk.mlp[2].bias),
+                    ln1_g=f32(blk.ln1.weight), ln1_b=f32(blk.ln1.bias), ln2_g=f32(blk.ln2.weight), ln2_b=f32(blk.ln2.bias)))
+        self.cache[dev] = (key, packed)
+        return packed
+
+
+class VisionTransformer(nn.Module):
+    """VisionTransformer (vit.py:120-169).  `forward(x)` -> list of `num_layers` feature maps (B, hidden, H/p, W/p).
+
+    Extensions (not in the reference): `x` may be uint8 (0..255) as well as float; `out_dtype` selects what is
+    returned -- "bf16" (default: token-major bf16, the MHAda tensor-core path's input) or "fp32" (the f32 residual
+    stream itself)."""
+
+    def __init__(self, patch_size: int = 8, num_layers: int = 3, num_heads: int = 8, hidden_dim: int = 512,
+                 mlp_dim: int = 2048, pos_embedding: bool = True):
+        super().__init__()
+        self.patch_size, self.num_layers, self.hidden_dim = patch_size, num_layers, hidden_dim
+        self.patch_embedding = PatchEmbedding(in_channels=3, patch_size=patch_size, hidden_dim=hidden_dim)
+        self.pos_embedding = PosEmbedding(patch_size=patch_size, embed_dim=hidden_dim) if pos_embedding else None
+        self.encoder = nn.ModuleList([EncoderBlock(num_heads=num_heads, hidden_dim=hidden_dim, mlp_dim=mlp_dim)
+                                      for _ in range(num_layers)])
+        self.num_heads, self.mlp_dim = num_heads, mlp_dim
+        self.precision = "auto"          # "auto" | "bf16": tcgen05 path.  "fp32" is not built (NotImplementedError)
+        self.out_dtype = "bf16"
+        self._weights = _VitWeights()
+
+    # ---- the reference op sequence (vit.py:148-169), differentiable; used only when gradients are required
+    def _forward_torch(self, x: torch.Tensor) -> List[torch.Tensor]:
+        x_shape = x.shape
+        out_h, out_w = x_shape[2] // self.patch_size, x_shape[3] // self.patch_size
+        x = self.patch_embedding(x)
+        if self.pos_embedding is not None:
+            x = x + self.pos_embedding(x_shape)
+        z = []
+        for layer in self.encoder:
+            x = layer(x)
+            z.append(x.permute(0, 2, 1).reshape(-1, self.hidden_dim, out_h, out_w))
+        return z
+
+    def forward(self, x: torch.Tensor) -> List[torch.Tensor]:
+        if x.dim() != 4 or x.shape[1] != 3:
+            raise RuntimeError(f"expected an image batch (B, 3, H, W), got {tuple(x.shape)}")
+        _require_cuda(x)
+        if _needs_grad(self, x):
+            return self._forward_torch(x)
+        if self.precision not in ("auto", "bf16", "fp32"):
+            raise ValueError(f"Unknown precision: {self.precision}")
+        if self.precision == "fp32":
+            raise NotImplementedError("the B200 ViT runs on the bf16 tensor-core kernels (f32 residual stream); "
+                                      "an fp32-arithmetic encoder is not built")
+        if self.out_dtype not in ("bf16", "fp32"):
+            raise ValueError(f"Unknown out_dtype: {self.out_dtype}")
+        P, D = self.patch_size, self.hidden_dim
+        B, _, Himg, Wimg = x.shape
+        if Himg % P or Wimg % P:
+            # the reference's strided convolution silently drops the remainder rows / columns (vit.py:109): crop alike
+            x = x[:, :, : Himg - Himg % P, : Wimg - Wimg % P]
+            Himg, Wimg = x.shape[2:]
+        if Himg < P or Wimg < P:
+            raise RuntimeError("image smaller than one patch")
+        if x.dtype == torch.uint8:
+            img, code = x.contiguous(), _lib.U8
+        else:
+            img, code = x.contiguous().float(), _lib.F32
+        L = _lib.lib()
+        h, w = Himg // P, Wimg // P
+        N = h * w
+        Wt = self._weights.get(self)
+        dev = x.device
+        a = _lib.VitArgs()
+        a.img_dtype, a.img = code, img.data_ptr()
+        a.B, a.Himg, a.Wimg, a.patch = B, Himg, Wimg, P
+        a.D, a.F, a.heads, a.n_layers = D, self.mlp_dim, self.num_heads, self.num_layers
+        a.w_patch, a.b_patch = Wt["w_patch"].data_ptr(), Wt["b_patch"].data_ptr()
+        pos = self.pos_embedding.token_table(h, w) if self.pos_embedding is not None else None
+        a.pos = pos.data_ptr() if pos is not None else None
+        f32_out = [torch.empty((B, h, w, D), dtype=torch.float32, device=dev) for _ in range(self.num_layers)]
+        bf_out = [torch.empty((B, h, w, D), dtype=torch.bfloat16, device=dev) for _ in range(self.num_layers)] \
+            if self.out_dtype == "bf16" else [None] * self.num_layers
+        if self.num_layers > _lib.VIT_MAX_LAYERS:
+            raise NotImplementedError(f"at most {_lib.VIT_MAX_LAYERS} encoder layers")
+        for l, lw in enumerate(Wt["layers"]):
+            for k, t in lw.items():
+                setattr(a.layers[l], k, t.data_ptr())
+            a.feat_f32[l] = f32_out[l].data_ptr()
+            a.feat_bf16[l] = bf_out[l].data_ptr() if bf_out[l] is not None else None
+        nbytes = L.mhada_vit_workspace(B, N, D, self.mlp_dim, 3 * P * P)
+        ws = _workspace(dev, nbytes)
+        a.ws, a.ws_bytes = ws.data_ptr(), ws.numel()
+        with torch.cuda.device(dev):
+            rc = L.mhada_vit_forward(ctypes.byref(a), _stream())
+        _lib.check("mhada_vit_forward", rc)
+        outs = bf_out if self.out_dtype == "bf16" else f32_out
+        return [t.permute(0, 3, 1, 2) for t in outs]          # (B, D, h, w) views, channels_last memory (vit.py:163-166)

@@ -84,8 +84,25 @@ GRAD_CASES = [
     dict(name="grad_layer_c128_h2", kind="grad", B=2, C=128, H=2, hw=(10, 10), hsws=(8, 9), gain=1.0, seed=71),
 ]
 
+VIT_CASES = [
+    # VisionTransformer (vit.py:120-169).  B > 1 pins the batch-axis attention of the reference.
+    dict(name="vit_b1_48x64", kind="vit", B=1, img=(48, 64), pos=True, seed=81, sub=1),
+    dict(name="vit_b3_40x64_nopos", kind="vit", B=3, img=(40, 64), pos=False, seed=82, sub=1),
+    dict(name="vit_b8_32x32", kind="vit", B=8, img=(32, 32), pos=True, seed=83, sub=1),
+    dict(name="vit_b2_256x256_sub", kind="vit", B=2, img=(256, 256), pos=True, seed=84, sub=13),       # 32 x 32 grid: table as is
+    dict(name="vit_b1_512x512_sub", kind="vit", B=1, img=(512, 512), pos=True, seed=85, sub=37),       # BASELINE configs[0] image
+    dict(name="vit_b1_512x512_nopos_sub", kind="vit", B=1, img=(512, 512), pos=False, seed=86, sub=37),
+]
+
+PIPELINE_CASES = [
+    # images -> vit_c, vit_s -> AdaAttnTransformerMultiHead -> decoded image (infer_image.py:82-86), end to end
+    dict(name="pipeline_b1_64x64", kind="pipeline", B=1, img=(64, 64), simg=(64, 64), seed=91, sub=1, img_sub=2),
+    dict(name="pipeline_b2_128x96", kind="pipeline", B=2, img=(128, 96), simg=(64, 80), seed=92, sub=3, img_sub=4),
+    dict(name="pipeline_b1_512x512_sub", kind="pipeline", B=1, img=(512, 512), simg=(512, 512), seed=93, sub=37, img_sub=8),
+]
+
 ALL_CASES = (LAYER_CASES + ADAATTN_CASES + FORLOSS_CASES + TRANSFORMER_CASES + SINGLE_HEAD_TRANSFORMER_CASES +
-             DECODER_CASES + GRAD_CASES)
+             DECODER_CASES + GRAD_CASES + VIT_CASES + PIPELINE_CASES)
 
 GRAD_KEYS = ("fc", "fs", "fcs", "f_list.0.weight", "f_list.1.bias", "g_list.1.weight", "g_list.0.bias",
              "h_list.0.weight", "h_list.1.bias", "out_conv.weight", "out_conv.bias")
@@ -166,6 +183,19 @@ def decoder_inputs(case: dict):
     h, w = case["hw"]
     x = synth.features(case["seed"], case["B"], 512, h, w, std=29.0, mean=-1.6)
     return x, synth.decoder_state(case["seed"])
+
+
+def vit_inputs(case: dict):
+    H, W = case["img"]
+    return synth.image_u8(case["seed"] * 10 + 1, case["B"], H, W), synth.vit_state(case["seed"], pos_embedding=case["pos"])
+
+
+def pipeline_inputs(case: dict):
+    """content / style images and the three state dicts of infer_image.py:51-57."""
+    s = case["seed"]
+    c = synth.image_u8(s * 10 + 1, case["B"], *case["img"])
+    st = synth.image_u8(s * 10 + 2, case["B"], *case["simg"])
+    return c, st, synth.vit_state(s, pos_embedding=True), synth.vit_state(s + 500, pos_embedding=False), synth.transformer_state(s)
 
 
 def token_sublattice(x: np.ndarray, sub: int) -> np.ndarray:

@@ -26,6 +26,7 @@ sys.path.insert(0, REF)
 from network.adaDecoder import (AdaAttN, AdaAttnForLoss, AdaAttnMultiHead,  # noqa: E402
                                 AdaAttnTransformer, AdaAttnTransformerMultiHead)
 from network.conv import Decoder  # noqa: E402
+from network.vit import VisionTransformer  # noqa: E402
 
 from . import cases, synth  # noqa: E402
 from .mhada_oracle import errors  # noqa: E402
@@ -124,6 +125,29 @@ def main(prefix: str = ""):
             o64, o32 = o["f64"].numpy(), o["f32"].numpy()
             arrays["out"] = o64.astype(np.float32)
             meta["out"] = summarize(o64); meta["ref32_vs_ref64"] = errors(o32, o64)
+        elif kind == "vit":
+            img, sd = cases.vit_inputs(case)
+            o = run_both(lambda: VisionTransformer(pos_embedding=case["pos"]), sd, (img,))
+            for l in range(3):
+                z64, z32 = o["f64"][l].numpy(), o["f32"][l].numpy()
+                arrays[f"z{l}"] = cases.token_sublattice(z64, case["sub"]).astype(np.float32)
+                meta[f"z{l}"] = summarize(z64); meta[f"z{l}_ref32_vs_ref64"] = errors(z32, z64)
+        elif kind == "pipeline":
+            c, st, sd_c, sd_s, sd_a = cases.pipeline_inputs(case)
+            res = {}
+            for name, dt in (("f64", torch.float64), ("f32", torch.float32)):
+                vc = VisionTransformer(pos_embedding=True).to(dt); vc.load_state_dict(synth.to_torch(sd_c, dt), strict=True)
+                vs = VisionTransformer(pos_embedding=False).to(dt); vs.load_state_dict(synth.to_torch(sd_s, dt), strict=True)
+                ada = AdaAttnTransformerMultiHead().to(dt); ada.load_state_dict(synth.to_torch(sd_a, dt), strict=True)
+                with torch.no_grad():                                           # infer_image.py:82-86
+                    fc = vc.eval()(T(c, dt)); fs = vs.eval()(T(st, dt))
+                    fcs, cs = ada.eval()(fc, fs)
+                res[name] = (fcs.numpy(), cs.numpy())
+            fcs64, cs64 = res["f64"]; fcs32, cs32 = res["f32"]
+            arrays["fcs"] = cases.token_sublattice(fcs64, case["sub"]).astype(np.float32)
+            arrays["cs"] = cases.pixel_sublattice(cs64, case["img_sub"]).astype(np.float32)
+            meta["fcs"] = summarize(fcs64); meta["cs"] = summarize(cs64)
+            meta["fcs_ref32_vs_ref64"] = errors(fcs32, fcs64); meta["cs_ref32_vs_ref64"] = errors(cs32, cs64)
         else:
             raise ValueError(kind)
         np.savez_compressed(os.path.join(OUT, case["name"] + ".npz"), **arrays)

@@ -154,6 +154,49 @@ def single_head_transformer_state(seed: int, num_layers: int = 3, qkv_dim: int =
     return sd
 
 
+def vit_state(seed: int, pos_embedding: bool = True, patch: int = 8, num_layers: int = 3, hidden: int = 512,
+              mlp: int = 2048) -> dict:
+    """Keys of VisionTransformer (MHAdaSTr/network/vit.py:120-146): patch_embedding.conv_proj, pos_embedding.pos_embed
+    (vit_c only), encoder.{l}.{attention.in_proj_weight/bias, attention.out_proj, mlp.0, mlp.2, ln1, ln2}.
+    Scales follow the PyTorch default initialisers; biases and LayerNorm affine parameters are perturbed away from
+    their 0 / 1 defaults so that every term of the forward is exercised."""
+    sd = {}
+    w, b = _conv_params(seed * 1000 + 1, hidden, 3, patch)
+    sd["patch_embedding.conv_proj.weight"], sd["patch_embedding.conv_proj.bias"] = w, b
+    if pos_embedding:
+        sd["pos_embedding.pos_embed"] = bellish(seed * 1000 + 2, (1, hidden, 32, 32), 0.0, 0.02)
+    for l in range(num_layers):
+        s0 = seed * 1000 + 10 + 20 * l
+        pre = f"encoder.{l}."
+        xav = np.sqrt(6.0 / (hidden + 3 * hidden))                    # xavier_uniform_ of in_proj_weight
+        sd[pre + "attention.in_proj_weight"] = uniform(s0, (3 * hidden, hidden), -xav, xav, stream=1)
+        sd[pre + "attention.in_proj_bias"] = uniform(s0, (3 * hidden,), -0.05, 0.05, stream=2)
+        kb = 1.0 / np.sqrt(hidden)
+        sd[pre + "attention.out_proj.weight"] = uniform(s0 + 1, (hidden, hidden), -kb, kb, stream=1)
+        sd[pre + "attention.out_proj.bias"] = uniform(s0 + 1, (hidden,), -0.05, 0.05, stream=2)
+        sd[pre + "mlp.0.weight"] = uniform(s0 + 2, (mlp, hidden), -kb, kb, stream=1)
+        sd[pre + "mlp.0.bias"] = uniform(s0 + 2, (mlp,), -kb, kb, stream=2)
+        km = 1.0 / np.sqrt(mlp)
+        sd[pre + "mlp.2.weight"] = uniform(s0 + 3, (hidden, mlp), -km, km, stream=1)
+        sd[pre + "mlp.2.bias"] = uniform(s0 + 3, (hidden,), -km, km, stream=2)
+        sd[pre + "ln1.weight"] = uniform(s0 + 4, (hidden,), 0.9, 1.1, stream=1)
+        sd[pre + "ln1.bias"] = uniform(s0 + 4, (hidden,), -0.1, 0.1, stream=2)
+        sd[pre + "ln2.weight"] = uniform(s0 + 5, (hidden,), 0.9, 1.1, stream=1)
+        sd[pre + "ln2.bias"] = uniform(s0 + 5, (hidden,), -0.1, 0.1, stream=2)
+    return sd
+
+
+def image_u8(seed: int, b: int, h: int, w: int) -> np.ndarray:
+    """(B,3,H,W) image with INTEGER values 0..255 as float64 (what toTensor255 yields for an 8-bit image,
+    MHAdaSTr/utilities.py:11-16); smooth + noisy so that patches differ."""
+    u = uniform01(seed, (b, 3, h, w))
+    yy = np.arange(h).reshape(1, 1, h, 1) / max(h - 1, 1)
+    xx = np.arange(w).reshape(1, 1, 1, w) / max(w - 1, 1)
+    ph = uniform01(seed, (b, 3, 1, 1), stream=5)
+    base = 0.5 + 0.35 * (2.0 * ((yy * (1.0 + ph) + xx * (2.0 - ph)) % 1.0) - 1.0)       # saw-tooth ramps, no libm
+    return np.floor(np.clip(0.6 * base + 0.4 * u, 0.0, 1.0) * 255.0)
+
+
 def to_torch(sd: dict, dtype=None):
     import torch
     out = {}

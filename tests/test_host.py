@@ -36,6 +36,22 @@ def test_state_dict_is_reference_compatible():
     assert M.AdaAttnForLoss(256, 448).state_dict() == {}
 
 
+def test_vit_state_dict_is_reference_compatible():
+    """vit.py:120-146 key surface (what infer_image.py:55-56 loads with strict=True)."""
+    for pos in (True, False):
+        m = M.VisionTransformer(pos_embedding=pos)
+        sd = synth.to_torch(synth.vit_state(3, pos_embedding=pos), torch.float32)
+        assert sorted(m.state_dict().keys()) == sorted(sd.keys())
+        m.load_state_dict(sd, strict=True)
+        for k, v in m.state_dict().items():
+            assert tuple(v.shape) == tuple(sd[k].shape), k
+    m = M.VisionTransformer()
+    assert m.patch_size == 8 and m.num_layers == 3 and m.hidden_dim == 512 and len(m.encoder) == 3
+    assert m.pos_embedding.pos_embed.shape == (1, 512, 32, 32)
+    with pytest.raises(RuntimeError, match="no CPU fallback"), torch.no_grad():
+        m(torch.zeros(1, 3, 16, 16))
+
+
 def test_attribute_surface():
     l = M.AdaAttnMultiHead(512, 8)
     for name in ("num_heads", "head_dim", "f_list", "g_list", "h_list", "norm_q_list", "norm_k_list",
@@ -73,7 +89,7 @@ def test_library_exports_every_declared_symbol(lib):
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.mhada_abi_version() == _lib.ABI_VERSION == 4
+    assert lib.mhada_abi_version() == _lib.ABI_VERSION == 5
 
 
 def test_abi_rejects_without_gpu_or_bad_args(lib):

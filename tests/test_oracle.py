@@ -82,6 +82,34 @@ def test_transformer_matches_reference(case, golden_index):
     _check_sums(cs, meta, "cs")
 
 
+@pytest.mark.parametrize("case", cases.VIT_CASES, ids=lambda c: c["name"])
+def test_vit_matches_reference(case, golden_index):
+    """oracle/vit_oracle.py (numpy float64 restatement of vit.py:45-169) against the unmodified reference's
+    VisionTransformer, including the batch-axis attention (B > 1) and the resized positional table."""
+    from oracle import vit_oracle as V
+    img, sd = cases.vit_inputs(case)
+    z = V.vision_transformer(img, sd)
+    meta = golden_index[case["name"]]
+    g = load_golden(case["name"])
+    for l in range(3):
+        _check(cases.token_sublattice(z[l], case["sub"]), g[f"z{l}"], meta, f"z{l}")
+        _check_sums(z[l], meta, f"z{l}")
+
+
+@pytest.mark.parametrize("case", [c for c in cases.PIPELINE_CASES if c["img"][0] <= 128], ids=lambda c: c["name"])
+def test_pipeline_matches_reference(case, golden_index):
+    """images -> ViT x2 -> MHAda x6 -> decoder (infer_image.py:82-86) through both oracles."""
+    from oracle import vit_oracle as V
+    c, st, sd_c, sd_s, sd_a = cases.pipeline_inputs(case)
+    fcs, cs = O.transformer_multi_head(V.vision_transformer(c, sd_c), V.vision_transformer(st, sd_s), sd_a)
+    meta = golden_index[case["name"]]
+    g = load_golden(case["name"])
+    e = O.errors(cases.token_sublattice(fcs, case["sub"]), g["fcs"])
+    assert e["max_abs"] <= 1e-6 * meta["fcs"]["absmax"], e          # six chained layers amplify the storage rounding
+    ec = O.errors(cases.pixel_sublattice(cs, case["img_sub"]), g["cs"])
+    assert ec["max_abs_rel"] <= 1e-5, ec
+
+
 def test_fp32_oracle_is_inside_reference_noise(golden_index):
     """The oracle evaluated in float32 must sit within a few x of the reference's own
     float32-vs-float64 deviation: it is the 'port' timed as cpu_baseline."""
