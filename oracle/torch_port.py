@@ -71,3 +71,32 @@ def transformer(fc, fs, sd: dict, num_layers: int = 3, num_heads: int = 8, decod
         fcs = mhada_layer(fc[i], fs[i], fcs, sd, f"adaAttnHead.{2 * i}.", num_heads)
         fcs = mhada_layer(fcs, fs[i], fcs, sd, f"adaAttnHead.{2 * i + 1}.", num_heads)
     return fcs, (decoder(fcs, sd) if decode else None)
+
+
+def vit(img, sd: dict, num_layers: int = 3, num_heads: int = 8, patch: int = 8):
+    """VisionTransformer.forward (vit.py:148-169) with functional ops: strided conv patch embedding, (resized)
+    positional table, per layer LayerNorm -> nn.MultiheadAttention semantics WITHOUT batch_first on a (B, N, D)
+    tensor (sequence axis = batch, vit.py:48,59) -> residual -> LayerNorm -> Linear / ReLU / Linear -> residual."""
+    b, _, hh, ww = img.shape
+    h, w = hh // patch, ww // patch
+    x = F.conv2d(img, sd["patch_embedding.conv_proj.weight"], sd["patch_embedding.conv_proj.bias"], stride=patch)
+    d = x.shape[1]
+    x = x.reshape(b, d, h * w).permute(0, 2, 1)
+    if "pos_embedding.pos_embed" in sd:
+        pe = sd["pos_embedding.pos_embed"]
+        if pe.shape[2] != h or pe.shape[3] != w:
+            pe = F.interpolate(pe, size=(h, w), mode="bilinear", align_corners=False)
+        x = x + pe.expand(b, -1, -1, -1).reshape(b, d, h * w).permute(0, 2, 1)
+    z = []
+    for l in range(num_layers):
+        p = f"encoder.{l}."
+        y = F.layer_norm(x, (d,), sd[p + "ln1.weight"], sd[p + "ln1.bias"], 1e-6)
+        y, _ = F.multi_head_attention_forward(
+            y, y, y, d, num_heads, sd[p + "attention.in_proj_weight"], sd[p + "attention.in_proj_bias"], None, None, False, 0.0,
+            sd[p + "attention.out_proj.weight"], sd[p + "attention.out_proj.bias"], training=False, need_weights=False)
+        x = y + x
+        y = F.layer_norm(x, (d,), sd[p + "ln2.weight"], sd[p + "ln2.bias"], 1e-6)
+        y = F.linear(F.relu(F.linear(y, sd[p + "mlp.0.weight"], sd[p + "mlp.0.bias"])), sd[p + "mlp.2.weight"], sd[p + "mlp.2.bias"])
+        x = x + y
+        z.append(x.permute(0, 2, 1).reshape(-1, d, h, w))
+    return z

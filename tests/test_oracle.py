@@ -176,6 +176,22 @@ def test_torch_port_matches_reference(golden_index):
     assert ec["max_abs_rel"] <= 1e-4, ec
 
 
+def test_torch_port_vit_matches_reference(golden_index):
+    """oracle/torch_port.vit (timed as part of the full-pipeline CPU number) against the reference ViT goldens,
+    batch-axis attention included."""
+    import torch
+    from oracle import torch_port
+    for name in ("vit_b3_40x64_nopos", "vit_b1_48x64"):
+        case = cases.by_name(name)
+        img, sd = cases.vit_inputs(case)
+        with torch.no_grad():
+            z = torch_port.vit(torch.from_numpy(img).float(), torch_port.prepare(sd))
+        g = load_golden(name)
+        for l in range(3):
+            e = O.errors(cases.token_sublattice(z[l].numpy(), case["sub"]), g[f"z{l}"])
+            assert e["max_abs_rel"] <= 5e-6, (name, l, e)
+
+
 @pytest.mark.parametrize("case", cases.GRAD_CASES, ids=lambda c: c["name"])
 def test_reference_gradients_agree_with_oracle_finite_differences(case, golden_index):
     """The golden gradients (reference autograd, float64) against directional finite differences of the numpy
