@@ -5,13 +5,15 @@
 // positional table :96-102 as a row-periodic residual), the in_proj / out_proj of nn.MultiheadAttention (:48,59),
 // the two nn.Linear of the MLP with the ReLU between them (:49-53,62-63) and both residual additions (:60,64).
 //
-// Structure: persistent CTAs (one per SM), 6 warps; a work item is one 128 x BN output tile, the BN tiles of the
+// Structure: persistent CTAs (one per SM), 10 warps; a work item is one 128 x BN output tile, the BN tiles of the
 // same 128 rows are consecutive items (x comes from HBM once and from L2 for the other column tiles):
 //   warp 0      TMA producer: x and W tiles -> 128B-swizzled shared memory, STAGES-deep mbarrier ring that runs
 //               straight across work items
 //   warp 1      tcgen05.mma issuer (one elected lane), M = 128, N = BN, accumulators DOUBLE-BUFFERED in TMEM
 //               (2 x BN columns): the MMAs of item n+1 overlap the epilogue of item n
-//   warps 2..5  epilogue: tcgen05.ld (lane = row) -> + bias (+ residual) (ReLU) ->
+//   warps 2..9  epilogue, TWO warps per TMEM lane quarter, each owning half of the tile's columns (a 128 x 256 tile has
+//               to leave TMEM in less than its ~2 us of MMAs): tcgen05.ld (lane = row) -> + bias (+ residual, the next
+//               32 columns prefetched while the current ones are processed) (ReLU) ->
 //                 bf16 result: packed into a 128B-swizzled staging slab (32 rows x 64 columns per warp, two slabs)
 //                              and written with ONE TMA STORE per slab (cp.async.bulk.tensor, rows past M clipped);
 //                 f32 result (the residual stream): 256-bit stores, 128 contiguous bytes per lane.
@@ -22,7 +24,7 @@
 
 namespace mh {
 
-constexpr int GM_BM = 128, GM_BK = 64, GM_THREADS = 192;
+constexpr int GM_BM = 128, GM_BK = 64, GM_EPI_WARPS = 8, GM_THREADS = 64 + 32 * GM_EPI_WARPS;
 constexpr uint32_t GM_STG_WARP = 2 * 32 * 128;   // two staging slabs (32 rows x 128 B) per epilogue warp
 
 struct GemmParams {
@@ -61,7 +63,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             for (int u = 0; u < 2; ++u) {
                 mbar_init(&acc_full[u], 1);
-                mbar_init(&acc_empty[u], 4);      // one arrive per epilogue warp
+                mbar_init(&acc_empty[u], GM_EPI_WARPS);      // one arrive per epilogue warp
             }
             fence_mbar_init();
         }
@@ -113,15 +115,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
     } else {
-        // epilogue warps 2..5 -> TMEM lane quarters 2, 3, 0, 1
+        // epilogue warps 2..9: TMEM lane quarter = warp % 4 (hardware rule), column half = (warp - 2) / 4
         const int quarter = warp & 3;
+        const int chalf = (warp - 2) >> 2;
+        constexpr int CW = BN / 2;                                             // columns per epilogue warp
         const int row = quarter * 32 + lane;
         uint8_t* stg = smem + STAGES * STAGE + (warp - 2) * GM_STG_WARP;      // 1024-byte aligned slabs
         const uint32_t swz = static_cast<uint32_t>(lane & 7);
         int nstore = 0;                                                        // TMA stores issued by this warp
         int n = 0;
         for (int it = blockIdx.x; it < p.items; it += gridDim.x, ++n) {
-            const int m0 = (it / p.ntiles) * GM_BM, n0 = (it % p.ntiles) * BN;
+            const int m0 = (it / p.ntiles) * GM_BM, n0 = (it % p.ntiles) * BN + chalf * CW;
             const int m = m0 + row;
             const bool row_ok = m < p.M;
             const int u = n & 1;
@@ -129,19 +133,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (p.resid && row_ok)
                 rrow = p.resid + static_cast<size_t>(p.resid_mod > 0 ? m % p.resid_mod : m) * p.ldr + n0;
             float* frow = (p.out_f32 && row_ok) ? p.out_f32 + static_cast<size_t>(m) * p.ldf + n0 : nullptr;
+            float4 rv[8];
+            if (rrow) {                                       // residual row segment: 128 contiguous bytes per lane,
+#pragma unroll                                                // fetched before the wait for the accumulator
+                for (int i = 0; i < 8; ++i) rv[i] = __ldg(reinterpret_cast<const float4*>(rrow) + i);
+            }
             mbar_wait(&acc_full[u], (n >> 1) & 1);
             tc_fence_after();
 #pragma unroll 1
-            for (int c = 0; c < BN; c += 32) {
-                float4 rv[8];
-                if (rrow) {                                   // residual row segment: 128 contiguous bytes per lane
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) rv[i] = __ldg(reinterpret_cast<const float4*>(rrow + c) + i);
-                }
+            for (int c = 0; c < CW; c += 32) {
                 uint32_t r[32];
-                tmem_ld_x32(tmem_addr(tmem, quarter * 32, u * BN + c), r);
+                tmem_ld_x32(tmem_addr(tmem, quarter * 32, u * BN + chalf * CW + c), r);
                 tmem_wait_ld();
-                if (c + 32 == BN) {                           // accumulator drained: the next-but-one item may start
+                if (c + 32 == CW) {                           // accumulator drained: the next-but-one item may start
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&acc_empty[u]);
@@ -153,6 +157,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         v[4 * i] += rv[i].x; v[4 * i + 1] += rv[i].y; v[4 * i + 2] += rv[i].z; v[4 * i + 3] += rv[i].w;
+                    }
+                    if (c + 32 < CW) {                        // next chunk's residual in flight behind the math / stores
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) rv[i] = __ldg(reinterpret_cast<const float4*>(rrow + c + 32) + i);
                     }
                 }
                 if (p.relu) {
@@ -229,7 +237,7 @@ static int launch_gemm_bn(const GemmDesc& d, cudaStream_t s) {
     p.has_bf16 = d.out_bf16 ? 1 : 0; p.relu = d.relu;
     p.M = d.M; p.ktiles = d.K / GM_BK; p.ntiles = d.N / BN;
     p.items = ((d.M + GM_BM - 1) / GM_BM) * p.ntiles;
-    constexpr size_t smem = STAGES * (GM_BM * GM_BK * 2 + BN * GM_BK * 2) + 4 * GM_STG_WARP + 1024;
+    constexpr size_t smem = STAGES * (GM_BM * GM_BK * 2 + BN * GM_BK * 2) + GM_EPI_WARPS * GM_STG_WARP + 1024;
     static DeviceOnce once;
     if (int e = smem_attr_once(once, reinterpret_cast<const void*>(gemm_tc_kernel<BN, STAGES>), smem, "gemm smem attr")) return e;
     const int n_sm = sm_count();
@@ -244,7 +252,7 @@ int launch_gemm_bf16(const GemmDesc& d, cudaStream_t s) {
         set_error("gemm_tc: needs K %% 64 == 0 and N %% 128 == 0, got M=%d N=%d K=%d", d.M, d.N, d.K);
         return MHADA_ERR_UNSUPPORTED;
     }
-    if (d.N % 256 == 0) return launch_gemm_bn<256, 4>(d, s);
+    if (d.N % 256 == 0) return launch_gemm_bn<256, 3>(d, s);     // 3 x 48 KB operand ring + 64 KB of staging slabs
     return launch_gemm_bn<128, 4>(d, s);
 }
 

@@ -164,6 +164,16 @@ int launch_linear_bf16(const void* x, int ldx, const float* w, const float* bias
     const size_t n = static_cast<size_t>(Cout) * Cin;
     f32_to_bf16_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(w, static_cast<__nv_bfloat16*>(ws), n);
     count_launch();
+#ifndef MHADA_LINEAR_OWN_KERNEL
+    // r2: the token GEMM of the ViT (gemm_tc.cu: 128 x 256 tiles, eight epilogue warps, TMA-store epilogue) also runs
+    // out_conv; linear_tc_kernel stays for Cout that is not a multiple of 128 (and behind -DMHADA_LINEAR_OWN_KERNEL)
+    if (Cout % 128 == 0) {
+        GemmDesc g{};
+        g.a = x; g.lda = ldx; g.w = ws; g.ldw = Cin; g.bias = bias; g.M = M; g.N = Cout; g.K = Cin;
+        g.out_bf16 = y; g.ldo = ldy;
+        return launch_gemm_bf16(g, s);
+    }
+#endif
     CUtensorMap tmA;
     uint64_t dimsA[2] = {static_cast<uint64_t>(Cin), static_cast<uint64_t>(M)};
     uint64_t strA[1] = {static_cast<uint64_t>(ldx) * 2};

@@ -133,54 +133,86 @@ int launch_layernorm(const float* x, int M, int C, const float* gamma, const flo
 }
 
 // ------------------------------------------------------------------------------------------------ batch-axis attention
-// warp = (token position n, head); the "sequence" is the B images.  q, k, v of the B images staged in shared memory
-// (f32), lane j < B owns key j for the logits, lane owns value columns 2*lane, 2*lane + 1 for the output.
+// warp = (token position n, head); the "sequence" is the B images.  q, k, v of the B images are staged in shared
+// memory as f32 (row pitch 68 words: the float4 reads below are bank-conflict free).  Work is spread over all 32
+// lanes: the B*B logits as (i, j) pairs, the B*64 outputs as (i, 4-channel group) items.
 constexpr int BA_HD = 64;
 constexpr int BA_WARPS = 8;
-constexpr int BA_PITCH = BA_HD + 1;
+constexpr int BA_PITCH = BA_HD + 4;
+__host__ __device__ constexpr int ba_warp_floats(int B) { return 3 * B * BA_PITCH + ((B * (B + 1) + 3) & ~3); }
 __global__ void __launch_bounds__(BA_WARPS * 32) batch_attn_kernel(const __nv_bfloat16* __restrict__ qkv, int B, int N,
                                                                    int heads, __nv_bfloat16* __restrict__ out) {
-    extern __shared__ float ba_smem[];
+    extern __shared__ __align__(16) float ba_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long item = static_cast<long long>(blockIdx.x) * BA_WARPS + warp;     // n * heads + h
+    const long long item = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + warp;     // n * heads + h
     if (item >= static_cast<long long>(N) * heads) return;
     const int n = static_cast<int>(item / heads), h = static_cast<int>(item % heads);
     const int D = heads * BA_HD;
-    float* q = ba_smem + static_cast<size_t>(warp) * 3 * B * BA_PITCH;
+    float* q = ba_smem + static_cast<size_t>(warp) * ba_warp_floats(B);
     float* k = q + B * BA_PITCH;
     float* v = k + B * BA_PITCH;
-    for (int b = 0; b < B; ++b) {
-        const uint32_t* base = reinterpret_cast<const uint32_t*>(qkv + (static_cast<size_t>(b) * N + n) * 3 * D + h * BA_HD);
-        const uint32_t wq = __ldg(base + lane), wk = __ldg(base + D / 2 + lane), wv = __ldg(base + D + lane);
-        q[b * BA_PITCH + 2 * lane] = bf16_lo(wq); q[b * BA_PITCH + 2 * lane + 1] = bf16_hi(wq);
-        k[b * BA_PITCH + 2 * lane] = bf16_lo(wk); k[b * BA_PITCH + 2 * lane + 1] = bf16_hi(wk);
-        v[b * BA_PITCH + 2 * lane] = bf16_lo(wv); v[b * BA_PITCH + 2 * lane + 1] = bf16_hi(wv);
+    float* sc = v + B * BA_PITCH;                      // [B][B + 1] logits, then probabilities
+    // stage: three coalesced 128-byte rows per image, four images in flight
+    for (int b0 = 0; b0 < B; b0 += 4) {
+        uint32_t w[4][3];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (b0 + u < B) {
+                const uint32_t* base = reinterpret_cast<const uint32_t*>(qkv + (static_cast<size_t>(b0 + u) * N + n) * 3 * D + h * BA_HD);
+                w[u][0] = __ldg(base + lane); w[u][1] = __ldg(base + D / 2 + lane); w[u][2] = __ldg(base + D + lane);
+            }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (b0 + u < B) {
+                const int o = (b0 + u) * BA_PITCH + 2 * lane;
+                *reinterpret_cast<float2*>(q + o) = make_float2(bf16_lo(w[u][0]), bf16_hi(w[u][0]));
+                *reinterpret_cast<float2*>(k + o) = make_float2(bf16_lo(w[u][1]), bf16_hi(w[u][1]));
+                *reinterpret_cast<float2*>(v + o) = make_float2(bf16_lo(w[u][2]), bf16_hi(w[u][2]));
+            }
     }
     __syncwarp();
-    const float scale = 0.125f;                       // 1 / sqrt(64)
-    for (int i = 0; i < B; ++i) {
-        float sc = -INFINITY;
-        if (lane < B) {
-            float acc = 0.f;
-#pragma unroll 16
-            for (int d = 0; d < BA_HD; ++d) acc = fmaf(q[i * BA_PITCH + d], k[lane * BA_PITCH + d], acc);
-            sc = acc * scale;
+    // logits: one (i, j) pair per lane and round
+    for (int pr = lane; pr < B * B; pr += 32) {
+        const int i = pr / B, j = pr % B;
+        const float4* qi = reinterpret_cast<const float4*>(q + i * BA_PITCH);
+        const float4* kj = reinterpret_cast<const float4*>(k + j * BA_PITCH);
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+        for (int d = 0; d < BA_HD / 4; ++d) {
+            const float4 x = qi[d], y = kj[d];
+            a0 = fmaf(x.x, y.x, a0); a1 = fmaf(x.y, y.y, a1); a2 = fmaf(x.z, y.z, a2); a3 = fmaf(x.w, y.w, a3);
         }
-        float mx = sc;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        float pj = lane < B ? __expf(sc - mx) : 0.f;
-        float sum = pj;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        pj /= sum;
-        float o0 = 0.f, o1 = 0.f;
+        sc[i * (B + 1) + j] = ((a0 + a1) + (a2 + a3)) * 0.125f;        // 1 / sqrt(64)
+    }
+    __syncwarp();
+    if (lane < B) {                                    // softmax of row `lane` over the B images
+        float* row = sc + lane * (B + 1);
+        float mx = row[0];
+        for (int j = 1; j < B; ++j) mx = fmaxf(mx, row[j]);
+        float sum = 0.f;
         for (int j = 0; j < B; ++j) {
-            const float pw = __shfl_sync(0xffffffffu, pj, j);
-            o0 = fmaf(pw, v[j * BA_PITCH + 2 * lane], o0);
-            o1 = fmaf(pw, v[j * BA_PITCH + 2 * lane + 1], o1);
+            const float e = __expf(row[j] - mx);
+            row[j] = e;
+            sum += e;
         }
-        reinterpret_cast<uint32_t*>(out + (static_cast<size_t>(i) * N + n) * D + h * BA_HD)[lane] = pack_bf16x2(o0, o1);
+        const float inv = 1.f / sum;
+        for (int j = 0; j < B; ++j) row[j] *= inv;
+    }
+    __syncwarp();
+    // outputs: (image i, 4-channel group) items; 16 consecutive lanes write one 128-byte row
+    for (int t = lane; t < B * (BA_HD / 4); t += 32) {
+        const int i = t / (BA_HD / 4), d4 = t % (BA_HD / 4);
+        const float* pi = sc + i * (B + 1);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < B; ++j) {
+            const float pw = pi[j];
+            const float4 y = reinterpret_cast<const float4*>(v + j * BA_PITCH)[d4];
+            acc.x = fmaf(pw, y.x, acc.x); acc.y = fmaf(pw, y.y, acc.y); acc.z = fmaf(pw, y.z, acc.z); acc.w = fmaf(pw, y.w, acc.w);
+        }
+        uint2 o;
+        o.x = pack_bf16x2(acc.x, acc.y);
+        o.y = pack_bf16x2(acc.z, acc.w);
+        reinterpret_cast<uint2*>(out + (static_cast<size_t>(i) * N + n) * D + h * BA_HD)[d4] = o;
     }
 }
 
@@ -189,13 +221,15 @@ int launch_batch_attn(const void* qkv, int B, int N, int heads, int hd, void* ou
         set_error("batch_attn: head_dim 64 and batch 1..32 are implemented, got head_dim %d, batch %d", hd, B);
         return MHADA_ERR_UNSUPPORTED;
     }
-    const size_t smem = static_cast<size_t>(BA_WARPS) * 3 * B * BA_PITCH * sizeof(float);
+    constexpr size_t kSmemCap = 200 * 1024;
+    const size_t per_warp = static_cast<size_t>(ba_warp_floats(B)) * sizeof(float);
+    int warps = static_cast<int>(kSmemCap / per_warp);
+    if (warps > BA_WARPS) warps = BA_WARPS;
+    const size_t smem = warps * per_warp;
     static DeviceOnce once;
-    if (int e = smem_attr_once(once, reinterpret_cast<const void*>(batch_attn_kernel), static_cast<size_t>(BA_WARPS) * 3 * 32 * BA_PITCH * sizeof(float),
-                               "batch_attn smem attr"))
-        return e;
+    if (int e = smem_attr_once(once, reinterpret_cast<const void*>(batch_attn_kernel), kSmemCap, "batch_attn smem attr")) return e;
     const long long items = static_cast<long long>(N) * heads;
-    batch_attn_kernel<<<static_cast<unsigned>((items + BA_WARPS - 1) / BA_WARPS), BA_WARPS * 32, smem, s>>>(
+    batch_attn_kernel<<<static_cast<unsigned>((items + warps - 1) / warps), warps * 32, smem, s>>>(
         static_cast<const __nv_bfloat16*>(qkv), B, N, heads, static_cast<__nv_bfloat16*>(out));
     count_launch();
     return check_cuda(cudaGetLastError(), "batch_attn launch");

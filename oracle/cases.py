@@ -66,7 +66,7 @@ TRANSFORMER_CASES = [
          sub=293, img_sub=24),
     dict(name="transformer_h4_32x32_sub", kind="transformer", B=1, hw=(32, 32), hsws=(32, 32), seed=59, sub=7,
          img_sub=4, heads=4),
-    dict(name="transformer_h4_64x64_sub", kind="transformer", B=2, hw=(64, 64), hsws=(48, 56), seed=60, sub=61,
+    dict(name="transformer_h4_64x64_sub", kind="transformer", B=2, hw=(64, 64), hsws=(48, 56), seed=63, sub=61,
          img_sub=8, heads=4),
 ]
 
@@ -97,7 +97,7 @@ VIT_CASES = [
 PIPELINE_CASES = [
     # images -> vit_c, vit_s -> AdaAttnTransformerMultiHead -> decoded image (infer_image.py:82-86), end to end
     dict(name="pipeline_b1_64x64", kind="pipeline", B=1, img=(64, 64), simg=(64, 64), seed=91, sub=1, img_sub=2),
-    dict(name="pipeline_b2_128x96", kind="pipeline", B=2, img=(128, 96), simg=(64, 80), seed=92, sub=3, img_sub=4),
+    dict(name="pipeline_b2_128x96", kind="pipeline", B=2, img=(128, 96), simg=(64, 80), seed=97, sub=3, img_sub=4),
     dict(name="pipeline_b1_512x512_sub", kind="pipeline", B=1, img=(512, 512), simg=(512, 512), seed=93, sub=37, img_sub=8),
 ]
 

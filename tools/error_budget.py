@@ -51,16 +51,17 @@ def layer(fc, fs, fcs, sd, prefix, H, cfg):
 def run(case, cfg):
     fc, fs, sd = cases.transformer_inputs(case)
     fcs = fc[0]
+    H = case.get("heads", 8)
     for i in range(3):
-        fcs = layer(fc[i], fs[i], fcs, sd, f"adaAttnHead.{2*i}.", 8, cfg)
-        fcs = layer(fcs, fs[i], fcs, sd, f"adaAttnHead.{2*i+1}.", 8, cfg)
+        fcs = layer(fc[i], fs[i], fcs, sd, f"adaAttnHead.{2*i}.", H, cfg)
+        fcs = layer(fcs, fs[i], fcs, sd, f"adaAttnHead.{2*i+1}.", H, cfg)
     return fcs
 
 if __name__ == "__main__":
     name = sys.argv[1] if len(sys.argv) > 1 else "transformer_8x8"
     case = cases.by_name(name)
     fc, fs, sd = cases.transformer_inputs(case)
-    want, _ = O.transformer_multi_head(fc, fs, sd, decode=False)
+    want, _ = O.transformer_multi_head(fc, fs, sd, num_heads=case.get("heads", 8), decode=False)
     base = dict(inp=None, w=None, qk=None, v=None, p=None, heads=None, out=None)
     allbf = dict(inp="bf16", w="bf16", qk="bf16", v="bf16", p="bf16", heads="bf16", out="bf16")
     def show(tag, cfg):
