@@ -186,6 +186,15 @@ MHADA_API int mhada_layer_forward_cached(int dtype, const void* fc, const void* 
  *     MHADA_BF16 only (the fp32 path keeps the library convolution). */
 MHADA_API int mhada_conv3x3_small(int dtype, const void* x, const float* w, const float* bias, int B, int H, int W, int Cin,
                                   int Cout, int relu, void* y, mhada_stream_t stream);
+/*     Decoder blocks 0..7 -- replaces ReflectionPad2d(1) + Conv2d(Cin, Cout, 3) + ReLU, conv.py:23-45, as an implicit
+ *     GEMM on tcgen05 (r1 called cuDNN here).  xp [B, H + 2, W + 2, Cin] bf16: the reflect-PADDED channels_last input
+ *     (from mhada_pad_reflect, or from a previous mhada_conv3x3 with out_padded = 1);
+ *     w bf16 [Cout][3][3][Cin] (conv weight permuted to (o, ky, kx, i)); bias float [Cout];
+ *     y bf16: out_padded = 0 -> [B, H, W, Cout]; out_padded = 1 -> [B, H + 2, W + 2, Cout] with the reflection ring
+ *     written by the epilogue, i.e. directly the next block's xp.  Cin % 64 == 0, Cout in {64, 128, 256}, H, W >= 2.
+ *     MHADA_BF16 only. */
+MHADA_API int mhada_conv3x3(int dtype, const void* xp, const void* w, const float* bias, int B, int H, int W, int Cin,
+                            int Cout, int relu, int out_padded, void* y, mhada_stream_t stream);
 MHADA_API int mhada_pad_reflect(int dtype, const void* x, int B, int H, int W, int C, int upsample, void* y,
                                 mhada_stream_t stream);
 

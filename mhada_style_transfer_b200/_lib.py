@@ -91,6 +91,8 @@ SIGNATURES = {
                                            c_size_t, c_void_p]),
     "mhada_conv3x3_small": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
                                     c_void_p]),
+    "mhada_conv3x3": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                              c_void_p]),
     "mhada_pad_reflect": (c_int, [c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "mhada_layer_workspace": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "mhada_layer_forward": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

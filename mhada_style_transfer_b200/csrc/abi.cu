@@ -504,6 +504,19 @@ int mhada_conv3x3_small(int dtype, const void* x, const float* w, const float* b
     return launch_conv3x3_small(x, w, bias, B, H, W, Cin, Cout, relu, y, static_cast<cudaStream_t>(stream));
 }
 
+int mhada_conv3x3(int dtype, const void* xp, const void* w, const float* bias, int B, int H, int W, int Cin, int Cout, int relu,
+                  int out_padded, void* y, mhada_stream_t stream) {
+    g_launches = 0;
+    REQUIRE(xp && w && bias && y, MHADA_ERR_ARG, "mhada_conv3x3: null pointer");
+    REQUIRE(dtype == MHADA_BF16, MHADA_ERR_UNSUPPORTED, "mhada_conv3x3: MHADA_BF16 only");
+    REQUIRE(B > 0 && H >= 2 && W >= 2 && Cin > 0 && Cout > 0, MHADA_ERR_ARG, "mhada_conv3x3: bad sizes (ReflectionPad2d(1) needs H, W >= 2)");
+    REQUIRE(Cin % 64 == 0 && (Cout == 64 || Cout == 128 || Cout == 256), MHADA_ERR_UNSUPPORTED,
+            "mhada_conv3x3: implemented for Cin %% 64 == 0 and Cout in {64, 128, 256}, got %d -> %d", Cin, Cout);
+    REQUIRE(aligned16(xp) && aligned16(w) && aligned32(y), MHADA_ERR_ARG, "mhada_conv3x3: xp, w 16-byte and y 32-byte aligned");
+    if (int e = device_check()) return e;
+    return launch_conv3x3_tc(xp, w, bias, B, H, W, Cin, Cout, relu, out_padded, y, static_cast<cudaStream_t>(stream));
+}
+
 int mhada_pad_reflect(int dtype, const void* x, int B, int H, int W, int C, int upsample, void* y,
                       mhada_stream_t stream) {
     REQUIRE(x && y, MHADA_ERR_ARG, "mhada_pad_reflect: null pointer");

@@ -1,0 +1,252 @@
+// Decoder blocks 0..7 on the tensor cores: ReflectionPad2d(1) + Conv2d(Cin, Cout, 3) + bias + ReLU as an
+// IMPLICIT GEMM on tcgen05, replacing `Conv` / `ConvReLU` of MHAdaSTr/network/conv.py:23-45 (used by Decoder, :75-100).
+// r1 ran these eight convolutions through cuDNN with a separate reflect-pad pass in front of each one.
+//
+//   out[b, y, x, co] = relu( bias[co] + sum_{ky, kx, ci} W[co, ci, ky, kx] * xp[b, y + ky, x + kx, ci] )
+//
+// xp is the reflect-PADDED channels_last activation [B, H + 2, W + 2, Cin] (bf16).  The GEMM view: M = output pixels,
+// N = Cout, K = 9 * Cin ordered (ky, kx, ci).  No im2col buffer exists: for tap (ky, kx) and a 64-channel chunk the A
+// operand of a TW x TH pixel tile is the 4-D TMA box {64 channels, TW, TH, 1} at (c0, x0 + kx, y0 + ky, b) of xp -- it
+// lands in shared memory as 128-byte pixel rows in exactly the K-major 128B-swizzled layout the MMA reads.
+//
+// Work item = MT sub-tiles of 128 pixels (a TW x (MT * 128 / TW) pixel block) x all Cout channels, MT * Cout = 256:
+// the weight tile of a k-step is loaded once per 128 * MT pixels, which keeps the L2 -> shared-memory traffic per FLOP
+// the same for Cout = 256, 128 and 64 (the L2 slice bandwidth, ~43 B/clk per SM, is what bounds these kernels).
+//   warp 0      TMA producer (A box + weight tile per k-step, mbarrier ring that runs across work items)
+//   warp 1      tcgen05.mma issuer, MT accumulators of Cout columns, DOUBLE-BUFFERED in TMEM (2 x 256 columns)
+//   warps 2..9  epilogue: TMEM -> + bias -> ReLU -> bf16 -> global, two warps per TMEM lane quarter
+// The epilogue can write the result ALREADY REFLECT-PADDED for the next block ([B, H + 2, W + 2, Cout]: interior pixel
+// plus up to three mirrored copies for pixels next to the border), which removes the pad-only pass between two
+// convolutions; blocks followed by the x2 bilinear up-sample (conv.py:61-72) write plain [B, H, W, Cout] for
+// pad_reflect_kernel<UP>.
+// Tensor-bound: 2 * B*H*W * Cout * 9*Cin FLOP per launch.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace mh {
+
+constexpr int CV_BK = 64, CV_EPI_WARPS = 8, CV_THREADS = 64 + 32 * CV_EPI_WARPS;
+
+struct ConvParams {
+    const float* bias;
+    __nv_bfloat16* out;
+    int B, H, W, Cin;
+    int TW, TR;             // tile: TW pixels wide, TR = MT * 128 / TW rows
+    int tiles_x, tiles_y, items;
+    int cchunks, ktiles;    // Cin / 64, 9 * cchunks
+    int relu, out_padded;
+};
+
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(CV_THREADS, 1)
+conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const ConvParams p) {
+    constexpr int MT = 256 / BN;
+    constexpr uint32_t A_BYTES = MT * 128 * CV_BK * 2, B_BYTES = BN * CV_BK * 2, STAGE = A_BYTES + B_BYTES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ uint64_t full[STAGES], empty[STAGES], acc_full[2], acc_empty[2];
+    __shared__ uint32_t tmem_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmX);
+        tma_prefetch_desc(&tmW);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < STAGES; ++s) {
+                mbar_init(&full[s], 1);
+                mbar_init(&empty[s], 1);
+            }
+            for (int u = 0; u < 2; ++u) {
+                mbar_init(&acc_full[u], 1);
+                mbar_init(&acc_empty[u], CV_EPI_WARPS);
+            }
+            fence_mbar_init();
+        }
+        __syncwarp();
+        tmem_alloc(&tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const int per_img = p.tiles_x * p.tiles_y;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            int g = 0;
+            for (int it = blockIdx.x; it < p.items; it += gridDim.x) {
+                const int b = it / per_img, t = it % per_img;
+                const int x0 = (t % p.tiles_x) * p.TW, y0 = (t / p.tiles_x) * p.TR;
+                for (int kt = 0; kt < p.ktiles; ++kt, ++g) {
+                    const int tap = kt / p.cchunks, cc = kt % p.cchunks;
+                    const int s = g % STAGES;
+                    mbar_wait(&empty[s], ((g / STAGES) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&full[s], STAGE);
+                    uint8_t* a = smem + s * STAGE;
+                    tma_load_4d(a, &tmX, &full[s], cc * CV_BK, x0 + tap % 3, y0 + tap / 3, b);
+                    tma_load_2d(a + A_BYTES, &tmW, &full[s], kt * CV_BK, 0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+            int g = 0, n = 0;
+            for (int it = blockIdx.x; it < p.items; it += gridDim.x, ++n) {
+                const int u = n & 1;
+                mbar_wait(&acc_empty[u], ((n >> 1) & 1) ^ 1);
+                tc_fence_after();
+                for (int kt = 0; kt < p.ktiles; ++kt, ++g) {
+                    const int s = g % STAGES;
+                    mbar_wait(&full[s], (g / STAGES) & 1);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + s * STAGE);
+                    const uint64_t db = make_smem_desc(a_addr + A_BYTES, 16, 1024);
+#pragma unroll
+                    for (int t = 0; t < MT; ++t) {
+                        const uint64_t da = make_smem_desc(a_addr + t * (128 * CV_BK * 2), 16, 1024);
+#pragma unroll
+                        for (int k = 0; k < CV_BK / 16; ++k)
+                            umma_ss(tmem + u * 256 + t * BN, desc_advance(da, k * 32), desc_advance(db, k * 32), idesc, (kt | k) != 0);
+                    }
+                    umma_commit(&empty[s]);
+                }
+                umma_commit(&acc_full[u]);
+            }
+        }
+    } else {
+        // epilogue warps 2..9: TMEM lane quarter = warp % 4; the 256 accumulator columns (MT sub-tiles x BN channels)
+        // are split in two halves between the two warps of a quarter
+        const int quarter = warp & 3;
+        const int chalf = (warp - 2) >> 2;
+        const int row = quarter * 32 + lane;
+        const int Hp = p.H + 2, Wp = p.W + 2;
+        int n = 0;
+        for (int it = blockIdx.x; it < p.items; it += gridDim.x, ++n) {
+            const int b = it / per_img, t = it % per_img;
+            const int x0 = (t % p.tiles_x) * p.TW, y0 = (t / p.tiles_x) * p.TR;
+            const int u = n & 1;
+            mbar_wait(&acc_full[u], (n >> 1) & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int cg = 0; cg < 128; cg += 32) {
+                const int col = chalf * 128 + cg;                 // accumulator column 0..255
+                const int st = col / BN, c = col % BN;            // sub-tile, channel offset
+                uint32_t r[32];
+                tmem_ld_x32(tmem_addr(tmem, quarter * 32, u * 256 + col), r);
+                tmem_wait_ld();
+                if (cg + 32 == 128) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&acc_empty[u]);
+                }
+                const int pi = st * 128 + row;                    // pixel index inside the TW x TR block
+                const int y = y0 + pi / p.TW, x = x0 + pi % p.TW;
+                if (y < p.H && x < p.W) {
+                    uint32_t o[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        float v0 = __uint_as_float(r[2 * i]) + __ldg(p.bias + c + 2 * i);
+                        float v1 = __uint_as_float(r[2 * i + 1]) + __ldg(p.bias + c + 2 * i + 1);
+                        if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+                        o[i] = pack_bf16x2(v0, v1);
+                    }
+                    if (!p.out_padded) {
+                        __nv_bfloat16* dst = p.out + ((static_cast<size_t>(b) * p.H + y) * p.W + x) * BN + c;
+                        st_global_256(dst, o);
+                        st_global_256(dst + 16, o + 8);
+                    } else {
+                        // interior position (y + 1, x + 1) of the padded map, plus the mirror images ReflectionPad2d(1)
+                        // takes from this pixel: row 1 -> padded row 0, row H-2 -> padded row H+1 (both when H == 3),
+                        // same for columns; a pixel next to a corner feeds up to nine positions
+                        __nv_bfloat16* img = p.out + static_cast<size_t>(b) * Hp * Wp * BN + c;
+                        int ys[3], xs[3], ny = 0, nx = 0;
+                        ys[ny++] = y + 1;
+                        if (y == 1) ys[ny++] = 0;
+                        if (y == p.H - 2) ys[ny++] = p.H + 1;
+                        xs[nx++] = x + 1;
+                        if (x == 1) xs[nx++] = 0;
+                        if (x == p.W - 2) xs[nx++] = p.W + 1;
+                        for (int a = 0; a < ny; ++a)
+                            for (int e = 0; e < nx; ++e) {
+                                __nv_bfloat16* dst = img + (static_cast<size_t>(ys[a]) * Wp + xs[e]) * BN;
+                                st_global_256(dst, o);
+                                st_global_256(dst + 16, o + 8);
+                            }
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+template <int BN, int STAGES>
+static int launch_conv_bn(const void* xp, const void* w, const float* bias, int B, int H, int W, int Cin, int relu,
+                          int out_padded, void* y, cudaStream_t s) {
+    constexpr int MT = 256 / BN;
+    ConvParams p;
+    // tile shape: as wide as the image allows (TMA boxes are rows of pixels), MT * 128 pixels in all
+    int TW = 128;
+    while (TW > 8 && TW / 2 >= W) TW /= 2;
+    if (TW > 128) TW = 128;
+    p.TW = TW;
+    p.TR = MT * 128 / TW;
+    if (p.TR > 256) {                        // TMA box limit: 256 per dimension
+        set_error("conv3x3_tc: image too narrow for the %d-pixel tile (W = %d)", MT * 128, W);
+        return MHADA_ERR_UNSUPPORTED;
+    }
+    CUtensorMap tmX, tmW;
+    {
+        uint64_t dims[4] = {static_cast<uint64_t>(Cin), static_cast<uint64_t>(W + 2), static_cast<uint64_t>(H + 2), static_cast<uint64_t>(B)};
+        uint64_t str[3] = {static_cast<uint64_t>(Cin) * 2, static_cast<uint64_t>(W + 2) * Cin * 2,
+                           static_cast<uint64_t>(H + 2) * (W + 2) * Cin * 2};
+        uint32_t box[4] = {CV_BK, static_cast<uint32_t>(p.TW), static_cast<uint32_t>(p.TR), 1};
+        if (int e = make_tmap(&tmX, xp, 2, 4, dims, str, box)) return e;
+    }
+    {
+        uint64_t dims[2] = {static_cast<uint64_t>(9) * Cin, static_cast<uint64_t>(BN)};
+        uint64_t str[1] = {static_cast<uint64_t>(9) * Cin * 2};
+        uint32_t box[2] = {CV_BK, BN};
+        if (int e = make_tmap(&tmW, w, 2, 2, dims, str, box)) return e;
+    }
+    p.bias = bias; p.out = static_cast<__nv_bfloat16*>(y);
+    p.B = B; p.H = H; p.W = W; p.Cin = Cin;
+    p.tiles_x = (W + p.TW - 1) / p.TW; p.tiles_y = (H + p.TR - 1) / p.TR;
+    p.items = B * p.tiles_x * p.tiles_y;
+    p.cchunks = Cin / CV_BK; p.ktiles = 9 * p.cchunks;
+    p.relu = relu; p.out_padded = out_padded;
+    constexpr size_t smem = STAGES * (MT * 128 * CV_BK * 2 + BN * CV_BK * 2) + 1024;
+    static DeviceOnce once;
+    if (int e = smem_attr_once(once, reinterpret_cast<const void*>(conv3x3_tc_kernel<BN, STAGES>), smem, "conv_tc smem attr")) return e;
+    const int n_sm = sm_count();
+    const int grid = p.items < n_sm ? p.items : n_sm;
+    conv3x3_tc_kernel<BN, STAGES><<<grid, CV_THREADS, smem, s>>>(tmX, tmW, p);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "conv3x3_tc launch");
+}
+
+int launch_conv3x3_tc(const void* xp, const void* w, const float* bias, int B, int H, int W, int Cin, int Cout, int relu,
+                      int out_padded, void* y, cudaStream_t s) {
+    if (Cin % CV_BK != 0 || (Cout != 64 && Cout != 128 && Cout != 256)) {
+        set_error("conv3x3_tc: implemented for Cin %% 64 == 0 and Cout in {64, 128, 256}, got %d -> %d", Cin, Cout);
+        return MHADA_ERR_UNSUPPORTED;
+    }
+    if (Cout == 256) return launch_conv_bn<256, 4>(xp, w, bias, B, H, W, Cin, relu, out_padded, y, s);
+    if (Cout == 128) return launch_conv_bn<128, 4>(xp, w, bias, B, H, W, Cin, relu, out_padded, y, s);
+    return launch_conv_bn<64, 3>(xp, w, bias, B, H, W, Cin, relu, out_padded, y, s);
+}
+
+}  // namespace mh

@@ -99,9 +99,13 @@ int make_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, cons
         set_error("cuTensorMapEncodeTiled not available from the driver");
         return MHADA_ERR_DRIVER;
     }
-    cuuint64_t gdim[3];
-    cuuint64_t gstr[2];
-    cuuint32_t bx[3], es[3];
+    cuuint64_t gdim[5];
+    cuuint64_t gstr[4];
+    cuuint32_t bx[5], es[5];
+    if (rank < 1 || rank > 5) {
+        set_error("make_tmap: rank %d", rank);
+        return MHADA_ERR_ARG;
+    }
     for (int i = 0; i < rank; ++i) {
         gdim[i] = dims[i];
         bx[i] = box[i];

@@ -192,7 +192,7 @@ def test_transformer_vs_reference_golden(case, precision, golden_index):
     else:
         assert ef["max_abs_rel"] <= bf16_tol(case), ef
         assert ec["max_abs_rel"] <= bf16_tol(case), ec
-        assert ef["fro_rel"] <= (3e-2 if case.get("heads", 8) == 4 else 1.5e-2), ef
+        assert ef["fro_rel"] <= (3e-2 if case.get("heads", 8) == 4 else bf16_tol(case)), ef
 
 
 # ---------------------------------------------------------------------------------------------------
