@@ -576,6 +576,17 @@ class _PadConv(nn.Module):
                             "b": self.conv.bias.detach().to(dtype)}
         return self._shadow["w"], self._shadow["b"]
 
+    def _packed_tc(self):
+        """bf16 [Cout][3][3][Cin] weights + f32 bias for mhada_conv3x3 (K ordered (ky, kx, ci)); cached per device."""
+        w, b = self.conv.weight, self.conv.bias
+        key = ("tc", w._version, b._version, w.data_ptr(), b.data_ptr(), w.dtype, str(w.device))
+        if self._shadow.get("tc_key") != key:
+            with torch.no_grad():
+                self._shadow["tc_w"] = w.detach().permute(0, 2, 3, 1).reshape(w.shape[0], -1).to(torch.bfloat16).contiguous()
+                self._shadow["tc_b"] = b.detach().float().contiguous()
+            self._shadow["tc_key"] = key
+        return self._shadow["tc_w"], self._shadow["tc_b"]
+
     def forward(self, x):
         w, b = self._weights(x.dtype)
         return F.conv2d(self.pad(x), w, b, self.conv.stride)
@@ -622,6 +633,21 @@ def _conv3x3_small_relu(x_tok: torch.Tensor, w: torch.Tensor, b: torch.Tensor) -
     return y
 
 
+def _conv3x3_tc_relu(xp_tok: torch.Tensor, w_packed: torch.Tensor, b: torch.Tensor, out_padded: bool) -> torch.Tensor:
+    """[B,H+2,W+2,Cin] bf16 reflect-padded -> conv3x3 + bias + ReLU on tcgen05 (mhada_conv3x3): [B,H,W,Cout], or
+    [B,H+2,W+2,Cout] with the reflection ring already written when `out_padded` (= the next block's input)."""
+    L = _lib.lib()
+    B, Hp, Wp, Cin = xp_tok.shape
+    H, W, Cout = Hp - 2, Wp - 2, w_packed.shape[0]
+    shape = (B, Hp, Wp, Cout) if out_padded else (B, H, W, Cout)
+    y = torch.empty(shape, dtype=torch.bfloat16, device=xp_tok.device)
+    with torch.cuda.device(xp_tok.device):
+        rc = L.mhada_conv3x3(_lib.BF16, _ptr(xp_tok), _ptr(w_packed), _ptr(b), B, H, W, Cin, Cout, 1, 1 if out_padded else 0,
+                             _ptr(y), _stream())
+    _lib.check("mhada_conv3x3", rc)
+    return y
+
+
 def _conv3x3_relu(xp_nchw: torch.Tensor, w: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     """3x3 conv (input already padded) + bias + ReLU as ONE cuDNN fused conv-bias-relu call (fp32 path of the decoder;
     the bf16 path runs mhada_conv3x3).  No fallback: if cuDNN rejects the shape the error propagates."""
@@ -629,9 +655,10 @@ def _conv3x3_relu(xp_nchw: torch.Tensor, w: torch.Tensor, b: torch.Tensor) -> to
 
 
 class Decoder(nn.Module):
-    """Decoder.forward (conv.py:75-100).  On the GPU every block runs as
-        [fused reflect-pad (+ x2 bilinear of the previous block)] -> cuDNN NHWC conv3x3 + bias + ReLU
-    so activations stay channels_last and each one is written once and read once between convolutions.
+    """Decoder.forward (conv.py:75-100).  bf16 path: own kernels only -- tcgen05 implicit-GEMM convolutions whose
+    epilogue writes the next block's reflect-padded input, the fused x2-bilinear + pad kernel after the three
+    up-sampling blocks, and the small 64 -> 3 kernel; activations stay channels_last.  fp32 path (the reference's
+    arithmetic): the pad kernel + cuDNN fp32 convolutions.
     CPU tensors raise (no CPU path); under autograd the plain differentiable PyTorch ops run on the GPU."""
 
     def __init__(self):
@@ -655,15 +682,38 @@ class Decoder(nn.Module):
         if fcs.shape[2] < 2 or fcs.shape[3] < 2:
             raise RuntimeError("Decoder needs at least 2x2 feature maps (ReflectionPad2d(1))")
         x = _token_major(fcs, fcs.dtype)                    # [B,h,w,512]
-        up = False
-        ctx = torch.backends.cudnn.flags(enabled=True, allow_tf32=False) if x.dtype == torch.float32 else _NullCtx()
-        with ctx:                                            # fp32 path: the reference's fp32 arithmetic, not TF32
-            for blk in self._blocks():
+        blocks = self._blocks()
+        if x.dtype == torch.bfloat16:
+            # bf16 path, own kernels only: blocks 0..7 = tcgen05 implicit GEMM (mhada_conv3x3) on reflect-padded input;
+            # a block whose successor is a plain convolution writes its output already padded (no pad pass between
+            # them), a block followed by the x2 up-sample hands it to the fused up-sample + pad kernel; the last block
+            # (64 -> 3) is the HBM-bound small kernel on unpadded input.
+            xp = _pad_reflect(x, False)                      # conv.py:26-27
+            for i, blk in enumerate(blocks):
                 cin, cout = blk.conv.conv.in_channels, blk.conv.conv.out_channels
-                if x.dtype == torch.bfloat16 and cin == 64 and cout <= 8 and not up and not blk.scale_factor:
-                    # last block (conv.py:90-93): pad + conv + ReLU in one own kernel, straight to NCHW planes
-                    y = _conv3x3_small_relu(x, blk.conv.conv.weight, blk.conv.conv.bias)
+                if cin == 64 and cout <= 8 and not blk.scale_factor:
+                    if xp is not None:
+                        raise RuntimeError("decoder: the 64 -> %d block expects an unpadded input" % cout)
+                    y = _conv3x3_small_relu(x, blk.conv.conv.weight, blk.conv.conv.bias)     # conv.py:90-93
+                    if i != len(blocks) - 1:
+                        raise RuntimeError("decoder: the small block must be the last one")
                     return y if y.dtype == in_dtype else y.to(in_dtype)
+                nxt = blocks[i + 1] if i + 1 < len(blocks) else None
+                nxt_small = nxt is not None and nxt.conv.conv.in_channels == 64 and nxt.conv.conv.out_channels <= 8
+                out_padded = nxt is not None and not blk.scale_factor and not nxt_small
+                w, b = blk.conv._packed_tc()
+                y = _conv3x3_tc_relu(xp, w, b, out_padded)
+                if out_padded:
+                    xp = y
+                elif blk.scale_factor:
+                    xp = _pad_reflect(y, True)               # conv.py:71 + the next block's pad, one pass
+                else:
+                    x, xp = y, None
+            y = x.permute(0, 3, 1, 2)
+            return y if y.dtype == in_dtype else y.to(in_dtype)
+        up = False
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):     # fp32 path: the reference's fp32 arithmetic
+            for blk in blocks:                               # (cuDNN convolutions, never TF32), pads by pad_reflect_kernel
                 xp = _pad_reflect(x, up)                     # conv.py:26-27 (+ :71 of the previous block)
                 w, b = blk.conv._weights(x.dtype)
                 y = _conv3x3_relu(xp.permute(0, 3, 1, 2), w, b)

@@ -248,6 +248,41 @@ def _attn_bf16_case(B, H, Nc, Ns, gain, ramp, d):
     assert e["max_abs_rel"] < 1.2e-2 and e["fro_rel"] < 4e-3, e
 
 
+# ------------------------------------------------------------------------------------------------ decoder convolutions
+@pytest.mark.parametrize("B,H,W,Cin,Cout,padded", [
+    (1, 5, 7, 512, 256, 0), (2, 10, 14, 256, 256, 1), (1, 20, 28, 256, 128, 0), (1, 40, 56, 128, 128, 1),
+    (1, 40, 56, 128, 64, 0), (2, 80, 112, 64, 64, 0), (1, 3, 3, 64, 64, 1), (1, 2, 2, 64, 128, 1), (1, 2, 9, 128, 256, 1),
+    (3, 64, 64, 512, 256, 0), (1, 128, 128, 256, 256, 1), (1, 130, 140, 64, 64, 1)])
+def test_conv3x3_tc(B, H, W, Cin, Cout, padded):
+    """mhada_conv3x3 (tcgen05 implicit GEMM) against the oracle's ReflectionPad2d(1) + Conv2d(3x3) + ReLU on the same
+    bf16-rounded input and weights; with `padded` the result must come back with its own reflection ring."""
+    L = _lib.lib()
+    x = synth.bellish(51, (B, Cin, H, W), 0.0, 1.0)
+    w = synth.uniform(52, (Cout, Cin, 3, 3), -1, 1) / np.sqrt(9 * Cin)
+    b = synth.uniform(53, (Cout,), -0.5, 0.5)
+    xt = torch.from_numpy(x).float().to(G.DEV).to(torch.bfloat16)
+    xr = xt.float().cpu().numpy().astype(np.float64)
+    xp = torch.nn.functional.pad(xt.float(), (1, 1, 1, 1), mode="reflect").to(torch.bfloat16).permute(0, 2, 3, 1).contiguous()
+    wt = torch.from_numpy(w).float().to(G.DEV).to(torch.bfloat16)
+    wr = wt.float().cpu().numpy().astype(np.float64)
+    wp = wt.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous()
+    bt = G.f32(b)
+    shape = (B, H + 2, W + 2, Cout) if padded else (B, H, W, Cout)
+    y = torch.full(shape, float("nan"), dtype=torch.bfloat16, device=G.DEV)
+    _lib.check("mhada_conv3x3", L.mhada_conv3x3(BF16, G.ptr(xp), G.ptr(wp), G.ptr(bt), B, H, W, Cin, Cout, 1, padded, G.ptr(y),
+                                               G.stream()))
+    torch.cuda.synchronize()
+    want = np.maximum(O.conv3x3_reflect(xr, wr, b.astype(np.float32).astype(np.float64)), 0.0)      # (B, Cout, H, W)
+    got = y.float().cpu().numpy().astype(np.float64).transpose(0, 3, 1, 2)
+    if padded:
+        assert np.isfinite(got).all()                         # every ring position was written
+        ring = np.pad(got[:, :, 1:-1, 1:-1], ((0, 0), (0, 0), (1, 1), (1, 1)), mode="reflect")
+        assert np.array_equal(ring, got)                      # the ring is the exact mirror of the interior
+        got = got[:, :, 1:-1, 1:-1]
+    e = O.errors(got, want)
+    assert e["max_abs_rel"] <= 4.5e-3, e
+
+
 # ------------------------------------------------------------------------------------------------ decoder glue
 @pytest.mark.parametrize("code", [F32, BF16])
 @pytest.mark.parametrize("B,H,W,C,up", [(2, 5, 7, 64, 0), (1, 5, 7, 64, 1), (1, 2, 2, 8, 1), (2, 16, 12, 256, 1),

@@ -25,6 +25,9 @@ S._attn_bf16_case(1, 2, 135, 143, 0.45, 2.0, 128)    # head_dim 128 (two chunks 
 S.test_linear(S.BF16, 130, 128, 64)
 S.test_linear(S.BF16, 300, 512, 512)
 S.test_in_stats(S.BF16, 1, 512, (9, 15))
+S.test_conv3x3_tc(1, 3, 3, 64, 64, 1)
+S.test_conv3x3_tc(2, 10, 14, 256, 256, 1)
+S.test_conv3x3_tc(1, 20, 28, 256, 128, 0)
 for args in ((300, 512, 192, "pos"), (70, 384, 64, "bf16"), (129, 512, 2048, "both"), (260, 2048, 512, "relu")):
     V.test_gemm(*args)
 V.test_layernorm(7, 128)
