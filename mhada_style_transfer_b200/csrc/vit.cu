@@ -134,24 +134,30 @@ int launch_layernorm(const float* x, int M, int C, const float* gamma, const flo
 
 // ------------------------------------------------------------------------------------------------ batch-axis attention
 // warp = (token position n, head); the "sequence" is the B images.  q, k, v of the B images are staged in shared
-// memory as f32 (row pitch 68 words: the float4 reads below are bank-conflict free).  Work is spread over all 32
-// lanes: the B*B logits as (i, j) pairs, the B*64 outputs as (i, 4-channel group) items.
+// memory.  Work is spread over all 32 lanes: the B*B logits as (i, j) pairs, the B*64 outputs as (i, 8-channel group)
+// items.
 constexpr int BA_HD = 64;
 constexpr int BA_WARPS = 8;
-constexpr int BA_PITCH = BA_HD + 4;
-__host__ __device__ constexpr int ba_warp_floats(int B) { return 3 * B * BA_PITCH + ((B * (B + 1) + 3) & ~3); }
+constexpr int BA_PITCH = BA_HD + 8;                    // bf16 elements per staged row (144 B: 16-byte reads of 8 rows hit 32 banks)
+__host__ __device__ constexpr int ba_warp_bytes(int B) { return 3 * B * BA_PITCH * 2 + ((B * (B + 1) * 4 + 15) & ~15); }
+__device__ __forceinline__ void ba_unpack8(const uint4& w, float (&f)[8]) {
+    f[0] = bf16_lo(w.x); f[1] = bf16_hi(w.x); f[2] = bf16_lo(w.y); f[3] = bf16_hi(w.y);
+    f[4] = bf16_lo(w.z); f[5] = bf16_hi(w.z); f[6] = bf16_lo(w.w); f[7] = bf16_hi(w.w);
+}
 __global__ void __launch_bounds__(BA_WARPS * 32) batch_attn_kernel(const __nv_bfloat16* __restrict__ qkv, int B, int N,
                                                                    int heads, __nv_bfloat16* __restrict__ out) {
-    extern __shared__ __align__(16) float ba_smem[];
+    extern __shared__ __align__(16) uint8_t ba_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long item = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + warp;     // n * heads + h
     if (item >= static_cast<long long>(N) * heads) return;
     const int n = static_cast<int>(item / heads), h = static_cast<int>(item % heads);
     const int D = heads * BA_HD;
-    float* q = ba_smem + static_cast<size_t>(warp) * ba_warp_floats(B);
-    float* k = q + B * BA_PITCH;
-    float* v = k + B * BA_PITCH;
-    float* sc = v + B * BA_PITCH;                      // [B][B + 1] logits, then probabilities
+    // q, k, v stay bf16 in shared memory (the shared-memory pipe, not the FMAs, bounds this kernel: f32 staging cost
+    // twice the wavefronts); they are widened in registers
+    __nv_bfloat16* q = reinterpret_cast<__nv_bfloat16*>(ba_smem + static_cast<size_t>(warp) * ba_warp_bytes(B));
+    __nv_bfloat16* k = q + B * BA_PITCH;
+    __nv_bfloat16* v = k + B * BA_PITCH;
+    float* sc = reinterpret_cast<float*>(v + B * BA_PITCH);      // [B][B + 1] logits, then probabilities
     // stage: three coalesced 128-byte rows per image, four images in flight
     for (int b0 = 0; b0 < B; b0 += 4) {
         uint32_t w[4][3];
@@ -165,22 +171,25 @@ __global__ void __launch_bounds__(BA_WARPS * 32) batch_attn_kernel(const __nv_bf
         for (int u = 0; u < 4; ++u)
             if (b0 + u < B) {
                 const int o = (b0 + u) * BA_PITCH + 2 * lane;
-                *reinterpret_cast<float2*>(q + o) = make_float2(bf16_lo(w[u][0]), bf16_hi(w[u][0]));
-                *reinterpret_cast<float2*>(k + o) = make_float2(bf16_lo(w[u][1]), bf16_hi(w[u][1]));
-                *reinterpret_cast<float2*>(v + o) = make_float2(bf16_lo(w[u][2]), bf16_hi(w[u][2]));
+                *reinterpret_cast<uint32_t*>(q + o) = w[u][0];
+                *reinterpret_cast<uint32_t*>(k + o) = w[u][1];
+                *reinterpret_cast<uint32_t*>(v + o) = w[u][2];
             }
     }
     __syncwarp();
     // logits: one (i, j) pair per lane and round
     for (int pr = lane; pr < B * B; pr += 32) {
         const int i = pr / B, j = pr % B;
-        const float4* qi = reinterpret_cast<const float4*>(q + i * BA_PITCH);
-        const float4* kj = reinterpret_cast<const float4*>(k + j * BA_PITCH);
+        const uint4* qi = reinterpret_cast<const uint4*>(q + i * BA_PITCH);
+        const uint4* kj = reinterpret_cast<const uint4*>(k + j * BA_PITCH);
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
-        for (int d = 0; d < BA_HD / 4; ++d) {
-            const float4 x = qi[d], y = kj[d];
-            a0 = fmaf(x.x, y.x, a0); a1 = fmaf(x.y, y.y, a1); a2 = fmaf(x.z, y.z, a2); a3 = fmaf(x.w, y.w, a3);
+        for (int d = 0; d < BA_HD / 8; ++d) {
+            float x[8], y[8];
+            ba_unpack8(qi[d], x);
+            ba_unpack8(kj[d], y);
+            a0 = fmaf(x[0], y[0], a0); a1 = fmaf(x[1], y[1], a1); a2 = fmaf(x[2], y[2], a2); a3 = fmaf(x[3], y[3], a3);
+            a0 = fmaf(x[4], y[4], a0); a1 = fmaf(x[5], y[5], a1); a2 = fmaf(x[6], y[6], a2); a3 = fmaf(x[7], y[7], a3);
         }
         sc[i * (B + 1) + j] = ((a0 + a1) + (a2 + a3)) * 0.125f;        // 1 / sqrt(64)
     }
@@ -199,20 +208,22 @@ __global__ void __launch_bounds__(BA_WARPS * 32) batch_attn_kernel(const __nv_bf
         for (int j = 0; j < B; ++j) row[j] *= inv;
     }
     __syncwarp();
-    // outputs: (image i, 4-channel group) items; 16 consecutive lanes write one 128-byte row
-    for (int t = lane; t < B * (BA_HD / 4); t += 32) {
-        const int i = t / (BA_HD / 4), d4 = t % (BA_HD / 4);
+    // outputs: (image i, 8-channel group) items; 8 consecutive lanes write one 128-byte row
+    for (int t = lane; t < B * (BA_HD / 8); t += 32) {
+        const int i = t / (BA_HD / 8), d8 = t % (BA_HD / 8);
         const float* pi = sc + i * (B + 1);
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         for (int j = 0; j < B; ++j) {
             const float pw = pi[j];
-            const float4 y = reinterpret_cast<const float4*>(v + j * BA_PITCH)[d4];
-            acc.x = fmaf(pw, y.x, acc.x); acc.y = fmaf(pw, y.y, acc.y); acc.z = fmaf(pw, y.z, acc.z); acc.w = fmaf(pw, y.w, acc.w);
+            float y[8];
+            ba_unpack8(reinterpret_cast<const uint4*>(v + j * BA_PITCH)[d8], y);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[e] = fmaf(pw, y[e], acc[e]);
         }
-        uint2 o;
-        o.x = pack_bf16x2(acc.x, acc.y);
-        o.y = pack_bf16x2(acc.z, acc.w);
-        reinterpret_cast<uint2*>(out + (static_cast<size_t>(i) * N + n) * D + h * BA_HD)[d4] = o;
+        uint4 o;
+        o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
+        o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
+        reinterpret_cast<uint4*>(out + (static_cast<size_t>(i) * N + n) * D + h * BA_HD)[d8] = o;
     }
 }
 
@@ -222,7 +233,7 @@ int launch_batch_attn(const void* qkv, int B, int N, int heads, int hd, void* ou
         return MHADA_ERR_UNSUPPORTED;
     }
     constexpr size_t kSmemCap = 200 * 1024;
-    const size_t per_warp = static_cast<size_t>(ba_warp_floats(B)) * sizeof(float);
+    const size_t per_warp = static_cast<size_t>(ba_warp_bytes(B));
     int warps = static_cast<int>(kSmemCap / per_warp);
     if (warps > BA_WARPS) warps = BA_WARPS;
     const size_t smem = warps * per_warp;

@@ -1,0 +1,15 @@
+#!/bin/bash
+# Round-2 ncu session: launch list of the default bench command, one --set full capture of every kernel of one e2e step.
+mkdir -p gpurun_out
+timeout 300 python tools/bench_vit.py --B 8 --img 512 > gpurun_out/vit_b8.json 2> gpurun_out/vit.err
+python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-also > gpurun_out/plain_bench.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/r02_launches.csv \
+    python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-also > gpurun_out/ncu_launches.log 2>&1
+echo "launch list exit $?"
+python tools/run_step.py --steps 2 > gpurun_out/plain_step.log 2>&1 &&
+NL=$(grep "^step 1" gpurun_out/plain_step.log | awk '{print $4}') && echo "launches per step: $NL" &&
+ncu --set full --clock-control none --import-source on \
+    -k regex:'gemm_tc|batch_attn|layernorm|patch_im2col|conv3x3|attn_tc|proj_tc|stats_partial|fold_stats|pad_reflect|f32_to_bf16' \
+    -s $NL -c $NL -o gpurun_out/r02_step python tools/run_step.py --steps 2 > gpurun_out/ncu_step.log 2>&1
+echo "full capture exit $?"
+cat gpurun_out/plain_step.log; tail -3 gpurun_out/ncu_step.log; cat gpurun_out/vit_b8.json; ls -la gpurun_out/*.ncu-rep
