@@ -96,3 +96,76 @@ def allreduce_gradients(module: torch.nn.Module, group=None, bucket_bytes: int =
         if size >= bucket_bytes:
             flush()
     flush()
+
+
+class OverlappedGradientAllReduce:
+    """Gradient averaging that OVERLAPS the backward pass (BASELINE configs[4]: train step with gradient all-reduce
+    over NVLink): parameters are grouped into ~`bucket_bytes` buckets in reverse registration order (the order in
+    which backward produces gradients); a post-accumulate-grad hook per parameter marks it ready, and as soon as a
+    bucket is complete its flattened gradients go out as one asynchronous all-reduce (NCCL runs it on its own
+    stream while autograd keeps computing).  `finish()` -- called between backward() and optimizer.step() -- waits
+    for the collectives and scatters the averages back into the .grad tensors.
+
+        sync = OverlappedGradientAllReduce([vit_c, vit_s, adaFormer])
+        loss.backward(); sync.finish(); opt.step()
+
+    The reference trains on one GPU (train_image.py:139-144: backward, three Adam steps, no synchronisation)."""
+
+    def __init__(self, modules, group=None, bucket_bytes: int = 32 << 20):
+        if isinstance(modules, torch.nn.Module):
+            modules = [modules]
+        self.group = group
+        self.world = dist.get_world_size(group)
+        params = [p for m in modules for p in m.parameters() if p.requires_grad]
+        self.buckets, cur, size = [], [], 0
+        for p in reversed(params):
+            cur.append(p)
+            size += p.numel() * p.element_size()
+            if size >= bucket_bytes:
+                self.buckets.append(cur)
+                cur, size = [], 0
+        if cur:
+            self.buckets.append(cur)
+        self._bucket_of = {id(p): i for i, b in enumerate(self.buckets) for p in b}
+        self._pending = [len(b) for b in self.buckets]
+        self._inflight = []            # (bucket index, flat tensor, work handle)
+        self._handles = [p.register_post_accumulate_grad_hook(self._on_grad) for p in params]
+        self.launched_in_backward = 0  # buckets whose all-reduce started before finish() (i.e. overlapped)
+
+    def _launch(self, i):
+        grads = [p.grad for p in self.buckets[i] if p.grad is not None]
+        if not grads:
+            return
+        flat = torch.cat([g.reshape(-1) for g in grads])
+        work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        self._inflight.append((i, flat, work))
+
+    def _on_grad(self, p):
+        i = self._bucket_of[id(p)]
+        self._pending[i] -= 1
+        if self._pending[i] == 0:
+            self._launch(i)
+            self.launched_in_backward += 1
+
+    def finish(self):
+        """Wait for the collectives, write the averaged gradients back, re-arm for the next step."""
+        for i, n in enumerate(self._pending):          # buckets with parameters that got no gradient this step
+            if 0 < n < len(self.buckets[i]) or (n == len(self.buckets[i]) and any(p.grad is not None for p in self.buckets[i])):
+                self._launch(i)
+        for i, flat, work in self._inflight:
+            work.wait()
+            flat.div_(self.world)
+            off = 0
+            for p in self.buckets[i]:
+                if p.grad is None:
+                    continue
+                n = p.grad.numel()
+                p.grad.copy_(flat[off: off + n].view_as(p.grad))
+                off += n
+        self._inflight = []
+        self._pending = [len(b) for b in self.buckets]
+
+    def remove(self):
+        for h in self._handles:
+            h.remove()
+        self._handles = []

@@ -72,3 +72,57 @@ def test_sharded_run_matches_unsharded(world, n_images):
     shape, same = q.get(timeout=10)
     assert shape == (n_images, 1, 2, 2) and same
     assert q.get(timeout=10) is True
+
+
+def _overlap_worker(rank, world, port, q):
+    from mhada_style_transfer_b200.sharding import OverlappedGradientAllReduce, allreduce_gradients
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.ReLU(), torch.nn.Linear(32, 32), torch.nn.ReLU(),
+                              torch.nn.Linear(32, 4))
+    unused = torch.nn.Linear(3, 3)                       # a module whose parameters get no gradient
+    ref = [p.detach().clone() for p in net.parameters()]
+    x = torch.randn(8, 16, generator=torch.Generator().manual_seed(1))
+    s, e = shard_range(8, rank, world)
+    sync = OverlappedGradientAllReduce([net, unused], bucket_bytes=256)        # several buckets
+    assert len(sync.buckets) >= 3
+    for step in range(2):                                # two steps: the hooks re-arm
+        for p in net.parameters():
+            p.grad = None
+        (net(x[s:e]).pow(2).sum() / 8 * world).backward()   # shard loss scaled so that the average = full-batch gradient
+        launched = sync.launched_in_backward
+        sync.finish()
+    got = [p.grad.clone() for p in net.parameters()]
+    # the plain (post-backward) all-reduce gives the same averages
+    for p in net.parameters():
+        p.grad = None
+    (net(x[s:e]).pow(2).sum() / 8 * world).backward()
+    sync.remove()
+    allreduce_gradients(net)
+    same = all(torch.allclose(a, p.grad, rtol=1e-6, atol=1e-7) for a, p in zip(got, net.parameters()))
+    # and both equal the full-batch gradient
+    full = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.ReLU(), torch.nn.Linear(32, 32), torch.nn.ReLU(),
+                               torch.nn.Linear(32, 4))
+    with torch.no_grad():
+        for p, r in zip(full.parameters(), ref):
+            p.copy_(r)
+    (full(x).pow(2).sum() / 8).backward()
+    close = all(torch.allclose(a, p.grad, rtol=1e-5, atol=1e-6) for a, p in zip(got, full.parameters()))
+    if rank == 0:
+        q.put((same, close, launched >= 2, unused.weight.grad is None))
+    dist.destroy_process_group()
+
+
+def test_overlapped_gradient_allreduce_matches_full_batch():
+    """BASELINE configs[4]: gradient all-reduce launched bucket by bucket from autograd hooks DURING backward."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_overlap_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get(timeout=10) == (True, True, True, True)
