@@ -48,6 +48,9 @@ WORKLOADS = {
     "cfg4": dict(B=2, hw=(135, 240), hsws=(64, 64), dtype="bf16", style_batch=1, cached_style=True,
                  desc="BASELINE configs[3]: 1080p frames (135x240 tokens) x one 512x512 style, bf16, style side cached, "
                       "2 frames per step per GPU"),
+    "cfg5": dict(B=8, hw=(32, 32), hsws=(32, 32), dtype="bf16", train=True,
+                 desc="BASELINE configs[4]: train_image.py-shaped step, batch 8 of 256x256 per GPU: ViT x2 + MHAda x6 + decoder "
+                      "forward, backward, gradient all-reduce over NVLink, Adam"),
     "cfg1": dict(B=1, hw=(64, 64), hsws=(64, 64), dtype="fp32",
                  desc="BASELINE configs[0]: single 512x512 content/style, fp32, MHAda x6 + decoder"),
 }
@@ -540,6 +543,105 @@ def measure(args, wl_name, ctx, steps, warmup, with_cpu_baseline):
     return line
 
 
+def measure_train(args, ctx, steps, warmup):
+    """BASELINE configs[4]: one training step per GPU on its own batch (data parallel), gradients averaged with the
+    bucketed all-reduce that is launched from autograd hooks DURING backward (sharding.OverlappedGradientAllReduce).
+    Forward: the CUDA kernels (bf16) for the six MHAda layers; ViT and decoder run their differentiable PyTorch op
+    sequence; backward of the layers = fp32 recompute with PyTorch ops (own backward kernels are SURVEY N4).
+    The VGG loss network needs downloaded weights (absent offline): the loss is a synthetic stand-in with the same
+    graph shape (pixel loss on cs against the content image + a feature term on fcs)."""
+    import torch.distributed as dist
+    from mhada_style_transfer_b200.sharding import OverlappedGradientAllReduce
+    wl = WORKLOADS["cfg5"]
+    rank, world, device = ctx["rank"], ctx["world"], ctx["device"]
+    B = wl["B"]
+    vit_c, vit_s, model = build_models(wl, device)
+    for m in (vit_c, vit_s, model):
+        m.train()
+    opts = [torch.optim.Adam(m.parameters(), lr=1e-4) for m in (vit_c, vit_s, model)]       # train_image.py:70-72
+    c_h, s_h = make_images(wl, seed=rank)
+    c_d, s_d = c_h.to(device), s_h.to(device)
+    sync = OverlappedGradientAllReduce([vit_c, vit_s, model]) if world > 1 else None
+    ev = {"bwd_end": [], "sync_end": []}
+
+    def step(c, s, record=False):
+        for o in opts:
+            o.zero_grad(set_to_none=True)
+        fc, fs = vit_c(c), vit_s(s)
+        fcs, cs = model(fc, fs)
+        loss = (cs.float() - c).pow(2).mean() * 1e-4 + fcs.float().pow(2).mean() * 1e-3
+        loss.backward()
+        if record:
+            e = torch.cuda.Event(enable_timing=True); e.record(); ev["bwd_end"].append(e)
+        if sync is not None:
+            sync.finish()
+        if record:
+            e = torch.cuda.Event(enable_timing=True); e.record(); ev["sync_end"].append(e)
+        for o in opts:
+            o.step()
+        return loss
+
+    def timed(fn, n, w):
+        for _ in range(w):
+            fn(False)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn(True)
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    sampler = ClockSampler(ctx["local"]) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms_dev = timed(lambda rec: step(c_d, s_d, rec), steps, warmup)
+    clocks = sampler.stop() if sampler else None
+    tail_ms = sum(a.elapsed_time(b) for a, b in zip(ev["bwd_end"], ev["sync_end"])) / max(len(ev["bwd_end"]), 1)
+    ev["bwd_end"].clear(); ev["sync_end"].clear()
+
+    def step_host(rec):
+        c = c_h.to(device, non_blocking=True)
+        s = s_h.to(device, non_blocking=True)
+        loss = step(c, s, rec)
+        return float(loss)                      # D2H of the step's result (the loss), synchronises like a logging trainer
+
+    ms_e2e = timed(step_host, steps, max(3, warmup // 2))
+    if rank != 0:
+        return None
+    images = B * world * steps
+    n_params = sum(p.numel() for m in (vit_c, vit_s, model) for p in m.parameters())
+    return {
+        "metric": "images_per_sec", "value": round(images / (ms_dev * 1e-3), 2), "unit": "images/s", "n_gpus": world,
+        "steps": steps, "warmup": warmup, "ms_per_step": round(ms_dev / steps, 4), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": wl["desc"], "images_per_gpu_per_step": B, "tokens": [wl["hw"][0] * wl["hw"][1]] * 2,
+                   "parameters": n_params, "optimizer": "3 x Adam(lr=1e-4) (train_image.py:70-72)",
+                   "loss": "synthetic (VGG19 weights cannot be downloaded offline): pixel term on cs + feature term on fcs",
+                   "forward": "MHAda layers on the bf16 CUDA kernels; ViT / decoder differentiable PyTorch ops",
+                   "backward": "fp32 recompute of each layer with PyTorch ops (no backward kernel yet)",
+                   "gradient_sync": "bucketed (32 MB) all-reduce launched from autograd hooks during backward, NCCL"},
+        "e2e": {"value": round(images / (ms_e2e * 1e-3), 2), "unit": "images/s",
+                "h2d_bytes_per_step": c_h.numel() * 4 + s_h.numel() * 4, "d2h_bytes_per_step": 4,
+                "ms_per_step": round(ms_e2e / steps, 4)},
+        "gradient_allreduce": {"exposed_ms_per_step": round(tail_ms, 4), "bytes": 4 * n_params,
+                               "note": "device time between the end of backward and the end of the last bucket's "
+                                       "all-reduce + copy-back: what the overlap does NOT hide (0 at one GPU)"},
+        "gpu_launches": None, "roofline": None, "clocks": clocks,
+    }
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -572,6 +674,13 @@ def main():
     _lib.check("mhada_device_check", L.mhada_device_check())
     ctx = {"rank": rank, "world": world, "local": local, "device": device, "L": L, "numa": numa}
 
+    if wl.get("train"):
+        line = measure_train(args, ctx, args.steps, args.warmup)
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     line = measure(args, args.workload, ctx, args.steps, args.warmup, with_cpu_baseline=(world == 1 and not args.no_cpu_baseline))
     if args.workload == "cfg2" and not args.no_also:
         # BASELINE configs[2]: the 1024^2 size the north-star attention target is stated on, in the same run

@@ -150,6 +150,8 @@ MHADA_API int mhada_linear(int dtype, const void* x, int ldx, const float* w, co
  * ---------------------------------------------------------------------------------------------- */
 #define MHADA_REUSE_FS_STATS 1
 #define MHADA_LAYER_COSINE 2   /* activation = "cosine" (adaDecoder.py:155-160); MHADA_F32 only */
+#define MHADA_WOUT_BF16 4      /* MHADA_BF16 path: w_out points to a bf16 [C][C] copy of out_conv.weight kept by the
+                                  caller (saves the per-call f32 -> bf16 conversion launch); C % 128 == 0 */
 MHADA_API size_t mhada_layer_workspace(int dtype, int B, int Nc, int Ns, int C, int H);
 MHADA_API int mhada_layer_forward(int dtype, const void* fc, const void* fs, const void* fcs, const float* w_fgh,
                         const float* b_fgh, const float* w_out, const float* b_out, int B, int Nc, int Ns, int C,

@@ -18,6 +18,7 @@ VIT_MAX_LAYERS = 8
 PROJ_Q, PROJ_KV = 1, 2
 REUSE_FS_STATS = 1
 LAYER_COSINE = 2
+WOUT_BF16 = 4
 ACT_SOFTMAX, ACT_COSINE = 0, 1
 
 

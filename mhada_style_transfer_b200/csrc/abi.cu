@@ -138,6 +138,8 @@ int layer_impl(const char* who, int dtype, const void* fc, const void* fs, const
     if (dtype == MHADA_BF16)
         REQUIRE(d == 64 || d == 128, MHADA_ERR_UNSUPPORTED,
                 "%s: the bf16 tensor-core path implements head_dim 64 and 128 (C/H = %d); use MHADA_F32", who, d);
+    REQUIRE(!(flags & MHADA_WOUT_BF16) || (dtype == MHADA_BF16 && w_out && C % 128 == 0 && aligned16(w_out)), MHADA_ERR_ARG,
+            "%s: MHADA_WOUT_BF16 needs the MHADA_BF16 path, a 16-byte aligned bf16 w_out and C %% 128 == 0", who);
     REQUIRE(!(flags & MHADA_LAYER_COSINE) || dtype == MHADA_F32, MHADA_ERR_UNSUPPORTED,
             "%s: the cosine activation (adaDecoder.py:20-34) runs on the MHADA_F32 path only", who);
     REQUIRE(aligned16(fc) && (!fs || aligned16(fs)) && aligned16(fcs) && aligned32(out) && aligned32(ws), MHADA_ERR_ARG,
@@ -227,7 +229,13 @@ int layer_impl(const char* who, int dtype, const void* fc, const void* fs, const
     // (4) out_conv                                                           adaDecoder.py:202-205
     if (w_out) {
         StageTimer timer(MHADA_STAGE_LINEAR, s);
-        if (dtype == MHADA_BF16) {
+        if (dtype == MHADA_BF16 && (flags & MHADA_WOUT_BF16)) {
+            // the caller keeps a bf16 copy of out_conv.weight: no per-call conversion launch
+            GemmDesc g{};
+            g.a = w.heads; g.lda = C; g.w = w_out; g.ldw = C; g.bias = b_out; g.M = B * Nc; g.N = C; g.K = C;
+            g.out_bf16 = out; g.ldo = C;
+            if (int e = launch_gemm_bf16(g, s)) return e;
+        } else if (dtype == MHADA_BF16) {
             if (int e = launch_linear_bf16(w.heads, C, w_out, b_out, B * Nc, C, C, out, C, w.lin_ws, s)) return e;
         } else {
             if (int e = launch_linear_f32(static_cast<const float*>(w.heads), C, w_out, b_out, B * Nc, C, C,
@@ -554,7 +562,7 @@ int mhada_layer_forward_cached(int dtype, const void* fc, const void* fcs, const
     REQUIRE(cache && aligned32(cache), MHADA_ERR_ARG, "mhada_layer_forward_cached: cache must be a 32-byte aligned pointer");
     REQUIRE(Bs == 1 || Bs == B, MHADA_ERR_ARG, "mhada_layer_forward_cached: style batch %d must be 1 or the content batch %d", Bs, B);
     return layer_impl("mhada_layer_forward_cached", dtype, fc, nullptr, fcs, cache, Bs, w_fgh, b_fgh, w_out, b_out, B, Nc, Ns,
-                      C, H, flags & ~MHADA_REUSE_FS_STATS, out, ws, ws_bytes, stream);
+                      C, H, flags & ~MHADA_REUSE_FS_STATS, out, ws, ws_bytes, stream);   /* MHADA_WOUT_BF16 passes through */
 }
 
 int mhada_style_precompute(int dtype, const void* fs, const float* w_fgh, const float* b_fgh, int Bs, int Ns, int C,

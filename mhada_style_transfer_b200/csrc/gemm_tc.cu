@@ -133,6 +133,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (p.resid && row_ok)
                 rrow = p.resid + static_cast<size_t>(p.resid_mod > 0 ? m % p.resid_mod : m) * p.ldr + n0;
             float* frow = (p.out_f32 && row_ok) ? p.out_f32 + static_cast<size_t>(m) * p.ldf + n0 : nullptr;
+            if (p.resid && it + static_cast<int>(gridDim.x) < p.items) {
+                // the NEXT item's residual segment of this lane's row (CW * 4 bytes) is pulled into L2 now: the
+                // register prefetch below only covers one chunk (~L2 latency), not a DRAM round trip (ncu r02: these
+                // epilogues sat on long-scoreboard stalls, 12.6 stalled warps per issue)
+                const int itn = it + gridDim.x;
+                const int mn = (itn / p.ntiles) * GM_BM + row;
+                if (mn < p.M) {
+                    const float* nx = p.resid + static_cast<size_t>(p.resid_mod > 0 ? mn % p.resid_mod : mn) * p.ldr +
+                                      (itn % p.ntiles) * BN + chalf * CW;
+#pragma unroll
+                    for (int i = 0; i < CW * 4 / 128; ++i)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + i * 32));
+                }
+            }
             float4 rv[8];
             if (rrow) {                                       // residual row segment: 128 contiguous bytes per lane,
 #pragma unroll                                                // fetched before the wait for the accumulator

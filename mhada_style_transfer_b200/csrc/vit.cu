@@ -227,10 +227,77 @@ __global__ void __launch_bounds__(BA_WARPS * 32) batch_attn_kernel(const __nv_bf
     }
 }
 
+// B <= 8 (the batch sizes the reference uses: 8 in train_image.py, 1 per frame in the inference scripts): the whole
+// problem of a (token position, head) -- S = Q K^T (8 x 8 x 64), softmax over the 8 images, O = P V (8 x 64 x 8) -- is
+// twelve warp-level mma.sync.m16n8k16 instructions on fragments loaded straight from global memory (rows = images,
+// lane (g, t) reads row g), no shared memory.  The V tile of every 8-channel group is transposed in registers with
+// movmatrix.  (ncu r02 of the SIMT kernel above: issue slots 82 % busy, ~1000 instructions per warp; this one ~110.)
+// The legacy warp MMA is the right tool here: one tcgen05 tile (M = 128) would need 16 token positions x 8 images
+// gathered into one operand, and the kernel is bandwidth-bound (2.1 MFLOP per 4 KB).
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                               uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t movmatrix_trans(uint32_t x) {
+    uint32_t y;
+    asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(y) : "r"(x));
+    return y;
+}
+__global__ void __launch_bounds__(256) batch_attn_mma_kernel(const __nv_bfloat16* __restrict__ qkv, int B, int N, int heads,
+                                                             __nv_bfloat16* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const long long item = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);     // n * heads + h
+    if (item >= static_cast<long long>(N) * heads) return;
+    const int n = static_cast<int>(item / heads), h = static_cast<int>(item % heads);
+    const int D = heads * BA_HD;
+    const int g = lane >> 2, t = lane & 3;
+    const bool row_ok = g < B;
+    const uint32_t* row = reinterpret_cast<const uint32_t*>(qkv + (static_cast<size_t>(row_ok ? g : 0) * N + n) * 3 * D + h * BA_HD);
+    uint32_t qa[8], kb[8], vv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {                      // word i*4 + t of the 32-word (64 x bf16) row of image g
+        qa[i] = row_ok ? __ldg(row + i * 4 + t) : 0u;
+        kb[i] = row_ok ? __ldg(row + D / 2 + i * 4 + t) : 0u;
+        vv[i] = row_ok ? __ldg(row + D + i * 4 + t) : 0u;
+    }
+    // S[g][j] = sum_d Q[g][d] K[j][d]: A rows 0..7 = images (rows 8..15 zero), B columns = images
+    float sc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) mma_bf16_16816(sc, qa[2 * kk], 0u, qa[2 * kk + 1], 0u, kb[2 * kk], kb[2 * kk + 1]);
+    // softmax over the images j = 2t, 2t + 1 of the four lanes of a row group
+    float s0 = (2 * t < B) ? sc[0] * 0.125f : -INFINITY, s1 = (2 * t + 1 < B) ? sc[1] * 0.125f : -INFINITY;
+    float mx = fmaxf(s0, s1);
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    const float e0 = __expf(s0 - mx), e1 = __expf(s1 - mx);
+    float sum = e0 + e1;
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+    const float inv = 1.f / sum;
+    const uint32_t pa = pack_bf16x2(e0 * inv, e1 * inv);            // A fragment of P: row g, k = 2t, 2t + 1 (k >= 8 zero)
+    uint32_t* orow = reinterpret_cast<uint32_t*>(out + (static_cast<size_t>(row_ok ? g : 0) * N + n) * D + h * BA_HD);
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {                   // 8 value channels per step: O[g][nt*8 + ..] = sum_j P[g][j] V[j][..]
+        const uint32_t vb = movmatrix_trans(vv[nt]);   // lane (g, t): V[2t][nt*8 + g], V[2t+1][nt*8 + g]
+        float o[4] = {0.f, 0.f, 0.f, 0.f};
+        mma_bf16_16816(o, pa, 0u, 0u, 0u, vb, 0u);
+        if (row_ok) orow[nt * 4 + t] = pack_bf16x2(o[0], o[1]);
+    }
+}
+
 int launch_batch_attn(const void* qkv, int B, int N, int heads, int hd, void* out, cudaStream_t s) {
     if (hd != BA_HD || B < 1 || B > 32) {
         set_error("batch_attn: head_dim 64 and batch 1..32 are implemented, got head_dim %d, batch %d", hd, B);
         return MHADA_ERR_UNSUPPORTED;
+    }
+    if (B <= 8) {
+        const long long items = static_cast<long long>(N) * heads;
+        batch_attn_mma_kernel<<<static_cast<unsigned>((items + 7) / 8), 256, 0, s>>>(static_cast<const __nv_bfloat16*>(qkv), B, N,
+                                                                                    heads, static_cast<__nv_bfloat16*>(out));
+        count_launch();
+        return check_cuda(cudaGetLastError(), "batch_attn_mma launch");
     }
     constexpr size_t kSmemCap = 200 * 1024;
     const size_t per_warp = static_cast<size_t>(ba_warp_bytes(B));

@@ -328,15 +328,15 @@ class _PackedWeights:
         hit = self.cache.get(dev)
         if hit is not None and hit[0] == key:
             return hit[1]
-        if True:
-            with torch.no_grad():
-                w = torch.stack([torch.stack([m.weight.reshape(m.weight.shape[0], -1) for m in g]) for g in groups])
-                b = torch.stack([torch.stack([m.bias for m in g]) for g in groups])
-                w = w.float().contiguous()
-                b = b.float().contiguous()
-                wo = out_conv.weight.reshape(out_conv.weight.shape[0], -1).float().contiguous() if out_conv is not None else None
-                bo = out_conv.bias.float().contiguous() if out_conv is not None else None
-            self.cache[dev] = (key, (w, b, wo, bo))
+        with torch.no_grad():
+            w = torch.stack([torch.stack([m.weight.reshape(m.weight.shape[0], -1) for m in g]) for g in groups])
+            b = torch.stack([torch.stack([m.bias for m in g]) for g in groups])
+            w = w.float().contiguous()
+            b = b.float().contiguous()
+            wo = out_conv.weight.reshape(out_conv.weight.shape[0], -1).float().contiguous() if out_conv is not None else None
+            bo = out_conv.bias.float().contiguous() if out_conv is not None else None
+            wo16 = wo.to(torch.bfloat16).contiguous() if wo is not None else None
+        self.cache[dev] = (key, (w, b, wo, bo, wo16))
         return self.cache[dev][1]
 
 
@@ -472,7 +472,7 @@ class AdaAttN(nn.Module):
 
     def _forward_nograd(self, fc, fs, fcs):
         dt = _resolve_precision(self.precision, fc.shape[1], fc, fs, fcs, activation=self.activation)
-        w, b, _, _ = self._packed.get([[self.f], [self.g], [self.h]], None)
+        w, b = self._packed.get([[self.f], [self.g], [self.h]], None)[:2]
         tfc, tfs = _token_major(fc, dt), _token_major(fs, dt)
         tfcs = tfc if _same_tensor(fc, fcs) else _token_major(fcs, dt)
         out = _layer_forward(dt, tfc, tfs, tfcs, w, b, None, None, 1, flags=_act_flags(self.activation)).permute(0, 3, 1, 2)
@@ -503,8 +503,13 @@ class AdaAttnMultiHead(nn.Module):
         self.precision = "auto"
         self._packed = _PackedWeights()
 
-    def packed_weights(self):
-        return self._packed.get([self.f_list, self.g_list, self.h_list], self.out_conv)
+    def packed_weights(self, dt=None):
+        """(w_fgh, b_fgh, w_out, b_out) as the ABI takes them; on the bf16 path w_out is the cached bf16 copy
+        (MHADA_WOUT_BF16) when the channel count allows it."""
+        w, b, wo, bo, wo16 = self._packed.get([self.f_list, self.g_list, self.h_list], self.out_conv)
+        if dt == torch.bfloat16 and wo16 is not None and wo16.shape[0] % 128 == 0:
+            return w, b, wo16, bo, _lib.WOUT_BF16
+        return w, b, wo, bo, 0
 
     def _check_shapes(self, fc, fs, fcs):
         _check_layer_shapes(self.num_heads * self.head_dim, fc, fs, fcs)
@@ -512,19 +517,19 @@ class AdaAttnMultiHead(nn.Module):
     def forward_tokens(self, dt, tfc, tfs, tfcs, out=None, reuse_fs_stats: bool = False):
         """Token-major entry used by the transformer to chain layers without layout round trips.
         reuse_fs_stats: `tfs` is the tensor the previous layer call on this stream used (same workspace)."""
-        w, b, wo, bo = self.packed_weights()
+        w, b, wo, bo, wflag = self.packed_weights(dt)
         return _layer_forward(dt, tfc, tfs, tfcs, w, b, wo, bo, self.num_heads, out,
-                              (_lib.REUSE_FS_STATS if reuse_fs_stats else 0) | _act_flags(self.activation))
+                              (_lib.REUSE_FS_STATS if reuse_fs_stats else 0) | _act_flags(self.activation) | wflag)
 
     def precompute_style_tokens(self, dt, tfs) -> torch.Tensor:
         """K, V', mu_v of this layer for token-major style features (one uint8 cache buffer)."""
-        w, b, _, _ = self.packed_weights()
+        w, b = self.packed_weights()[:2]
         return _style_precompute(dt, tfs, w, b, self.num_heads)
 
     def forward_tokens_cached(self, dt, tfc, tfcs, cache: torch.Tensor, style_batch: int, style_tokens: int):
-        w, b, wo, bo = self.packed_weights()
+        w, b, wo, bo, wflag = self.packed_weights(dt)
         return _layer_forward_cached(dt, tfc, tfcs, cache, style_batch, style_tokens, w, b, wo, bo, self.num_heads,
-                                     _act_flags(self.activation))
+                                     _act_flags(self.activation) | wflag)
 
     def _stacked_params(self):
         d = self.head_dim
