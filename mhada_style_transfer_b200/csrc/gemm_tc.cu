@@ -16,7 +16,9 @@
 //               32 columns prefetched while the current ones are processed) (ReLU) ->
 //                 bf16 result: packed into a 128B-swizzled staging slab (32 rows x 64 columns per warp, two slabs)
 //                              and written with ONE TMA STORE per slab (cp.async.bulk.tensor, rows past M clipped);
-//                 f32 result (the residual stream): 256-bit stores, 128 contiguous bytes per lane.
+//                 f32 result (the residual stream): the residual tile comes IN by TMA (one 32 x 32 tile ahead), the sum
+//                              goes OUT by TMA store from the same slab (thread-per-row global accesses made these
+//                              epilogues L1-tag-bound).
 // BN = 256 keeps the shared-memory operand traffic of the SS-mode MMAs at 96 B/clk (a 128 x 128 tile needs the
 // full 128 B/clk of the SM).  Compute-bound for K >= 512: 2*M*N*K FLOP; HBM bytes 2*M*K + 2*N*K + (2|4|6)*M*N.
 #include "common.h"
@@ -31,9 +33,12 @@ struct GemmParams {
     const float* bias;     // [N] or nullptr
     const float* resid;    // f32 [*, ldr] or nullptr
     float* out_f32;        // f32 [M, ldf] or nullptr
+    __nv_bfloat16* out_bf16;   // bf16 [M, ldo] (direct stores when an f32 result is written too)
+    int ldo;
     int ldr, resid_mod;    // residual row = m % resid_mod when resid_mod > 0 (positional table), else m
     int ldf;
     int has_bf16;          // bf16 result through the tensor map tmC
+    int resid_tma;         // residual tiles come through tmR (row-periodic tables only when resid_mod % 32 == 0)
     int relu;
     int M, ktiles, ntiles, items;
 };
@@ -41,11 +46,13 @@ struct GemmParams {
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(GM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmF,
+               const __grid_constant__ CUtensorMap tmR, const GemmParams p) {
     constexpr uint32_t A_BYTES = GM_BM * GM_BK * 2, B_BYTES = BN * GM_BK * 2, STAGE = A_BYTES + B_BYTES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     __shared__ uint64_t full[STAGES], empty[STAGES], acc_full[2], acc_empty[2];
+    __shared__ uint64_t rbar[GM_EPI_WARPS][2];       // residual tile landed in slab s of epilogue warp w
     __shared__ uint32_t tmem_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -54,6 +61,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         if (p.has_bf16) tma_prefetch_desc(&tmC);
+        if (p.out_f32) tma_prefetch_desc(&tmF);
+        if (p.resid_tma) tma_prefetch_desc(&tmR);
     }
     if (warp == 1) {
         if (lane == 0) {
@@ -64,6 +73,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int u = 0; u < 2; ++u) {
                 mbar_init(&acc_full[u], 1);
                 mbar_init(&acc_empty[u], GM_EPI_WARPS);      // one arrive per epilogue warp
+            }
+            for (int w = 0; w < GM_EPI_WARPS; ++w) {
+                mbar_init(&rbar[w][0], 1);
+                mbar_init(&rbar[w][1], 1);
             }
             fence_mbar_init();
         }
@@ -123,35 +136,106 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint8_t* stg = smem + STAGES * STAGE + (warp - 2) * GM_STG_WARP;      // 1024-byte aligned slabs
         const uint32_t swz = static_cast<uint32_t>(lane & 7);
         int nstore = 0;                                                        // TMA stores issued by this warp
+        if (p.out_f32) {
+            // ---- f32 result (the residual stream): BOTH directions go through the staging slabs with TMA.  A
+            // thread-per-row access touches 32 different 128-byte lines per warp instruction: the residual loads and
+            // 256-bit stores of a 128 x 256 tile cost ~13 k L1 tag cycles (6.8 us against 2.1 us of MMAs; ncu r02:
+            // long-scoreboard + LSU-throttle stalls, 58 us for out_proj against 24 us for the bf16-only out_conv).
+            // The residual tile of the NEXT 32-column chunk (or of the next work item's first chunk) is in flight
+            // while the current one is processed; the sum is written back into the same slab and stored from there.
+            uint64_t* rb = rbar[warp - 2];
+            constexpr int NCH = CW / 32;
+            const int my_items = (p.items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+            const int total = my_items * NCH;                                   // chunks this warp will process
+            auto coords = [&](int k, int& col, int& rowbase) {                   // chunk k -> output column / row of its tile
+                const int it = blockIdx.x + (k / NCH) * gridDim.x;
+                col = (it % p.ntiles) * BN + chalf * CW + (k % NCH) * 32;
+                rowbase = (it / p.ntiles) * GM_BM + quarter * 32;
+            };
+            auto issue_resid = [&](int k) {                                      // lane 0 only
+                int col, rowbase;
+                coords(k, col, rowbase);
+                uint8_t* slab = stg + (k & 1) * 4096;
+                mbar_arrive_expect_tx(&rb[k & 1], 4096);
+                tma_load_2d(slab, &tmR, &rb[k & 1], col, p.resid_mod > 0 ? rowbase % p.resid_mod : rowbase);
+            };
+            if (p.resid_tma && total > 0 && lane == 0) issue_resid(0);
+            int k = 0;
+            for (int it = blockIdx.x; it < p.items; it += gridDim.x) {
+                const int n = k / NCH;
+                const int m0 = (it / p.ntiles) * GM_BM, n0 = (it % p.ntiles) * BN + chalf * CW;
+                const int m = m0 + row;
+                const bool row_ok = m < p.M;
+                const int u = n & 1;
+                const float* rrow = nullptr;                                     // direct residual loads (table rows that wrap)
+                if (p.resid && !p.resid_tma && row_ok)
+                    rrow = p.resid + static_cast<size_t>(p.resid_mod > 0 ? m % p.resid_mod : m) * p.ldr + n0;
+                mbar_wait(&acc_full[u], (n >> 1) & 1);
+                tc_fence_after();
+#pragma unroll 1
+                for (int c = 0; c < CW; c += 32, ++k) {
+                    uint8_t* slab = stg + (k & 1) * 4096;
+                    // the other slab was the source of the previous chunk's store: once that store has read it, the
+                    // next chunk's residual may land there
+                    if (lane == 0) {
+                        tma_store_wait_read<0>();
+                        if (p.resid_tma && k + 1 < total) issue_resid(k + 1);
+                    }
+                    uint32_t r[32];
+                    tmem_ld_x32(tmem_addr(tmem, quarter * 32, u * BN + chalf * CW + c), r);
+                    tmem_wait_ld();
+                    if (c + 32 == CW) {                       // accumulator drained: the next-but-one item may start
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&acc_empty[u]);
+                    }
+                    float v[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) + (p.bias ? __ldg(p.bias + n0 + c + i) : 0.f);
+                    if (p.resid_tma) {
+                        mbar_wait(&rb[k & 1], (k >> 1) & 1);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const float4 x = *reinterpret_cast<const float4*>(slab + lane * 128 + ((static_cast<uint32_t>(q) ^ swz) << 4));
+                            v[4 * q] += x.x; v[4 * q + 1] += x.y; v[4 * q + 2] += x.z; v[4 * q + 3] += x.w;
+                        }
+                    } else if (rrow) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const float4 x = __ldg(reinterpret_cast<const float4*>(rrow + c) + q);
+                            v[4 * q] += x.x; v[4 * q + 1] += x.y; v[4 * q + 2] += x.z; v[4 * q + 3] += x.w;
+                        }
+                    }
+                    if (p.relu) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+                    }
+                    __syncwarp();                             // every lane has read its residual row (and lane 0 has waited)
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        *reinterpret_cast<float4*>(slab + lane * 128 + ((static_cast<uint32_t>(q) ^ swz) << 4)) =
+                            make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&tmF, slab, n0 + c, m0 + quarter * 32);
+                        tma_store_commit();
+                    }
+                    if (p.has_bf16 && row_ok) {               // the rounded copy (fc2 -> feature map): 64 bytes per lane
+                        uint32_t o[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) o[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+                        __nv_bfloat16* dst = p.out_bf16 + static_cast<size_t>(m) * p.ldo + n0 + c;
+                        st_global_256(dst, o);
+                        st_global_256(dst + 16, o + 8);
+                    }
+                }
+            }
+        } else {
         int n = 0;
         for (int it = blockIdx.x; it < p.items; it += gridDim.x, ++n) {
             const int m0 = (it / p.ntiles) * GM_BM, n0 = (it % p.ntiles) * BN + chalf * CW;
-            const int m = m0 + row;
-            const bool row_ok = m < p.M;
             const int u = n & 1;
-            const float* rrow = nullptr;
-            if (p.resid && row_ok)
-                rrow = p.resid + static_cast<size_t>(p.resid_mod > 0 ? m % p.resid_mod : m) * p.ldr + n0;
-            float* frow = (p.out_f32 && row_ok) ? p.out_f32 + static_cast<size_t>(m) * p.ldf + n0 : nullptr;
-            if (p.resid && it + static_cast<int>(gridDim.x) < p.items) {
-                // the NEXT item's residual segment of this lane's row (CW * 4 bytes) is pulled into L2 now: the
-                // register prefetch below only covers one chunk (~L2 latency), not a DRAM round trip (ncu r02: these
-                // epilogues sat on long-scoreboard stalls, 12.6 stalled warps per issue)
-                const int itn = it + gridDim.x;
-                const int mn = (itn / p.ntiles) * GM_BM + row;
-                if (mn < p.M) {
-                    const float* nx = p.resid + static_cast<size_t>(p.resid_mod > 0 ? mn % p.resid_mod : mn) * p.ldr +
-                                      (itn % p.ntiles) * BN + chalf * CW;
-#pragma unroll
-                    for (int i = 0; i < CW * 4 / 128; ++i)
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + i * 32));
-                }
-            }
-            float4 rv[8];
-            if (rrow) {                                       // residual row segment: 128 contiguous bytes per lane,
-#pragma unroll                                                // fetched before the wait for the accumulator
-                for (int i = 0; i < 8; ++i) rv[i] = __ldg(reinterpret_cast<const float4*>(rrow) + i);
-            }
             mbar_wait(&acc_full[u], (n >> 1) & 1);
             tc_fence_after();
 #pragma unroll 1
@@ -167,25 +251,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 float v[32];
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) + (p.bias ? __ldg(p.bias + n0 + c + i) : 0.f);
-                if (rrow) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        v[4 * i] += rv[i].x; v[4 * i + 1] += rv[i].y; v[4 * i + 2] += rv[i].z; v[4 * i + 3] += rv[i].w;
-                    }
-                    if (c + 32 < CW) {                        // next chunk's residual in flight behind the math / stores
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) rv[i] = __ldg(reinterpret_cast<const float4*>(rrow + c + 32) + i);
-                    }
-                }
                 if (p.relu) {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
                 }
-                if (frow) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) st_global_256(frow + c + 8 * i, reinterpret_cast<const uint32_t*>(v + 8 * i));
-                }
-                if (p.has_bf16) {
+                {
                     const int half = (c >> 5) & 1;            // which 32-column half of the 64-column slab
                     uint8_t* slab = stg + (nstore & 1) * (32 * 128);
                     if (half == 0) {
@@ -215,6 +285,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
             }
         }
+        }
         if (lane == 0) tma_store_wait<0>();
     }
     tc_fence_before();
@@ -237,7 +308,7 @@ static int launch_gemm_bn(const GemmDesc& d, cudaStream_t s) {
         uint32_t box[2] = {GM_BK, BN};
         if (int e = make_tmap_bf16(&tmB, d.w, 2, dims, str, box)) return e;
     }
-    if (d.out_bf16) {
+    if (d.out_bf16 && !d.out_f32) {
         uint64_t dims[2] = {static_cast<uint64_t>(d.N), static_cast<uint64_t>(d.M)};
         uint64_t str[1] = {static_cast<uint64_t>(d.ldo) * 2};
         uint32_t box[2] = {64, 32};
@@ -245,7 +316,23 @@ static int launch_gemm_bn(const GemmDesc& d, cudaStream_t s) {
     } else {
         tmC = tmA;      // never dereferenced
     }
+    CUtensorMap tmF = tmA, tmR = tmA;
+    if (d.out_f32) {
+        uint64_t dims[2] = {static_cast<uint64_t>(d.N), static_cast<uint64_t>(d.M)};
+        uint64_t str[1] = {static_cast<uint64_t>(d.ldf) * 4};
+        uint32_t box[2] = {32, 32};
+        if (int e = make_tmap(&tmF, d.out_f32, 4, 2, dims, str, box)) return e;
+    }
+    // residual tiles by TMA when the 32-row slabs never wrap around a row-periodic table
+    const bool resid_tma = d.out_f32 && d.resid && (d.resid_mod == 0 || d.resid_mod % 32 == 0) && d.ldr % 4 == 0;
+    if (resid_tma) {
+        uint64_t dims[2] = {static_cast<uint64_t>(d.N), static_cast<uint64_t>(d.resid_mod > 0 ? d.resid_mod : d.M)};
+        uint64_t str[1] = {static_cast<uint64_t>(d.ldr) * 4};
+        uint32_t box[2] = {32, 32};
+        if (int e = make_tmap(&tmR, d.resid, 4, 2, dims, str, box)) return e;
+    }
     GemmParams p;
+    p.out_bf16 = static_cast<__nv_bfloat16*>(d.out_bf16); p.ldo = d.ldo; p.resid_tma = resid_tma ? 1 : 0;
     p.bias = d.bias; p.resid = d.resid; p.out_f32 = d.out_f32;
     p.ldr = d.ldr; p.resid_mod = d.resid_mod; p.ldf = d.ldf;
     p.has_bf16 = d.out_bf16 ? 1 : 0; p.relu = d.relu;
@@ -256,7 +343,7 @@ static int launch_gemm_bn(const GemmDesc& d, cudaStream_t s) {
     if (int e = smem_attr_once(once, reinterpret_cast<const void*>(gemm_tc_kernel<BN, STAGES>), smem, "gemm smem attr")) return e;
     const int n_sm = sm_count();
     const int grid = p.items < n_sm ? p.items : n_sm;
-    gemm_tc_kernel<BN, STAGES><<<grid, GM_THREADS, smem, s>>>(tmA, tmB, tmC, p);
+    gemm_tc_kernel<BN, STAGES><<<grid, GM_THREADS, smem, s>>>(tmA, tmB, tmC, tmF, tmR, p);
     count_launch();
     return check_cuda(cudaGetLastError(), "gemm_tc launch");
 }

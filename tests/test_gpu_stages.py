@@ -252,7 +252,9 @@ def _attn_bf16_case(B, H, Nc, Ns, gain, ramp, d):
 @pytest.mark.parametrize("B,H,W,Cin,Cout,padded", [
     (1, 5, 7, 512, 256, 0), (2, 10, 14, 256, 256, 1), (1, 20, 28, 256, 128, 0), (1, 40, 56, 128, 128, 1),
     (1, 40, 56, 128, 64, 0), (2, 80, 112, 64, 64, 0), (1, 3, 3, 64, 64, 1), (1, 2, 2, 64, 128, 1), (1, 2, 9, 128, 256, 1),
-    (3, 64, 64, 512, 256, 0), (1, 128, 128, 256, 256, 1), (1, 130, 140, 64, 64, 1)])
+    (3, 64, 64, 512, 256, 0), (1, 128, 128, 256, 256, 1), (1, 130, 140, 64, 64, 1),
+    # W > 64 with Cout 64 / 128: the halo variant (one box per (ky, channel chunk) serves the three kx taps)
+    (1, 72, 200, 128, 128, 1), (2, 33, 129, 256, 128, 0), (1, 7, 65, 192, 64, 1), (1, 256, 256, 128, 64, 0)])
 def test_conv3x3_tc(B, H, W, Cin, Cout, padded):
     """mhada_conv3x3 (tcgen05 implicit GEMM) against the oracle's ReflectionPad2d(1) + Conv2d(3x3) + ReLU on the same
     bf16-rounded input and weights; with `padded` the result must come back with its own reflection ring."""
