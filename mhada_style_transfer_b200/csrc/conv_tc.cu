@@ -205,8 +205,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 // the L2 -> shared-memory traffic and the nine taps re-read it nine times (ncu r02: 38-41 % tensor-pipe activity at
 // Cout = 64).  Here a k-step is (ky, 64-channel chunk): ONE box {64 channels, 128 + 2 pixels, MT rows} is loaded and
 // serves the three kx taps -- the tap shifts the operand by kx pixel rows (128 B each) inside the swizzled tile: the
-// descriptor start address moves by kx * 128 B and its base-offset field carries the phase of the 8-row swizzle
-// pattern ((address >> 7) & 7), which is what that field exists for.  Sub-tile = one image row of 128 pixels.
+// descriptor start address simply moves by kx * 128 B.  MEASURED (r2, tests/test_gpu_stages.py::test_conv3x3_tc): the
+// 128B swizzle of a K-major operand is a function of the ABSOLUTE shared-memory address (bits [4,7) ^= bits [7,10)),
+// exactly what TMA wrote, so a start that is 128-byte but not 1024-byte aligned needs NO base-offset field; setting the
+// descriptor's base offset to (address >> 7) & 7 applies the phase twice and gives wrong results (MHADA_CONV_HALO=2
+// keeps that variant for the record).  Sub-tile = one image row of 128 pixels.
 constexpr int CVH_TW = 128, CVH_ROW = CVH_TW + 2;
 __host__ __device__ constexpr uint32_t cvh_a_bytes(int MT) { return (static_cast<uint32_t>(MT) * CVH_ROW * 128u + 1023u) & ~1023u; }
 __device__ __forceinline__ uint64_t make_smem_desc_rowshift(uint32_t smem_addr, uint32_t sbo_bytes, int with_base_offset) {
@@ -401,13 +404,14 @@ int launch_conv3x3_tc(const void* xp, const void* w, const float* bias, int B, i
         set_error("conv3x3_tc: implemented for Cin %% 64 == 0 and Cout in {64, 128, 256}, got %d -> %d", Cin, Cout);
         return MHADA_ERR_UNSUPPORTED;
     }
-    // MHADA_CONV_HALO: 0 = off, 1 = on with the descriptor base-offset field (default), 2 = on without it (diagnostic)
+    // MHADA_CONV_HALO (development switch): 0 = halo variant off, 1 = on (default), 2 = on WITH the descriptor
+    // base-offset field set (measured wrong, see conv3x3_halo_kernel)
     static const int halo_mode = [] {
         const char* e = getenv("MHADA_CONV_HALO");
         return e ? atoi(e) : 1;
     }();
-    if (halo_mode && W > 64 && Cout == 128) return launch_conv_halo<128, 2>(xp, w, bias, B, H, W, Cin, relu, out_padded, y, halo_mode == 1, s);
-    if (halo_mode && W > 64 && Cout == 64) return launch_conv_halo<64, 2>(xp, w, bias, B, H, W, Cin, relu, out_padded, y, halo_mode == 1, s);
+    if (halo_mode && W > 64 && Cout == 128) return launch_conv_halo<128, 2>(xp, w, bias, B, H, W, Cin, relu, out_padded, y, halo_mode == 2, s);
+    if (halo_mode && W > 64 && Cout == 64) return launch_conv_halo<64, 2>(xp, w, bias, B, H, W, Cin, relu, out_padded, y, halo_mode == 2, s);
     if (Cout == 256) return launch_conv_bn<256, 4>(xp, w, bias, B, H, W, Cin, relu, out_padded, y, s);
     if (Cout == 128) return launch_conv_bn<128, 4>(xp, w, bias, B, H, W, Cin, relu, out_padded, y, s);
     return launch_conv_bn<64, 3>(xp, w, bias, B, H, W, Cin, relu, out_padded, y, s);
