@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define MHADA_ABI_VERSION 5
+#define MHADA_ABI_VERSION 6
 
 #if defined(__GNUC__)
 #define MHADA_API __attribute__((visibility("default")))
@@ -257,6 +257,24 @@ MHADA_API int mhada_gemm_bf16(const void* x, int lda, const void* w, int ldw, co
 MHADA_API int mhada_layernorm(const float* x, int M, int C, const float* gamma, const float* beta, float eps,
                               void* y_bf16, mhada_stream_t stream);
 MHADA_API int mhada_batch_attn(const void* qkv, int B, int N, int heads, int hd, void* out, mhada_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (8) AdaAttnForLoss on the tensor cores -- replaces AdaAttnForLoss.forward, MHAdaSTr/network/adaDecoder.py:53-81
+ *     (lossfn.py:26-34 calls it on concatenated VGG features: d_qk = 448 / 960 / 1472, d_v = 256 / 512):
+ *         Q = IN(c_1x), K = IN(s_1x), V = s_x;  A = softmax(Q K^T);  out = sqrt(max(A V^2 - (A V)^2, 1e-6)) * IN(c_x) + A V
+ *     All tensors bf16, token-major with pitch = their channel count: c_x, out [B, Nc, dv]; s_x [B, Ns, dv];
+ *     c_1x [B, Nc, dqk]; s_1x [B, Ns, dqk].  dqk % 64 == 0, dv % 64 == 0.  ws: mhada_forloss_workspace(...) bytes.
+ *     (mhada_attn with MHADA_F32 remains the reference-arithmetic path for any dqk / dv.)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct mhada_forloss_args {
+    int B, Nc, Ns, dqk, dv;
+    const void *c_x, *s_x, *c_1x, *s_1x;
+    void* out;
+    void* ws;
+    size_t ws_bytes;
+} mhada_forloss_args;
+MHADA_API size_t mhada_forloss_workspace(int B, int Nc, int Ns, int dqk, int dv);
+MHADA_API int mhada_forloss_forward(const mhada_forloss_args* args, mhada_stream_t stream);
 
 /* Number of kernel launches the last mhada_layer_forward on this thread issued (bench bookkeeping). */
 MHADA_API int mhada_last_launch_count(void);

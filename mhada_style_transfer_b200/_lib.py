@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libmhada_b200.so")
 
 F32, BF16, U8 = 0, 1, 2
-ABI_VERSION = 5
+ABI_VERSION = 6
 VIT_MAX_LAYERS = 8
 PROJ_Q, PROJ_KV = 1, 2
 REUSE_FS_STATS = 1
@@ -55,6 +55,13 @@ class VitArgs(ctypes.Structure):
     ]
 
 
+class ForlossArgs(ctypes.Structure):
+    """mhada_forloss_args (include/mhada_b200.h)."""
+    _fields_ = [("B", c_int), ("Nc", c_int), ("Ns", c_int), ("dqk", c_int), ("dv", c_int),
+                ("c_x", c_void_p), ("s_x", c_void_p), ("c_1x", c_void_p), ("s_1x", c_void_p), ("out", c_void_p),
+                ("ws", c_void_p), ("ws_bytes", c_size_t)]
+
+
 # name -> (restype, argtypes); kept in one table so tests can check the export list against the header
 SIGNATURES = {
     "mhada_abi_version": (c_int, []),
@@ -77,6 +84,8 @@ SIGNATURES = {
     "mhada_linear_workspace": (c_size_t, [c_int, c_int, c_int]),
     "mhada_linear": (c_int, [c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int,
                              c_void_p, c_size_t, c_void_p]),
+    "mhada_forloss_workspace": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    "mhada_forloss_forward": (c_int, [POINTER(ForlossArgs), c_void_p]),
     "mhada_vit_workspace": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "mhada_vit_forward": (c_int, [POINTER(VitArgs), c_void_p]),
     "mhada_patch_im2col": (c_int, [c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),

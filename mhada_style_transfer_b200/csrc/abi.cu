@@ -512,6 +512,29 @@ int mhada_conv3x3_small(int dtype, const void* x, const float* w, const float* b
     return launch_conv3x3_small(x, w, bias, B, H, W, Cin, Cout, relu, y, static_cast<cudaStream_t>(stream));
 }
 
+size_t mhada_forloss_workspace(int B, int Nc, int Ns, int dqk, int dv) {
+    if (B <= 0 || Nc <= 0 || Ns <= 0 || dqk <= 0 || dv <= 0) return 0;
+    return forloss_workspace(B, Nc, Ns, dqk, dv);
+}
+
+int mhada_forloss_forward(const mhada_forloss_args* a, mhada_stream_t stream) {
+    g_launches = 0;
+    REQUIRE(a, MHADA_ERR_ARG, "mhada_forloss_forward: null args");
+    REQUIRE(a->c_x && a->s_x && a->c_1x && a->s_1x && a->out && a->ws, MHADA_ERR_ARG, "mhada_forloss_forward: null pointer");
+    REQUIRE(a->B > 0 && a->Nc > 0 && a->Ns > 0 && a->dqk > 0 && a->dv > 0, MHADA_ERR_ARG, "mhada_forloss_forward: bad sizes");
+    REQUIRE(a->dqk % 64 == 0 && a->dv % 64 == 0, MHADA_ERR_UNSUPPORTED,
+            "mhada_forloss_forward: the tensor-core path needs dqk %% 64 == 0 and dv %% 64 == 0, got %d / %d (use mhada_attn, MHADA_F32)",
+            a->dqk, a->dv);
+    REQUIRE(aligned16(a->c_x) && aligned16(a->s_x) && aligned16(a->c_1x) && aligned16(a->s_1x) && aligned16(a->out) && aligned32(a->ws),
+            MHADA_ERR_ARG, "mhada_forloss_forward: misaligned pointer");
+    REQUIRE(a->ws_bytes >= forloss_workspace(a->B, a->Nc, a->Ns, a->dqk, a->dv), MHADA_ERR_WORKSPACE,
+            "mhada_forloss_forward: workspace %zu < %zu", a->ws_bytes, forloss_workspace(a->B, a->Nc, a->Ns, a->dqk, a->dv));
+    if (int e = device_check()) return e;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    StageTimer timer(MHADA_STAGE_ATTN, s);
+    return forloss_forward(*a, s);
+}
+
 int mhada_conv3x3(int dtype, const void* xp, const void* w, const float* bias, int B, int H, int W, int Cin, int Cout, int relu,
                   int out_padded, void* y, mhada_stream_t stream) {
     g_launches = 0;

@@ -109,6 +109,10 @@ int launch_batch_attn(const void* qkv, int B, int N, int heads, int hd, void* ou
 size_t vit_workspace(int B, int N, int D, int F, int K0);
 int vit_forward(const mhada_vit_args& a, cudaStream_t s);
 
+// AdaAttnForLoss on the tensor cores (forloss_tc.cu)
+size_t forloss_workspace(int B, int Nc, int Ns, int dqk, int dv);
+int forloss_forward(const mhada_forloss_args& a, cudaStream_t s);
+
 // decoder blocks 0..7: reflect-padded NHWC input -> conv3x3 + bias + ReLU on tcgen05 (conv_tc.cu)
 int launch_conv3x3_tc(const void* xp, const void* w, const float* bias, int B, int H, int W, int Cin, int Cout, int relu,
                       int out_padded, void* y, cudaStream_t s);

@@ -388,6 +388,9 @@ class AdaAttnForLoss(nn.Module):
         self.norm_k = nn.InstanceNorm2d(qk_dim, affine=False)
         self.norm_v = nn.InstanceNorm2d(v_dim, affine=False)
         self.activation = _make_activation(activation)
+        self.precision = "auto"        # "fp32": SIMT kernels (the reference's arithmetic, any widths); "bf16": tensor cores
+                                       # (mhada_forloss_forward; softmax, widths multiples of 64); "auto": bf16 for
+                                       # bf16 / fp16 inputs when the shape allows it, else fp32
 
     def forward(self, c_x, s_x, c_1x, s_1x):
         _require_cuda(c_x, s_x, c_1x, s_1x)
@@ -398,9 +401,46 @@ class AdaAttnForLoss(nn.Module):
             return _ForLossFn.apply(self._forward_nograd, _is_cosine(self.activation), c_x, s_x, c_1x, s_1x)
         return self._forward_nograd(c_x, s_x, c_1x, s_1x)
 
+    def _tc_ok(self, c_x, c_1x) -> bool:
+        return (not _is_cosine(self.activation)) and c_x.shape[1] % 64 == 0 and c_1x.shape[1] % 64 == 0
+
+    def _forward_tc(self, c_x, s_x, c_1x, s_1x):
+        """bf16 tensor-core path (forloss_tc.cu): logits of one image materialised, contractions on the token GEMM."""
+        L = _lib.lib()
+        dt = torch.bfloat16
+        tq, tk, tv, tx = (_token_major(t, dt) for t in (c_1x, s_1x, s_x, c_x))
+        B, h, w, dv = tx.shape
+        dqk = tq.shape[3]
+        Nc, Ns = tq.shape[1] * tq.shape[2], tk.shape[1] * tk.shape[2]
+        if tv.shape[1] * tv.shape[2] != Ns or h * w != Nc or tk.shape[3] != dqk or tv.shape[3] != dv:
+            raise RuntimeError("AdaAttnForLoss: inconsistent shapes")
+        if not (tq.shape[0] == tk.shape[0] == tv.shape[0] == B):
+            raise RuntimeError(f"AdaAttnForLoss: batch sizes differ: c_x {B}, s_x {tv.shape[0]}, c_1x {tq.shape[0]}, "
+                               f"s_1x {tk.shape[0]}")
+        out = torch.empty((B, h, w, dv), dtype=dt, device=tx.device)
+        ws = _workspace(tx.device, L.mhada_forloss_workspace(B, Nc, Ns, dqk, dv))
+        a = _lib.ForlossArgs()
+        a.B, a.Nc, a.Ns, a.dqk, a.dv = B, Nc, Ns, dqk, dv
+        a.c_x, a.s_x, a.c_1x, a.s_1x, a.out = tx.data_ptr(), tv.data_ptr(), tq.data_ptr(), tk.data_ptr(), out.data_ptr()
+        a.ws, a.ws_bytes = ws.data_ptr(), ws.numel()
+        with torch.cuda.device(tx.device):
+            _lib.check("mhada_forloss_forward", L.mhada_forloss_forward(ctypes.byref(a), _stream()))
+        res = out.permute(0, 3, 1, 2)
+        return res if res.dtype == c_x.dtype else res.to(c_x.dtype)
+
     def _forward_nograd(self, c_x, s_x, c_1x, s_1x):
         if any(t.dim() != 4 for t in (c_x, s_x, c_1x, s_1x)):
             raise RuntimeError("AdaAttnForLoss: inputs must be (b, c, h, w)")
+        if self.precision not in ("auto", "fp32", "bf16"):
+            raise ValueError(f"Unknown precision: {self.precision}")
+        if self.precision == "bf16":
+            if not self._tc_ok(c_x, c_1x):
+                raise NotImplementedError("AdaAttnForLoss: the tensor-core path needs the softmax activation and channel "
+                                          "counts that are multiples of 64; use precision='fp32'")
+            return self._forward_tc(c_x, s_x, c_1x, s_1x)
+        if self.precision == "auto" and self._tc_ok(c_x, c_1x) and \
+                all(t.dtype in (torch.bfloat16, torch.float16) for t in (c_x, s_x, c_1x, s_1x)):
+            return self._forward_tc(c_x, s_x, c_1x, s_1x)
         L = _lib.lib()
         dt = torch.float32
         tq, tk, tv, tx = (_token_major(t, dt) for t in (c_1x, s_1x, s_x, c_x))

@@ -138,6 +138,43 @@ def test_forloss_fp32(case, golden_index):
     assert e["max_abs"] <= fp32_tol(golden_index[case["name"]]["ref32_vs_ref64"]), e
 
 
+@pytest.mark.parametrize("case", [c for c in cases.FORLOSS_CASES if "activation" not in c], ids=lambda c: c["name"])
+def test_forloss_bf16_tensor_core_path(case, golden_index):
+    """AdaAttnForLoss on the tensor cores (mhada_forloss_forward: logits materialised per image, every contraction on the
+    tcgen05 token GEMM) against the reference goldens of the three VGG shapes (d_qk 448 / 960 / 1472)."""
+    args = [dev(a) for a in cases.forloss_inputs(case)]
+    m = M.AdaAttnForLoss(case["v"], case["qk"]).to(DEV).eval()
+    m.precision = "bf16"
+    with torch.no_grad():
+        out = m(*args)
+        auto = M.AdaAttnForLoss(case["v"], case["qk"]).to(DEV).eval()(*[a.bfloat16() for a in args])      # bf16 in -> same path
+    assert out.dtype == torch.float32 and auto.dtype == torch.bfloat16
+    e = O.errors(out.cpu().numpy(), load_golden(case["name"])["out"])
+    ntok = case["hsws"][0] * case["hsws"][1]
+    assert e["max_abs_rel"] <= (BF16_REL if ntok >= 100 else 4e-2), e
+    assert O.errors(auto.float().cpu().numpy(), load_golden(case["name"])["out"])["max_abs_rel"] <= 4e-2
+
+
+def test_forloss_bf16_vs_oracle_at_training_size():
+    """relu3_1 shape at 1024 x 900 tokens (ragged key count -> padded key tile), batch 2, against the float64 oracle."""
+    case = dict(B=2, v=256, qk=448, hw=(32, 32), hsws=(30, 30), seed=45)
+    args = cases.forloss_inputs(case)
+    want = O.ada_attn_for_loss(*args)
+    m = M.AdaAttnForLoss(256, 448).to(DEV).eval()
+    m.precision = "bf16"
+    with torch.no_grad():
+        got = m(*[dev(a) for a in args])
+        m.precision = "fp32"
+        ref32 = m(*[dev(a) for a in args])
+    e = O.errors(got.cpu().numpy(), want)
+    assert e["max_abs_rel"] <= BF16_REL and e["fro_rel"] <= 1e-2, e
+    assert O.errors(ref32.cpu().numpy(), want)["max_abs"] <= FP32_MAX_ABS
+    with torch.no_grad(), pytest.raises(NotImplementedError):
+        mc = M.AdaAttnForLoss(256, 448, "cosine").to(DEV)
+        mc.precision = "bf16"
+        mc(*[dev(a) for a in args])
+
+
 @pytest.mark.parametrize("case", cases.DECODER_CASES, ids=lambda c: c["name"])
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 2e-2)])
 def test_decoder_vs_reference_golden(case, dtype, tol, golden_index):

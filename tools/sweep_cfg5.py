@@ -55,10 +55,12 @@ def main():
         m = M.AdaAttnForLoss(v, qk).to(dev).eval()
         cx, sx = (torch.randn(8, v, n_side, n_side, device=dev) for _ in range(2))
         c1, s1 = (torch.randn(8, qk, n_side, n_side, device=dev) for _ in range(2))
-        with torch.no_grad():
-            ms = best_ms(lambda: m(cx, sx, c1, s1))
-        print(json.dumps({"case": "forloss", "level": name, "v_dim": v, "qk_dim": qk, "tokens": n_side * n_side, "batch": 8,
-                          "precision": "fp32", "ms": round(ms, 4)}), flush=True)
+        for prec in ("fp32", "bf16"):
+            m.precision = prec
+            with torch.no_grad():
+                ms = best_ms(lambda: m(cx, sx, c1, s1))
+            print(json.dumps({"case": "forloss", "level": name, "v_dim": v, "qk_dim": qk, "tokens": n_side * n_side, "batch": 8,
+                              "precision": prec, "ms": round(ms, 4)}), flush=True)
     # (3) train step: batch 8 of 256 x 256 images -> 32 x 32 tokens; kernels forward, recompute backward, Adam
     m = set_precision(M.AdaAttnTransformerMultiHead().to(dev).train(), "bf16")
     opt = torch.optim.Adam(m.parameters(), lr=1e-4)
