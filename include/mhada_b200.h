@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define MHADA_ABI_VERSION 6
+#define MHADA_ABI_VERSION 7
 
 #if defined(__GNUC__)
 #define MHADA_API __attribute__((visibility("default")))
@@ -262,11 +262,15 @@ MHADA_API int mhada_batch_attn(const void* qkv, int B, int N, int heads, int hd,
  * (8) AdaAttnForLoss on the tensor cores -- replaces AdaAttnForLoss.forward, MHAdaSTr/network/adaDecoder.py:53-81
  *     (lossfn.py:26-34 calls it on concatenated VGG features: d_qk = 448 / 960 / 1472, d_v = 256 / 512):
  *         Q = IN(c_1x), K = IN(s_1x), V = s_x;  A = softmax(Q K^T);  out = sqrt(max(A V^2 - (A V)^2, 1e-6)) * IN(c_x) + A V
- *     All tensors bf16, token-major with pitch = their channel count: c_x, out [B, Nc, dv]; s_x [B, Ns, dv];
- *     c_1x [B, Nc, dqk]; s_1x [B, Ns, dqk].  dqk % 64 == 0, dv % 64 == 0.  ws: mhada_forloss_workspace(...) bytes.
+ *     All tensors in `dtype` (f32 or bf16), token-major with pitch = their channel count: c_x, out [B, Nc, dv];
+ *     s_x [B, Ns, dv]; c_1x [B, Nc, dqk]; s_1x [B, Ns, dqk].  dqk % 64 == 0, dv % 64 == 0.
+ *     ws: mhada_forloss_workspace(...) bytes.  The contractions run on bf16 tcgen05 MMAs with f32 accumulation; the
+ *     normalised Q / K are split in two bf16 terms each (three products, one GEMM) and V^2 in an exact hi + lo pair,
+ *     because these logits are 448..1472 terms wide and the attention is sharp (csrc/forloss_tc.cu, "Numerics").
  *     (mhada_attn with MHADA_F32 remains the reference-arithmetic path for any dqk / dv.)
  * ---------------------------------------------------------------------------------------------- */
 typedef struct mhada_forloss_args {
+    int dtype;                 /* MHADA_F32 or MHADA_BF16: storage type of the four inputs and of out */
     int B, Nc, Ns, dqk, dv;
     const void *c_x, *s_x, *c_1x, *s_1x;
     void* out;

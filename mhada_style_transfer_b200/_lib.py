@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libmhada_b200.so")
 
 F32, BF16, U8 = 0, 1, 2
-ABI_VERSION = 6
+ABI_VERSION = 7
 VIT_MAX_LAYERS = 8
 PROJ_Q, PROJ_KV = 1, 2
 REUSE_FS_STATS = 1
@@ -57,7 +57,7 @@ class VitArgs(ctypes.Structure):
 
 class ForlossArgs(ctypes.Structure):
     """mhada_forloss_args (include/mhada_b200.h)."""
-    _fields_ = [("B", c_int), ("Nc", c_int), ("Ns", c_int), ("dqk", c_int), ("dv", c_int),
+    _fields_ = [("dtype", c_int), ("B", c_int), ("Nc", c_int), ("Ns", c_int), ("dqk", c_int), ("dv", c_int),
                 ("c_x", c_void_p), ("s_x", c_void_p), ("c_1x", c_void_p), ("s_1x", c_void_p), ("out", c_void_p),
                 ("ws", c_void_p), ("ws_bytes", c_size_t)]
 

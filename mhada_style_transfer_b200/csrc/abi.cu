@@ -522,6 +522,7 @@ int mhada_forloss_forward(const mhada_forloss_args* a, mhada_stream_t stream) {
     REQUIRE(a, MHADA_ERR_ARG, "mhada_forloss_forward: null args");
     REQUIRE(a->c_x && a->s_x && a->c_1x && a->s_1x && a->out && a->ws, MHADA_ERR_ARG, "mhada_forloss_forward: null pointer");
     REQUIRE(a->B > 0 && a->Nc > 0 && a->Ns > 0 && a->dqk > 0 && a->dv > 0, MHADA_ERR_ARG, "mhada_forloss_forward: bad sizes");
+    REQUIRE(a->dtype == MHADA_F32 || a->dtype == MHADA_BF16, MHADA_ERR_ARG, "mhada_forloss_forward: bad dtype %d", a->dtype);
     REQUIRE(a->dqk % 64 == 0 && a->dv % 64 == 0, MHADA_ERR_UNSUPPORTED,
             "mhada_forloss_forward: the tensor-core path needs dqk %% 64 == 0 and dv %% 64 == 0, got %d / %d (use mhada_attn, MHADA_F32)",
             a->dqk, a->dv);

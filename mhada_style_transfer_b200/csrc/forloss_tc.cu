@@ -6,14 +6,25 @@
 // The streaming kernel (attn_tc.cu) keeps Q of two query tiles and a K ring in shared memory: at d_qk >= 256 they no
 // longer fit (r1 ran these shapes on the fp32 SIMT kernel: 52 ms for relu3_1 at batch 8).  These problems are small in
 // tokens (N <= 4096 at the 256 x 256 training resolution) and wide in channels, so here the logits ARE materialised,
-// per image, in HBM/L2 -- but every contraction runs on tcgen05 through the token GEMM (gemm_tc.cu):
-//   1. statistics of c_1x, s_1x, c_x, s_x (stats.cu);  Qn = log2(e) * IN(c_1x), Kn = IN(s_1x) as bf16, key rows
-//      padded to a multiple of 128 with zeros (normalize_rows_kernel)
-//   2. V' = [V - mu_v | (V - mu_v)^2]^T as bf16 [2 dv][Ns_pad] (vprime_t_kernel; centring as in the layer path)
-//   3. per image: S = Qn Kn^T (f32 [Nc][Ns_pad], GEMM)  ->  P = 2^(S - rowmax) as bf16, row sums of the ROUNDED
-//      weights (softmax_rows_kernel)  ->  O = P V'^T (f32 [Nc][2 dv], GEMM)
-//   4. out = sqrt(max(E - M^2, 1e-6)) * IN(c_x) + M + mu_v  (forloss_finalize_kernel)
-// FLOPs 2 Nc Ns (d_qk + 2 d_v) per image; the materialised S / P of one image (<= 100 MB) are reused image by image.
+// per image, in HBM/L2 -- but every contraction runs on tcgen05 through the token GEMM (gemm_tc.cu).
+//
+// Numerics.  Two things make this shape harder than the 64-wide heads of the layers (measured against the reference's
+// float64 goldens, tools/error_budget.py style emulation; a plain bf16 pipeline is 5-9e-2 off):
+//  (a) the logits are sums of 448..1472 products of unit-variance values (std ~ 20-40): rounding Q^ / K^ to bf16 moves a
+//      logit by ~0.1, i.e. the weights by 10 %.  The operands are therefore split in two bf16 terms, x = hi + lo, and the
+//      three leading products are taken in ONE GEMM by concatenating along the contraction axis:
+//      [Qh | Ql | Qh] . [Kh | Kh | Kl]^T  (K = 3 d_qk; the logits are then good to ~1e-4);
+//  (b) the attention is sharp (often one key carries a row), so Var = A V^2 - (A V)^2 cancels almost completely: the
+//      squares must be the squares of the ROUNDED centred values and must be exact: V' = [vr | hi(vr^2) | lo(vr^2)] with
+//      vr = bf16(V - mu_v); vr^2 has at most 16 significant bits, so hi + lo represent it exactly.
+//   1. statistics of c_1x, s_1x, c_x, s_x (stats.cu);  Q3 = split(log2(e) * IN(c_1x)), K3 = split(IN(s_1x)) as bf16, key
+//      rows padded to a multiple of 128 with zeros (normalize_rows_kernel)
+//   2. V'^T as bf16 [NV][Ns_pad], NV = 3 dv rounded up to 128 (vprime_t_kernel)
+//   3. per image: S = Q3 K3^T (f32 [Nc][Ns_pad], GEMM)  ->  P = 2^(S - rowmax) as bf16, row sums of the ROUNDED
+//      weights (softmax_rows_kernel)  ->  O = P V'^T (f32 [Nc][NV], GEMM)
+//   4. out = sqrt(max(E - M^2, 1e-6)) * IN(c_x) + M + mu_v,  E = O_hi + O_lo  (forloss_finalize_kernel)
+// FLOPs 2 Nc Ns (3 d_qk + 3 d_v) per image; the materialised S / P of one image (<= 100 MB) are reused image by image.
+// Inputs and output are all f32 or all bf16 (f32 inputs are NOT rounded before the normalisation).
 #include "common.h"
 #include "ptx.cuh"
 
@@ -21,10 +32,26 @@ namespace mh {
 
 constexpr float FL_LOG2E = 1.4426950408889634f;
 
-// y[b, n, c] = scale * (x[b, n, c] - mean[b, c]) * rstd[b, c]  as bf16, rows n in [N, Npad) zero.  8 channels per thread.
-__global__ void __launch_bounds__(256) normalize_rows_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ mean,
-                                                             const float* __restrict__ rstd, float scale, int B, int N, int Npad,
-                                                             int C, __nv_bfloat16* __restrict__ y) {
+__device__ __forceinline__ void load8(const float* p, float* v) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float* v) {
+    const uint4 w = __ldg(reinterpret_cast<const uint4*>(p));
+    v[0] = bf16_lo(w.x); v[1] = bf16_hi(w.x); v[2] = bf16_lo(w.y); v[3] = bf16_hi(w.y);
+    v[4] = bf16_lo(w.z); v[5] = bf16_hi(w.z); v[6] = bf16_lo(w.w); v[7] = bf16_hi(w.w);
+}
+__device__ __forceinline__ float ldf(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float ldf(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ void stf(float* p, float v) { *p = v; }
+__device__ __forceinline__ void stf(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+// t = scale * (x[b, n, c] - mean[b, c]) * rstd[b, c] split as hi = bf16(t), lo = bf16(t - hi); row of 3 C bf16:
+// role 0 (queries) [hi | lo | hi], role 1 (keys) [hi | hi | lo]; rows n in [N, Npad) zero.  8 channels per thread.
+template <typename T>
+__global__ void __launch_bounds__(256) normalize_rows_kernel(const T* __restrict__ x, const float* __restrict__ mean,
+                                                             const float* __restrict__ rstd, float scale, int role, int B, int N,
+                                                             int Npad, int C, __nv_bfloat16* __restrict__ y) {
     const int cv = C / 8;
     const size_t total = static_cast<size_t>(B) * Npad * cv;
     const size_t t = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
@@ -32,25 +59,34 @@ __global__ void __launch_bounds__(256) normalize_rows_kernel(const __nv_bfloat16
     const int c = static_cast<int>(t % cv) * 8;
     const int n = static_cast<int>((t / cv) % Npad);
     const int b = static_cast<int>(t / (static_cast<size_t>(cv) * Npad));
-    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+    uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = hi;
     if (n < N) {
-        const uint4 w = __ldg(reinterpret_cast<const uint4*>(x + (static_cast<size_t>(b) * N + n) * C + c));
-        const float4 m0 = __ldg(reinterpret_cast<const float4*>(mean + static_cast<size_t>(b) * C + c));
-        const float4 m1 = __ldg(reinterpret_cast<const float4*>(mean + static_cast<size_t>(b) * C + c) + 1);
-        const float4 r0 = __ldg(reinterpret_cast<const float4*>(rstd + static_cast<size_t>(b) * C + c));
-        const float4 r1 = __ldg(reinterpret_cast<const float4*>(rstd + static_cast<size_t>(b) * C + c) + 1);
-        o.x = pack_bf16x2((bf16_lo(w.x) - m0.x) * r0.x * scale, (bf16_hi(w.x) - m0.y) * r0.y * scale);
-        o.y = pack_bf16x2((bf16_lo(w.y) - m0.z) * r0.z * scale, (bf16_hi(w.y) - m0.w) * r0.w * scale);
-        o.z = pack_bf16x2((bf16_lo(w.z) - m1.x) * r1.x * scale, (bf16_hi(w.z) - m1.y) * r1.y * scale);
-        o.w = pack_bf16x2((bf16_lo(w.w) - m1.z) * r1.z * scale, (bf16_hi(w.w) - m1.w) * r1.w * scale);
+        float v[8], m[8], r[8];
+        load8(x + (static_cast<size_t>(b) * N + n) * C + c, v);
+        load8(mean + static_cast<size_t>(b) * C + c, m);
+        load8(rstd + static_cast<size_t>(b) * C + c, r);
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float t0 = (v[2 * i] - m[2 * i]) * r[2 * i] * scale, t1 = (v[2 * i + 1] - m[2 * i + 1]) * r[2 * i + 1] * scale;
+            h[i] = pack_bf16x2(t0, t1);
+            l[i] = pack_bf16x2(t0 - bf16_lo(h[i]), t1 - bf16_hi(h[i]));
+        }
+        hi = make_uint4(h[0], h[1], h[2], h[3]);
+        lo = make_uint4(l[0], l[1], l[2], l[3]);
     }
-    *reinterpret_cast<uint4*>(y + (static_cast<size_t>(b) * Npad + n) * C + c) = o;
+    __nv_bfloat16* row = y + (static_cast<size_t>(b) * Npad + n) * 3 * C + c;
+    *reinterpret_cast<uint4*>(row) = hi;
+    *reinterpret_cast<uint4*>(row + C) = role == 0 ? lo : hi;
+    *reinterpret_cast<uint4*>(row + 2 * C) = role == 0 ? hi : lo;
 }
 
-// vt[b][c][n] = v[b, n, c] - mu[b, c];  vt[b][dv + c][n] = (that)^2 (squared in f32);  n >= N -> 0.  32 x 32 tiles
-// through shared memory: reads are coalesced along channels, writes along tokens.
-__global__ void __launch_bounds__(256) vprime_t_kernel(const __nv_bfloat16* __restrict__ v, const float* __restrict__ mu, int N,
-                                                       int Npad, int dv, __nv_bfloat16* __restrict__ vt) {
+// vr = bf16(v[b, n, c] - mu[b, c]);  vt[b][c][n] = vr;  vt[b][dv + c][n] = hi(vr^2);  vt[b][2 dv + c][n] = lo(vr^2)
+// (vr^2 is exact in f32 and hi + lo is exact: see (b) above);  n >= N -> 0; rows [3 dv, NV) are zeroed by the caller.
+// 32 x 32 tiles through shared memory: reads are coalesced along channels, writes along tokens.
+template <typename T>
+__global__ void __launch_bounds__(256) vprime_t_kernel(const T* __restrict__ v, const float* __restrict__ mu, int N, int Npad,
+                                                       int dv, int NV, __nv_bfloat16* __restrict__ vt) {
     __shared__ float tile[32][33];
     const int b = blockIdx.z, n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
@@ -58,7 +94,7 @@ __global__ void __launch_bounds__(256) vprime_t_kernel(const __nv_bfloat16* __re
     for (int r = ty; r < 32; r += 8) {
         const int n = n0 + r, c = c0 + tx;
         float val = 0.f;
-        if (n < N && c < dv) val = __bfloat162float(v[(static_cast<size_t>(b) * N + n) * dv + c]) - __ldg(mu + static_cast<size_t>(b) * dv + c);
+        if (n < N && c < dv) val = ldf(v + (static_cast<size_t>(b) * N + n) * dv + c) - __ldg(mu + static_cast<size_t>(b) * dv + c);
         tile[r][tx] = val;
     }
     __syncthreads();
@@ -66,10 +102,13 @@ __global__ void __launch_bounds__(256) vprime_t_kernel(const __nv_bfloat16* __re
     for (int r = ty; r < 32; r += 8) {
         const int c = c0 + r, n = n0 + tx;
         if (c < dv && n < Npad) {
-            const float val = (n < N) ? tile[tx][r] : 0.f;
-            __nv_bfloat16* o = vt + (static_cast<size_t>(b) * 2 * dv + c) * Npad + n;
-            o[0] = __float2bfloat16_rn(val);
-            o[static_cast<size_t>(dv) * Npad] = __float2bfloat16_rn(val * val);
+            const __nv_bfloat16 vr = __float2bfloat16_rn((n < N) ? tile[tx][r] : 0.f);
+            const float vf = __bfloat162float(vr), sq = vf * vf;
+            const __nv_bfloat16 hi = __float2bfloat16_rn(sq);
+            __nv_bfloat16* o = vt + (static_cast<size_t>(b) * NV + c) * Npad + n;
+            o[0] = vr;
+            o[static_cast<size_t>(dv) * Npad] = hi;
+            o[static_cast<size_t>(2 * dv) * Npad] = __float2bfloat16_rn(sq - __bfloat162float(hi));
         }
     }
 }
@@ -119,33 +158,36 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restri
     }
 }
 
-// out[n, c] = sqrt(max(E - M^2, 1e-6)) * (x[n, c] - mean_x[c]) * rstd_x[c] + M + mu_v[c],  M = o[n, c] / l, E = o[n, dv + c] / l
+// out[n, c] = sqrt(max(E - M^2, 1e-6)) * (x[n, c] - mean_x[c]) * rstd_x[c] + M + mu_v[c],
+// M = o[n, c] / l, E = (o[n, dv + c] + o[n, 2 dv + c]) / l
+template <typename T>
 __global__ void __launch_bounds__(256) forloss_finalize_kernel(const float* __restrict__ o, const float* __restrict__ lsum,
-                                                               const __nv_bfloat16* __restrict__ x, const float* __restrict__ mean_x,
+                                                               const T* __restrict__ x, const float* __restrict__ mean_x,
                                                                const float* __restrict__ rstd_x, const float* __restrict__ mu_v,
-                                                               int Nc, int dv, __nv_bfloat16* __restrict__ out) {
+                                                               int Nc, int dv, int NV, T* __restrict__ out) {
     const int cv = dv / 2;
     const size_t t = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
     if (t >= static_cast<size_t>(Nc) * cv) return;
     const int c = static_cast<int>(t % cv) * 2, n = static_cast<int>(t / cv);
     const float inv = 1.f / __ldg(lsum + n);
-    const float2 m2 = __ldg(reinterpret_cast<const float2*>(o + static_cast<size_t>(n) * 2 * dv + c));
-    const float2 e2 = __ldg(reinterpret_cast<const float2*>(o + static_cast<size_t>(n) * 2 * dv + dv + c));
-    const uint32_t xw = __ldg(reinterpret_cast<const uint32_t*>(x + static_cast<size_t>(n) * dv + c));
-    float r[2];
+    const float* orow = o + static_cast<size_t>(n) * NV + c;
+    const float2 m2 = __ldg(reinterpret_cast<const float2*>(orow));
+    const float2 eh = __ldg(reinterpret_cast<const float2*>(orow + dv));
+    const float2 el = __ldg(reinterpret_cast<const float2*>(orow + 2 * dv));
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
-        const float m = (e ? m2.y : m2.x) * inv, ex = (e ? e2.y : e2.x) * inv;
+        const float m = (e ? m2.y : m2.x) * inv, ex = ((e ? eh.y : eh.x) + (e ? el.y : el.x)) * inv;
         const float sd = sqrtf(fmaxf(fmaf(-m, m, ex), 1e-6f));
-        const float xf = e ? bf16_hi(xw) : bf16_lo(xw);
-        r[e] = fmaf(sd, (xf - __ldg(mean_x + c + e)) * __ldg(rstd_x + c + e), m + __ldg(mu_v + c + e));
+        const float xf = ldf(x + static_cast<size_t>(n) * dv + c + e);
+        stf(out + static_cast<size_t>(n) * dv + c + e,
+            fmaf(sd, (xf - __ldg(mean_x + c + e)) * __ldg(rstd_x + c + e), m + __ldg(mu_v + c + e)));
     }
-    *reinterpret_cast<uint32_t*>(out + static_cast<size_t>(n) * dv + c) = pack_bf16x2(r[0], r[1]);
 }
 
 struct ForlossWs {
     float *mean_q, *rstd_q, *mean_k, *rstd_k, *mean_x, *rstd_x, *mean_v, *rstd_v, *stats_ws, *s, *o, *lsum;
     __nv_bfloat16 *qn, *kn, *vt, *p;
+    int Npad, NV;
     size_t total;
 };
 static ForlossWs forloss_carve(int B, int Nc, int Ns, int dqk, int dv, uint8_t* base) {
@@ -156,7 +198,8 @@ static ForlossWs forloss_carve(int B, int Nc, int Ns, int dqk, int dv, uint8_t* 
         off += align_up(bytes, 1024);
         return p;
     };
-    const int Npad = (Ns + 127) / 128 * 128;
+    const int Npad = (Ns + 127) / 128 * 128, NV = (3 * dv + 127) / 128 * 128;
+    w.Npad = Npad; w.NV = NV;
     const size_t sq = static_cast<size_t>(B) * dqk * 4, sv = static_cast<size_t>(B) * dv * 4;
     w.mean_q = static_cast<float*>(take(sq)); w.rstd_q = static_cast<float*>(take(sq));
     w.mean_k = static_cast<float*>(take(sq)); w.rstd_k = static_cast<float*>(take(sq));
@@ -166,63 +209,74 @@ static ForlossWs forloss_carve(int B, int Nc, int Ns, int dqk, int dv, uint8_t* 
     const size_t sb2 = stats_workspace(B, Nc < Ns ? Nc : Ns, dqk > dv ? dqk : dv);
     if (sb2 > sb) sb = sb2;
     w.stats_ws = static_cast<float*>(take(sb));
-    w.qn = static_cast<__nv_bfloat16*>(take(static_cast<size_t>(B) * Nc * dqk * 2));
-    w.kn = static_cast<__nv_bfloat16*>(take(static_cast<size_t>(B) * Npad * dqk * 2));
-    w.vt = static_cast<__nv_bfloat16*>(take(static_cast<size_t>(B) * 2 * dv * Npad * 2));
+    w.qn = static_cast<__nv_bfloat16*>(take(static_cast<size_t>(B) * Nc * 3 * dqk * 2));
+    w.kn = static_cast<__nv_bfloat16*>(take(static_cast<size_t>(B) * Npad * 3 * dqk * 2));
+    w.vt = static_cast<__nv_bfloat16*>(take(static_cast<size_t>(B) * NV * Npad * 2));
     w.s = static_cast<float*>(take(static_cast<size_t>(Nc) * Npad * 4));           // one image at a time
     w.p = static_cast<__nv_bfloat16*>(take(static_cast<size_t>(Nc) * Npad * 2));
-    w.o = static_cast<float*>(take(static_cast<size_t>(Nc) * 2 * dv * 4));
+    w.o = static_cast<float*>(take(static_cast<size_t>(Nc) * NV * 4));
     w.lsum = static_cast<float*>(take(static_cast<size_t>(Nc) * 4));
     w.total = off;
     return w;
 }
 size_t forloss_workspace(int B, int Nc, int Ns, int dqk, int dv) { return forloss_carve(B, Nc, Ns, dqk, dv, nullptr).total; }
 
-int forloss_forward(const mhada_forloss_args& a, cudaStream_t s) {
+template <typename T>
+static int forloss_forward_t(const mhada_forloss_args& a, cudaStream_t s) {
     const int B = a.B, Nc = a.Nc, Ns = a.Ns, dqk = a.dqk, dv = a.dv;
-    const int Npad = (Ns + 127) / 128 * 128;
+    const int dtype = a.dtype;
     ForlossWs w = forloss_carve(B, Nc, Ns, dqk, dv, static_cast<uint8_t*>(a.ws));
+    const int Npad = w.Npad, NV = w.NV;
     // 1. statistics (adaDecoder.py:55, :60, :81; the mean of V for the centring)
-    if (int e = launch_stats(a.c_1x, MHADA_BF16, B, Nc, dqk, dqk, w.mean_q, w.rstd_q, w.stats_ws, s)) return e;
-    if (int e = launch_stats(a.s_1x, MHADA_BF16, B, Ns, dqk, dqk, w.mean_k, w.rstd_k, w.stats_ws, s)) return e;
-    if (int e = launch_stats(a.c_x, MHADA_BF16, B, Nc, dv, dv, w.mean_x, w.rstd_x, w.stats_ws, s)) return e;
-    if (int e = launch_stats(a.s_x, MHADA_BF16, B, Ns, dv, dv, w.mean_v, w.rstd_v, w.stats_ws, s)) return e;
-    // 2. normalised operands
+    if (int e = launch_stats(a.c_1x, dtype, B, Nc, dqk, dqk, w.mean_q, w.rstd_q, w.stats_ws, s)) return e;
+    if (int e = launch_stats(a.s_1x, dtype, B, Ns, dqk, dqk, w.mean_k, w.rstd_k, w.stats_ws, s)) return e;
+    if (int e = launch_stats(a.c_x, dtype, B, Nc, dv, dv, w.mean_x, w.rstd_x, w.stats_ws, s)) return e;
+    if (int e = launch_stats(a.s_x, dtype, B, Ns, dv, dv, w.mean_v, w.rstd_v, w.stats_ws, s)) return e;
+    // 2. normalised, split operands
     {
         const size_t tq = static_cast<size_t>(B) * Nc * (dqk / 8), tk = static_cast<size_t>(B) * Npad * (dqk / 8);
-        normalize_rows_kernel<<<static_cast<unsigned>((tq + 255) / 256), 256, 0, s>>>(
-            static_cast<const __nv_bfloat16*>(a.c_1x), w.mean_q, w.rstd_q, FL_LOG2E, B, Nc, Nc, dqk, w.qn);
+        normalize_rows_kernel<T><<<static_cast<unsigned>((tq + 255) / 256), 256, 0, s>>>(
+            static_cast<const T*>(a.c_1x), w.mean_q, w.rstd_q, FL_LOG2E, 0, B, Nc, Nc, dqk, w.qn);
         count_launch();
-        normalize_rows_kernel<<<static_cast<unsigned>((tk + 255) / 256), 256, 0, s>>>(
-            static_cast<const __nv_bfloat16*>(a.s_1x), w.mean_k, w.rstd_k, 1.f, B, Ns, Npad, dqk, w.kn);
+        normalize_rows_kernel<T><<<static_cast<unsigned>((tk + 255) / 256), 256, 0, s>>>(
+            static_cast<const T*>(a.s_1x), w.mean_k, w.rstd_k, 1.f, 1, B, Ns, Npad, dqk, w.kn);
         count_launch();
+        if (NV > 3 * dv)                                        // padding rows of V'^T (GEMM N is a multiple of 128)
+            for (int b = 0; b < B; ++b)
+                if (int e = check_cuda(cudaMemsetAsync(w.vt + (static_cast<size_t>(b) * NV + 3 * dv) * Npad, 0,
+                                                       static_cast<size_t>(NV - 3 * dv) * Npad * 2, s), "forloss memset"))
+                    return e;
         dim3 g(static_cast<unsigned>(Npad / 32), static_cast<unsigned>((dv + 31) / 32), static_cast<unsigned>(B));
-        vprime_t_kernel<<<g, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(a.s_x), w.mean_v, Ns, Npad, dv, w.vt);
+        vprime_t_kernel<T><<<g, 256, 0, s>>>(static_cast<const T*>(a.s_x), w.mean_v, Ns, Npad, dv, NV, w.vt);
         count_launch();
         if (int e = check_cuda(cudaGetLastError(), "forloss prepare launch")) return e;
     }
     // 3. per image: logits, weights, moments; 4. epilogue
     for (int b = 0; b < B; ++b) {
         GemmDesc g{};
-        g.a = w.qn + static_cast<size_t>(b) * Nc * dqk; g.lda = dqk;
-        g.w = w.kn + static_cast<size_t>(b) * Npad * dqk; g.ldw = dqk;
-        g.M = Nc; g.N = Npad; g.K = dqk; g.out_f32 = w.s; g.ldf = Npad;
+        g.a = w.qn + static_cast<size_t>(b) * Nc * 3 * dqk; g.lda = 3 * dqk;
+        g.w = w.kn + static_cast<size_t>(b) * Npad * 3 * dqk; g.ldw = 3 * dqk;
+        g.M = Nc; g.N = Npad; g.K = 3 * dqk; g.out_f32 = w.s; g.ldf = Npad;
         if (int e = launch_gemm_bf16(g, s)) return e;                                              // :70 (bmm in Softmax)
         softmax_rows_kernel<<<Nc, 256, 0, s>>>(w.s, Ns, Npad, w.p, w.lsum);
         count_launch();
         g = GemmDesc{};
         g.a = w.p; g.lda = Npad;
-        g.w = w.vt + static_cast<size_t>(b) * 2 * dv * Npad; g.ldw = Npad;
-        g.M = Nc; g.N = 2 * dv; g.K = Npad; g.out_f32 = w.o; g.ldf = 2 * dv;
+        g.w = w.vt + static_cast<size_t>(b) * NV * Npad; g.ldw = Npad;
+        g.M = Nc; g.N = NV; g.K = Npad; g.out_f32 = w.o; g.ldf = NV;
         if (int e = launch_gemm_bf16(g, s)) return e;                                              // :71, :74
         const size_t tf = static_cast<size_t>(Nc) * (dv / 2);
-        forloss_finalize_kernel<<<static_cast<unsigned>((tf + 255) / 256), 256, 0, s>>>(
-            w.o, w.lsum, static_cast<const __nv_bfloat16*>(a.c_x) + static_cast<size_t>(b) * Nc * dv, w.mean_x + static_cast<size_t>(b) * dv,
-            w.rstd_x + static_cast<size_t>(b) * dv, w.mean_v + static_cast<size_t>(b) * dv, Nc, dv,
-            static_cast<__nv_bfloat16*>(a.out) + static_cast<size_t>(b) * Nc * dv);                 // :74-81
+        forloss_finalize_kernel<T><<<static_cast<unsigned>((tf + 255) / 256), 256, 0, s>>>(
+            w.o, w.lsum, static_cast<const T*>(a.c_x) + static_cast<size_t>(b) * Nc * dv, w.mean_x + static_cast<size_t>(b) * dv,
+            w.rstd_x + static_cast<size_t>(b) * dv, w.mean_v + static_cast<size_t>(b) * dv, Nc, dv, NV,
+            static_cast<T*>(a.out) + static_cast<size_t>(b) * Nc * dv);                             // :74-81
         count_launch();
     }
     return check_cuda(cudaGetLastError(), "forloss launch");
+}
+
+int forloss_forward(const mhada_forloss_args& a, cudaStream_t s) {
+    return a.dtype == MHADA_F32 ? forloss_forward_t<float>(a, s) : forloss_forward_t<__nv_bfloat16>(a, s);
 }
 
 }  // namespace mh

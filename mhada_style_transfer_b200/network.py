@@ -405,9 +405,10 @@ class AdaAttnForLoss(nn.Module):
         return (not _is_cosine(self.activation)) and c_x.shape[1] % 64 == 0 and c_1x.shape[1] % 64 == 0
 
     def _forward_tc(self, c_x, s_x, c_1x, s_1x):
-        """bf16 tensor-core path (forloss_tc.cu): logits of one image materialised, contractions on the token GEMM."""
+        """Tensor-core path (forloss_tc.cu): logits of one image materialised, contractions on the token GEMM.  f32
+        inputs are handed over as f32 (the kernels normalise first and round / split afterwards)."""
         L = _lib.lib()
-        dt = torch.bfloat16
+        dt = torch.float32 if all(t.dtype == torch.float32 for t in (c_x, s_x, c_1x, s_1x)) else torch.bfloat16
         tq, tk, tv, tx = (_token_major(t, dt) for t in (c_1x, s_1x, s_x, c_x))
         B, h, w, dv = tx.shape
         dqk = tq.shape[3]
@@ -420,6 +421,7 @@ class AdaAttnForLoss(nn.Module):
         out = torch.empty((B, h, w, dv), dtype=dt, device=tx.device)
         ws = _workspace(tx.device, L.mhada_forloss_workspace(B, Nc, Ns, dqk, dv))
         a = _lib.ForlossArgs()
+        a.dtype = _code(dt)
         a.B, a.Nc, a.Ns, a.dqk, a.dv = B, Nc, Ns, dqk, dv
         a.c_x, a.s_x, a.c_1x, a.s_1x, a.out = tx.data_ptr(), tv.data_ptr(), tq.data_ptr(), tk.data_ptr(), out.data_ptr()
         a.ws, a.ws_bytes = ws.data_ptr(), ws.numel()

@@ -141,18 +141,22 @@ def test_forloss_fp32(case, golden_index):
 @pytest.mark.parametrize("case", [c for c in cases.FORLOSS_CASES if "activation" not in c], ids=lambda c: c["name"])
 def test_forloss_bf16_tensor_core_path(case, golden_index):
     """AdaAttnForLoss on the tensor cores (mhada_forloss_forward: logits materialised per image, every contraction on the
-    tcgen05 token GEMM) against the reference goldens of the three VGG shapes (d_qk 448 / 960 / 1472)."""
+    tcgen05 token GEMM, Q / K split in two bf16 terms, exact V^2) against the reference goldens of the three VGG shapes
+    (d_qk 448 / 960 / 1472).  bf16 INPUTS are judged against the float64 oracle evaluated on those rounded inputs: the
+    rounding of a caller's tensors is not the module's error (these logits amplify it to several per cent)."""
     args = [dev(a) for a in cases.forloss_inputs(case)]
     m = M.AdaAttnForLoss(case["v"], case["qk"]).to(DEV).eval()
     m.precision = "bf16"
+    args16 = [a.bfloat16() for a in args]
     with torch.no_grad():
         out = m(*args)
-        auto = M.AdaAttnForLoss(case["v"], case["qk"]).to(DEV).eval()(*[a.bfloat16() for a in args])      # bf16 in -> same path
+        auto = M.AdaAttnForLoss(case["v"], case["qk"]).to(DEV).eval()(*args16)      # bf16 in -> same path
     assert out.dtype == torch.float32 and auto.dtype == torch.bfloat16
     e = O.errors(out.cpu().numpy(), load_golden(case["name"])["out"])
-    ntok = case["hsws"][0] * case["hsws"][1]
-    assert e["max_abs_rel"] <= (BF16_REL if ntok >= 100 else 4e-2), e
-    assert O.errors(auto.float().cpu().numpy(), load_golden(case["name"])["out"])["max_abs_rel"] <= 4e-2
+    assert e["max_abs_rel"] <= BF16_REL and e["fro_rel"] <= 5e-3, e
+    want16 = O.ada_attn_for_loss(*[a.float().cpu().numpy().astype(np.float64) for a in args16])
+    e16 = O.errors(auto.float().cpu().numpy(), want16)
+    assert e16["max_abs_rel"] <= BF16_REL and e16["fro_rel"] <= 5e-3, e16
 
 
 def test_forloss_bf16_vs_oracle_at_training_size():
@@ -167,8 +171,11 @@ def test_forloss_bf16_vs_oracle_at_training_size():
         m.precision = "fp32"
         ref32 = m(*[dev(a) for a in args])
     e = O.errors(got.cpu().numpy(), want)
-    assert e["max_abs_rel"] <= BF16_REL and e["fro_rel"] <= 1e-2, e
-    assert O.errors(ref32.cpu().numpy(), want)["max_abs"] <= FP32_MAX_ABS
+    assert e["max_abs_rel"] <= BF16_REL and e["fro_rel"] <= 5e-3, e
+    # fp32 kernels on the same case: sharp rows make Var = E - M^2 cancel, so fp32 arithmetic (the reference's included,
+    # SURVEY D8) is good to ~2^-12 |v| here, not to 1e-3 absolute: absmax 16 -> 3e-3
+    e32 = O.errors(ref32.cpu().numpy(), want)
+    assert e32["max_abs"] <= max(FP32_MAX_ABS, 3e-4 * e32["absmax"]), e32
     with torch.no_grad(), pytest.raises(NotImplementedError):
         mc = M.AdaAttnForLoss(256, 448, "cosine").to(DEV)
         mc.precision = "bf16"

@@ -34,7 +34,10 @@ def layer(fc, fs, fcs, sd, prefix, H, cfg):
             xc = fc_r[bi, sl].reshape(d, -1).T; xs = fs_r[bi, sl].reshape(d, -1).T
             Q[bi] = xc @ wq.T + bq; K[bi] = xs @ wk.T + bk; V[bi] = xs @ wv.T + bv; muv[bi] = bh - bv
         Q = rnd(Q * np.log2(np.e), cfg["qk"]); K = rnd(K, cfg["qk"])
-        V2 = rnd(V * V, cfg["v"]); V = rnd(V, cfg["v"])
+        if cfg.get("v2_consistent"):            # square the ROUNDED V~ (experiment: mixed result on the layer path, not adopted)
+            V = rnd(V, cfg["v"]); V2 = rnd(V * V, cfg["v"])
+        else:
+            V2 = rnd(V * V, cfg["v"]); V = rnd(V, cfg["v"])
         S = Q @ K.transpose(0, 2, 1)
         S = S - S.max(-1, keepdims=True)
         P = rnd(np.exp2(S), cfg["p"])
@@ -68,7 +71,8 @@ if __name__ == "__main__":
         e = O.errors(run(case, cfg), want)
         print(f"{tag:42s} max_abs_rel {e['max_abs_rel']:.4f}  fro_rel {e['fro_rel']:.4f}")
     show("exact restatement", base)
-    show("all bf16 (current kernels)", allbf)
+    show("all bf16, squares of unrounded V~ (r1)", allbf)
+    show("all bf16, squares of ROUNDED V~", dict(allbf, v2_consistent=True))
     for k in base:
         show(f"only {k} bf16", dict(base, **{k: "bf16"}))
     for k in base:
