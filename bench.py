@@ -547,7 +547,8 @@ def measure_train(args, ctx, steps, warmup):
     """BASELINE configs[4]: one training step per GPU on its own batch (data parallel), gradients averaged with the
     bucketed all-reduce that is launched from autograd hooks DURING backward (sharding.OverlappedGradientAllReduce).
     Forward: the CUDA kernels (bf16) for the six MHAda layers; ViT and decoder run their differentiable PyTorch op
-    sequence; backward of the layers = fp32 recompute with PyTorch ops (own backward kernels are SURVEY N4).
+    sequence; backward of the layers = mhada_layer_backward (own kernels; MHADA_BACKWARD_IMPL=torch switches
+    to the fp32 PyTorch recompute for an A/B).
     The VGG loss network needs downloaded weights (absent offline): the loss is a synthetic stand-in with the same
     graph shape (pixel loss on cs against the content image + a feature term on fcs)."""
     import torch.distributed as dist
@@ -630,7 +631,10 @@ def measure_train(args, ctx, steps, warmup):
                    "parameters": n_params, "optimizer": "3 x Adam(lr=1e-4) (train_image.py:70-72)",
                    "loss": "synthetic (VGG19 weights cannot be downloaded offline): pixel term on cs + feature term on fcs",
                    "forward": "MHAda layers on the bf16 CUDA kernels; ViT / decoder differentiable PyTorch ops",
-                   "backward": "fp32 recompute of each layer with PyTorch ops (no backward kernel yet)",
+                   "backward": ("fp32 recompute of each layer with PyTorch ops (MHADA_BACKWARD_IMPL=torch)"
+                                if os.environ.get("MHADA_BACKWARD_IMPL") == "torch" else
+                                "mhada_layer_backward: flash-style attention backward kernels (V' = [V | V^2]), the other "
+                                "contractions on the tcgen05 token GEMM; ViT / decoder backward = PyTorch autograd"),
                    "gradient_sync": "bucketed (32 MB) all-reduce launched from autograd hooks during backward, NCCL"},
         "e2e": {"value": round(images / (ms_e2e * 1e-3), 2), "unit": "images/s",
                 "h2d_bytes_per_step": c_h.numel() * 4 + s_h.numel() * 4, "d2h_bytes_per_step": 4,

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define MHADA_ABI_VERSION 7
+#define MHADA_ABI_VERSION 8
 
 #if defined(__GNUC__)
 #define MHADA_API __attribute__((visibility("default")))
@@ -279,6 +279,38 @@ typedef struct mhada_forloss_args {
 } mhada_forloss_args;
 MHADA_API size_t mhada_forloss_workspace(int B, int Nc, int Ns, int dqk, int dv);
 MHADA_API int mhada_forloss_forward(const mhada_forloss_args* args, mhada_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (9) Backward of one layer -- replaces what torch.autograd does for AdaAttnMultiHead.forward,
+ *     MHAdaSTr/network/adaDecoder.py:162-206, inside the training step train_image.py:105-144 (loss.backward()).
+ *     MHADA_BF16 path, head_dim 64, softmax activation, out_conv present.  The forward intermediates are RECOMPUTED
+ *     (statistics, folded projections, attention) -- nothing but the layer inputs has to be kept from the forward.
+ *     fc, fs, fcs, d_out: bf16 token-major as in (5) (fcs may alias fc);  weights as in (5), w_out f32 [C][C].
+ *     Gradients: d_fc, d_fcs f32 [B, Nc, C], d_fs f32 [B, Ns, C] (when fcs aliases fc the caller adds d_fc + d_fcs);
+ *     d_w_fgh f32 [3][H][d][d], d_b_fgh f32 [3][H][d], d_w_out f32 [C][C], d_b_out f32 [C].
+ *     The attention part is a FlashAttention-style backward with value operand V' = [V~ | V~^2] (csrc/attn_bwd.cu);
+ *     every other contraction runs on the tcgen05 token GEMM.  Deterministic (no atomics).
+ *     ws: mhada_layer_backward_workspace(B, Nc, Ns, C, H) bytes.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct mhada_layer_bwd_args {
+    int B, Nc, Ns, C, H;
+    const void *fc, *fs, *fcs;
+    const float *w_fgh, *b_fgh, *w_out, *b_out;
+    const void* d_out;
+    float *d_fc, *d_fs, *d_fcs;
+    float *d_w_fgh, *d_b_fgh, *d_w_out, *d_b_out;
+    void* ws;
+    size_t ws_bytes;
+} mhada_layer_bwd_args;
+MHADA_API size_t mhada_layer_backward_workspace(int B, int Nc, int Ns, int C, int H);
+MHADA_API int mhada_layer_backward(const mhada_layer_bwd_args* args, mhada_stream_t stream);
+/*     The attention stage of (9) alone (stage tests): q (pre-multiplied by log2 e), k bf16 [B, N, C], v bf16 [B, Ns, 2C]
+ *     as mhada_proj writes them, x = fcs bf16 with its statistics, g = dL/d(heads) f32 [B, Nc, C].  Outputs: d_o bf16
+ *     [B, Nc, 2C] (per head [dM~ | dE]), lse (log2 units) and delta f32 [B, H, Nc], d_xhat = dL/d(IN(fcs)) f32 [B, Nc, C],
+ *     d_q, d_k, d_v bf16 (natural units; d_v is the gradient of V, the squares already folded in). */
+MHADA_API int mhada_attn_bwd(int B, int H, int Nc, int Ns, const void* q, const void* k, const void* v, const void* x,
+                             const float* x_mean, const float* x_rstd, const float* g, void* d_o, float* lse, float* delta,
+                             float* d_xhat, void* d_q, void* d_k, void* d_v, mhada_stream_t stream);
 
 /* Number of kernel launches the last mhada_layer_forward on this thread issued (bench bookkeeping). */
 MHADA_API int mhada_last_launch_count(void);

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libmhada_b200.so")
 
 F32, BF16, U8 = 0, 1, 2
-ABI_VERSION = 7
+ABI_VERSION = 8
 VIT_MAX_LAYERS = 8
 PROJ_Q, PROJ_KV = 1, 2
 REUSE_FS_STATS = 1
@@ -62,6 +62,17 @@ class ForlossArgs(ctypes.Structure):
                 ("ws", c_void_p), ("ws_bytes", c_size_t)]
 
 
+class LayerBwdArgs(ctypes.Structure):
+    """mhada_layer_bwd_args (include/mhada_b200.h)."""
+    _fields_ = [("B", c_int), ("Nc", c_int), ("Ns", c_int), ("C", c_int), ("H", c_int),
+                ("fc", c_void_p), ("fs", c_void_p), ("fcs", c_void_p),
+                ("w_fgh", c_void_p), ("b_fgh", c_void_p), ("w_out", c_void_p), ("b_out", c_void_p),
+                ("d_out", c_void_p),
+                ("d_fc", c_void_p), ("d_fs", c_void_p), ("d_fcs", c_void_p),
+                ("d_w_fgh", c_void_p), ("d_b_fgh", c_void_p), ("d_w_out", c_void_p), ("d_b_out", c_void_p),
+                ("ws", c_void_p), ("ws_bytes", c_size_t)]
+
+
 # name -> (restype, argtypes); kept in one table so tests can check the export list against the header
 SIGNATURES = {
     "mhada_abi_version": (c_int, []),
@@ -86,6 +97,9 @@ SIGNATURES = {
                              c_void_p, c_size_t, c_void_p]),
     "mhada_forloss_workspace": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "mhada_forloss_forward": (c_int, [POINTER(ForlossArgs), c_void_p]),
+    "mhada_layer_backward_workspace": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    "mhada_layer_backward": (c_int, [POINTER(LayerBwdArgs), c_void_p]),
+    "mhada_attn_bwd": (c_int, [c_int, c_int, c_int, c_int] + [c_void_p] * 15),
     "mhada_vit_workspace": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "mhada_vit_forward": (c_int, [POINTER(VitArgs), c_void_p]),
     "mhada_patch_im2col": (c_int, [c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),

@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmhada_b200.so")
-SOURCES = ["host_util.cu", "stats.cu", "simt_f32.cu", "linear_tc.cu", "proj_tc.cu", "attn_tc.cu", "gemm_tc.cu", "vit.cu", "forloss_tc.cu", "pad_nhwc.cu", "conv_small.cu", "conv_tc.cu", "abi.cu"]
+SOURCES = ["host_util.cu", "stats.cu", "simt_f32.cu", "linear_tc.cu", "proj_tc.cu", "attn_tc.cu", "gemm_tc.cu", "vit.cu", "forloss_tc.cu", "attn_bwd.cu", "layer_bwd.cu", "pad_nhwc.cu", "conv_small.cu", "conv_tc.cu", "abi.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",

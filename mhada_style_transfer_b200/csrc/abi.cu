@@ -246,6 +246,54 @@ int layer_impl(const char* who, int dtype, const void* fc, const void* fs, const
     return 0;
 }
 
+// ---- backward of a layer: workspace = the forward workspace (recompute) + the gradient intermediates
+struct BwdWs {
+    void* fwd;                 // LayerWs region (MHADA_BF16)
+    size_t fwd_bytes;
+    void *heads, *woT, *wbd, *d_o, *dq, *dk, *dv, *tA, *tB, *partial, *sums;
+    float *dcat, *lse, *delta, *dxhat, *gq, *gk, *gv, *dwfull;
+    int Mpad_c, Mpad_s;
+    size_t total;
+};
+
+BwdWs carve_bwd(int B, int Nc, int Ns, int C, int H, uint8_t* base) {
+    BwdWs w;
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        void* p = base ? base + off : nullptr;
+        off += align_up(bytes, 256);
+        return p;
+    };
+    w.fwd_bytes = carve(MHADA_BF16, B, Nc, Ns, C, H, nullptr).total;
+    w.fwd = take(w.fwd_bytes);
+    const size_t Mc = static_cast<size_t>(B) * Nc, Ms = static_cast<size_t>(B) * Ns;
+    w.Mpad_c = static_cast<int>((Mc + 63) / 64 * 64);
+    w.Mpad_s = static_cast<int>((Ms + 63) / 64 * 64);
+    const size_t Mpad = w.Mpad_c > w.Mpad_s ? w.Mpad_c : w.Mpad_s;
+    w.heads = take(Mc * C * 2);
+    w.woT = take(static_cast<size_t>(C) * C * 2);
+    w.wbd = take(static_cast<size_t>(3) * C * C * 2);
+    w.dcat = static_cast<float*>(take(Mc * C * 4));
+    w.d_o = take(Mc * 2 * C * 2);
+    w.lse = static_cast<float*>(take(static_cast<size_t>(B) * H * Nc * 4));
+    w.delta = static_cast<float*>(take(static_cast<size_t>(B) * H * Nc * 4));
+    w.dxhat = static_cast<float*>(take(Mc * C * 4));
+    w.dq = take(Mc * C * 2);
+    w.dk = take(Ms * C * 2);
+    w.dv = take(Ms * C * 2);
+    w.gq = static_cast<float*>(take(Mc * C * 4));
+    w.gk = static_cast<float*>(take(Ms * C * 4));
+    w.gv = static_cast<float*>(take(Ms * C * 4));
+    w.tA = take(static_cast<size_t>(C) * Mpad * 2);
+    w.tB = take(static_cast<size_t>(C) * Mpad * 2);
+    w.dwfull = static_cast<float*>(take(static_cast<size_t>(C) * C * 4));
+    const size_t pb = token_sums_workspace(B, Nc > Ns ? Nc : Ns, C), pb2 = token_sums_workspace(B, Nc < Ns ? Nc : Ns, C);
+    w.partial = take(pb > pb2 ? pb : pb2);
+    w.sums = take(static_cast<size_t>(B) * C * 8);
+    w.total = off;
+    return w;
+}
+
 }  // namespace
 
 extern "C" {
@@ -612,6 +660,101 @@ int mhada_style_precompute(int dtype, const void* fs, const float* w_fgh, const 
                                 d, nullptr, cv.k, cv.v, cv.mu_v, w.proj_ws, s);
     return launch_proj_f32(MHADA_PROJ_KV, nullptr, static_cast<const float*>(fs), nullptr, nullptr, w.mean_s, w.rstd_s, w_fgh,
                            b_fgh, 0, Bs, 0, Ns, H, d, nullptr, static_cast<float*>(cv.k), static_cast<float*>(cv.v), cv.mu_v, s);
+}
+
+size_t mhada_layer_backward_workspace(int B, int Nc, int Ns, int C, int H) {
+    if (B <= 0 || Nc <= 0 || Ns <= 0 || C <= 0 || H <= 0 || C % H != 0) return 0;
+    return carve_bwd(B, Nc, Ns, C, H, nullptr).total;
+}
+
+int mhada_attn_bwd(int B, int H, int Nc, int Ns, const void* q, const void* k, const void* v, const void* x,
+                   const float* x_mean, const float* x_rstd, const float* g, void* d_o, float* lse, float* delta,
+                   float* d_xhat, void* d_q, void* d_k, void* d_v, mhada_stream_t stream) {
+    g_launches = 0;
+    REQUIRE(q && k && v && x && x_mean && x_rstd && g && d_o && lse && delta && d_xhat && d_q && d_k && d_v, MHADA_ERR_ARG,
+            "mhada_attn_bwd: null pointer");
+    REQUIRE(B > 0 && H > 0 && Nc > 0 && Ns > 0, MHADA_ERR_ARG, "mhada_attn_bwd: bad sizes");
+    REQUIRE(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(x) && aligned16(g) && aligned16(d_o) && aligned16(d_xhat) &&
+                aligned16(d_q) && aligned16(d_k) && aligned16(d_v),
+            MHADA_ERR_ARG, "mhada_attn_bwd: pointers must be 16-byte aligned");
+    if (int e = device_check()) return e;
+    return launch_attn_bwd(B, H, Nc, Ns, H * 64, q, k, v, x, x_mean, x_rstd, g, d_o, lse, delta, d_xhat, d_q, d_k, d_v,
+                           static_cast<cudaStream_t>(stream));
+}
+
+int mhada_layer_backward(const mhada_layer_bwd_args* a, mhada_stream_t stream) {
+    REQUIRE(a, MHADA_ERR_ARG, "mhada_layer_backward: null args");
+    REQUIRE(a->fc && a->fs && a->fcs && a->w_fgh && a->b_fgh && a->w_out && a->b_out && a->d_out && a->ws, MHADA_ERR_ARG,
+            "mhada_layer_backward: null input pointer");
+    REQUIRE(a->d_fc && a->d_fs && a->d_fcs && a->d_w_fgh && a->d_b_fgh && a->d_w_out && a->d_b_out, MHADA_ERR_ARG,
+            "mhada_layer_backward: null output pointer");
+    const int B = a->B, Nc = a->Nc, Ns = a->Ns, C = a->C, H = a->H;
+    REQUIRE(B > 0 && Nc > 0 && Ns > 0 && C > 0 && H > 0 && C % H == 0, MHADA_ERR_ARG, "mhada_layer_backward: bad sizes");
+    REQUIRE(C / H == 64 && C % 128 == 0, MHADA_ERR_UNSUPPORTED,
+            "mhada_layer_backward: implemented for head_dim 64 and C %% 128 == 0 (C=%d, H=%d)", C, H);
+    REQUIRE(aligned16(a->fc) && aligned16(a->fs) && aligned16(a->fcs) && aligned16(a->d_out) && aligned16(a->d_fc) &&
+                aligned16(a->d_fs) && aligned16(a->d_fcs) && aligned32(a->ws),
+            MHADA_ERR_ARG, "mhada_layer_backward: misaligned pointer");
+    BwdWs w = carve_bwd(B, Nc, Ns, C, H, static_cast<uint8_t*>(a->ws));
+    REQUIRE(a->ws_bytes >= w.total, MHADA_ERR_WORKSPACE, "mhada_layer_backward: workspace %zu < %zu", a->ws_bytes, w.total);
+    if (int e = device_check()) return e;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int d = 64, Mc = B * Nc, Ms = B * Ns;
+    // (0) recompute the forward up to the attention output (statistics, Q, K, V', heads)       adaDecoder.py:173-198
+    if (int e = layer_impl("mhada_layer_backward", MHADA_BF16, a->fc, a->fs, a->fcs, nullptr, 0, a->w_fgh, a->b_fgh, nullptr,
+                           nullptr, B, Nc, Ns, C, H, 0, w.heads, w.fwd, w.fwd_bytes, stream))
+        return e;
+    int launches = g_launches;
+    LayerWs f = carve(MHADA_BF16, B, Nc, Ns, C, H, static_cast<uint8_t*>(w.fwd));
+    const float *mean_x = a->fcs != a->fc ? f.mean_x : f.mean_c, *rstd_x = a->fcs != a->fc ? f.rstd_x : f.rstd_c;
+    auto gemm = [&](const void* A, int lda, const void* W, int ldw, int M, int N, int K, float* out, int ldf) {
+        GemmDesc g{};
+        g.a = A; g.lda = lda; g.w = W; g.ldw = ldw; g.M = M; g.N = N; g.K = K; g.out_f32 = out; g.ldf = ldf;
+        return launch_gemm_bf16(g, s);
+    };
+    // (1) out_conv backward                                                                    adaDecoder.py:202-205
+    if (int e = launch_transpose_norm(a->w_out, MHADA_F32, C, C, C, C, C, nullptr, nullptr, w.woT, s)) return e;
+    if (int e = gemm(a->d_out, C, w.woT, C, Mc, C, C, w.dcat, C)) return e;                         // d(cat) = d(out) Wo
+    if (int e = launch_transpose_norm(a->d_out, MHADA_BF16, C, Mc, w.Mpad_c, C, Nc, nullptr, nullptr, w.tA, s)) return e;
+    if (int e = launch_transpose_norm(w.heads, MHADA_BF16, C, Mc, w.Mpad_c, C, Nc, nullptr, nullptr, w.tB, s)) return e;
+    if (int e = gemm(w.tA, w.Mpad_c, w.tB, w.Mpad_c, C, C, w.Mpad_c, a->d_w_out, C)) return e;      // dWo = d(out)^T cat
+    if (int e = launch_token_sums(a->d_out, MHADA_BF16, nullptr, nullptr, nullptr, B, Nc, C, w.partial, nullptr, a->d_b_out, s))
+        return e;
+    // (2) attention backward                                                                   adaDecoder.py:186-198
+    if (int e = launch_attn_bwd(B, H, Nc, Ns, C, f.q, f.k, f.v, a->fcs, mean_x, rstd_x, w.dcat, w.d_o, w.lse, w.delta, w.dxhat,
+                                w.dq, w.dk, w.dv, s))
+        return e;
+    // (3) projections backward: inputs                                                         adaDecoder.py:173-183
+    if (int e = launch_blockdiag_t(a->w_fgh, H, d, w.wbd, s)) return e;
+    const uint16_t* wbd = static_cast<const uint16_t*>(w.wbd);      // bf16 [3][C][C]
+    const size_t CC = static_cast<size_t>(C) * C;
+    if (int e = gemm(w.dq, C, wbd, C, Mc, C, C, w.gq, C)) return e;                                 // d(IN(fc)) = dQ Wf
+    if (int e = gemm(w.dk, C, wbd + CC, C, Ms, C, C, w.gk, C)) return e;                            // d(IN(fs)) = dK Wg
+    if (int e = gemm(w.dv, C, wbd + 2 * CC, C, Ms, C, C, w.gv, C)) return e;                        // d(fs) via V = dV Wh
+    // (4) projections backward: weights and biases
+    struct Role { const void* dy; const void* x; const float *mean, *rstd; int N, M, Mpad; };
+    const Role roles[3] = {{w.dq, a->fc, f.mean_c, f.rstd_c, Nc, Mc, w.Mpad_c},
+                           {w.dk, a->fs, f.mean_s, f.rstd_s, Ns, Ms, w.Mpad_s},
+                           {w.dv, a->fs, nullptr, nullptr, Ns, Ms, w.Mpad_s}};
+    for (int r = 0; r < 3; ++r) {
+        const Role& R = roles[r];
+        if (int e = launch_transpose_norm(R.dy, MHADA_BF16, C, R.M, R.Mpad, C, R.N, nullptr, nullptr, w.tA, s)) return e;
+        if (int e = launch_transpose_norm(R.x, MHADA_BF16, C, R.M, R.Mpad, C, R.N, R.mean, R.rstd, w.tB, s)) return e;
+        if (int e = gemm(w.tA, R.Mpad, w.tB, R.Mpad, C, C, R.Mpad, w.dwfull, C)) return e;
+        if (int e = launch_extract_blockdiag(w.dwfull, H, d, a->d_w_fgh + static_cast<size_t>(r) * H * d * d, s)) return e;
+        if (int e = launch_token_sums(R.dy, MHADA_BF16, nullptr, nullptr, nullptr, B, R.N, C, w.partial, nullptr,
+                                      a->d_b_fgh + static_cast<size_t>(r) * C, s))
+            return e;
+    }
+    // (5) instance-norm backward                                                               adaDecoder.py:147-149
+    if (int e = launch_token_sums(w.gq, MHADA_F32, a->fc, f.mean_c, f.rstd_c, B, Nc, C, w.partial, w.sums, nullptr, s)) return e;
+    if (int e = launch_in_bwd_apply(w.gq, a->fc, f.mean_c, f.rstd_c, w.sums, nullptr, B, Nc, C, a->d_fc, s)) return e;
+    if (int e = launch_token_sums(w.gk, MHADA_F32, a->fs, f.mean_s, f.rstd_s, B, Ns, C, w.partial, w.sums, nullptr, s)) return e;
+    if (int e = launch_in_bwd_apply(w.gk, a->fs, f.mean_s, f.rstd_s, w.sums, w.gv, B, Ns, C, a->d_fs, s)) return e;
+    if (int e = launch_token_sums(w.dxhat, MHADA_F32, a->fcs, mean_x, rstd_x, B, Nc, C, w.partial, w.sums, nullptr, s)) return e;
+    if (int e = launch_in_bwd_apply(w.dxhat, a->fcs, mean_x, rstd_x, w.sums, nullptr, B, Nc, C, a->d_fcs, s)) return e;
+    g_launches += launches;
+    return 0;
 }
 
 }  // extern "C"

@@ -113,6 +113,20 @@ int vit_forward(const mhada_vit_args& a, cudaStream_t s);
 size_t forloss_workspace(int B, int Nc, int Ns, int dqk, int dv);
 int forloss_forward(const mhada_forloss_args& a, cudaStream_t s);
 
+// backward of a layer: attention backward kernels (attn_bwd.cu) and the helpers around the GEMMs (layer_bwd.cu)
+int launch_attn_bwd(int B, int H, int Nc, int Ns, int C, const void* q, const void* k, const void* v, const void* x,
+                    const float* x_mean, const float* x_rstd, const float* g, void* d_o, float* lse, float* delta,
+                    float* d_xhat, void* d_q, void* d_k, void* d_v, cudaStream_t s);
+int launch_transpose_norm(const void* in, int in_dtype, int ld, int M, int Mpad, int C, int N, const float* mean, const float* rstd,
+                          void* out, cudaStream_t s);
+int launch_blockdiag_t(const float* w, int H, int d, void* out, cudaStream_t s);
+int launch_extract_blockdiag(const float* full, int H, int d, float* dw, cudaStream_t s);
+size_t token_sums_workspace(int B, int N, int C);
+int launch_token_sums(const void* g, int g_dtype, const void* x, const float* mean, const float* rstd, int B, int N, int C,
+                      void* partial, void* sums, float* bias, cudaStream_t s);
+int launch_in_bwd_apply(const float* g, const void* x, const float* mean, const float* rstd, const void* sums, const float* add,
+                        int B, int N, int C, float* dx, cudaStream_t s);
+
 // decoder blocks 0..7: reflect-padded NHWC input -> conv3x3 + bias + ReLU on tcgen05 (conv_tc.cu)
 int launch_conv3x3_tc(const void* xp, const void* w, const float* bias, int B, int H, int W, int Cin, int Cout, int relu,
                       int out_padded, void* y, cudaStream_t s);

@@ -14,13 +14,16 @@ Precision (`module.precision`, default "auto"):
 There is no CPU path: CPU tensors raise.
 
 Training (train_image.py:105-144): the FORWARD always runs the CUDA kernels.  When gradients are required the
-layers become autograd Functions whose BACKWARD recomputes the layer with PyTorch ops in fp32 and differentiates
-that (cuBLAS through torch; own backward kernels are SURVEY N4), and the decoder takes the plain differentiable
-PyTorch path.  Gradients are checked against the reference's float64 autograd (tests/golden/grad_*).
+layers become autograd Functions.  On the bf16 path at head_dim 64 (the configuration every reference script uses) the
+BACKWARD runs own kernels too (mhada_layer_backward, SURVEY N4: flash-style attention backward with V' = [V~ | V~^2],
+the other contractions on the tcgen05 token GEMM).  Elsewhere (fp32 path, head_dim != 64, cosine, AdaAttN,
+AdaAttnForLoss) it recomputes the layer with PyTorch ops in fp32 and differentiates that.  The decoder takes the plain
+differentiable PyTorch path.  Gradients are checked against the reference's float64 autograd (tests/golden/grad_*).
 """
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import List, Sequence
 
 import torch
@@ -128,12 +131,50 @@ def _layer_math_torch(fc, fs, fcs, wf, bf, wg, bg, wh, bh, wo, bo, num_heads: in
     return cat.reshape(B, C, h, w)
 
 
+def _layer_backward_kernels(num_heads, fc, fs, fcs, wf, bf, wg, bg, wh, bh, wo, bo, grad_out):
+    """Backward of one layer on the B200 kernels (mhada_layer_backward: recomputed forward intermediates, flash-style
+    attention backward, every other contraction on the tcgen05 token GEMM).  Returns the eleven gradients."""
+    L = _lib.lib()
+    dt = torch.bfloat16
+    tfc, tfs = _token_major(fc, dt), _token_major(fs, dt)
+    tfcs = tfc if _same_tensor(fc, fcs) else _token_major(fcs, dt)
+    dout = _token_major(grad_out, dt)
+    B, h, w, C = tfc.shape
+    Nc, Ns = h * w, tfs.shape[1] * tfs.shape[2]
+    dev = tfc.device
+    with torch.no_grad():
+        w_fgh = torch.stack([wf, wg, wh]).float().contiguous()
+        b_fgh = torch.stack([bf, bg, bh]).float().contiguous()
+        wo_f, bo_f = wo.float().contiguous(), bo.float().contiguous()
+    f32 = dict(dtype=torch.float32, device=dev)
+    d_fc, d_fcs = torch.empty((B, h, w, C), **f32), torch.empty((B, h, w, C), **f32)
+    d_fs = torch.empty(tfs.shape, **f32)
+    d_w_fgh, d_b_fgh = torch.empty_like(w_fgh), torch.empty_like(b_fgh)
+    d_wo, d_bo = torch.empty_like(wo_f), torch.empty_like(bo_f)
+    ws = _workspace(dev, L.mhada_layer_backward_workspace(B, Nc, Ns, C, num_heads))
+    a = _lib.LayerBwdArgs()
+    a.B, a.Nc, a.Ns, a.C, a.H = B, Nc, Ns, C, num_heads
+    a.fc, a.fs, a.fcs = tfc.data_ptr(), tfs.data_ptr(), tfcs.data_ptr()
+    a.w_fgh, a.b_fgh, a.w_out, a.b_out = w_fgh.data_ptr(), b_fgh.data_ptr(), wo_f.data_ptr(), bo_f.data_ptr()
+    a.d_out = dout.data_ptr()
+    a.d_fc, a.d_fs, a.d_fcs = d_fc.data_ptr(), d_fs.data_ptr(), d_fcs.data_ptr()
+    a.d_w_fgh, a.d_b_fgh, a.d_w_out, a.d_b_out = d_w_fgh.data_ptr(), d_b_fgh.data_ptr(), d_wo.data_ptr(), d_bo.data_ptr()
+    a.ws, a.ws_bytes = ws.data_ptr(), ws.numel()
+    with torch.cuda.device(dev):
+        _lib.check("mhada_layer_backward", L.mhada_layer_backward(ctypes.byref(a), _stream()))
+    nchw = lambda t, ref: t.permute(0, 3, 1, 2).to(ref.dtype)
+    return (nchw(d_fc, fc), nchw(d_fs, fs), nchw(d_fcs, fcs),
+            d_w_fgh[0].to(wf.dtype), d_b_fgh[0].to(bf.dtype), d_w_fgh[1].to(wg.dtype), d_b_fgh[1].to(bg.dtype),
+            d_w_fgh[2].to(wh.dtype), d_b_fgh[2].to(bh.dtype), d_wo.to(wo.dtype), d_bo.to(bo.dtype))
+
+
 class _MhadaLayerFn(torch.autograd.Function):
-    """Forward: the CUDA kernels.  Backward: recompute with _layer_math_torch in fp32 and differentiate."""
+    """Forward: the CUDA kernels.  Backward: mhada_layer_backward (own kernels) when `kernel_bwd`, else recompute with
+    _layer_math_torch in fp32 and differentiate that."""
 
     @staticmethod
-    def forward(ctx, run_forward, num_heads, has_out, cosine, fc, fs, fcs, wf, bf, wg, bg, wh, bh, wo, bo):
-        ctx.num_heads, ctx.has_out, ctx.cosine = num_heads, has_out, cosine
+    def forward(ctx, run_forward, num_heads, has_out, cosine, kernel_bwd, fc, fs, fcs, wf, bf, wg, bg, wh, bh, wo, bo):
+        ctx.num_heads, ctx.has_out, ctx.cosine, ctx.kernel_bwd = num_heads, has_out, cosine, kernel_bwd
         ctx.save_for_backward(fc, fs, fcs, wf, bf, wg, bg, wh, bh, wo, bo)
         with torch.no_grad():
             return run_forward(fc, fs, fcs)
@@ -141,17 +182,21 @@ class _MhadaLayerFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out):
         saved = ctx.saved_tensors
+        if ctx.kernel_bwd:
+            grads = _layer_backward_kernels(ctx.num_heads, *saved, grad_out)
+            need = ctx.needs_input_grad[5:]
+            return (None, None, None, None, None, *[g if n else None for g, n in zip(grads, need)])
         with torch.enable_grad():
             leaves = [t.detach().float().requires_grad_(True) for t in saved]
             fc, fs, fcs, wf, bf, wg, bg, wh, bh, wo, bo = leaves
             out = _layer_math_torch(fc, fs, fcs, wf, bf, wg, bg, wh, bh, wo if ctx.has_out else None,
                                     bo if ctx.has_out else None, ctx.num_heads, ctx.cosine)
-            need = [i for i, ng in enumerate(ctx.needs_input_grad[4:]) if ng and (ctx.has_out or i < 9)]
+            need = [i for i, ng in enumerate(ctx.needs_input_grad[5:]) if ng and (ctx.has_out or i < 9)]
             grads = torch.autograd.grad(out, [leaves[i] for i in need], grad_out.float(), allow_unused=True)
         full = [None] * len(leaves)
         for i, g in zip(need, grads):
             full[i] = None if g is None else g.to(saved[i].dtype)
-        return (None, None, None, None, *full)
+        return (None, None, None, None, None, *full)
 
 
 def _forloss_math_torch(c_x, s_x, c_1x, s_1x, cosine: bool):
@@ -508,8 +553,8 @@ class AdaAttN(nn.Module):
             params = [t.reshape(1, *shape) for m in (self.f, self.g, self.h)
                       for t, shape in ((m.weight, (d, d)), (m.bias, (d,)))]
             none = fc.new_zeros(0)
-            return _MhadaLayerFn.apply(self._forward_nograd, 1, False, _is_cosine(self.activation), fc, fs, fcs, *params,
-                                       none, none)
+            return _MhadaLayerFn.apply(self._forward_nograd, 1, False, _is_cosine(self.activation), False, fc, fs, fcs,
+                                       *params, none, none)
         return self._forward_nograd(fc, fs, fcs)
 
     def _forward_nograd(self, fc, fs, fcs):
@@ -543,6 +588,9 @@ class AdaAttnMultiHead(nn.Module):
         self.out_conv = nn.Conv2d(qkv_dim, qkv_dim, kernel_size=1)
         self.activation = _make_activation(activation)
         self.precision = "auto"
+        # "auto": own backward kernels where implemented, else the PyTorch recompute; "kernels" / "torch" force one
+        # (tests, A/B timing; MHADA_BACKWARD_IMPL sets the default of new modules)
+        self.backward_impl = os.environ.get("MHADA_BACKWARD_IMPL", "auto")
         self._packed = _PackedWeights()
 
     def packed_weights(self, dt=None):
@@ -586,11 +634,21 @@ class AdaAttnMultiHead(nn.Module):
         _require_cuda(fc, fs, fcs)
         _check_activation(self.activation)
         if _needs_grad(self, fc, fs, fcs):
-            # kernels forward, PyTorch recompute backward (module docstring); torch.stack keeps the graph to the
-            # per-head Conv2d parameters
-            return _MhadaLayerFn.apply(self._forward_nograd, self.num_heads, True, _is_cosine(self.activation), fc, fs, fcs,
-                                       *self._stacked_params())
+            # kernels forward AND backward on the bf16 path at head_dim 64 (mhada_layer_backward); otherwise the
+            # PyTorch recompute backward (module docstring); torch.stack keeps the graph to the per-head Conv2d parameters
+            return _MhadaLayerFn.apply(self._forward_nograd, self.num_heads, True, _is_cosine(self.activation),
+                                       self._kernel_backward(fc, fs, fcs), fc, fs, fcs, *self._stacked_params())
         return self._forward_nograd(fc, fs, fcs)
+
+    def _kernel_backward(self, fc, fs, fcs) -> bool:
+        """mhada_layer_backward covers the bf16 path with head_dim 64, softmax, C a multiple of 128."""
+        if self.backward_impl not in ("auto", "kernels", "torch"):
+            raise ValueError(f"Unknown backward_impl: {self.backward_impl}")
+        ok = (not _is_cosine(self.activation) and self.head_dim == 64 and (self.num_heads * 64) % 128 == 0 and
+              _resolve_precision(self.precision, self.head_dim, fc, fs, fcs, activation=self.activation) == torch.bfloat16)
+        if self.backward_impl == "kernels" and not ok:
+            raise NotImplementedError("backward_impl='kernels' needs the bf16 path, softmax, head_dim 64 and C % 128 == 0")
+        return ok and self.backward_impl != "torch"
 
     def _forward_nograd(self, fc, fs, fcs):
         dt = _resolve_precision(self.precision, self.head_dim, fc, fs, fcs, activation=self.activation)

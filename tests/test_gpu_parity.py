@@ -423,12 +423,75 @@ def test_layer_gradients_bf16_forward():
     fc, fs, fcs, sd, G = cases.grad_inputs(case)
     m = build_layer(case, sd)
     m.precision = "bf16"
+    m.backward_impl = "torch"                       # the fp32 recompute backward behind the bf16 kernels forward
     tin = [dev(a).requires_grad_(True) for a in (fc, fs, fcs)]
     out = m(*tin)
     (out * dev(G)).sum().backward()
     g = load_golden(case["name"])
     assert O.errors(tin[0].grad.cpu().numpy(), g["fc"])["max_abs_rel"] <= 2e-4
     assert O.errors(m.out_conv.weight.grad.cpu().numpy(), g["out_conv__weight"])["max_abs_rel"] <= 2e-4
+
+
+def _grads_of(m, tin, G_):
+    out = m(*tin)
+    (out.float() * G_).sum().backward()
+    got = {"fc": tin[0].grad, "fs": tin[1].grad, "fcs": tin[2].grad}
+    got.update({k: p.grad for k, p in m.named_parameters()})
+    return out.detach(), got
+
+
+def _check_kernel_grads(got, want, max_rel, fro_rel):
+    """bf16 gradients: each within max_rel of its own range plus 5e-3 of the largest gradient of the layer (d/d(g bias)
+    is exactly zero in exact arithmetic: a constant added to every logit of a row cancels in the softmax), and within
+    fro_rel in Frobenius norm unless it is one of those vanishing gradients."""
+    scale = max(float(np.abs(v).max()) for v in want.values())
+    for k, w in want.items():
+        eg = O.errors(got[k], w)
+        assert eg["max_abs"] <= max_rel * eg["absmax"] + 5e-3 * scale, (k, eg)
+        if eg["absmax"] > 1e-2 * scale:
+            assert eg["fro_rel"] <= fro_rel, (k, eg)
+
+
+@pytest.mark.parametrize("case", cases.GRAD_CASES, ids=lambda c: c["name"])
+def test_layer_backward_kernels_vs_reference_autograd(case, golden_index):
+    """forward AND backward on own kernels (mhada_layer_backward: flash-style attention backward, the other
+    contractions on the tcgen05 GEMM) against the reference's float64 autograd gradients.  100 x 72 tokens: the bf16
+    rounding of the INPUT feature maps alone moves the instance-norm statistics by a per cent at this token count
+    (forward parity on these fixtures is 2-4e-2 too); measured 7e-2 max / 2e-2 Frobenius."""
+    fc, fs, fcs, sd, G = cases.grad_inputs(case)
+    m = build_layer(case, sd)
+    m.precision = "bf16"
+    m.backward_impl = "kernels"
+    tin = [dev(a).requires_grad_(True) for a in (fc, fs, fcs)]
+    _, got = _grads_of(m, tin, dev(G))
+    g = load_golden(case["name"])
+    _check_kernel_grads({k: got[k].float().cpu().numpy() for k in cases.GRAD_KEYS},
+                        {k: g[k.replace(".", "__")] for k in cases.GRAD_KEYS}, 1.2e-1, 3.5e-2)
+
+
+@pytest.mark.parametrize("B,H,hw,hsws,alias,max_rel,fro_rel", [(2, 8, (32, 32), (32, 32), False, 3e-2, 2e-2),
+                                                               (1, 8, (20, 13), (17, 9), True, 1.5e-1, 4e-2)])
+def test_layer_backward_kernels_vs_recompute(B, H, hw, hsws, alias, max_rel, fro_rel):
+    """The kernel backward against the fp32 PyTorch recompute backward of the same module at the training resolution
+    (1024 tokens, 8 heads: 3e-2 / 2e-2), and on small ragged sizes with fcs aliasing fc (layer 0 of the transformer,
+    adaDecoder.py:262; few tokens -> looser, see the test above)."""
+    C = 64 * H
+    case = dict(B=B, C=C, H=H, hw=hw, hsws=hsws, gain=1.0, seed=73)
+    fc, fs, fcs, sd = cases.layer_inputs(case)
+    G_ = dev(synth.bellish(997, fc.shape, 0.0, 1.0))
+    res = {}
+    for impl in ("kernels", "torch"):
+        m = build_layer(case, sd)
+        m.precision = "bf16"
+        m.backward_impl = impl
+        a, b_ = dev(fc).requires_grad_(True), dev(fs).requires_grad_(True)
+        c = a if alias else dev(fcs).requires_grad_(True)
+        out = m(a, b_, c)
+        (out.float() * G_).sum().backward()
+        res[impl] = {"fc": a.grad, "fs": b_.grad, **({} if alias else {"fcs": c.grad}),
+                     **{k: p.grad for k, p in m.named_parameters()}}
+    _check_kernel_grads({k: v.float().cpu().numpy() for k, v in res["kernels"].items()},
+                        {k: v.float().cpu().numpy() for k, v in res["torch"].items()}, max_rel, fro_rel)
 
 
 def test_cosine_layer_gradient_matches_oracle_finite_difference():
@@ -532,7 +595,8 @@ def _ddp_worker(rank, world, port, q):
         worst = 0.0
         for a, b in zip(m.parameters(), full.parameters()):
             d = (a.grad - b.grad).abs().max().item()
-            worst = max(worst, d / (b.grad.abs().max().item() + 1e-3 * scale))
+            worst = max(worst, d / (b.grad.abs().max().item() + 1e-2 * scale))   # vanishing gradients (g biases): f32
+                                                                               # summation order of O(scale) terms
         q.put(worst)
     dist.barrier()
     dist.destroy_process_group()
