@@ -306,7 +306,7 @@ MHADA_API size_t mhada_layer_backward_workspace(int B, int Nc, int Ns, int C, in
 MHADA_API int mhada_layer_backward(const mhada_layer_bwd_args* args, mhada_stream_t stream);
 /*     The attention stage of (9) alone (stage tests): q (pre-multiplied by log2 e), k bf16 [B, N, C], v bf16 [B, Ns, 2C]
  *     as mhada_proj writes them, x = fcs bf16 with its statistics, g = dL/d(heads) f32 [B, Nc, C].  Outputs: d_o bf16
- *     [B, Nc, 2C] (per head [dM~ | dE]), lse (log2 units) and delta f32 [B, H, Nc], d_xhat = dL/d(IN(fcs)) f32 [B, Nc, C],
+ *     [B, Nc, 4C] (per head [dM~ | dE] as two bf16 terms: hi 128 columns, lo 128 columns), lse (log2 units) and delta f32 [B, H, Nc], d_xhat = dL/d(IN(fcs)) f32 [B, Nc, C],
  *     d_q, d_k, d_v bf16 (natural units; d_v is the gradient of V, the squares already folded in). */
 MHADA_API int mhada_attn_bwd(int B, int H, int Nc, int Ns, const void* q, const void* k, const void* v, const void* x,
                              const float* x_mean, const float* x_rstd, const float* g, void* d_o, float* lse, float* delta,

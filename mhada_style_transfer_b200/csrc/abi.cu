@@ -274,7 +274,7 @@ BwdWs carve_bwd(int B, int Nc, int Ns, int C, int H, uint8_t* base) {
     w.woT = take(static_cast<size_t>(C) * C * 2);
     w.wbd = take(static_cast<size_t>(3) * C * C * 2);
     w.dcat = static_cast<float*>(take(Mc * C * 4));
-    w.d_o = take(Mc * 2 * C * 2);
+    w.d_o = take(Mc * 4 * C * 2);
     w.lse = static_cast<float*>(take(static_cast<size_t>(B) * H * Nc * 4));
     w.delta = static_cast<float*>(take(static_cast<size_t>(B) * H * Nc * 4));
     w.dxhat = static_cast<float*>(take(Mc * C * 4));

@@ -12,7 +12,8 @@
 //
 // Three kernels, all warp-level mma.sync.m16n8k16 (bf16) on 64 x 64 tiles staged in shared memory by cp.async:
 //   attn_bwd_prep_kernel : per query tile, streaming pass over the keys (online softmax) -> row log-sum-exp L (log2
-//                          units), then the element-wise part above in its epilogue: dO' (bf16), delta, d(IN(fcs)).
+//                          units), then the element-wise part above in its epilogue: dO' (two bf16 terms, hi + lo),
+//                          delta, d(IN(fcs)).
 //   attn_bwd_dq_kernel   : per query tile, loop over key tiles:   dQ += dS K     (dS stays in registers)
 //   attn_bwd_dkv_kernel  : per key tile, loop over query tiles:   dV' += P^T dO', dK += dS^T Q   (P, dS through smem)
 // No atomics: every output element has one owner, results are deterministic.  At the training resolution (256 x 256
@@ -93,7 +94,7 @@ struct BwdParams {
     const __nv_bfloat16* x;             // fcs [B,Nc,C]
     const float *x_mean, *x_rstd;       // [B,C]
     const float* g;                     // dL/d(cat) [B,Nc,C]
-    __nv_bfloat16* d_o;                 // dO' [B,Nc,2C] (per head [dM~ | dE])
+    __nv_bfloat16* d_o;                 // dO' [B,Nc,4C] (per head [dM~ | dE] hi, then [dM~ | dE] lo: two bf16 terms)
     float *lse, *delta;                 // [B,H,Nc]
     float* d_xhat;                      // d(IN(fcs)) [B,Nc,C]
     __nv_bfloat16 *d_q, *d_k, *d_v;     // [B,Nc,C], [B,Ns,C], [B,Ns,C]
@@ -115,9 +116,12 @@ __device__ __forceinline__ void logits_tile(float (&s)[8][4], const uint32_t (&q
 }
 
 // dA (16 rows x 64 keys per warp) = dO'frag . V'^T, V' tile [key][128] in shared memory
+template <bool ZERO>
 __device__ __forceinline__ void dattn_tile(float (&da)[8][4], const uint32_t (&dof)[8][4], uint32_t vs, int lane) {
+    if (ZERO) {
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) da[nt][0] = da[nt][1] = da[nt][2] = da[nt][3] = 0.f;
+        for (int nt = 0; nt < 8; ++nt) da[nt][0] = da[nt][1] = da[nt][2] = da[nt][3] = 0.f;
+    }
 #pragma unroll
     for (int n2 = 0; n2 < 4; ++n2)
 #pragma unroll
@@ -222,7 +226,7 @@ __global__ void __launch_bounds__(128) attn_bwd_prep_kernel(const BwdParams p) {
             const float* mu = p.x_mean + static_cast<size_t>(b) * C + h * 64;
             const float* rs = p.x_rstd + static_cast<size_t>(b) * C + h * 64;
             float* dxrow = p.d_xhat + row * C + h * 64;
-            __nv_bfloat16* dorow = p.d_o + row * 2 * C + h * 128;
+            __nv_bfloat16* dorow = p.d_o + row * 4 * C + h * 256;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int c = j * 8 + 2 * t;
@@ -243,14 +247,20 @@ __global__ void __launch_bounds__(128) attn_bwd_prep_kernel(const BwdParams p) {
                     de[e] = dvar;
                     mo[e] = M; eo[e] = E;
                 }
-                // delta from the ROUNDED dO' (what dA = dO' V'^T is computed from): sum_j P_ij dA_ij = delta_i has to
-                // hold for the operands actually used, or P (dA - delta) keeps a bias of 2^-9 |dO'| |O'| per row
+                // dO' as TWO bf16 terms (hi + lo).  dA - delta = sum_c [dM (v - M) + dE (v^2 - E)] cancels between the
+                // dM and the dE products when a row is sharp (dVar = g x^ / (2 sigma) grows as sigma -> 0): with one bf16
+                // term the cancellation residue carries 2^-9 of the LARGE terms (measured: dV 28 % off at logit std 6.5).
+                // delta is taken from the same rounded values, so sum_j P_ij dA_ij = delta_i holds for the operands used.
                 const uint32_t wm = pack_bf16x2(dm[0], dm[1]), we = pack_bf16x2(de[0], de[1]);
-                delta = fmaf(bf16_lo(wm), mo[0], fmaf(bf16_hi(wm), mo[1], delta));
-                delta = fmaf(bf16_lo(we), eo[0], fmaf(bf16_hi(we), eo[1], delta));
+                const uint32_t lm = pack_bf16x2(dm[0] - bf16_lo(wm), dm[1] - bf16_hi(wm));
+                const uint32_t le = pack_bf16x2(de[0] - bf16_lo(we), de[1] - bf16_hi(we));
+                delta = fmaf(bf16_lo(wm) + bf16_lo(lm), mo[0], fmaf(bf16_hi(wm) + bf16_hi(lm), mo[1], delta));
+                delta = fmaf(bf16_lo(we) + bf16_lo(le), eo[0], fmaf(bf16_hi(we) + bf16_hi(le), eo[1], delta));
                 *reinterpret_cast<float2*>(dxrow + c) = make_float2(dx[0], dx[1]);
                 *reinterpret_cast<uint32_t*>(dorow + c) = wm;
                 *reinterpret_cast<uint32_t*>(dorow + 64 + c) = we;
+                *reinterpret_cast<uint32_t*>(dorow + 128 + c) = lm;
+                *reinterpret_cast<uint32_t*>(dorow + 192 + c) = le;
             }
         }
         delta = quad_sum(delta);
@@ -274,15 +284,22 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const BwdParams p) {
     const uint32_t ks = smem_u32(ks_), vs = smem_u32(vs_);
     const int qvalid = min(BW_T, Nc - q0);
 
+    const __nv_bfloat16* dorow = p.d_o + (static_cast<size_t>(b) * Nc + q0) * 4 * C + h * 256;
     load_tile<64, BW_P64>(ks_, p.q + (static_cast<size_t>(b) * Nc + q0) * C + h * 64, C, qvalid);
-    load_tile<128, BW_P128>(vs_, p.d_o + (static_cast<size_t>(b) * Nc + q0) * 2 * C + h * 128, 2 * C, qvalid);
+    load_tile<128, BW_P128>(vs_, dorow, 4 * C, qvalid);
     cp_commit_wait();
     __syncthreads();
-    uint32_t qf[4][4], dof[8][4];
+    uint32_t qf[4][4], dof[8][4], dol[8][4];
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) ldsm_x4(qf[kk], addr_a(ks, BW_P64, warp * 16, kk * 16, lane));
 #pragma unroll
     for (int kk = 0; kk < 8; ++kk) ldsm_x4(dof[kk], addr_a(vs, BW_P128, warp * 16, kk * 16, lane));
+    __syncthreads();
+    load_tile<128, BW_P128>(vs_, dorow + 128, 4 * C, qvalid);
+    cp_commit_wait();
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) ldsm_x4(dol[kk], addr_a(vs, BW_P128, warp * 16, kk * 16, lane));
     float L[2], D[2];
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
@@ -304,7 +321,8 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const BwdParams p) {
         __syncthreads();
         float s[8][4], da[8][4];
         logits_tile(s, qf, ks, lane);
-        dattn_tile(da, dof, vs, lane);
+        dattn_tile<true>(da, dof, vs, lane);
+        dattn_tile<false>(da, dol, vs, lane);
         uint32_t ds[8][2];
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
@@ -347,7 +365,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const BwdParams p) {
 // dV' = P^T dO', dK = dS^T Q; one CTA per (key tile, head, image), loop over query tiles.  Step A: warp = 16 query rows
 // (S, dA, P, dS -> shared memory); step B: warp = 16 keys (the contraction runs over the 64 query rows of the tile).
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr size_t BW_DKV_SMEM = (4 * BW_T * BW_P64 + 2 * BW_T * BW_P128) * 2 + 2 * BW_T * 4;
+constexpr size_t BW_DKV_SMEM = (4 * BW_T * BW_P64 + 3 * BW_T * BW_P128) * 2 + 2 * BW_T * 4;
 
 __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const BwdParams p) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -357,13 +375,14 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const BwdParams p) {
     __nv_bfloat16* dss_ = ps_ + BW_T * BW_P64;
     __nv_bfloat16* vs_ = dss_ + BW_T * BW_P64;
     __nv_bfloat16* dos_ = vs_ + BW_T * BW_P128;
-    float* ls_ = reinterpret_cast<float*>(dos_ + BW_T * BW_P128);
+    __nv_bfloat16* dol_ = dos_ + BW_T * BW_P128;
+    float* ls_ = reinterpret_cast<float*>(dol_ + BW_T * BW_P128);
     float* dl_ = ls_ + BW_T;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
     const int k0 = blockIdx.x * BW_T, h = blockIdx.y, b = blockIdx.z;
     const int C = p.C, Nc = p.Nc, Ns = p.Ns;
     const uint32_t ks = smem_u32(ks_), qs = smem_u32(qs_), ps = smem_u32(ps_), dss = smem_u32(dss_), vs = smem_u32(vs_),
-                   dos = smem_u32(dos_);
+                   dos = smem_u32(dos_), dol = smem_u32(dol_);
     const int kvalid = min(BW_T, Ns - k0);
 
     load_tile<64, BW_P64>(ks_, p.k + (static_cast<size_t>(b) * Ns + k0) * C + h * 64, C, kvalid);
@@ -379,7 +398,8 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const BwdParams p) {
         __syncthreads();                                   // step B of the previous tile is done with Q, dO', P, dS
         const int qvalid = min(BW_T, Nc - q0);
         load_tile<64, BW_P64>(qs_, p.q + (static_cast<size_t>(b) * Nc + q0) * C + h * 64, C, qvalid);
-        load_tile<128, BW_P128>(dos_, p.d_o + (static_cast<size_t>(b) * Nc + q0) * 2 * C + h * 128, 2 * C, qvalid);
+        load_tile<128, BW_P128>(dos_, p.d_o + (static_cast<size_t>(b) * Nc + q0) * 4 * C + h * 256, 4 * C, qvalid);
+        load_tile<128, BW_P128>(dol_, p.d_o + (static_cast<size_t>(b) * Nc + q0) * 4 * C + h * 256 + 128, 4 * C, qvalid);
         if (threadIdx.x < BW_T) {
             const int n = q0 + threadIdx.x;
             const size_t i = (static_cast<size_t>(b) * p.H + h) * Nc + n;
@@ -409,14 +429,17 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const BwdParams p) {
             }
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk) {
-                uint32_t a[4];
+                uint32_t a[4], al[4];
                 ldsm_x4(a, addr_a(dos, BW_P128, warp * 16, kk * 16, lane));
+                ldsm_x4(al, addr_a(dol, BW_P128, warp * 16, kk * 16, lane));
 #pragma unroll
                 for (int n2 = 0; n2 < 4; ++n2) {
                     uint32_t bb[4];
                     ldsm_x4(bb, addr_b(vs, BW_P128, n2 * 16, kk * 16, lane));
                     mma16816(da[2 * n2], a, bb[0], bb[1]);
                     mma16816(da[2 * n2 + 1], a, bb[2], bb[3]);
+                    mma16816(da[2 * n2], al, bb[0], bb[1]);
+                    mma16816(da[2 * n2 + 1], al, bb[2], bb[3]);
                 }
             }
             const int r0 = warp * 16 + g;
@@ -441,10 +464,13 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const BwdParams p) {
             ldsm_x4_t(ad, addr_at(dss, BW_P64, kk * 16, warp * 16, lane));
 #pragma unroll
             for (int n2 = 0; n2 < 8; ++n2) {
-                uint32_t bb[4];
+                uint32_t bb[4], bl[4];
                 ldsm_x4_t(bb, addr_bt(dos, BW_P128, kk * 16, n2 * 16, lane));
+                ldsm_x4_t(bl, addr_bt(dol, BW_P128, kk * 16, n2 * 16, lane));
                 mma16816(dv[2 * n2], ap, bb[0], bb[1]);
                 mma16816(dv[2 * n2 + 1], ap, bb[2], bb[3]);
+                mma16816(dv[2 * n2], ap, bl[0], bl[1]);
+                mma16816(dv[2 * n2 + 1], ap, bl[2], bl[3]);
             }
 #pragma unroll
             for (int n2 = 0; n2 < 4; ++n2) {

@@ -384,12 +384,12 @@ def _attn_bwd_reference(q2, k, v, vsq, x, mean, rstd, g, H):
 
 
 @pytest.mark.parametrize("B,H,Nc,Ns,sharp", [(1, 2, 64, 64, 1.0), (2, 2, 100, 72, 1.0), (1, 8, 256, 200, 1.0),
-                                             (2, 2, 130, 1, 1.0), (1, 2, 192, 320, 2.0)])
+                                             (2, 2, 130, 1, 1.0), (1, 2, 192, 320, 2.0), (1, 2, 192, 320, 4.0)])
 def test_attn_bwd(B, H, Nc, Ns, sharp):
     """mhada_attn_bwd (flash-style backward with V' = [V~ | V~^2], mma.sync kernels) against float64 autograd on the
-    same bf16 operands: ragged tiles, a single key, sharper rows (logits x4: std 6.5, against 2.7 in the model at
-    random init).  The one-hot limit is ill-conditioned for ANY arithmetic (Var -> 0, dVar = g x^ / (2 sigma) explodes
-    or is cut by the clamp) and in bf16 the two halves of dO' then cancel: not a test case."""
+    same bf16 operands: ragged tiles, a single key (A = 1, Var = rounding noise), sharper rows (logits x4 and x16: std
+    6.5 and 26, against 2.7 in the model at random init; towards the one-hot limit Var -> 0 and dVar = g x^ / (2 sigma)
+    grows without bound, so the tolerance widens there)."""
     L = _lib.lib()
     C = H * 64
     bf = lambda a: torch.from_numpy(np.ascontiguousarray(a)).float().to(G.DEV).bfloat16().contiguous()
@@ -403,7 +403,7 @@ def test_attn_bwd(B, H, Nc, Ns, sharp):
     vf = v.float().view(B, Ns, H, 64)
     vsq = (vf * vf).bfloat16()
     vp = torch.cat([vf.bfloat16(), vsq], dim=3).reshape(B, Ns, 2 * C).contiguous()             # V' as mhada_proj writes it
-    d_o = torch.empty(B, Nc, 2 * C, dtype=torch.bfloat16, device=G.DEV)
+    d_o = torch.empty(B, Nc, 4 * C, dtype=torch.bfloat16, device=G.DEV)
     lse = torch.empty(B, H, Nc, dtype=torch.float32, device=G.DEV)
     delta = torch.empty_like(lse)
     dxh = torch.empty(B, Nc, C, dtype=torch.float32, device=G.DEV)
@@ -418,7 +418,7 @@ def test_attn_bwd(B, H, Nc, Ns, sharp):
     assert (lse.double() - rlse).abs().max().item() <= 2e-3
     for name, got, want in (("dxhat", dxh, rxh), ("dq", dq, rq), ("dk", dk, rk), ("dv", dv, rv)):
         e = O.errors(got.float().cpu().numpy(), want.cpu().numpy())
-        # Ns = 1: dq and dk are exactly zero in exact arithmetic -> absolute floor (operands are O(100)); sharper rows: 5e-2
-        tol = 5e-2 if sharp > 1 else 2e-2
-        print(name, e)
+        # Ns = 1: dq and dk are exactly zero in exact arithmetic -> absolute floor (operands are O(100)).  Measured 2-5e-3
+        # everywhere (dO' travels as two bf16 terms) except at logits x16, where dv reaches 9e-2 max / 8e-3 Frobenius
+        tol = 1e-1 if sharp > 2 else 2e-2
         assert e["max_abs"] <= tol * e["absmax"] + 5e-2 and (e["absmax"] < 1e-6 or e["fro_rel"] <= tol / 2), (name, e)
