@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define MHADA_ABI_VERSION 8
+#define MHADA_ABI_VERSION 9
 
 #if defined(__GNUC__)
 #define MHADA_API __attribute__((visibility("default")))
@@ -311,6 +311,18 @@ MHADA_API int mhada_layer_backward(const mhada_layer_bwd_args* args, mhada_strea
 MHADA_API int mhada_attn_bwd(int B, int H, int Nc, int Ns, const void* q, const void* k, const void* v, const void* x,
                              const float* x_mean, const float* x_rstd, const float* g, void* d_o, float* lse, float* delta,
                              float* d_xhat, void* d_q, void* d_k, void* d_v, mhada_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (10) Helpers of the training path (backward of y = x W^T + b on the token GEMM): dW = dy^T x needs both operands with
+ *     the TOKEN axis contiguous, db = column sums of dy.
+ *     mhada_transpose_bf16: x [M, ld] (MHADA_F32 or MHADA_BF16) -> out bf16 [C][Mpad], out[c][m] = x[m][c], columns
+ *                           M <= m < Mpad zero (Mpad % 64 == 0 so that it can be the K axis of mhada_gemm_bf16);
+ *     mhada_colsum:         out f32 [C] = sum over the M rows of x [M, C] (two-stage, deterministic);
+ *                           C even, <= 2048; ws: mhada_colsum_workspace(M, C) bytes.
+ * ---------------------------------------------------------------------------------------------- */
+MHADA_API int mhada_transpose_bf16(const void* x, int dtype, int ld, int M, int C, int Mpad, void* out, mhada_stream_t stream);
+MHADA_API size_t mhada_colsum_workspace(int M, int C);
+MHADA_API int mhada_colsum(const void* x, int dtype, int M, int C, void* ws, size_t ws_bytes, float* out, mhada_stream_t stream);
 
 /* Number of kernel launches the last mhada_layer_forward on this thread issued (bench bookkeeping). */
 MHADA_API int mhada_last_launch_count(void);

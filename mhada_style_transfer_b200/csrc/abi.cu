@@ -757,4 +757,26 @@ int mhada_layer_backward(const mhada_layer_bwd_args* a, mhada_stream_t stream) {
     return 0;
 }
 
+int mhada_transpose_bf16(const void* x, int dtype, int ld, int M, int C, int Mpad, void* out, mhada_stream_t stream) {
+    REQUIRE(x && out, MHADA_ERR_ARG, "mhada_transpose_bf16: null pointer");
+    REQUIRE(dtype == MHADA_F32 || dtype == MHADA_BF16, MHADA_ERR_ARG, "mhada_transpose_bf16: bad dtype %d", dtype);
+    REQUIRE(M > 0 && C > 0 && ld >= C && Mpad >= M, MHADA_ERR_ARG, "mhada_transpose_bf16: bad sizes");
+    if (int e = device_check()) return e;
+    return launch_transpose_norm(x, dtype, ld, M, Mpad, C, M, nullptr, nullptr, out, static_cast<cudaStream_t>(stream));
+}
+
+size_t mhada_colsum_workspace(int M, int C) {
+    if (M <= 0 || C <= 0) return 0;
+    return token_sums_workspace(1, M, C);
+}
+
+int mhada_colsum(const void* x, int dtype, int M, int C, void* ws, size_t ws_bytes, float* out, mhada_stream_t stream) {
+    REQUIRE(x && ws && out, MHADA_ERR_ARG, "mhada_colsum: null pointer");
+    REQUIRE(dtype == MHADA_F32 || dtype == MHADA_BF16, MHADA_ERR_ARG, "mhada_colsum: bad dtype %d", dtype);
+    REQUIRE(M > 0 && C > 0, MHADA_ERR_ARG, "mhada_colsum: bad sizes");
+    REQUIRE(ws_bytes >= token_sums_workspace(1, M, C), MHADA_ERR_WORKSPACE, "mhada_colsum: workspace too small");
+    if (int e = device_check()) return e;
+    return launch_token_sums(x, dtype, nullptr, nullptr, nullptr, 1, M, C, ws, nullptr, out, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

@@ -15,12 +15,16 @@ Reference quirk kept on purpose: `nn.MultiheadAttention` is built
 (B, N, D), so it attends ACROSS THE BATCH for every token position.  The kernels reproduce that, so an image's
 features depend on the other images of its batch exactly as in the reference.
 
-There is no CPU path.  Under autograd (train_image.py:103-108) the forward runs the reference's own op sequence
-with PyTorch ops on the GPU (differentiable); own backward kernels are SURVEY N4.
+There is no CPU path.  Under autograd (train_image.py:103-108) the encoder runs the reference's op sequence with every
+Linear layer (in_proj, out_proj, the MLP: > 95 % of its FLOPs) on the tcgen05 token GEMM, forward AND backward
+(`_LinearTC`: dx = dy W and dW = dy^T x are the same GEMM kernel on transposed operands); LayerNorm, ReLU, the residual
+adds, the 8-long batch-axis attention and the patch convolution stay differentiable PyTorch ops.  `train_impl = "torch"`
+(or MHADA_VIT_TRAIN_IMPL=torch) keeps the plain fp32 PyTorch sequence (r1 / early r2: fp32 SIMT GEMMs, 20 ms per step).
 """
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import List
 
 import torch
@@ -31,6 +35,77 @@ from . import _lib
 from .network import _needs_grad, _require_cuda, _stream, _workspace
 
 __all__ = ["VisionTransformer", "EncoderBlock", "PatchEmbedding", "PosEmbedding"]
+
+
+def _gemm_bf16(a16: torch.Tensor, w16: torch.Tensor, bias, M: int, N: int, K: int) -> torch.Tensor:
+    """f32 [M, N] = a16 [M, >=K] . w16 [N, >=K]^T (+ bias) on the tcgen05 token GEMM (mhada_gemm_bf16)."""
+    L = _lib.lib()
+    out = torch.empty((M, N), dtype=torch.float32, device=a16.device)
+    with torch.cuda.device(a16.device):
+        rc = L.mhada_gemm_bf16(a16.data_ptr(), a16.stride(0), w16.data_ptr(), w16.stride(0),
+                               bias.data_ptr() if bias is not None else None, M, N, K, None, 0, out.data_ptr(), N, None, 0, 0, 0,
+                               _stream())
+    _lib.check("mhada_gemm_bf16", rc)
+    return out
+
+
+def _transpose_bf16(x: torch.Tensor, M: int, C: int) -> torch.Tensor:
+    """bf16 [C, Mpad] = x[M, C]^T, token axis padded with zeros to a multiple of 64 (mhada_transpose_bf16)."""
+    L = _lib.lib()
+    Mpad = (M + 63) // 64 * 64
+    out = torch.empty((C, Mpad), dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = L.mhada_transpose_bf16(x.data_ptr(), _lib.BF16 if x.dtype == torch.bfloat16 else _lib.F32, x.stride(0), M, C, Mpad,
+                                    out.data_ptr(), _stream())
+    _lib.check("mhada_transpose_bf16", rc)
+    return out
+
+
+def _colsum(x: torch.Tensor, M: int, C: int) -> torch.Tensor:
+    L = _lib.lib()
+    out = torch.empty((C,), dtype=torch.float32, device=x.device)
+    ws = _workspace(x.device, L.mhada_colsum_workspace(M, C))
+    with torch.cuda.device(x.device):
+        rc = L.mhada_colsum(x.data_ptr(), _lib.BF16 if x.dtype == torch.bfloat16 else _lib.F32, M, C, ws.data_ptr(), ws.numel(),
+                            out.data_ptr(), _stream())
+    _lib.check("mhada_colsum", rc)
+    return out
+
+
+class _LinearTC(torch.autograd.Function):
+    """y = x W^T + b with bf16 operands / f32 accumulation on the tcgen05 token GEMM, forward and backward:
+    dx = dy W (the weight transposed), dW = dy^T x (both operands transposed so that the tokens are the contraction axis),
+    db = column sums of dy.  Needs in_features and out_features to be multiples of 128."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        K, N = x.shape[-1], weight.shape[0]
+        x2 = x.reshape(-1, K)
+        M = x2.shape[0]
+        x16 = x2.to(torch.bfloat16).contiguous()
+        w16 = weight.detach().to(torch.bfloat16).contiguous()
+        y = _gemm_bf16(x16, w16, bias.detach().float().contiguous() if bias is not None else None, M, N, K)
+        ctx.save_for_backward(x16, w16)
+        ctx.in_shape, ctx.has_bias, ctx.dtypes = x.shape, bias is not None, (x.dtype, weight.dtype)
+        return y.view(*x.shape[:-1], N)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x16, w16 = ctx.saved_tensors
+        M, K = x16.shape
+        N = w16.shape[0]
+        dy2 = dy.reshape(M, N)
+        dy2 = dy2 if dy2.is_contiguous() else dy2.contiguous()
+        dy16 = dy2.to(torch.bfloat16)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = _gemm_bf16(dy16, _transpose_bf16(w16, N, K), None, M, K, N).view(ctx.in_shape).to(ctx.dtypes[0])
+        if ctx.needs_input_grad[1]:
+            dyT, xT = _transpose_bf16(dy16, M, N), _transpose_bf16(x16, M, K)
+            dw = _gemm_bf16(dyT, xT, None, N, K, dyT.shape[1]).to(ctx.dtypes[1])
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = _colsum(dy2, M, N)
+        return dx, dw, db
 
 
 class EncoderBlock(nn.Module):
@@ -48,6 +123,20 @@ class EncoderBlock(nn.Module):
         x, _ = self.attention(x, x, x, need_weights=False)
         x = x + input
         return x + self.mlp(self.ln2(x))
+
+    def forward_train_tc(self, input: torch.Tensor):
+        """The same block (vit.py:54-64) with its four Linear layers on the tcgen05 GEMM (forward and backward).
+        nn.MultiheadAttention without batch_first reads (B, N, D) as (sequence = B, batch = N): attention across the
+        images of the batch per token position, scale 1 / sqrt(head_dim), no dropout."""
+        a = self.attention
+        L, Nn, D = input.shape
+        H = a.num_heads
+        qkv = _LinearTC.apply(self.ln1(input), a.in_proj_weight, a.in_proj_bias)
+        q, k, v = (t.reshape(L, Nn, H, D // H).permute(1, 2, 0, 3) for t in qkv.chunk(3, dim=-1))    # (N, H, L, hd)
+        o = F.scaled_dot_product_attention(q, k, v).permute(2, 0, 1, 3).reshape(L, Nn, D)
+        x = _LinearTC.apply(o, a.out_proj.weight, a.out_proj.bias) + input
+        hdn = torch.relu(_LinearTC.apply(self.ln2(x), self.mlp[0].weight, self.mlp[0].bias))
+        return x + _LinearTC.apply(hdn, self.mlp[2].weight, self.mlp[2].bias)
 
 
 class PosEmbedding(nn.Module):
@@ -143,6 +232,9 @@ class VisionTransformer(nn.Module):
         self.num_heads, self.mlp_dim = num_heads, mlp_dim
         self.precision = "auto"          # "auto" | "bf16": tcgen05 path.  "fp32" is not built (NotImplementedError)
         self.out_dtype = "bf16"
+        # training forward / backward: "auto" = Linear layers on the tcgen05 GEMM when the widths allow it, "kernels"
+        # forces that, "torch" = the plain fp32 PyTorch op sequence
+        self.train_impl = os.environ.get("MHADA_VIT_TRAIN_IMPL", "auto")
         self._weights = _VitWeights()
 
     # ---- the reference op sequence (vit.py:148-169), differentiable; used only when gradients are required
@@ -152,9 +244,15 @@ class VisionTransformer(nn.Module):
         x = self.patch_embedding(x)
         if self.pos_embedding is not None:
             x = x + self.pos_embedding(x_shape)
+        if self.train_impl not in ("auto", "kernels", "torch"):
+            raise ValueError(f"Unknown train_impl: {self.train_impl}")
+        tc_ok = self.hidden_dim % 128 == 0 and self.mlp_dim % 128 == 0
+        if self.train_impl == "kernels" and not tc_ok:
+            raise NotImplementedError("train_impl='kernels' needs hidden_dim and mlp_dim to be multiples of 128")
+        use_tc = tc_ok and self.train_impl != "torch"
         z = []
         for layer in self.encoder:
-            x = layer(x)
+            x = layer.forward_train_tc(x) if use_tc else layer(x)
             z.append(x.permute(0, 2, 1).reshape(-1, self.hidden_dim, out_h, out_w))
         return z
 

@@ -179,6 +179,33 @@ def test_vit_trains():
     assert all(p.grad is not None and torch.isfinite(p.grad).all().item() for p in m.parameters())
 
 
+@pytest.mark.parametrize("B,hw,pos", [(2, (64, 64), True), (1, (40, 72), False), (3, (32, 48), True)])
+def test_vit_training_gemm_path_vs_torch(B, hw, pos):
+    """Training mode: the Linear layers on the tcgen05 GEMM forward AND backward (_LinearTC) against the plain fp32
+    PyTorch op sequence of the same module: features and every parameter gradient.  bf16 operands -> 2e-2 of each
+    gradient's own range (5e-3 of the largest for the vanishing ones), 1e-2 in Frobenius norm."""
+    torch.manual_seed(3)
+    m = M.VisionTransformer(pos_embedding=pos).to(DEV).train()
+    img = torch.rand(B, 3, *hw, device=DEV) * 255
+    G_ = [torch.randn(B, 512, hw[0] // 8, hw[1] // 8, device=DEV) for _ in range(3)]
+    res = {}
+    for impl in ("kernels", "torch"):
+        m.train_impl = impl
+        m.zero_grad(set_to_none=True)
+        z = m(img)
+        sum((t.float() * g).sum() for t, g in zip(z, G_)).backward()
+        res[impl] = ([t.detach().float() for t in z], {k: p.grad.clone() for k, p in m.named_parameters()})
+    for a, b in zip(*[res[i][0] for i in ("kernels", "torch")]):
+        e = O.errors(a.cpu().numpy(), b.cpu().numpy())
+        assert e["max_abs_rel"] <= 2e-2 and e["fro_rel"] <= 5e-3, e
+    scale = max(v.abs().max().item() for v in res["torch"][1].values())
+    for k, want in res["torch"][1].items():
+        e = O.errors(res["kernels"][1][k].float().cpu().numpy(), want.float().cpu().numpy())
+        assert e["max_abs"] <= 2e-2 * e["absmax"] + 5e-3 * scale, (k, e)
+        if e["absmax"] > 1e-2 * scale:
+            assert e["fro_rel"] <= 1e-2, (k, e)
+
+
 @pytest.mark.parametrize("case", cases.PIPELINE_CASES, ids=lambda c: c["name"])
 def test_pipeline_vs_reference_golden(case, golden_index):
     """infer_image.py:82-86 end to end -- fc = vit_c(c); fs = vit_s(s); fcs, cs = adaFormer(fc, fs) -- against the
