@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define MHADA_ABI_VERSION 9
+#define MHADA_ABI_VERSION 10
 
 #if defined(__GNUC__)
 #define MHADA_API __attribute__((visibility("default")))
@@ -320,6 +320,14 @@ MHADA_API int mhada_attn_bwd(int B, int H, int Nc, int Ns, const void* q, const 
  *     mhada_colsum:         out f32 [C] = sum over the M rows of x [M, C] (two-stage, deterministic);
  *                           C even, <= 2048; ws: mhada_colsum_workspace(M, C) bytes.
  * ---------------------------------------------------------------------------------------------- */
+/*     mhada_gemm_bf16_splitk: out_f32 [M, ldf] = x . w^T like mhada_gemm_bf16 (f32 result only, no bias / residual), with the
+ *                           K range split over extra work items of the same kernel when M x N has too few tiles to fill
+ *                           the GPU (dW = dy^T x: a 512 x 512 result over K = 8192 tokens is 8 tiles); partial tiles go
+ *                           to ws (mhada_gemm_splitk_workspace bytes; 0 or NULL = no split) and are added in a fixed
+ *                           order. */
+MHADA_API size_t mhada_gemm_splitk_workspace(int M, int N, int K);
+MHADA_API int mhada_gemm_bf16_splitk(const void* x, int lda, const void* w, int ldw, int M, int N, int K, float* out_f32,
+                                     int ldf, void* ws, size_t ws_bytes, mhada_stream_t stream);
 MHADA_API int mhada_transpose_bf16(const void* x, int dtype, int ld, int M, int C, int Mpad, void* out, mhada_stream_t stream);
 MHADA_API size_t mhada_colsum_workspace(int M, int C);
 MHADA_API int mhada_colsum(const void* x, int dtype, int M, int C, void* ws, size_t ws_bytes, float* out, mhada_stream_t stream);

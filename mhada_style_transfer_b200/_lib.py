@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libmhada_b200.so")
 
 F32, BF16, U8 = 0, 1, 2
-ABI_VERSION = 9
+ABI_VERSION = 10
 VIT_MAX_LAYERS = 8
 PROJ_Q, PROJ_KV = 1, 2
 REUSE_FS_STATS = 1
@@ -100,6 +100,9 @@ SIGNATURES = {
     "mhada_layer_backward_workspace": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "mhada_layer_backward": (c_int, [POINTER(LayerBwdArgs), c_void_p]),
     "mhada_attn_bwd": (c_int, [c_int, c_int, c_int, c_int] + [c_void_p] * 15),
+    "mhada_gemm_splitk_workspace": (c_size_t, [c_int, c_int, c_int]),
+    "mhada_gemm_bf16_splitk": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p,
+                                       c_size_t, c_void_p]),
     "mhada_transpose_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "mhada_colsum_workspace": (c_size_t, [c_int, c_int]),
     "mhada_colsum": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p, c_void_p]),

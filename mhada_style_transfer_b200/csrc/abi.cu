@@ -250,7 +250,8 @@ int layer_impl(const char* who, int dtype, const void* fc, const void* fs, const
 struct BwdWs {
     void* fwd;                 // LayerWs region (MHADA_BF16)
     size_t fwd_bytes;
-    void *heads, *woT, *wbd, *d_o, *dq, *dk, *dv, *tA, *tB, *partial, *sums;
+    void *heads, *woT, *wbd, *d_o, *dq, *dk, *dv, *tA, *tB, *partial, *sums, *splitk;
+    size_t splitk_bytes;
     float *dcat, *lse, *delta, *dxhat, *gq, *gk, *gv, *dwfull;
     int Mpad_c, Mpad_s;
     size_t total;
@@ -290,6 +291,10 @@ BwdWs carve_bwd(int B, int Nc, int Ns, int C, int H, uint8_t* base) {
     const size_t pb = token_sums_workspace(B, Nc > Ns ? Nc : Ns, C), pb2 = token_sums_workspace(B, Nc < Ns ? Nc : Ns, C);
     w.partial = take(pb > pb2 ? pb : pb2);
     w.sums = take(static_cast<size_t>(B) * C * 8);
+    w.splitk_bytes = gemm_splitk_workspace(C, C, static_cast<int>(Mpad));
+    const size_t sk2 = gemm_splitk_workspace(C, C, w.Mpad_c < w.Mpad_s ? w.Mpad_c : w.Mpad_s);
+    if (sk2 > w.splitk_bytes) w.splitk_bytes = sk2;
+    w.splitk = take(w.splitk_bytes);
     w.total = off;
     return w;
 }
@@ -712,12 +717,17 @@ int mhada_layer_backward(const mhada_layer_bwd_args* a, mhada_stream_t stream) {
         g.a = A; g.lda = lda; g.w = W; g.ldw = ldw; g.M = M; g.N = N; g.K = K; g.out_f32 = out; g.ldf = ldf;
         return launch_gemm_bf16(g, s);
     };
+    auto gemm_wgrad = [&](const void* A, const void* W, int Mpad, float* out) {       // C x C result, K = tokens: split-K
+        GemmDesc g{};
+        g.a = A; g.lda = Mpad; g.w = W; g.ldw = Mpad; g.M = C; g.N = C; g.K = Mpad; g.out_f32 = out; g.ldf = C;
+        return launch_gemm_bf16_splitk(g, w.splitk, w.splitk_bytes, s);
+    };
     // (1) out_conv backward                                                                    adaDecoder.py:202-205
     if (int e = launch_transpose_norm(a->w_out, MHADA_F32, C, C, C, C, C, nullptr, nullptr, w.woT, s)) return e;
     if (int e = gemm(a->d_out, C, w.woT, C, Mc, C, C, w.dcat, C)) return e;                         // d(cat) = d(out) Wo
     if (int e = launch_transpose_norm(a->d_out, MHADA_BF16, C, Mc, w.Mpad_c, C, Nc, nullptr, nullptr, w.tA, s)) return e;
     if (int e = launch_transpose_norm(w.heads, MHADA_BF16, C, Mc, w.Mpad_c, C, Nc, nullptr, nullptr, w.tB, s)) return e;
-    if (int e = gemm(w.tA, w.Mpad_c, w.tB, w.Mpad_c, C, C, w.Mpad_c, a->d_w_out, C)) return e;      // dWo = d(out)^T cat
+    if (int e = gemm_wgrad(w.tA, w.tB, w.Mpad_c, a->d_w_out)) return e;                             // dWo = d(out)^T cat
     if (int e = launch_token_sums(a->d_out, MHADA_BF16, nullptr, nullptr, nullptr, B, Nc, C, w.partial, nullptr, a->d_b_out, s))
         return e;
     // (2) attention backward                                                                   adaDecoder.py:186-198
@@ -740,7 +750,7 @@ int mhada_layer_backward(const mhada_layer_bwd_args* a, mhada_stream_t stream) {
         const Role& R = roles[r];
         if (int e = launch_transpose_norm(R.dy, MHADA_BF16, C, R.M, R.Mpad, C, R.N, nullptr, nullptr, w.tA, s)) return e;
         if (int e = launch_transpose_norm(R.x, MHADA_BF16, C, R.M, R.Mpad, C, R.N, R.mean, R.rstd, w.tB, s)) return e;
-        if (int e = gemm(w.tA, R.Mpad, w.tB, R.Mpad, C, C, R.Mpad, w.dwfull, C)) return e;
+        if (int e = gemm_wgrad(w.tA, w.tB, R.Mpad, w.dwfull)) return e;
         if (int e = launch_extract_blockdiag(w.dwfull, H, d, a->d_w_fgh + static_cast<size_t>(r) * H * d * d, s)) return e;
         if (int e = launch_token_sums(R.dy, MHADA_BF16, nullptr, nullptr, nullptr, B, R.N, C, w.partial, nullptr,
                                       a->d_b_fgh + static_cast<size_t>(r) * C, s))
@@ -777,6 +787,22 @@ int mhada_colsum(const void* x, int dtype, int M, int C, void* ws, size_t ws_byt
     REQUIRE(ws_bytes >= token_sums_workspace(1, M, C), MHADA_ERR_WORKSPACE, "mhada_colsum: workspace too small");
     if (int e = device_check()) return e;
     return launch_token_sums(x, dtype, nullptr, nullptr, nullptr, 1, M, C, ws, nullptr, out, static_cast<cudaStream_t>(stream));
+}
+
+size_t mhada_gemm_splitk_workspace(int M, int N, int K) { return gemm_splitk_workspace(M, N, K); }
+
+int mhada_gemm_bf16_splitk(const void* x, int lda, const void* w, int ldw, int M, int N, int K, float* out_f32, int ldf,
+                           void* ws, size_t ws_bytes, mhada_stream_t stream) {
+    REQUIRE(x && w && out_f32, MHADA_ERR_ARG, "mhada_gemm_bf16_splitk: null pointer");
+    REQUIRE(M > 0 && N > 0 && K > 0 && lda >= K && ldw >= K, MHADA_ERR_ARG, "mhada_gemm_bf16_splitk: bad sizes");
+    REQUIRE(K % 64 == 0 && N % 128 == 0, MHADA_ERR_UNSUPPORTED, "mhada_gemm_bf16_splitk: needs K %% 64 == 0 and N %% 128 == 0, got N=%d K=%d", N, K);
+    REQUIRE(lda % 8 == 0 && ldw % 8 == 0 && aligned16(x) && aligned16(w), MHADA_ERR_ARG,
+            "mhada_gemm_bf16_splitk: operands must be 16-byte aligned with pitches multiples of 8");
+    REQUIRE(ldf >= N && ldf % 8 == 0 && aligned32(out_f32) && (!ws || aligned32(ws)), MHADA_ERR_ARG, "mhada_gemm_bf16_splitk: bad output / workspace");
+    if (int e = device_check()) return e;
+    GemmDesc g{};
+    g.a = x; g.lda = lda; g.w = w; g.ldw = ldw; g.M = M; g.N = N; g.K = K; g.out_f32 = out_f32; g.ldf = ldf;
+    return launch_gemm_bf16_splitk(g, ws, ws_bytes, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -102,6 +102,9 @@ struct GemmDesc {
     int relu;
 };
 int launch_gemm_bf16(const GemmDesc& d, cudaStream_t s);
+// same, f32 result only, K split over extra work items when the output has too few tiles to fill the GPU (weight gradients)
+size_t gemm_splitk_workspace(int M, int N, int K);
+int launch_gemm_bf16_splitk(const GemmDesc& d, void* ws, size_t ws_bytes, cudaStream_t s);
 int launch_patch_im2col(int img_dtype, const void* img, int B, int Himg, int Wimg, int patch, void* a0, cudaStream_t s);
 int launch_layernorm(const float* x, int M, int C, const float* gamma, const float* beta, float eps, void* y_bf16,
                      cudaStream_t s);

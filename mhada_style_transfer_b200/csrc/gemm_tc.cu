@@ -41,6 +41,8 @@ struct GemmParams {
     int resid_tma;         // residual tiles come through tmR (row-periodic tables only when resid_mod % 32 == 0)
     int relu;
     int M, ktiles, ntiles, items;
+    int tiles_mn;          // output tiles of one K split (= items without split-K)
+    int split_rows;        // split-K: partial s is written at row s * split_rows of the f32 output (a multiple of 128)
 };
 
 template <int BN, int STAGES>
@@ -93,14 +95,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (elect_one()) {
             int g = 0;                                            // running k-tile counter of this CTA
             for (int it = blockIdx.x; it < p.items; it += gridDim.x) {
-                const int m0 = (it / p.ntiles) * GM_BM, n0 = (it % p.ntiles) * BN;
+                const int sp = it / p.tiles_mn, r = it - sp * p.tiles_mn;       // K split, tile within the split
+                const int m0 = (r / p.ntiles) * GM_BM, n0 = (r % p.ntiles) * BN;
+                const int k0 = sp * p.ktiles * GM_BK;
                 for (int kt = 0; kt < p.ktiles; ++kt, ++g) {
                     const int s = g % STAGES;
                     mbar_wait(&empty[s], ((g / STAGES) & 1) ^ 1);
                     mbar_arrive_expect_tx(&full[s], STAGE);
                     uint8_t* a = smem + s * STAGE;
-                    tma_load_2d(a, &tmA, &full[s], kt * GM_BK, m0);
-                    tma_load_2d(a + A_BYTES, &tmB, &full[s], kt * GM_BK, n0);
+                    tma_load_2d(a, &tmA, &full[s], k0 + kt * GM_BK, m0);
+                    tma_load_2d(a + A_BYTES, &tmB, &full[s], k0 + kt * GM_BK, n0);
                 }
             }
         }
@@ -163,7 +167,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             int k = 0;
             for (int it = blockIdx.x; it < p.items; it += gridDim.x) {
                 const int n = k / NCH;
-                const int m0 = (it / p.ntiles) * GM_BM, n0 = (it % p.ntiles) * BN + chalf * CW;
+                const int sp = it / p.tiles_mn, rt = it - sp * p.tiles_mn;
+                const int m0 = (rt / p.ntiles) * GM_BM, n0 = (rt % p.ntiles) * BN + chalf * CW;
                 const int m = m0 + row;
                 const bool row_ok = m < p.M;
                 const int u = n & 1;
@@ -218,7 +223,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) {
-                        tma_store_2d(&tmF, slab, n0 + c, m0 + quarter * 32);
+                        tma_store_2d(&tmF, slab, n0 + c, sp * p.split_rows + m0 + quarter * 32);
                         tma_store_commit();
                     }
                     if (p.has_bf16 && row_ok) {               // the rounded copy (fc2 -> feature map): 64 bytes per lane
@@ -294,7 +299,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 template <int BN, int STAGES>
-static int launch_gemm_bn(const GemmDesc& d, cudaStream_t s) {
+static int launch_gemm_bn(const GemmDesc& d, int ksplit, cudaStream_t s) {
+    const int Mp = (d.M + GM_BM - 1) / GM_BM * GM_BM;
     CUtensorMap tmA, tmB, tmC;
     {
         uint64_t dims[2] = {static_cast<uint64_t>(d.K), static_cast<uint64_t>(d.M)};
@@ -318,7 +324,8 @@ static int launch_gemm_bn(const GemmDesc& d, cudaStream_t s) {
     }
     CUtensorMap tmF = tmA, tmR = tmA;
     if (d.out_f32) {
-        uint64_t dims[2] = {static_cast<uint64_t>(d.N), static_cast<uint64_t>(d.M)};
+        // split-K: the partial results of split s occupy rows [s Mp, s Mp + M) of the output
+        uint64_t dims[2] = {static_cast<uint64_t>(d.N), static_cast<uint64_t>(ksplit > 1 ? (ksplit - 1) * Mp + d.M : d.M)};
         uint64_t str[1] = {static_cast<uint64_t>(d.ldf) * 4};
         uint32_t box[2] = {32, 32};
         if (int e = make_tmap(&tmF, d.out_f32, 4, 2, dims, str, box)) return e;
@@ -336,8 +343,10 @@ static int launch_gemm_bn(const GemmDesc& d, cudaStream_t s) {
     p.bias = d.bias; p.resid = d.resid; p.out_f32 = d.out_f32;
     p.ldr = d.ldr; p.resid_mod = d.resid_mod; p.ldf = d.ldf;
     p.has_bf16 = d.out_bf16 ? 1 : 0; p.relu = d.relu;
-    p.M = d.M; p.ktiles = d.K / GM_BK; p.ntiles = d.N / BN;
-    p.items = ((d.M + GM_BM - 1) / GM_BM) * p.ntiles;
+    p.M = d.M; p.ktiles = d.K / GM_BK / ksplit; p.ntiles = d.N / BN;
+    p.tiles_mn = ((d.M + GM_BM - 1) / GM_BM) * p.ntiles;
+    p.items = p.tiles_mn * ksplit;
+    p.split_rows = Mp;
     constexpr size_t smem = STAGES * (GM_BM * GM_BK * 2 + BN * GM_BK * 2) + GM_EPI_WARPS * GM_STG_WARP + 1024;
     static DeviceOnce once;
     if (int e = smem_attr_once(once, reinterpret_cast<const void*>(gemm_tc_kernel<BN, STAGES>), smem, "gemm smem attr")) return e;
@@ -353,8 +362,66 @@ int launch_gemm_bf16(const GemmDesc& d, cudaStream_t s) {
         set_error("gemm_tc: needs K %% 64 == 0 and N %% 128 == 0, got M=%d N=%d K=%d", d.M, d.N, d.K);
         return MHADA_ERR_UNSUPPORTED;
     }
-    if (d.N % 256 == 0) return launch_gemm_bn<256, 3>(d, s);     // 3 x 48 KB operand ring + 64 KB of staging slabs
-    return launch_gemm_bn<128, 4>(d, s);
+    if (d.N % 256 == 0) return launch_gemm_bn<256, 3>(d, 1, s);     // 3 x 48 KB operand ring + 64 KB of staging slabs
+    return launch_gemm_bn<128, 4>(d, 1, s);
+}
+
+// ---- split-K (the weight-gradient GEMMs of the training path: C x C outputs, K = all tokens of the batch) ----------
+// A 512 x 512 x 8192 GEMM is 8 output tiles: 8 of 148 SMs busy.  The K range is cut in `ksplit` slices that run as
+// independent work items of the SAME persistent kernel (the k coordinate of the TMA loads is offset by the slice), each
+// writing its partial tile to its own rows of a scratch buffer; splitk_reduce_kernel adds them in a fixed order.
+static int pick_ksplit(int M, int N, int K) {
+    const int bn = N % 256 == 0 ? 256 : 128;
+    const int tiles = ((M + GM_BM - 1) / GM_BM) * (N / bn);
+    const int ktiles = K / GM_BK;
+    int best = 1;
+    for (int s = 2; s <= 32; ++s) {
+        if (ktiles % s != 0 || ktiles / s < 4) continue;
+        if (tiles * s <= 2 * sm_count()) best = s;       // at most two rounds of work items
+    }
+    return best;
+}
+
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ part, int splits, size_t split_stride, int M,
+                                                            int N, int ldp, float* __restrict__ out, int ldo) {
+    const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    const int nv = N / 4;
+    if (i >= static_cast<size_t>(M) * nv) return;
+    const int m = static_cast<int>(i / nv), n = static_cast<int>(i % nv) * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < splits; ++s) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(part + s * split_stride + static_cast<size_t>(m) * ldp + n));
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    *reinterpret_cast<float4*>(out + static_cast<size_t>(m) * ldo + n) = acc;
+}
+
+size_t gemm_splitk_workspace(int M, int N, int K) {
+    if (M <= 0 || N <= 0 || K <= 0 || K % GM_BK != 0 || N % 128 != 0) return 0;
+    const int ks = pick_ksplit(M, N, K);
+    if (ks <= 1) return 0;
+    const size_t Mp = static_cast<size_t>(M + GM_BM - 1) / GM_BM * GM_BM;
+    return ks * Mp * N * sizeof(float);
+}
+
+// f32 result only, no bias / residual / ReLU: out_f32 [M, ldf] = a . w^T with the K range split when that fills the GPU
+int launch_gemm_bf16_splitk(const GemmDesc& d, void* ws, size_t ws_bytes, cudaStream_t s) {
+    if (d.M <= 0 || d.N <= 0 || d.K <= 0 || d.K % GM_BK != 0 || d.N % 128 != 0 || !d.out_f32 || d.out_bf16 || d.bias || d.resid || d.relu) {
+        set_error("gemm_tc split-K: f32 result only, K %% 64 == 0, N %% 128 == 0 (M=%d N=%d K=%d)", d.M, d.N, d.K);
+        return MHADA_ERR_UNSUPPORTED;
+    }
+    const int ks = pick_ksplit(d.M, d.N, d.K);
+    if (ks <= 1 || !ws || ws_bytes < gemm_splitk_workspace(d.M, d.N, d.K)) return launch_gemm_bf16(d, s);
+    GemmDesc p = d;
+    p.out_f32 = static_cast<float*>(ws);
+    p.ldf = d.N;
+    if (int e = d.N % 256 == 0 ? launch_gemm_bn<256, 3>(p, ks, s) : launch_gemm_bn<128, 4>(p, ks, s)) return e;
+    const size_t Mp = static_cast<size_t>(d.M + GM_BM - 1) / GM_BM * GM_BM;
+    const size_t n = static_cast<size_t>(d.M) * (d.N / 4);
+    splitk_reduce_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(static_cast<const float*>(ws), ks, Mp * d.N, d.M, d.N,
+                                                                                d.N, d.out_f32, d.ldf);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "splitk_reduce launch");
 }
 
 }  // namespace mh

@@ -20,33 +20,43 @@ namespace {
 __device__ __forceinline__ float ldv(const float* p) { return __ldg(p); }
 __device__ __forceinline__ float ldv(const __nv_bfloat16* p) { return __bfloat162float(*p); }
 
+__device__ __forceinline__ float2 ldv2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+__device__ __forceinline__ float2 ldv2(const __nv_bfloat16* p) {
+    const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(p));
+    return make_float2(bf16_lo(w), bf16_hi(w));
+}
+
 // out[c][m] = bf16(norm(in[m][c])) for m < M, 0 for M <= m < Mpad;  norm = (x - mean[b][c]) * rstd[b][c] with b = m / N
-// when mean != nullptr.  32 x 32 tiles through shared memory.
+// when mean != nullptr.  64 x 64 tiles through shared memory, two elements per access on both sides (C and Mpad even).
 template <typename T>
 __global__ void __launch_bounds__(256) transpose_norm_kernel(const T* __restrict__ in, int ld, int M, int Mpad, int C, int N,
                                                              const float* __restrict__ mean, const float* __restrict__ rstd,
                                                              __nv_bfloat16* __restrict__ out) {
-    __shared__ float tile[32][33];
-    const int m0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    __shared__ float tile[64][65];
+    const int m0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 pairs x 8
 #pragma unroll
-    for (int r = ty; r < 32; r += 8) {
-        const int m = m0 + r, c = c0 + tx;
-        float v = 0.f;
+    for (int r = ty; r < 64; r += 8) {
+        const int m = m0 + r, c = c0 + 2 * tx;
+        float2 v = make_float2(0.f, 0.f);
         if (m < M && c < C) {
-            v = ldv(in + static_cast<size_t>(m) * ld + c);
+            v = ldv2(in + static_cast<size_t>(m) * ld + c);
             if (mean) {
                 const int b = m / N;
-                v = (v - __ldg(mean + static_cast<size_t>(b) * C + c)) * __ldg(rstd + static_cast<size_t>(b) * C + c);
+                const float2 mu = __ldg(reinterpret_cast<const float2*>(mean + static_cast<size_t>(b) * C + c));
+                const float2 rs = __ldg(reinterpret_cast<const float2*>(rstd + static_cast<size_t>(b) * C + c));
+                v = make_float2((v.x - mu.x) * rs.x, (v.y - mu.y) * rs.y);
             }
         }
-        tile[r][tx] = v;
+        tile[r][2 * tx] = v.x;
+        tile[r][2 * tx + 1] = v.y;
     }
     __syncthreads();
 #pragma unroll
-    for (int r = ty; r < 32; r += 8) {
-        const int c = c0 + r, m = m0 + tx;
-        if (c < C && m < Mpad) out[static_cast<size_t>(c) * Mpad + m] = __float2bfloat16_rn(tile[tx][r]);
+    for (int r = ty; r < 64; r += 8) {
+        const int c = c0 + r, m = m0 + 2 * tx;
+        if (c < C && m < Mpad)
+            *reinterpret_cast<uint32_t*>(out + static_cast<size_t>(c) * Mpad + m) = pack_bf16x2(tile[2 * tx][r], tile[2 * tx + 1][r]);
     }
 }
 
@@ -70,28 +80,34 @@ __global__ void __launch_bounds__(256) extract_blockdiag_kernel(const float* __r
     dw[i] = __ldg(full + static_cast<size_t>(h * d + o) * C + h * d + ii);
 }
 
-// partial[b][split][c] = (sum_n g, sum_n g x^) over the rows of the split; thread = two channels.
+constexpr int TS_ROWS = 32;      // token rows per CTA of the first stage
+
+// partial[b][split][c] = (sum_n g, sum_n g x^) over the TS_ROWS rows of the split; thread = two channels, the row loop
+// is unrolled so that eight independent loads are in flight per thread.
 template <typename TG, typename TX>
 __global__ void __launch_bounds__(1024) token_sums_kernel(const TG* __restrict__ g, const TX* __restrict__ x,
                                                           const float* __restrict__ mean, const float* __restrict__ rstd, int N, int C,
-                                                          int rows_per_split, float2* __restrict__ partial) {
+                                                          float2* __restrict__ partial) {
     const int c = threadIdx.x * 2;
     if (c >= C) return;
     const int split = blockIdx.x, b = blockIdx.y, splits = gridDim.x;
-    const int n0 = split * rows_per_split, n1 = min(N, n0 + rows_per_split);
+    const int n0 = split * TS_ROWS, n1 = min(N, n0 + TS_ROWS);
     float mu0 = 0.f, mu1 = 0.f, r0 = 0.f, r1 = 0.f;
     if (x) {
         mu0 = __ldg(mean + static_cast<size_t>(b) * C + c); mu1 = __ldg(mean + static_cast<size_t>(b) * C + c + 1);
         r0 = __ldg(rstd + static_cast<size_t>(b) * C + c); r1 = __ldg(rstd + static_cast<size_t>(b) * C + c + 1);
     }
     float s0 = 0.f, s1 = 0.f, t0 = 0.f, t1 = 0.f;
+    const size_t base = static_cast<size_t>(b) * N * C + c;
+#pragma unroll 8
     for (int n = n0; n < n1; ++n) {
-        const size_t off = (static_cast<size_t>(b) * N + n) * C + c;
-        const float g0 = ldv(g + off), g1 = ldv(g + off + 1);
-        s0 += g0; s1 += g1;
+        const size_t off = base + static_cast<size_t>(n) * C;
+        const float2 gv = ldv2(g + off);
+        s0 += gv.x; s1 += gv.y;
         if (x) {
-            t0 = fmaf(g0, (ldv(x + off) - mu0) * r0, t0);
-            t1 = fmaf(g1, (ldv(x + off + 1) - mu1) * r1, t1);
+            const float2 xv = ldv2(x + off);
+            t0 = fmaf(gv.x, (xv.x - mu0) * r0, t0);
+            t1 = fmaf(gv.y, (xv.y - mu1) * r1, t1);
         }
     }
     float2* o = partial + (static_cast<size_t>(b) * splits + split) * C + c;
@@ -99,22 +115,29 @@ __global__ void __launch_bounds__(1024) token_sums_kernel(const TG* __restrict__
     o[1] = make_float2(s1, t1);
 }
 
-// sums[b][c] = sum over splits;  with bias != nullptr also bias[c] = sum_b sums[b][c].x  (one thread per channel)
+// sums != nullptr: sums[b][c] = sum over the splits of image b = blockIdx.y;  else bias[c] = sum over splits AND images of
+// the first component.  Block = 32 channels x 8 lanes over the partials, fixed-order tree in shared memory.
 __global__ void __launch_bounds__(256) finish_sums_kernel(const float2* __restrict__ partial, int B, int splits, int C,
                                                           float2* __restrict__ sums, float* __restrict__ bias) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    float tot = 0.f;
-    for (int b = 0; b < B; ++b) {
-        float s = 0.f, t = 0.f;
-        for (int k = 0; k < splits; ++k) {
-            const float2 v = __ldg(partial + (static_cast<size_t>(b) * splits + k) * C + c);
+    __shared__ float2 red[8][33];
+    const int cl = threadIdx.x & 31, lane8 = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cl;
+    float s = 0.f, t = 0.f;
+    if (c < C) {
+        const int first = sums ? blockIdx.y * splits : 0, count = sums ? splits : B * splits;
+        for (int k = lane8; k < count; k += 8) {
+            const float2 v = __ldg(partial + static_cast<size_t>(first + k) * C + c);
             s += v.x; t += v.y;
         }
-        if (sums) sums[static_cast<size_t>(b) * C + c] = make_float2(s, t);
-        tot += s;
     }
-    if (bias) bias[c] = tot;
+    red[lane8][cl] = make_float2(s, t);
+    __syncthreads();
+    if (lane8 == 0 && c < C) {
+#pragma unroll
+        for (int k = 1; k < 8; ++k) { s += red[k][cl].x; t += red[k][cl].y; }
+        if (sums) sums[static_cast<size_t>(blockIdx.y) * C + c] = make_float2(s, t);
+        else bias[c] = s;
+    }
 }
 
 // dx[b][n][c] = rstd (g - s/N - x^ t/N) (+ add[b][n][c]);   four channels per thread
@@ -148,16 +171,17 @@ __global__ void __launch_bounds__(256) in_bwd_apply_kernel(const float* __restri
     *reinterpret_cast<float4*>(dx + off) = make_float4(o[0], o[1], o[2], o[3]);
 }
 
-int sums_splits(int N) {
-    int s = (N + 63) / 64;
-    return s < 1 ? 1 : (s > 64 ? 64 : s);
-}
+int sums_splits(int N) { return (N + TS_ROWS - 1) / TS_ROWS; }
 
 }  // namespace
 
 int launch_transpose_norm(const void* in, int in_dtype, int ld, int M, int Mpad, int C, int N, const float* mean, const float* rstd,
                           void* out, cudaStream_t s) {
-    const dim3 grid(static_cast<unsigned>((Mpad + 31) / 32), static_cast<unsigned>((C + 31) / 32));
+    if (C % 2 != 0 || Mpad % 2 != 0 || ld % 2 != 0) {
+        set_error("transpose_norm: C, ld and Mpad must be even (C=%d ld=%d Mpad=%d)", C, ld, Mpad);
+        return MHADA_ERR_UNSUPPORTED;
+    }
+    const dim3 grid(static_cast<unsigned>((Mpad + 63) / 64), static_cast<unsigned>((C + 63) / 64));
     if (in_dtype == MHADA_F32)
         transpose_norm_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(in), ld, M, Mpad, C, N, mean, rstd,
                                                           static_cast<__nv_bfloat16*>(out));
@@ -192,19 +216,23 @@ int launch_token_sums(const void* g, int g_dtype, const void* x, const float* me
         set_error("token_sums: C must be even and <= 2048, got %d", C);
         return MHADA_ERR_UNSUPPORTED;
     }
+    if ((sums != nullptr) == (bias != nullptr)) {
+        set_error("token_sums: exactly one of sums / bias");
+        return MHADA_ERR_ARG;
+    }
     const int splits = sums_splits(N);
-    const int rows = (N + splits - 1) / splits;
     const dim3 grid(static_cast<unsigned>(splits), static_cast<unsigned>(B));
     const int threads = (C / 2 + 31) / 32 * 32;
     float2* part = static_cast<float2*>(partial);
     const __nv_bfloat16* xb = static_cast<const __nv_bfloat16*>(x);
     if (g_dtype == MHADA_F32)
-        token_sums_kernel<float, __nv_bfloat16><<<grid, threads, 0, s>>>(static_cast<const float*>(g), xb, mean, rstd, N, C, rows, part);
+        token_sums_kernel<float, __nv_bfloat16><<<grid, threads, 0, s>>>(static_cast<const float*>(g), xb, mean, rstd, N, C, part);
     else
         token_sums_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, threads, 0, s>>>(static_cast<const __nv_bfloat16*>(g), xb, mean, rstd, N,
-                                                                                 C, rows, part);
+                                                                                 C, part);
     count_launch();
-    finish_sums_kernel<<<static_cast<unsigned>((C + 255) / 256), 256, 0, s>>>(part, B, splits, C, static_cast<float2*>(sums), bias);
+    const dim3 fgrid(static_cast<unsigned>((C + 31) / 32), static_cast<unsigned>(sums ? B : 1));
+    finish_sums_kernel<<<fgrid, 256, 0, s>>>(part, B, splits, C, static_cast<float2*>(sums), bias);
     count_launch();
     return check_cuda(cudaGetLastError(), "token_sums launch");
 }

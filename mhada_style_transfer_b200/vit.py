@@ -49,6 +49,19 @@ def _gemm_bf16(a16: torch.Tensor, w16: torch.Tensor, bias, M: int, N: int, K: in
     return out
 
 
+def _gemm_bf16_splitk(a16: torch.Tensor, w16: torch.Tensor, M: int, N: int, K: int) -> torch.Tensor:
+    """f32 [M, N] = a16 . w16^T with the contraction split over extra work items (weight gradients: K = tokens)."""
+    L = _lib.lib()
+    out = torch.empty((M, N), dtype=torch.float32, device=a16.device)
+    nb = L.mhada_gemm_splitk_workspace(M, N, K)
+    ws = _workspace(a16.device, nb) if nb else None
+    with torch.cuda.device(a16.device):
+        rc = L.mhada_gemm_bf16_splitk(a16.data_ptr(), a16.stride(0), w16.data_ptr(), w16.stride(0), M, N, K, out.data_ptr(), N,
+                                      ws.data_ptr() if ws is not None else None, ws.numel() if ws is not None else 0, _stream())
+    _lib.check("mhada_gemm_bf16_splitk", rc)
+    return out
+
+
 def _transpose_bf16(x: torch.Tensor, M: int, C: int) -> torch.Tensor:
     """bf16 [C, Mpad] = x[M, C]^T, token axis padded with zeros to a multiple of 64 (mhada_transpose_bf16)."""
     L = _lib.lib()
@@ -102,7 +115,7 @@ class _LinearTC(torch.autograd.Function):
             dx = _gemm_bf16(dy16, _transpose_bf16(w16, N, K), None, M, K, N).view(ctx.in_shape).to(ctx.dtypes[0])
         if ctx.needs_input_grad[1]:
             dyT, xT = _transpose_bf16(dy16, M, N), _transpose_bf16(x16, M, K)
-            dw = _gemm_bf16(dyT, xT, None, N, K, dyT.shape[1]).to(ctx.dtypes[1])
+            dw = _gemm_bf16_splitk(dyT, xT, N, K, dyT.shape[1]).to(ctx.dtypes[1])
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = _colsum(dy2, M, N)
         return dx, dw, db
