@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define MHADA_ABI_VERSION 10
+#define MHADA_ABI_VERSION 11
 
 #if defined(__GNUC__)
 #define MHADA_API __attribute__((visibility("default")))
@@ -257,6 +257,9 @@ MHADA_API int mhada_gemm_bf16(const void* x, int lda, const void* w, int ldw, co
 MHADA_API int mhada_layernorm(const float* x, int M, int C, const float* gamma, const float* beta, float eps,
                               void* y_bf16, mhada_stream_t stream);
 MHADA_API int mhada_batch_attn(const void* qkv, int B, int N, int heads, int hd, void* out, mhada_stream_t stream);
+/*     backward of mhada_batch_attn for the training step (B <= 8): d_out bf16 [B, N, heads*hd] -> d_qkv bf16 [B, N, 3*heads*hd] */
+MHADA_API int mhada_batch_attn_bwd(const void* qkv, const void* d_out, int B, int N, int heads, int hd, void* d_qkv,
+                                   mhada_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * (8) AdaAttnForLoss on the tensor cores -- replaces AdaAttnForLoss.forward, MHAdaSTr/network/adaDecoder.py:53-81

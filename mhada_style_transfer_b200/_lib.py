@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libmhada_b200.so")
 
 F32, BF16, U8 = 0, 1, 2
-ABI_VERSION = 10
+ABI_VERSION = 11
 VIT_MAX_LAYERS = 8
 PROJ_Q, PROJ_KV = 1, 2
 REUSE_FS_STATS = 1
@@ -113,6 +113,7 @@ SIGNATURES = {
                                 c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
     "mhada_layernorm": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p]),
     "mhada_batch_attn": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "mhada_batch_attn_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "mhada_style_cache_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "mhada_style_precompute": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_size_t,
                                        c_void_p, c_size_t, c_void_p]),

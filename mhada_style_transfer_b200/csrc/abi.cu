@@ -805,4 +805,12 @@ int mhada_gemm_bf16_splitk(const void* x, int lda, const void* w, int ldw, int M
     return launch_gemm_bf16_splitk(g, ws, ws_bytes, static_cast<cudaStream_t>(stream));
 }
 
+int mhada_batch_attn_bwd(const void* qkv, const void* d_out, int B, int N, int heads, int hd, void* d_qkv, mhada_stream_t stream) {
+    REQUIRE(qkv && d_out && d_qkv, MHADA_ERR_ARG, "mhada_batch_attn_bwd: null pointer");
+    REQUIRE(B > 0 && N > 0 && heads > 0 && hd > 0, MHADA_ERR_ARG, "mhada_batch_attn_bwd: bad sizes");
+    REQUIRE(aligned16(qkv) && aligned16(d_out) && aligned16(d_qkv), MHADA_ERR_ARG, "mhada_batch_attn_bwd: misaligned pointer");
+    if (int e = device_check()) return e;
+    return launch_batch_attn_bwd(qkv, d_out, B, N, heads, hd, d_qkv, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

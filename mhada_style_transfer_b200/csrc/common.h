@@ -109,6 +109,7 @@ int launch_patch_im2col(int img_dtype, const void* img, int B, int Himg, int Wim
 int launch_layernorm(const float* x, int M, int C, const float* gamma, const float* beta, float eps, void* y_bf16,
                      cudaStream_t s);
 int launch_batch_attn(const void* qkv, int B, int N, int heads, int hd, void* out, cudaStream_t s);
+int launch_batch_attn_bwd(const void* qkv, const void* dout, int B, int N, int heads, int hd, void* dqkv, cudaStream_t s);
 size_t vit_workspace(int B, int N, int D, int F, int K0);
 int vit_forward(const mhada_vit_args& a, cudaStream_t s);
 

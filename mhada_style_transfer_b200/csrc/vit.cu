@@ -287,6 +287,98 @@ __global__ void __launch_bounds__(256) batch_attn_mma_kernel(const __nv_bfloat16
     }
 }
 
+// Backward of the batch-axis attention for the training step (train_image.py:103-144 through vit.py:59), B <= 8:
+// one warp per (token position, head), lane = two of the 64 channels.  The 8 x 8 logits S = Q K^T / 8 and dP = dO V^T are
+// warp-wide dot products (butterfly sums: every lane ends up with all of them), the rest is lane-local:
+//     P = softmax_rows(S),  dV = P^T dO,  dS = P (dP - rowsum(P dP)) / 8,  dQ = dS K,  dK = dS^T Q.
+// ~2000 instructions per warp, bandwidth-bound like the forward (reads qkv + dO, writes dqkv: 14 bytes per qkv element).
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__global__ void __launch_bounds__(256) batch_attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout,
+                                                             int B, int N, int heads, __nv_bfloat16* __restrict__ dqkv) {
+    const int lane = threadIdx.x & 31;
+    const long long item = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);     // n * heads + h
+    if (item >= static_cast<long long>(N) * heads) return;
+    const int n = static_cast<int>(item / heads), h = static_cast<int>(item % heads);
+    const int D = heads * BA_HD;
+    float q[8][2], k[8][2], v[8][2], g[8][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        q[i][0] = q[i][1] = k[i][0] = k[i][1] = v[i][0] = v[i][1] = g[i][0] = g[i][1] = 0.f;
+        if (i < B) {
+            const uint32_t* row = reinterpret_cast<const uint32_t*>(qkv + (static_cast<size_t>(i) * N + n) * 3 * D + h * BA_HD) + lane;
+            const uint32_t wq = __ldg(row), wk = __ldg(row + D / 2), wv = __ldg(row + D);
+            const uint32_t wg = __ldg(reinterpret_cast<const uint32_t*>(dout + (static_cast<size_t>(i) * N + n) * D + h * BA_HD) + lane);
+            q[i][0] = bf16_lo(wq); q[i][1] = bf16_hi(wq); k[i][0] = bf16_lo(wk); k[i][1] = bf16_hi(wk);
+            v[i][0] = bf16_lo(wv); v[i][1] = bf16_hi(wv); g[i][0] = bf16_lo(wg); g[i][1] = bf16_hi(wg);
+        }
+    }
+    float p[8][8], dp[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            p[i][j] = dp[i][j] = 0.f;
+            if (i < B && j < B) {
+                p[i][j] = warp_sum(fmaf(q[i][0], k[j][0], q[i][1] * k[j][1])) * 0.125f;
+                dp[i][j] = warp_sum(fmaf(g[i][0], v[j][0], g[i][1] * v[j][1]));
+            }
+        }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        if (i >= B) continue;
+        float mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (j < B) mx = fmaxf(mx, p[i][j]);
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            p[i][j] = j < B ? __expf(p[i][j] - mx) : 0.f;
+            sum += p[i][j];
+        }
+        const float inv = 1.f / sum;
+        float dsum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            p[i][j] *= inv;
+            dsum = fmaf(p[i][j], dp[i][j], dsum);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dp[i][j] = p[i][j] * (dp[i][j] - dsum) * 0.125f;      // dS (with the 1 / sqrt(hd) of S)
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        if (r >= B) continue;
+        float dq0 = 0.f, dq1 = 0.f, dk0 = 0.f, dk1 = 0.f, dv0 = 0.f, dv1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            dq0 = fmaf(dp[r][j], k[j][0], dq0); dq1 = fmaf(dp[r][j], k[j][1], dq1);      // dQ[r] = sum_j dS[r][j] K[j]
+            dk0 = fmaf(dp[j][r], q[j][0], dk0); dk1 = fmaf(dp[j][r], q[j][1], dk1);      // dK[r] = sum_i dS[i][r] Q[i]
+            dv0 = fmaf(p[j][r], g[j][0], dv0); dv1 = fmaf(p[j][r], g[j][1], dv1);        // dV[r] = sum_i P[i][r] dO[i]
+        }
+        uint32_t* orow = reinterpret_cast<uint32_t*>(dqkv + (static_cast<size_t>(r) * N + n) * 3 * D + h * BA_HD) + lane;
+        orow[0] = pack_bf16x2(dq0, dq1);
+        orow[D / 2] = pack_bf16x2(dk0, dk1);
+        orow[D] = pack_bf16x2(dv0, dv1);
+    }
+}
+
+int launch_batch_attn_bwd(const void* qkv, const void* dout, int B, int N, int heads, int hd, void* dqkv, cudaStream_t s) {
+    if (hd != BA_HD || B < 1 || B > 8) {
+        set_error("batch_attn_bwd: head_dim 64 and batch 1..8 are implemented, got head_dim %d, batch %d", hd, B);
+        return MHADA_ERR_UNSUPPORTED;
+    }
+    const long long items = static_cast<long long>(N) * heads;
+    batch_attn_bwd_kernel<<<static_cast<unsigned>((items + 7) / 8), 256, 0, s>>>(
+        static_cast<const __nv_bfloat16*>(qkv), static_cast<const __nv_bfloat16*>(dout), B, N, heads, static_cast<__nv_bfloat16*>(dqkv));
+    count_launch();
+    return check_cuda(cudaGetLastError(), "batch_attn_bwd launch");
+}
+
 int launch_batch_attn(const void* qkv, int B, int N, int heads, int hd, void* out, cudaStream_t s) {
     if (hd != BA_HD || B < 1 || B > 32) {
         set_error("batch_attn: head_dim 64 and batch 1..32 are implemented, got head_dim %d, batch %d", hd, B);

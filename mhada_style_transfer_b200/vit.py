@@ -37,13 +37,14 @@ from .network import _needs_grad, _require_cuda, _stream, _workspace
 __all__ = ["VisionTransformer", "EncoderBlock", "PatchEmbedding", "PosEmbedding"]
 
 
-def _gemm_bf16(a16: torch.Tensor, w16: torch.Tensor, bias, M: int, N: int, K: int) -> torch.Tensor:
-    """f32 [M, N] = a16 [M, >=K] . w16 [N, >=K]^T (+ bias) on the tcgen05 token GEMM (mhada_gemm_bf16)."""
+def _gemm_bf16(a16: torch.Tensor, w16: torch.Tensor, bias, M: int, N: int, K: int, out_dtype=torch.float32) -> torch.Tensor:
+    """[M, N] (f32 or bf16) = a16 [M, >=K] . w16 [N, >=K]^T (+ bias) on the tcgen05 token GEMM (mhada_gemm_bf16)."""
     L = _lib.lib()
-    out = torch.empty((M, N), dtype=torch.float32, device=a16.device)
+    out = torch.empty((M, N), dtype=out_dtype, device=a16.device)
+    o16, o32 = (out.data_ptr(), None) if out_dtype == torch.bfloat16 else (None, out.data_ptr())
     with torch.cuda.device(a16.device):
         rc = L.mhada_gemm_bf16(a16.data_ptr(), a16.stride(0), w16.data_ptr(), w16.stride(0),
-                               bias.data_ptr() if bias is not None else None, M, N, K, None, 0, out.data_ptr(), N, None, 0, 0, 0,
+                               bias.data_ptr() if bias is not None else None, M, N, K, o16, N, o32, N, None, 0, 0, 0,
                                _stream())
     _lib.check("mhada_gemm_bf16", rc)
     return out
@@ -91,13 +92,13 @@ class _LinearTC(torch.autograd.Function):
     db = column sums of dy.  Needs in_features and out_features to be multiples of 128."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias):
+    def forward(ctx, x, weight, bias, out_dtype=torch.float32):
         K, N = x.shape[-1], weight.shape[0]
         x2 = x.reshape(-1, K)
         M = x2.shape[0]
         x16 = x2.to(torch.bfloat16).contiguous()
         w16 = weight.detach().to(torch.bfloat16).contiguous()
-        y = _gemm_bf16(x16, w16, bias.detach().float().contiguous() if bias is not None else None, M, N, K)
+        y = _gemm_bf16(x16, w16, bias.detach().float().contiguous() if bias is not None else None, M, N, K, out_dtype)
         ctx.save_for_backward(x16, w16)
         ctx.in_shape, ctx.has_bias, ctx.dtypes = x.shape, bias is not None, (x.dtype, weight.dtype)
         return y.view(*x.shape[:-1], N)
@@ -118,7 +119,38 @@ class _LinearTC(torch.autograd.Function):
             dw = _gemm_bf16_splitk(dyT, xT, N, K, dyT.shape[1]).to(ctx.dtypes[1])
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = _colsum(dy2, M, N)
-        return dx, dw, db
+        return dx, dw, db, None
+
+
+class _BatchAttnFn(torch.autograd.Function):
+    """The batch_first=False attention of the encoder block (vit.py:48,59) on own kernels, forward
+    (mhada_batch_attn) and backward (mhada_batch_attn_bwd): qkv bf16 [B, N, 3 D] -> bf16 [B, N, D], B <= 8."""
+
+    @staticmethod
+    def forward(ctx, qkv, heads):
+        B, N, D3 = qkv.shape
+        D = D3 // 3
+        qkv = qkv.contiguous()
+        out = torch.empty((B, N, D), dtype=torch.bfloat16, device=qkv.device)
+        with torch.cuda.device(qkv.device):
+            rc = _lib.lib().mhada_batch_attn(qkv.data_ptr(), B, N, heads, D // heads, out.data_ptr(), _stream())
+        _lib.check("mhada_batch_attn", rc)
+        ctx.save_for_backward(qkv)
+        ctx.heads = heads
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (qkv,) = ctx.saved_tensors
+        B, N, D3 = qkv.shape
+        D = D3 // 3
+        dout = dout.to(torch.bfloat16).contiguous()
+        dqkv = torch.empty_like(qkv)
+        with torch.cuda.device(qkv.device):
+            rc = _lib.lib().mhada_batch_attn_bwd(qkv.data_ptr(), dout.data_ptr(), B, N, ctx.heads, D // ctx.heads, dqkv.data_ptr(),
+                                                 _stream())
+        _lib.check("mhada_batch_attn_bwd", rc)
+        return dqkv, None
 
 
 class EncoderBlock(nn.Module):
@@ -144,11 +176,15 @@ class EncoderBlock(nn.Module):
         a = self.attention
         L, Nn, D = input.shape
         H = a.num_heads
-        qkv = _LinearTC.apply(self.ln1(input), a.in_proj_weight, a.in_proj_bias)
-        q, k, v = (t.reshape(L, Nn, H, D // H).permute(1, 2, 0, 3) for t in qkv.chunk(3, dim=-1))    # (N, H, L, hd)
-        o = F.scaled_dot_product_attention(q, k, v).permute(2, 0, 1, 3).reshape(L, Nn, D)
+        bf16 = torch.bfloat16        # in_proj and fc1 feed ops that round to bf16 anyway: the GEMM writes bf16 directly
+        qkv = _LinearTC.apply(self.ln1(input), a.in_proj_weight, a.in_proj_bias, bf16)
+        if L <= 8 and D // H == 64:
+            o = _BatchAttnFn.apply(qkv, H)                                                            # own kernels
+        else:
+            q, k, v = (t.reshape(L, Nn, H, D // H).permute(1, 2, 0, 3) for t in qkv.float().chunk(3, dim=-1))   # (N, H, L, hd)
+            o = F.scaled_dot_product_attention(q, k, v).permute(2, 0, 1, 3).reshape(L, Nn, D)
         x = _LinearTC.apply(o, a.out_proj.weight, a.out_proj.bias) + input
-        hdn = torch.relu(_LinearTC.apply(self.ln2(x), self.mlp[0].weight, self.mlp[0].bias))
+        hdn = torch.relu(_LinearTC.apply(self.ln2(x), self.mlp[0].weight, self.mlp[0].bias, bf16))
         return x + _LinearTC.apply(hdn, self.mlp[2].weight, self.mlp[2].bias)
 
 

@@ -179,10 +179,31 @@ def test_vit_trains():
     assert all(p.grad is not None and torch.isfinite(p.grad).all().item() for p in m.parameters())
 
 
-@pytest.mark.parametrize("B,hw,pos", [(2, (64, 64), True), (1, (40, 72), False), (3, (32, 48), True)])
+@pytest.mark.parametrize("B,N,heads", [(8, 100, 8), (3, 37, 2), (1, 16, 8)])
+def test_batch_attn_bwd(B, N, heads):
+    """mhada_batch_attn_bwd against float64 autograd of softmax(Q K^T / 8) V over the batch axis, on the same bf16 qkv."""
+    from mhada_style_transfer_b200 import _lib
+    L = _lib.lib()
+    D = heads * 64
+    torch.manual_seed(5)
+    qkv = (torch.randn(B, N, 3 * D, device=DEV) * 1.5).bfloat16().contiguous()
+    dout = torch.randn(B, N, D, device=DEV).bfloat16().contiguous()
+    dqkv = torch.empty_like(qkv)
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.check("mhada_batch_attn_bwd", L.mhada_batch_attn_bwd(qkv.data_ptr(), dout.data_ptr(), B, N, heads, 64, dqkv.data_ptr(), st))
+    torch.cuda.synchronize()
+    x = qkv.double().requires_grad_(True)
+    q, k, v = (t.reshape(B, N, heads, 64).permute(1, 2, 0, 3) for t in x.chunk(3, dim=-1))
+    o = (torch.softmax(q @ k.transpose(2, 3) / 8.0, dim=-1) @ v).permute(2, 0, 1, 3).reshape(B, N, D)
+    (o * dout.double()).sum().backward()
+    e = O.errors(dqkv.float().cpu().numpy(), x.grad.cpu().numpy())
+    assert e["max_abs_rel"] <= 1e-2 and e["fro_rel"] <= 5e-3, e
+
+
+@pytest.mark.parametrize("B,hw,pos", [(2, (64, 64), True), (1, (40, 72), False), (3, (32, 48), True), (8, (32, 32), True)])
 def test_vit_training_gemm_path_vs_torch(B, hw, pos):
-    """Training mode: the Linear layers on the tcgen05 GEMM forward AND backward (_LinearTC) against the plain fp32
-    PyTorch op sequence of the same module: features and every parameter gradient.  bf16 operands -> 2e-2 of each
+    """Training mode: the Linear layers on the tcgen05 GEMM forward AND backward (_LinearTC) and the batch-axis attention
+    on own kernels (mhada_batch_attn / mhada_batch_attn_bwd) against the plain fp32 PyTorch op sequence of the same module: features and every parameter gradient.  bf16 operands -> 2e-2 of each
     gradient's own range (5e-3 of the largest for the vanishing ones), 1e-2 in Frobenius norm."""
     torch.manual_seed(3)
     m = M.VisionTransformer(pos_embedding=pos).to(DEV).train()
