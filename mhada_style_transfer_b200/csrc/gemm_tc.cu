@@ -377,7 +377,7 @@ static int pick_ksplit(int M, int N, int K) {
     int best = 1;
     for (int s = 2; s <= 32; ++s) {
         if (ktiles % s != 0 || ktiles / s < 4) continue;
-        if (tiles * s <= 2 * sm_count()) best = s;       // at most two rounds of work items
+        if (tiles * s <= sm_count()) best = s;           // one round of work items: more splits only add partial-tile traffic
     }
     return best;
 }
