@@ -21,6 +21,8 @@
 //                              epilogues L1-tag-bound).
 // BN = 256 keeps the shared-memory operand traffic of the SS-mode MMAs at 96 B/clk (a 128 x 128 tile needs the
 // full 128 B/clk of the SM).  Compute-bound for K >= 512: 2*M*N*K FLOP; HBM bytes 2*M*K + 2*N*K + (2|4|6)*M*N.
+#include <cstdlib>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -45,12 +47,38 @@ struct GemmParams {
     int split_rows;        // split-K: partial s is written at row s * split_rows of the f32 output (a multiple of 128)
 };
 
-template <int BN, int STAGES>
+// v[i] = acc[i] + bias[col + i], i < 32: eight 16-byte loads (the same for every lane: L1 broadcast) instead of 32 scalar
+// ones; the launcher guarantees a 16-byte aligned bias pointer, col is a multiple of 32
+__device__ __forceinline__ void add_bias32(float (&v)[32], const uint32_t (&r)[32], const float* __restrict__ bias, int col) {
+    if (bias) {
+        const float4* b4 = reinterpret_cast<const float4*>(bias + col);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const float4 b = __ldg(b4 + q);
+            v[4 * q] = __uint_as_float(r[4 * q]) + b.x; v[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + b.y;
+            v[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + b.z; v[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + b.w;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+    }
+}
+
+// NCTA = 2: a CTA PAIR (cluster of two, the two SMs of a TPC) works on one 256 x BN tile with tcgen05.mma.cta_group::2:
+// each CTA loads its 128 rows of x and HALF of the W tile (32 KB per k-step instead of 48 KB: the L2 -> SM operand
+// stream was what bounded the single-CTA kernel), the leader (cluster rank 0) issues the M = 256 MMAs for
+// both, each CTA's TMEM receives its 128 x BN slice and its own epilogue warps drain it.  TMA bytes of both CTAs are
+// counted on the leader's `full` barrier; tcgen05.commit multicasts `empty` / `acc_full` to both CTAs; the epilogue
+// warps of both CTAs arrive on the leader's `acc_empty`.
+template <int BN, int STAGES, int NCTA>
 __global__ void __launch_bounds__(GM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmF,
                const __grid_constant__ CUtensorMap tmR, const GemmParams p) {
-    constexpr uint32_t A_BYTES = GM_BM * GM_BK * 2, B_BYTES = BN * GM_BK * 2, STAGE = A_BYTES + B_BYTES;
+    constexpr uint32_t A_BYTES = GM_BM * GM_BK * 2, B_BYTES = (BN / NCTA) * GM_BK * 2, STAGE = A_BYTES + B_BYTES;
+    constexpr int TM = GM_BM * NCTA;                       // output rows of a work item
+    const int cta_rank = NCTA == 2 ? static_cast<int>(cluster_ctarank()) : 0;
+    const int worker = static_cast<int>(blockIdx.x) / NCTA, nworkers = static_cast<int>(gridDim.x) / NCTA;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     __shared__ uint64_t full[STAGES], empty[STAGES], acc_full[2], acc_empty[2];
@@ -74,7 +102,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             for (int u = 0; u < 2; ++u) {
                 mbar_init(&acc_full[u], 1);
-                mbar_init(&acc_empty[u], GM_EPI_WARPS);      // one arrive per epilogue warp
+                mbar_init(&acc_empty[u], GM_EPI_WARPS * NCTA);   // one arrive per epilogue warp (of both CTAs of a pair)
             }
             for (int w = 0; w < GM_EPI_WARPS; ++w) {
                 mbar_init(&rbar[w][0], 1);
@@ -83,36 +111,48 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             fence_mbar_init();
         }
         __syncwarp();
-        tmem_alloc(&tmem_slot, 2 * BN);
-        tmem_relinquish();
+        if (NCTA == 2) {
+            tmem_alloc2(&tmem_slot, 2 * BN);
+            tmem_relinquish2();
+        } else {
+            tmem_alloc(&tmem_slot, 2 * BN);
+            tmem_relinquish();
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if (NCTA == 2) cluster_sync_all();     // the peer's barriers are initialised before anything arrives on them
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
 
     if (warp == 0) {
         if (elect_one()) {
             int g = 0;                                            // running k-tile counter of this CTA
-            for (int it = blockIdx.x; it < p.items; it += gridDim.x) {
+            for (int it = worker; it < p.items; it += nworkers) {
                 const int sp = it / p.tiles_mn, r = it - sp * p.tiles_mn;       // K split, tile within the split
-                const int m0 = (r / p.ntiles) * GM_BM, n0 = (r % p.ntiles) * BN;
+                const int m0 = (r / p.ntiles) * TM + cta_rank * GM_BM, n0 = (r % p.ntiles) * BN + cta_rank * (BN / NCTA);
                 const int k0 = sp * p.ktiles * GM_BK;
                 for (int kt = 0; kt < p.ktiles; ++kt, ++g) {
                     const int s = g % STAGES;
                     mbar_wait(&empty[s], ((g / STAGES) & 1) ^ 1);
-                    mbar_arrive_expect_tx(&full[s], STAGE);
                     uint8_t* a = smem + s * STAGE;
-                    tma_load_2d(a, &tmA, &full[s], k0 + kt * GM_BK, m0);
-                    tma_load_2d(a + A_BYTES, &tmB, &full[s], k0 + kt * GM_BK, n0);
+                    if (NCTA == 2) {
+                        if (cta_rank == 0) mbar_arrive_expect_tx(&full[s], 2 * STAGE);      // the pair's bytes, one barrier
+                        tma_load_2d_pair(a, &tmA, &full[s], k0 + kt * GM_BK, m0);
+                        tma_load_2d_pair(a + A_BYTES, &tmB, &full[s], k0 + kt * GM_BK, n0);
+                    } else {
+                        mbar_arrive_expect_tx(&full[s], STAGE);
+                        tma_load_2d(a, &tmA, &full[s], k0 + kt * GM_BK, m0);
+                        tma_load_2d(a + A_BYTES, &tmB, &full[s], k0 + kt * GM_BK, n0);
+                    }
                 }
             }
         }
     } else if (warp == 1) {
-        if (elect_one()) {
-            constexpr uint32_t idesc = make_idesc_bf16(GM_BM, BN, 0, 0);
+        if (cta_rank == 0 && elect_one()) {
+            constexpr uint32_t idesc = make_idesc_bf16(TM, BN, 0, 0);
             int g = 0, n = 0;
-            for (int it = blockIdx.x; it < p.items; it += gridDim.x, ++n) {
+            for (int it = worker; it < p.items; it += nworkers, ++n) {
                 const int u = n & 1;
                 mbar_wait(&acc_empty[u], ((n >> 1) & 1) ^ 1);     // the epilogue has drained this accumulator buffer
                 tc_fence_after();
@@ -124,11 +164,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint64_t da = make_smem_desc(a_addr, 16, 1024);
                     const uint64_t db = make_smem_desc(a_addr + A_BYTES, 16, 1024);
 #pragma unroll
-                    for (int k = 0; k < GM_BK / 16; ++k)
-                        umma_ss(tmem + u * BN, desc_advance(da, k * 32), desc_advance(db, k * 32), idesc, (kt | k) != 0);
-                    umma_commit(&empty[s]);
+                    for (int k = 0; k < GM_BK / 16; ++k) {
+                        if (NCTA == 2) umma_ss_pair(tmem + u * BN, desc_advance(da, k * 32), desc_advance(db, k * 32), idesc, (kt | k) != 0);
+                        else umma_ss(tmem + u * BN, desc_advance(da, k * 32), desc_advance(db, k * 32), idesc, (kt | k) != 0);
+                    }
+                    if (NCTA == 2) umma_commit_pair(&empty[s], 3);
+                    else umma_commit(&empty[s]);
                 }
-                umma_commit(&acc_full[u]);
+                if (NCTA == 2) umma_commit_pair(&acc_full[u], 3);
+                else umma_commit(&acc_full[u]);
             }
         }
     } else {
@@ -149,12 +193,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // while the current one is processed; the sum is written back into the same slab and stored from there.
             uint64_t* rb = rbar[warp - 2];
             constexpr int NCH = CW / 32;
-            const int my_items = (p.items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+            const int my_items = (p.items - worker + nworkers - 1) / nworkers;
             const int total = my_items * NCH;                                   // chunks this warp will process
             auto coords = [&](int k, int& col, int& rowbase) {                   // chunk k -> output column / row of its tile
-                const int it = blockIdx.x + (k / NCH) * gridDim.x;
+                const int it = worker + (k / NCH) * nworkers;
                 col = (it % p.ntiles) * BN + chalf * CW + (k % NCH) * 32;
-                rowbase = (it / p.ntiles) * GM_BM + quarter * 32;
+                rowbase = (it / p.ntiles) * TM + cta_rank * GM_BM + quarter * 32;
             };
             auto issue_resid = [&](int k) {                                      // lane 0 only
                 int col, rowbase;
@@ -165,10 +209,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             };
             if (p.resid_tma && total > 0 && lane == 0) issue_resid(0);
             int k = 0;
-            for (int it = blockIdx.x; it < p.items; it += gridDim.x) {
+            for (int it = worker; it < p.items; it += nworkers) {
                 const int n = k / NCH;
                 const int sp = it / p.tiles_mn, rt = it - sp * p.tiles_mn;
-                const int m0 = (rt / p.ntiles) * GM_BM, n0 = (rt % p.ntiles) * BN + chalf * CW;
+                const int m0 = (rt / p.ntiles) * TM + cta_rank * GM_BM, n0 = (rt % p.ntiles) * BN + chalf * CW;
                 const int m = m0 + row;
                 const bool row_ok = m < p.M;
                 const int u = n & 1;
@@ -192,11 +236,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (c + 32 == CW) {                       // accumulator drained: the next-but-one item may start
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(&acc_empty[u]);
+                        if (lane == 0) {
+                            if (NCTA == 2) mbar_arrive_leader(&acc_empty[u]);
+                            else mbar_arrive(&acc_empty[u]);
+                        }
                     }
                     float v[32];
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) + (p.bias ? __ldg(p.bias + n0 + c + i) : 0.f);
+                    add_bias32(v, r, p.bias, n0 + c);
                     if (p.resid_tma) {
                         mbar_wait(&rb[k & 1], (k >> 1) & 1);
 #pragma unroll
@@ -238,8 +284,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         } else {
         int n = 0;
-        for (int it = blockIdx.x; it < p.items; it += gridDim.x, ++n) {
-            const int m0 = (it / p.ntiles) * GM_BM, n0 = (it % p.ntiles) * BN + chalf * CW;
+        for (int it = worker; it < p.items; it += nworkers, ++n) {
+            const int m0 = (it / p.ntiles) * TM + cta_rank * GM_BM, n0 = (it % p.ntiles) * BN + chalf * CW;
             const int u = n & 1;
             mbar_wait(&acc_full[u], (n >> 1) & 1);
             tc_fence_after();
@@ -251,11 +297,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (c + 32 == CW) {                           // accumulator drained: the next-but-one item may start
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&acc_empty[u]);
+                    if (lane == 0) {
+                        if (NCTA == 2) mbar_arrive_leader(&acc_empty[u]);
+                        else mbar_arrive(&acc_empty[u]);
+                    }
                 }
                 float v[32];
-#pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) + (p.bias ? __ldg(p.bias + n0 + c + i) : 0.f);
+                add_bias32(v, r, p.bias, n0 + c);
                 if (p.relu) {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
@@ -294,13 +342,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) tma_store_wait<0>();
     }
     tc_fence_before();
-    __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem, 2 * BN);
+    if (NCTA == 2) {
+        cluster_sync_all();                 // neither CTA leaves (or frees TMEM) while its peer may still use it
+        if (warp == 1) tmem_dealloc2(tmem, 2 * BN);
+    } else {
+        __syncthreads();
+        if (warp == 1) tmem_dealloc(tmem, 2 * BN);
+    }
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int NCTA>
 static int launch_gemm_bn(const GemmDesc& d, int ksplit, cudaStream_t s) {
-    const int Mp = (d.M + GM_BM - 1) / GM_BM * GM_BM;
+    constexpr int TM = GM_BM * NCTA;
+    const int Mp = (d.M + TM - 1) / TM * TM;
     CUtensorMap tmA, tmB, tmC;
     {
         uint64_t dims[2] = {static_cast<uint64_t>(d.K), static_cast<uint64_t>(d.M)};
@@ -311,7 +365,7 @@ static int launch_gemm_bn(const GemmDesc& d, int ksplit, cudaStream_t s) {
     {
         uint64_t dims[2] = {static_cast<uint64_t>(d.K), static_cast<uint64_t>(d.N)};
         uint64_t str[1] = {static_cast<uint64_t>(d.ldw) * 2};
-        uint32_t box[2] = {GM_BK, BN};
+        uint32_t box[2] = {GM_BK, BN / NCTA};
         if (int e = make_tmap_bf16(&tmB, d.w, 2, dims, str, box)) return e;
     }
     if (d.out_bf16 && !d.out_f32) {
@@ -344,15 +398,30 @@ static int launch_gemm_bn(const GemmDesc& d, int ksplit, cudaStream_t s) {
     p.ldr = d.ldr; p.resid_mod = d.resid_mod; p.ldf = d.ldf;
     p.has_bf16 = d.out_bf16 ? 1 : 0; p.relu = d.relu;
     p.M = d.M; p.ktiles = d.K / GM_BK / ksplit; p.ntiles = d.N / BN;
-    p.tiles_mn = ((d.M + GM_BM - 1) / GM_BM) * p.ntiles;
+    p.tiles_mn = ((d.M + TM - 1) / TM) * p.ntiles;
     p.items = p.tiles_mn * ksplit;
     p.split_rows = Mp;
-    constexpr size_t smem = STAGES * (GM_BM * GM_BK * 2 + BN * GM_BK * 2) + GM_EPI_WARPS * GM_STG_WARP + 1024;
+    constexpr size_t smem = STAGES * (GM_BM * GM_BK * 2 + (BN / NCTA) * GM_BK * 2) + GM_EPI_WARPS * GM_STG_WARP + 1024;
     static DeviceOnce once;
-    if (int e = smem_attr_once(once, reinterpret_cast<const void*>(gemm_tc_kernel<BN, STAGES>), smem, "gemm smem attr")) return e;
-    const int n_sm = sm_count();
-    const int grid = p.items < n_sm ? p.items : n_sm;
-    gemm_tc_kernel<BN, STAGES><<<grid, GM_THREADS, smem, s>>>(tmA, tmB, tmC, tmF, tmR, p);
+    if (int e = smem_attr_once(once, reinterpret_cast<const void*>(gemm_tc_kernel<BN, STAGES, NCTA>), smem, "gemm smem attr")) return e;
+    const int n_workers = sm_count() / NCTA;
+    const int grid = (p.items < n_workers ? p.items : n_workers) * NCTA;
+    if (NCTA == 1) {
+        gemm_tc_kernel<BN, STAGES, NCTA><<<grid, GM_THREADS, smem, s>>>(tmA, tmB, tmC, tmF, tmR, p);
+    } else {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(static_cast<unsigned>(grid));
+        cfg.blockDim = dim3(GM_THREADS);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = NCTA; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        if (int e = check_cuda(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES, NCTA>, tmA, tmB, tmC, tmF, tmR, p), "gemm_tc pair launch"))
+            return e;
+    }
     count_launch();
     return check_cuda(cudaGetLastError(), "gemm_tc launch");
 }
@@ -362,8 +431,18 @@ int launch_gemm_bf16(const GemmDesc& d, cudaStream_t s) {
         set_error("gemm_tc: needs K %% 64 == 0 and N %% 128 == 0, got M=%d N=%d K=%d", d.M, d.N, d.K);
         return MHADA_ERR_UNSUPPORTED;
     }
-    if (d.N % 256 == 0) return launch_gemm_bn<256, 3>(d, 1, s);     // 3 x 48 KB operand ring + 64 KB of staging slabs
-    return launch_gemm_bn<128, 4>(d, 1, s);
+    if (d.bias && (reinterpret_cast<uintptr_t>(d.bias) & 15) != 0) {
+        set_error("gemm_tc: bias must be 16-byte aligned");
+        return MHADA_ERR_ARG;
+    }
+    if (d.N % 256 == 0) {
+        // CTA pairs (256 x 256 tiles) when there is at least one full round of pair tiles; MHADA_GEMM_PAIR=0 keeps the
+        // single-CTA kernel (A/B switch for measurements)
+        static const bool pair_ok = [] { const char* e = getenv("MHADA_GEMM_PAIR"); return !(e && e[0] == '0'); }();
+        if (pair_ok && d.M >= 256 * (sm_count() / 2) / (d.N / 256)) return launch_gemm_bn<256, 4, 2>(d, 1, s);
+        return launch_gemm_bn<256, 3, 1>(d, 1, s);                   // 3 x 48 KB operand ring + 64 KB of staging slabs
+    }
+    return launch_gemm_bn<128, 4, 1>(d, 1, s);
 }
 
 // ---- split-K (the weight-gradient GEMMs of the training path: C x C outputs, K = all tokens of the batch) ----------
@@ -415,7 +494,7 @@ int launch_gemm_bf16_splitk(const GemmDesc& d, void* ws, size_t ws_bytes, cudaSt
     GemmDesc p = d;
     p.out_f32 = static_cast<float*>(ws);
     p.ldf = d.N;
-    if (int e = d.N % 256 == 0 ? launch_gemm_bn<256, 3>(p, ks, s) : launch_gemm_bn<128, 4>(p, ks, s)) return e;
+    if (int e = d.N % 256 == 0 ? launch_gemm_bn<256, 3, 1>(p, ks, s) : launch_gemm_bn<128, 4, 1>(p, ks, s)) return e;
     const size_t Mp = static_cast<size_t>(d.M + GM_BM - 1) / GM_BM * GM_BM;
     const size_t n = static_cast<size_t>(d.M) * (d.N / 4);
     splitk_reduce_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(static_cast<const float*>(ws), ks, Mp * d.N, d.M, d.N,

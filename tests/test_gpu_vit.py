@@ -36,7 +36,11 @@ def bf(x):
     (260, 2048, 512, "relu"),       # mlp[0] + ReLU -> bf16
     (129, 512, 2048, "both"),       # mlp[2] + residual -> f32 and bf16
     (70, 384, 64, "bf16"),          # N % 256 != 0 -> 128-column tiles, M < one tile
-    (33000, 1536, 512, "bf16"),     # more items than CTAs: persistent loop, staging-slab reuse
+    (33000, 1536, 512, "bf16"),     # more items than CTAs: persistent loop, staging-slab reuse; CTA-pair kernel (M = 256 tiles)
+    (20000, 512, 512, "resid"),     # CTA pairs, f32 result + residual through TMA, ragged last pair tile
+    (12100, 512, 2048, "both"),     # CTA pairs, f32 + bf16 results, long K
+    (10000, 512, 192, "pos"),       # CTA pairs, row-periodic residual that wraps inside a slab (direct loads)
+    (9600, 2048, 512, "relu"),      # CTA pairs, eight column tiles per row block
 ])
 def test_gemm(M_, N, K, mode):
     L = _lib.lib()
