@@ -146,3 +146,44 @@ def test_abi_argument_checks_of_the_newer_entry_points(lib):
     ms, n = ctypes.c_float(0), ctypes.c_int(0)
     assert lib.mhada_profile_stage(9, ctypes.byref(ms), ctypes.byref(n)) == -1
     assert lib.mhada_profile_stage(0, ctypes.byref(ms), ctypes.byref(n)) == 0
+
+
+def test_backward_path_selection_is_host_logic():
+    """which backward a layer takes (own kernels / fp32 recompute) is decided on the host from the precision,
+    the head width and the activation; bad switches raise where they are read."""
+    x16, x32 = torch.zeros(1, 512, 4, 4, dtype=torch.bfloat16), torch.zeros(1, 512, 4, 4)
+    m = M.AdaAttnMultiHead(512, 8)
+    assert m.backward_impl in ("auto", "kernels", "torch")
+    m.backward_impl = "auto"
+    assert m._kernel_backward(x16, x16, x16) is True                 # bf16 inputs, head_dim 64 -> mhada_layer_backward
+    assert m._kernel_backward(x32, x32, x32) is False                # fp32 inputs -> fp32 path -> recompute backward
+    m.precision = "bf16"
+    assert m._kernel_backward(x32, x32, x32) is True
+    m.backward_impl = "torch"
+    assert m._kernel_backward(x16, x16, x16) is False
+    m.backward_impl = "nope"
+    with pytest.raises(ValueError, match="backward_impl"):
+        m._kernel_backward(x16, x16, x16)
+    m4 = M.AdaAttnMultiHead(512, 4)                                   # head_dim 128: tensor-core forward, recompute backward
+    assert m4._kernel_backward(x16, x16, x16) is False
+    m4.backward_impl = "kernels"
+    with pytest.raises(NotImplementedError):
+        m4._kernel_backward(x16, x16, x16)
+    mc = M.AdaAttnMultiHead(512, 8, activation="cosine")
+    assert mc._kernel_backward(x32, x32, x32) is False
+    v = M.VisionTransformer()
+    assert v.train_impl in ("auto", "kernels", "torch")
+
+
+def test_backward_abi_argument_checks(lib):
+    a = _lib.LayerBwdArgs()
+    assert lib.mhada_layer_backward(None, None) == -1
+    assert lib.mhada_layer_backward(ctypes.byref(a), None) == -1 and b"null" in lib.mhada_last_error()
+    assert lib.mhada_layer_backward_workspace(8, 1024, 1024, 512, 8) > lib.mhada_layer_workspace(_lib.BF16, 8, 1024, 1024, 512, 8)
+    assert lib.mhada_layer_backward_workspace(8, 1024, 1024, 512, 7) == 0
+    assert lib.mhada_attn_bwd(1, 1, 1, 1, *([None] * 15)) == -1
+    assert lib.mhada_batch_attn_bwd(None, None, 1, 1, 1, 64, None, None) == -1
+    assert lib.mhada_transpose_bf16(None, 0, 4, 4, 4, 64, None, None) == -1
+    assert lib.mhada_colsum(None, 0, 4, 4, None, 0, None, None) == -1
+    assert lib.mhada_gemm_splitk_workspace(512, 512, 8192) > 0 and lib.mhada_gemm_splitk_workspace(512, 500, 8192) == 0
+    assert lib.mhada_gemm_bf16_splitk(None, 64, None, 64, 1, 128, 64, None, 128, None, 0, None) == -1
