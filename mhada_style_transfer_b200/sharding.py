@@ -155,13 +155,17 @@ class OverlappedGradientAllReduce:
         for i, flat, work in self._inflight:
             work.wait()
             flat.div_(self.world)
-            off = 0
+            grads, views, off = [], [], 0
             for p in self.buckets[i]:
                 if p.grad is None:
                     continue
                 n = p.grad.numel()
-                p.grad.copy_(flat[off: off + n].view_as(p.grad))
+                grads.append(p.grad)
+                views.append(flat[off: off + n].view_as(p.grad))
                 off += n
+            # ONE multi-tensor copy per bucket: a copy_ per parameter is ~400 launches at the very end of the step,
+            # where nothing is left to hide them behind (1.4 of the 1.6 ms "exposed all-reduce" of the r2 runs)
+            torch._foreach_copy_(grads, views)
         self._inflight = []
         self._pending = [len(b) for b in self.buckets]
 
