@@ -144,6 +144,8 @@ MHADA_API int mhada_linear(int dtype, const void* x, int ldx, const float* w, co
  *     fcs may alias fc (layer 0 of the transformer, adaDecoder.py:262).  out must not alias inputs.
  *     w_fgh / b_fgh as in (2); w_out float [C][C], b_out float [C]; both may be NULL together to
  *     skip out_conv (the single-head AdaAttN, adaDecoder.py:102-131).
+ *     MHADA_BF16 head widths: 64 and 128 run the streaming tcgen05 kernel; multiples of 128 above that (1- and 2-head
+ *     layers, AdaAttN) run per-head projections on the token GEMM and the materialised attention of (8).
  *     ws: mhada_layer_workspace(dtype, B, Nc, Ns, C, H) bytes.
  *     flags: MHADA_REUSE_FS_STATS when `fs` and `ws` are the ones passed to the previous call on this stream
  *     (the two layers of a level share fs, adaDecoder.py:264-265): its statistics are not recomputed.

@@ -23,8 +23,8 @@ size_t esize(int dtype) { return dtype == MHADA_BF16 ? 2 : 4; }
 
 struct LayerWs {
     float *mean_c, *rstd_c, *mean_s, *rstd_s, *mean_x, *rstd_x, *mu_v;
-    void *stats_ws, *proj_ws, *q, *k, *v, *heads, *lin_ws;
-    size_t stats_bytes, proj_bytes, lin_bytes, total;
+    void *stats_ws, *proj_ws, *q, *k, *v, *heads, *lin_ws, *wide;
+    size_t stats_bytes, proj_bytes, lin_bytes, wide_bytes, total;
 };
 
 LayerWs carve(int dtype, int B, int Nc, int Ns, int C, int H, uint8_t* base) {
@@ -47,12 +47,15 @@ LayerWs carve(int dtype, int B, int Nc, int Ns, int C, int H, uint8_t* base) {
     if (sb2 > w.stats_bytes) w.stats_bytes = sb2;
     w.stats_ws = take(w.stats_bytes);
     const int d = C / H;
-    w.proj_bytes = dtype == MHADA_BF16 ? proj_bf16_workspace(B, H, d) : 0;
+    const bool wide = dtype == MHADA_BF16 && d > 128;      // wide heads: projections + materialised attention (forloss_tc.cu)
+    w.proj_bytes = dtype == MHADA_BF16 && !wide ? proj_bf16_workspace(B, H, d) : 0;
     w.proj_ws = take(w.proj_bytes);
     const size_t e = esize(dtype);
-    w.q = take(static_cast<size_t>(B) * Nc * C * e);
-    w.k = take(static_cast<size_t>(B) * Ns * C * e);
-    w.v = take(static_cast<size_t>(B) * Ns * C * e * (dtype == MHADA_BF16 ? 2 : 1));
+    w.q = take(wide ? 0 : static_cast<size_t>(B) * Nc * C * e);
+    w.k = take(wide ? 0 : static_cast<size_t>(B) * Ns * C * e);
+    w.v = take(wide ? 0 : static_cast<size_t>(B) * Ns * C * e * (dtype == MHADA_BF16 ? 2 : 1));
+    w.wide_bytes = wide ? layer_wide_workspace(B, Nc, Ns, C, H) : 0;
+    w.wide = take(w.wide_bytes);
     w.heads = take(static_cast<size_t>(B) * Nc * C * e);
     w.lin_bytes = dtype == MHADA_BF16 ? linear_bf16_workspace(C, C) : 0;
     w.lin_ws = take(w.lin_bytes);
@@ -135,9 +138,11 @@ int layer_impl(const char* who, int dtype, const void* fc, const void* fs, const
     REQUIRE(dtype == MHADA_F32 || dtype == MHADA_BF16, MHADA_ERR_ARG, "%s: bad dtype %d", who, dtype);
     REQUIRE(out != fc && out != fs && out != fcs, MHADA_ERR_ARG, "%s: out must not alias an input", who);
     const int d = C / H;
+    const bool wide = dtype == MHADA_BF16 && d > 128;
     if (dtype == MHADA_BF16)
-        REQUIRE(d == 64 || d == 128, MHADA_ERR_UNSUPPORTED,
-                "%s: the bf16 tensor-core path implements head_dim 64 and 128 (C/H = %d); use MHADA_F32", who, d);
+        REQUIRE(d == 64 || d == 128 || (d % 128 == 0 && !cache), MHADA_ERR_UNSUPPORTED,
+                "%s: the bf16 tensor-core path implements head_dim 64, 128 and (without a style cache) multiples of 128 "
+                "(C/H = %d); use MHADA_F32", who, d);
     REQUIRE(!(flags & MHADA_WOUT_BF16) || (dtype == MHADA_BF16 && w_out && C % 128 == 0 && aligned16(w_out)), MHADA_ERR_ARG,
             "%s: MHADA_WOUT_BF16 needs the MHADA_BF16 path, a 16-byte aligned bf16 w_out and C %% 128 == 0", who);
     REQUIRE(!(flags & MHADA_LAYER_COSINE) || dtype == MHADA_F32, MHADA_ERR_UNSUPPORTED,
@@ -164,7 +169,27 @@ int layer_impl(const char* who, int dtype, const void* fc, const void* fs, const
     }
     const int parts = cache ? MHADA_PROJ_Q : (MHADA_PROJ_Q | MHADA_PROJ_KV);
     const bool fs_stats = !cache && !(flags & MHADA_REUSE_FS_STATS);
-    if (dtype == MHADA_BF16) {
+    if (wide) {
+        // wide heads (head_dim 256 / 512): full statistics, per-head projections on the token GEMM, materialised attention
+        {
+            const void* xs[3];
+            float* ms[3];
+            float* rs[3];
+            int ns[3];
+            int n = 0;
+            xs[n] = fc; ms[n] = w.mean_c; rs[n] = w.rstd_c; ns[n] = Nc; ++n;
+            if (fs_stats) { xs[n] = fs; ms[n] = w.mean_s; rs[n] = w.rstd_s; ns[n] = Ns; ++n; }
+            if (fcs != fc) { xs[n] = fcs; ms[n] = w.mean_x; rs[n] = w.rstd_x; ns[n] = Nc; ++n; }
+            StageTimer timer(MHADA_STAGE_STATS, s);
+            if (int e = launch_stats_multi(n, xs, ns, ms, rs, dtype, B, C, C, static_cast<float*>(w.stats_ws), s)) return e;
+        }
+        {
+            StageTimer timer(MHADA_STAGE_ATTN, s);
+            if (int e = layer_wide_attention(fc, fs, fcs, w.mean_c, w.rstd_c, w.mean_s, w.rstd_s, mean_x, rstd_x, w_fgh, b_fgh, B, Nc,
+                                             Ns, C, H, w_out ? w.heads : out, w.wide, s))
+                return e;
+        }
+    } else if (dtype == MHADA_BF16) {
         // bf16 path: first pass of the statistics, then ONE kernel that finishes them and folds them into the
         // projection weights (fold_stats_kernel), then the persistent projection kernel
         const void* xs[3];
@@ -218,6 +243,7 @@ int layer_impl(const char* who, int dtype, const void* fc, const void* fs, const
     }
     // (3) attention + fused epilogue                                         adaDecoder.py:186-198
     mhada_attn_args a{};
+    if (!wide) {
     a.dtype = dtype; a.B = B; a.H = H; a.Nc = Nc; a.Ns = Ns; a.dqk = d; a.dv = d;
     a.q = w.q; a.k = cache ? cv.k : w.k; a.v = cache ? cv.v : w.v; a.x = fcs;
     a.out = w_out ? w.heads : out;
@@ -226,6 +252,7 @@ int layer_impl(const char* who, int dtype, const void* fc, const void* fs, const
     a.kv_batch = cache ? Bs : B;
     a.activation = (flags & MHADA_LAYER_COSINE) ? MHADA_ACT_COSINE : MHADA_ACT_SOFTMAX;
     if (int e = attn_dispatch(a, s)) return e;
+    }
     // (4) out_conv                                                           adaDecoder.py:202-205
     if (w_out) {
         StageTimer timer(MHADA_STAGE_LINEAR, s);

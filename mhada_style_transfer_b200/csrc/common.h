@@ -116,6 +116,11 @@ int vit_forward(const mhada_vit_args& a, cudaStream_t s);
 // AdaAttnForLoss on the tensor cores (forloss_tc.cu)
 size_t forloss_workspace(int B, int Nc, int Ns, int dqk, int dv);
 int forloss_forward(const mhada_forloss_args& a, cudaStream_t s);
+// layers with wide heads (head_dim a multiple of 128 above 128) on the same materialised core
+size_t layer_wide_workspace(int B, int Nc, int Ns, int C, int H);
+int layer_wide_attention(const void* fc, const void* fs, const void* fcs, const float* mean_c, const float* rstd_c,
+                         const float* mean_s, const float* rstd_s, const float* mean_x, const float* rstd_x, const float* w_fgh,
+                         const float* b_fgh, int B, int Nc, int Ns, int C, int H, void* heads, void* ws, cudaStream_t s);
 
 // backward of a layer: attention backward kernels (attn_bwd.cu) and the helpers around the GEMMs (layer_bwd.cu)
 int launch_attn_bwd(int B, int H, int Nc, int Ns, int C, const void* q, const void* k, const void* v, const void* x,

@@ -46,12 +46,13 @@ __device__ __forceinline__ float ldf(const __nv_bfloat16* p) { return __bfloat16
 __device__ __forceinline__ void stf(float* p, float v) { *p = v; }
 __device__ __forceinline__ void stf(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 
-// t = scale * (x[b, n, c] - mean[b, c]) * rstd[b, c] split as hi = bf16(t), lo = bf16(t - hi); row of 3 C bf16:
-// role 0 (queries) [hi | lo | hi], role 1 (keys) [hi | hi | lo]; rows n in [N, Npad) zero.  8 channels per thread.
+// t = scale * (x[b, n, c] - mean[b, c]) * rstd[b, c] (or scale * x when mean == nullptr) split as hi = bf16(t),
+// lo = bf16(t - hi); row of 3 C bf16: role 0 (queries) [hi | lo | hi], role 1 (keys) [hi | hi | lo]; rows n in [N, Npad)
+// zero.  x has row pitch ldx, the statistics row pitch lds (a head's slice of a wider tensor).  8 channels per thread.
 template <typename T>
-__global__ void __launch_bounds__(256) normalize_rows_kernel(const T* __restrict__ x, const float* __restrict__ mean,
-                                                             const float* __restrict__ rstd, float scale, int role, int B, int N,
-                                                             int Npad, int C, __nv_bfloat16* __restrict__ y) {
+__global__ void __launch_bounds__(256) normalize_rows_kernel(const T* __restrict__ x, int ldx, const float* __restrict__ mean,
+                                                             const float* __restrict__ rstd, int lds, float scale, int role, int B,
+                                                             int N, int Npad, int C, __nv_bfloat16* __restrict__ y) {
     const int cv = C / 8;
     const size_t total = static_cast<size_t>(B) * Npad * cv;
     const size_t t = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
@@ -62,9 +63,14 @@ __global__ void __launch_bounds__(256) normalize_rows_kernel(const T* __restrict
     uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = hi;
     if (n < N) {
         float v[8], m[8], r[8];
-        load8(x + (static_cast<size_t>(b) * N + n) * C + c, v);
-        load8(mean + static_cast<size_t>(b) * C + c, m);
-        load8(rstd + static_cast<size_t>(b) * C + c, r);
+        load8(x + (static_cast<size_t>(b) * N + n) * ldx + c, v);
+        if (mean) {
+            load8(mean + static_cast<size_t>(b) * lds + c, m);
+            load8(rstd + static_cast<size_t>(b) * lds + c, r);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { m[i] = 0.f; r[i] = 1.f; }
+        }
         uint32_t h[4], l[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -83,10 +89,11 @@ __global__ void __launch_bounds__(256) normalize_rows_kernel(const T* __restrict
 
 // vr = bf16(v[b, n, c] - mu[b, c]);  vt[b][c][n] = vr;  vt[b][dv + c][n] = hi(vr^2);  vt[b][2 dv + c][n] = lo(vr^2)
 // (vr^2 is exact in f32 and hi + lo is exact: see (b) above);  n >= N -> 0; rows [3 dv, NV) are zeroed by the caller.
-// 32 x 32 tiles through shared memory: reads are coalesced along channels, writes along tokens.
+// v has row pitch ldv, mu row pitch ldm.  32 x 32 tiles through shared memory: reads are coalesced along channels,
+// writes along tokens.
 template <typename T>
-__global__ void __launch_bounds__(256) vprime_t_kernel(const T* __restrict__ v, const float* __restrict__ mu, int N, int Npad,
-                                                       int dv, int NV, __nv_bfloat16* __restrict__ vt) {
+__global__ void __launch_bounds__(256) vprime_t_kernel(const T* __restrict__ v, int ldv, const float* __restrict__ mu, int ldm, int N,
+                                                       int Npad, int dv, int NV, __nv_bfloat16* __restrict__ vt) {
     __shared__ float tile[32][33];
     const int b = blockIdx.z, n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
@@ -94,7 +101,7 @@ __global__ void __launch_bounds__(256) vprime_t_kernel(const T* __restrict__ v, 
     for (int r = ty; r < 32; r += 8) {
         const int n = n0 + r, c = c0 + tx;
         float val = 0.f;
-        if (n < N && c < dv) val = ldf(v + (static_cast<size_t>(b) * N + n) * dv + c) - __ldg(mu + static_cast<size_t>(b) * dv + c);
+        if (n < N && c < dv) val = ldf(v + (static_cast<size_t>(b) * N + n) * ldv + c) - __ldg(mu + static_cast<size_t>(b) * ldm + c);
         tile[r][tx] = val;
     }
     __syncthreads();
@@ -159,12 +166,12 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restri
 }
 
 // out[n, c] = sqrt(max(E - M^2, 1e-6)) * (x[n, c] - mean_x[c]) * rstd_x[c] + M + mu_v[c],
-// M = o[n, c] / l, E = (o[n, dv + c] + o[n, 2 dv + c]) / l
+// M = o[n, c] / l, E = (o[n, dv + c] + o[n, 2 dv + c]) / l;  x has row pitch ldx, out row pitch ldo
 template <typename T>
 __global__ void __launch_bounds__(256) forloss_finalize_kernel(const float* __restrict__ o, const float* __restrict__ lsum,
-                                                               const T* __restrict__ x, const float* __restrict__ mean_x,
+                                                               const T* __restrict__ x, int ldx, const float* __restrict__ mean_x,
                                                                const float* __restrict__ rstd_x, const float* __restrict__ mu_v,
-                                                               int Nc, int dv, int NV, T* __restrict__ out) {
+                                                               int Nc, int dv, int NV, T* __restrict__ out, int ldo) {
     const int cv = dv / 2;
     const size_t t = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
     if (t >= static_cast<size_t>(Nc) * cv) return;
@@ -178,80 +185,78 @@ __global__ void __launch_bounds__(256) forloss_finalize_kernel(const float* __re
     for (int e = 0; e < 2; ++e) {
         const float m = (e ? m2.y : m2.x) * inv, ex = ((e ? eh.y : eh.x) + (e ? el.y : el.x)) * inv;
         const float sd = sqrtf(fmaxf(fmaf(-m, m, ex), 1e-6f));
-        const float xf = ldf(x + static_cast<size_t>(n) * dv + c + e);
-        stf(out + static_cast<size_t>(n) * dv + c + e,
+        const float xf = ldf(x + static_cast<size_t>(n) * ldx + c + e);
+        stf(out + static_cast<size_t>(n) * ldo + c + e,
             fmaf(sd, (xf - __ldg(mean_x + c + e)) * __ldg(rstd_x + c + e), m + __ldg(mu_v + c + e)));
     }
 }
 
-struct ForlossWs {
-    float *mean_q, *rstd_q, *mean_k, *rstd_k, *mean_x, *rstd_x, *mean_v, *rstd_v, *stats_ws, *s, *o, *lsum;
+// ---- the materialised attention core: one (head of a) problem for all B images -------------------------------------
+struct MatWs {
+    float *s, *o, *lsum;
     __nv_bfloat16 *qn, *kn, *vt, *p;
     int Npad, NV;
-    size_t total;
 };
-static ForlossWs forloss_carve(int B, int Nc, int Ns, int dqk, int dv, uint8_t* base) {
-    ForlossWs w;
+struct Carver {
+    uint8_t* base;
     size_t off = 0;
-    auto take = [&](size_t bytes) {
+    void* take(size_t bytes) {
         void* p = base ? base + off : nullptr;
         off += align_up(bytes, 1024);
         return p;
-    };
-    const int Npad = (Ns + 127) / 128 * 128, NV = (3 * dv + 127) / 128 * 128;
-    w.Npad = Npad; w.NV = NV;
-    const size_t sq = static_cast<size_t>(B) * dqk * 4, sv = static_cast<size_t>(B) * dv * 4;
-    w.mean_q = static_cast<float*>(take(sq)); w.rstd_q = static_cast<float*>(take(sq));
-    w.mean_k = static_cast<float*>(take(sq)); w.rstd_k = static_cast<float*>(take(sq));
-    w.mean_x = static_cast<float*>(take(sv)); w.rstd_x = static_cast<float*>(take(sv));
-    w.mean_v = static_cast<float*>(take(sv)); w.rstd_v = static_cast<float*>(take(sv));
-    size_t sb = stats_workspace(B, Nc > Ns ? Nc : Ns, dqk > dv ? dqk : dv);
-    const size_t sb2 = stats_workspace(B, Nc < Ns ? Nc : Ns, dqk > dv ? dqk : dv);
-    if (sb2 > sb) sb = sb2;
-    w.stats_ws = static_cast<float*>(take(sb));
-    w.qn = static_cast<__nv_bfloat16*>(take(static_cast<size_t>(B) * Nc * 3 * dqk * 2));
-    w.kn = static_cast<__nv_bfloat16*>(take(static_cast<size_t>(B) * Npad * 3 * dqk * 2));
-    w.vt = static_cast<__nv_bfloat16*>(take(static_cast<size_t>(B) * NV * Npad * 2));
-    w.s = static_cast<float*>(take(static_cast<size_t>(Nc) * Npad * 4));           // one image at a time
-    w.p = static_cast<__nv_bfloat16*>(take(static_cast<size_t>(Nc) * Npad * 2));
-    w.o = static_cast<float*>(take(static_cast<size_t>(Nc) * NV * 4));
-    w.lsum = static_cast<float*>(take(static_cast<size_t>(Nc) * 4));
-    w.total = off;
+    }
+};
+static MatWs mat_carve(Carver& cv, int B, int Nc, int Ns, int dqk, int dv) {
+    MatWs w;
+    w.Npad = (Ns + 127) / 128 * 128;
+    w.NV = (3 * dv + 127) / 128 * 128;
+    w.qn = static_cast<__nv_bfloat16*>(cv.take(static_cast<size_t>(B) * Nc * 3 * dqk * 2));
+    w.kn = static_cast<__nv_bfloat16*>(cv.take(static_cast<size_t>(B) * w.Npad * 3 * dqk * 2));
+    w.vt = static_cast<__nv_bfloat16*>(cv.take(static_cast<size_t>(B) * w.NV * w.Npad * 2));
+    w.s = static_cast<float*>(cv.take(static_cast<size_t>(Nc) * w.Npad * 4));           // one image at a time
+    w.p = static_cast<__nv_bfloat16*>(cv.take(static_cast<size_t>(Nc) * w.Npad * 2));
+    w.o = static_cast<float*>(cv.take(static_cast<size_t>(Nc) * w.NV * 4));
+    w.lsum = static_cast<float*>(cv.take(static_cast<size_t>(Nc) * 4));
     return w;
 }
-size_t forloss_workspace(int B, int Nc, int Ns, int dqk, int dv) { return forloss_carve(B, Nc, Ns, dqk, dv, nullptr).total; }
 
-template <typename T>
-static int forloss_forward_t(const mhada_forloss_args& a, cudaStream_t s) {
-    const int B = a.B, Nc = a.Nc, Ns = a.Ns, dqk = a.dqk, dv = a.dv;
-    const int dtype = a.dtype;
-    ForlossWs w = forloss_carve(B, Nc, Ns, dqk, dv, static_cast<uint8_t*>(a.ws));
-    const int Npad = w.Npad, NV = w.NV;
-    // 1. statistics (adaDecoder.py:55, :60, :81; the mean of V for the centring)
-    if (int e = launch_stats(a.c_1x, dtype, B, Nc, dqk, dqk, w.mean_q, w.rstd_q, w.stats_ws, s)) return e;
-    if (int e = launch_stats(a.s_1x, dtype, B, Ns, dqk, dqk, w.mean_k, w.rstd_k, w.stats_ws, s)) return e;
-    if (int e = launch_stats(a.c_x, dtype, B, Nc, dv, dv, w.mean_x, w.rstd_x, w.stats_ws, s)) return e;
-    if (int e = launch_stats(a.s_x, dtype, B, Ns, dv, dv, w.mean_v, w.rstd_v, w.stats_ws, s)) return e;
-    // 2. normalised, split operands
+// TQ: storage type of q, k, v;  TX: storage type of x and out.  q / k are normalised with (mean, rstd) when given.
+template <typename TQ, typename TX>
+struct MatAttn {
+    int B, Nc, Ns, dqk, dv;
+    const TQ *q, *k, *v;
+    int ldq, ldk, ldv;
+    const float *q_mean, *q_rstd, *k_mean, *k_rstd;   // [B][lds_qk] or nullptr
+    const float* v_mean;                              // [B][lds_xv]: centring of V, added back as mu_v
+    const TX* x;
+    int ldx;
+    const float *x_mean, *x_rstd;                     // [B][lds_xv]
+    int lds_qk, lds_xv;                               // row pitch of the q / k statistics and of the v / x statistics
+    TX* out;
+    int ldo;
+};
+
+template <typename TQ, typename TX>
+static int mat_attention(const MatAttn<TQ, TX>& a, const MatWs& w, cudaStream_t s) {
+    const int B = a.B, Nc = a.Nc, Ns = a.Ns, dqk = a.dqk, dv = a.dv, Npad = w.Npad, NV = w.NV;
     {
         const size_t tq = static_cast<size_t>(B) * Nc * (dqk / 8), tk = static_cast<size_t>(B) * Npad * (dqk / 8);
-        normalize_rows_kernel<T><<<static_cast<unsigned>((tq + 255) / 256), 256, 0, s>>>(
-            static_cast<const T*>(a.c_1x), w.mean_q, w.rstd_q, FL_LOG2E, 0, B, Nc, Nc, dqk, w.qn);
+        normalize_rows_kernel<TQ><<<static_cast<unsigned>((tq + 255) / 256), 256, 0, s>>>(a.q, a.ldq, a.q_mean, a.q_rstd, a.lds_qk, FL_LOG2E,
+                                                                                          0, B, Nc, Nc, dqk, w.qn);
         count_launch();
-        normalize_rows_kernel<T><<<static_cast<unsigned>((tk + 255) / 256), 256, 0, s>>>(
-            static_cast<const T*>(a.s_1x), w.mean_k, w.rstd_k, 1.f, 1, B, Ns, Npad, dqk, w.kn);
+        normalize_rows_kernel<TQ><<<static_cast<unsigned>((tk + 255) / 256), 256, 0, s>>>(a.k, a.ldk, a.k_mean, a.k_rstd, a.lds_qk, 1.f, 1,
+                                                                                          B, Ns, Npad, dqk, w.kn);
         count_launch();
         if (NV > 3 * dv)                                        // padding rows of V'^T (GEMM N is a multiple of 128)
             for (int b = 0; b < B; ++b)
                 if (int e = check_cuda(cudaMemsetAsync(w.vt + (static_cast<size_t>(b) * NV + 3 * dv) * Npad, 0,
-                                                       static_cast<size_t>(NV - 3 * dv) * Npad * 2, s), "forloss memset"))
+                                                       static_cast<size_t>(NV - 3 * dv) * Npad * 2, s), "materialised attention memset"))
                     return e;
         dim3 g(static_cast<unsigned>(Npad / 32), static_cast<unsigned>((dv + 31) / 32), static_cast<unsigned>(B));
-        vprime_t_kernel<T><<<g, 256, 0, s>>>(static_cast<const T*>(a.s_x), w.mean_v, Ns, Npad, dv, NV, w.vt);
+        vprime_t_kernel<TQ><<<g, 256, 0, s>>>(a.v, a.ldv, a.v_mean, a.lds_xv, Ns, Npad, dv, NV, w.vt);
         count_launch();
-        if (int e = check_cuda(cudaGetLastError(), "forloss prepare launch")) return e;
+        if (int e = check_cuda(cudaGetLastError(), "materialised attention prepare launch")) return e;
     }
-    // 3. per image: logits, weights, moments; 4. epilogue
     for (int b = 0; b < B; ++b) {
         GemmDesc g{};
         g.a = w.qn + static_cast<size_t>(b) * Nc * 3 * dqk; g.lda = 3 * dqk;
@@ -266,17 +271,134 @@ static int forloss_forward_t(const mhada_forloss_args& a, cudaStream_t s) {
         g.M = Nc; g.N = NV; g.K = Npad; g.out_f32 = w.o; g.ldf = NV;
         if (int e = launch_gemm_bf16(g, s)) return e;                                              // :71, :74
         const size_t tf = static_cast<size_t>(Nc) * (dv / 2);
-        forloss_finalize_kernel<T><<<static_cast<unsigned>((tf + 255) / 256), 256, 0, s>>>(
-            w.o, w.lsum, static_cast<const T*>(a.c_x) + static_cast<size_t>(b) * Nc * dv, w.mean_x + static_cast<size_t>(b) * dv,
-            w.rstd_x + static_cast<size_t>(b) * dv, w.mean_v + static_cast<size_t>(b) * dv, Nc, dv, NV,
-            static_cast<T*>(a.out) + static_cast<size_t>(b) * Nc * dv);                             // :74-81
+        forloss_finalize_kernel<TX><<<static_cast<unsigned>((tf + 255) / 256), 256, 0, s>>>(
+            w.o, w.lsum, a.x + static_cast<size_t>(b) * Nc * a.ldx, a.ldx, a.x_mean + static_cast<size_t>(b) * a.lds_xv,
+            a.x_rstd + static_cast<size_t>(b) * a.lds_xv, a.v_mean + static_cast<size_t>(b) * a.lds_xv, Nc, dv, NV,
+            a.out + static_cast<size_t>(b) * Nc * a.ldo, a.ldo);                                    // :74-81
         count_launch();
     }
-    return check_cuda(cudaGetLastError(), "forloss launch");
+    return check_cuda(cudaGetLastError(), "materialised attention launch");
+}
+
+// ---- AdaAttnForLoss ---------------------------------------------------------------------------------------------------
+struct ForlossWs {
+    float *mean_q, *rstd_q, *mean_k, *rstd_k, *mean_x, *rstd_x, *mean_v, *rstd_v, *stats_ws;
+    MatWs m;
+    size_t total;
+};
+static ForlossWs forloss_carve(int B, int Nc, int Ns, int dqk, int dv, uint8_t* base) {
+    ForlossWs w;
+    Carver cv{base};
+    const int cmax = dqk > dv ? dqk : dv;
+    const size_t sq = static_cast<size_t>(B) * cmax * 4;
+    w.mean_q = static_cast<float*>(cv.take(sq)); w.rstd_q = static_cast<float*>(cv.take(sq));
+    w.mean_k = static_cast<float*>(cv.take(sq)); w.rstd_k = static_cast<float*>(cv.take(sq));
+    w.mean_x = static_cast<float*>(cv.take(sq)); w.rstd_x = static_cast<float*>(cv.take(sq));
+    w.mean_v = static_cast<float*>(cv.take(sq)); w.rstd_v = static_cast<float*>(cv.take(sq));
+    size_t sb = stats_workspace(B, Nc > Ns ? Nc : Ns, cmax);
+    const size_t sb2 = stats_workspace(B, Nc < Ns ? Nc : Ns, cmax);
+    if (sb2 > sb) sb = sb2;
+    w.stats_ws = static_cast<float*>(cv.take(sb));
+    w.m = mat_carve(cv, B, Nc, Ns, dqk, dv);
+    w.total = cv.off;
+    return w;
+}
+size_t forloss_workspace(int B, int Nc, int Ns, int dqk, int dv) { return forloss_carve(B, Nc, Ns, dqk, dv, nullptr).total; }
+
+template <typename T>
+static int forloss_forward_t(const mhada_forloss_args& a, cudaStream_t s) {
+    const int B = a.B, Nc = a.Nc, Ns = a.Ns, dqk = a.dqk, dv = a.dv;
+    const int dtype = a.dtype;
+    ForlossWs w = forloss_carve(B, Nc, Ns, dqk, dv, static_cast<uint8_t*>(a.ws));
+    // statistics (adaDecoder.py:55, :60, :81; the mean of V for the centring); launch_stats writes [B][C] rows
+    if (int e = launch_stats(a.c_1x, dtype, B, Nc, dqk, dqk, w.mean_q, w.rstd_q, w.stats_ws, s)) return e;
+    if (int e = launch_stats(a.s_1x, dtype, B, Ns, dqk, dqk, w.mean_k, w.rstd_k, w.stats_ws, s)) return e;
+    if (int e = launch_stats(a.c_x, dtype, B, Nc, dv, dv, w.mean_x, w.rstd_x, w.stats_ws, s)) return e;
+    if (int e = launch_stats(a.s_x, dtype, B, Ns, dv, dv, w.mean_v, w.rstd_v, w.stats_ws, s)) return e;
+    MatAttn<T, T> m{};
+    m.B = B; m.Nc = Nc; m.Ns = Ns; m.dqk = dqk; m.dv = dv;
+    m.q = static_cast<const T*>(a.c_1x); m.k = static_cast<const T*>(a.s_1x); m.v = static_cast<const T*>(a.s_x);
+    m.ldq = dqk; m.ldk = dqk; m.ldv = dv;
+    m.q_mean = w.mean_q; m.q_rstd = w.rstd_q; m.k_mean = w.mean_k; m.k_rstd = w.rstd_k;
+    m.v_mean = w.mean_v; m.x = static_cast<const T*>(a.c_x); m.ldx = dv; m.x_mean = w.mean_x; m.x_rstd = w.rstd_x;
+    m.lds_qk = dqk; m.lds_xv = dv; m.out = static_cast<T*>(a.out); m.ldo = dv;
+    return mat_attention(m, w.m, s);
 }
 
 int forloss_forward(const mhada_forloss_args& a, cudaStream_t s) {
     return a.dtype == MHADA_F32 ? forloss_forward_t<float>(a, s) : forloss_forward_t<__nv_bfloat16>(a, s);
+}
+
+// ---- MHAda layers with WIDE heads (head_dim 256 / 512: one- and two-head AdaAttnMultiHead, AdaAttN, AdaAttnTransformer;
+//      adaDecoder.py:102-131, :162-206) on the tensor cores.  Q of two query tiles plus a K ring of such heads do not fit
+//      the streaming kernel's shared memory (r1 / early r2 ran them on the fp32 SIMT kernels: 16.4 ms per 4096^2 layer);
+//      here the projections run per head on the token GEMM (split operands, f32 results) and the attention through the
+//      materialised core above -- same split-operand numerics: given its (bf16) inputs this path is good to ~3e-3.
+struct WideWs {
+    __nv_bfloat16 *x3, *w3;
+    float *q, *k, *v, *mean_v, *rstd_v, *stats_ws;
+    MatWs m;
+    size_t total;
+};
+static WideWs wide_carve(int B, int Nc, int Ns, int C, int H, uint8_t* base) {
+    WideWs w;
+    Carver cv{base};
+    const int d = C / H;
+    const size_t nmax = static_cast<size_t>(B) * (Nc > Ns ? Nc : Ns);
+    w.x3 = static_cast<__nv_bfloat16*>(cv.take(nmax * 3 * d * 2));            // split operand of ONE head's projection
+    w.w3 = static_cast<__nv_bfloat16*>(cv.take(static_cast<size_t>(d) * 3 * d * 2));
+    w.q = static_cast<float*>(cv.take(static_cast<size_t>(B) * Nc * C * 4));
+    w.k = static_cast<float*>(cv.take(static_cast<size_t>(B) * Ns * C * 4));
+    w.v = static_cast<float*>(cv.take(static_cast<size_t>(B) * Ns * C * 4));
+    w.mean_v = static_cast<float*>(cv.take(static_cast<size_t>(B) * C * 4));
+    w.rstd_v = static_cast<float*>(cv.take(static_cast<size_t>(B) * C * 4));
+    w.stats_ws = static_cast<float*>(cv.take(stats_workspace(B, Ns, C)));
+    w.m = mat_carve(cv, B, Nc, Ns, d, d);
+    w.total = cv.off;
+    return w;
+}
+size_t layer_wide_workspace(int B, int Nc, int Ns, int C, int H) { return wide_carve(B, Nc, Ns, C, H, nullptr).total; }
+
+// fc, fs, fcs bf16 [B, N, C]; statistics of all three already computed ([B][C]); heads bf16 [B, Nc, C] (before out_conv)
+int layer_wide_attention(const void* fc, const void* fs, const void* fcs, const float* mean_c, const float* rstd_c,
+                         const float* mean_s, const float* rstd_s, const float* mean_x, const float* rstd_x, const float* w_fgh,
+                         const float* b_fgh, int B, int Nc, int Ns, int C, int H, void* heads, void* ws, cudaStream_t s) {
+    const int d = C / H;
+    WideWs w = wide_carve(B, Nc, Ns, C, H, static_cast<uint8_t*>(ws));
+    const __nv_bfloat16 *xfc = static_cast<const __nv_bfloat16*>(fc), *xfs = static_cast<const __nv_bfloat16*>(fs);
+    // per-head 1x1 projections (adaDecoder.py:173-183) as d x d GEMMs with SPLIT operands: IN(x) = hi + lo and
+    // W = hi + lo as bf16 pairs, the three leading products in one GEMM over K = 3 d ([xh | xl | xh] . [Wh | Wh | Wl]^T),
+    // so Q, K, V are good to ~2^-16 and the only bf16 rounding left in front of the logits is the caller's input
+    for (int h = 0; h < H; ++h) {
+        const struct { const __nv_bfloat16* x; const float *mean, *rstd; int N; float* y; int role; } jobs[3] = {
+            {xfc, mean_c, rstd_c, Nc, w.q, 0}, {xfs, mean_s, rstd_s, Ns, w.k, 1}, {xfs, nullptr, nullptr, Ns, w.v, 2}};
+        for (const auto& j : jobs) {
+            const size_t tx = static_cast<size_t>(B) * j.N * (d / 8), tw = static_cast<size_t>(d) * (d / 8);
+            normalize_rows_kernel<__nv_bfloat16><<<static_cast<unsigned>((tx + 255) / 256), 256, 0, s>>>(
+                j.x + h * d, C, j.mean ? j.mean + h * d : nullptr, j.rstd ? j.rstd + h * d : nullptr, C, 1.f, 0, B, j.N, j.N, d, w.x3);
+            count_launch();
+            normalize_rows_kernel<float><<<static_cast<unsigned>((tw + 255) / 256), 256, 0, s>>>(
+                w_fgh + (static_cast<size_t>(j.role) * H + h) * d * d, d, nullptr, nullptr, 0, 1.f, 1, 1, d, d, d, w.w3);
+            count_launch();
+            GemmDesc g{};
+            g.a = w.x3; g.lda = 3 * d; g.w = w.w3; g.ldw = 3 * d;
+            g.bias = b_fgh + (static_cast<size_t>(j.role) * H + h) * d;
+            g.M = B * j.N; g.N = d; g.K = 3 * d; g.out_f32 = j.y + h * d; g.ldf = C;
+            if (int e = launch_gemm_bf16(g, s)) return e;
+        }
+    }
+    if (int e = launch_stats(w.v, MHADA_F32, B, Ns, C, C, w.mean_v, w.rstd_v, w.stats_ws, s)) return e;     // mu_v (centring)
+    for (int h = 0; h < H; ++h) {
+        MatAttn<float, __nv_bfloat16> m{};
+        m.B = B; m.Nc = Nc; m.Ns = Ns; m.dqk = d; m.dv = d;
+        m.q = w.q + h * d; m.k = w.k + h * d; m.v = w.v + h * d; m.ldq = C; m.ldk = C; m.ldv = C;
+        m.v_mean = w.mean_v + h * d;
+        m.x = static_cast<const __nv_bfloat16*>(fcs) + h * d; m.ldx = C; m.x_mean = mean_x + h * d; m.x_rstd = rstd_x + h * d;
+        m.lds_qk = C; m.lds_xv = C;
+        m.out = static_cast<__nv_bfloat16*>(heads) + h * d; m.ldo = C;
+        if (int e = mat_attention(m, w.m, s)) return e;                                                    // :186-198
+    }
+    return 0;
 }
 
 }  // namespace mh

@@ -9,8 +9,8 @@ CUDA stream.  PyTorch is used for memory, streams and the decoder convolutions o
 
 Precision (`module.precision`, default "auto"):
   "fp32"  true-fp32 SIMT kernels (the reference's arithmetic; any head_dim)
-  "bf16"  tcgen05 tensor-core kernels, bf16 storage / fp32 accumulate (head_dim 64 or 128)
-  "auto"  bf16 path when the inputs are bf16/fp16 and head_dim is 64 or 128, else fp32 path
+  "bf16"  tcgen05 tensor-core kernels, bf16 storage / fp32 accumulate (head_dim 64, 128 or a multiple of 128)
+  "auto"  bf16 path when the inputs are bf16/fp16 and the head width allows it, else fp32 path
 There is no CPU path: CPU tensors raise.
 
 Training (train_image.py:105-144): the FORWARD always runs the CUDA kernels.  When gradients are required the
@@ -262,7 +262,13 @@ def _code(dtype: torch.dtype) -> int:
     return _lib.BF16 if dtype == torch.bfloat16 else _lib.F32
 
 
-_TC_HEAD_DIMS = (64, 128)      # head dims the tcgen05 kernels implement (128: value columns in two slices of 64)
+_TC_HEAD_DIMS = (64, 128)      # head dims the STREAMING tcgen05 kernel implements (128: value columns in two slices of 64)
+
+
+def _tc_head_ok(head_dim: int) -> bool:
+    """Streaming kernel for 64 / 128; wider heads (multiples of 128: 1- and 2-head layers, AdaAttN) run per-head
+    projections on the token GEMM and the materialised tensor-core attention (forloss_tc.cu)."""
+    return head_dim in _TC_HEAD_DIMS or (head_dim > 128 and head_dim % 128 == 0)
 
 
 def _is_cosine(activation) -> bool:
@@ -283,12 +289,12 @@ def _resolve_precision_softmax(precision: str, head_dim: int, *inputs) -> torch.
     if precision == "fp32":
         return torch.float32
     if precision == "bf16":
-        if head_dim not in _TC_HEAD_DIMS:
-            raise NotImplementedError(f"the bf16 tensor-core path implements head_dim 64 and 128, got {head_dim}; "
-                                      "use precision='fp32'")
+        if not _tc_head_ok(head_dim):
+            raise NotImplementedError(f"the bf16 tensor-core path implements head_dim 64, 128 and multiples of 128, got "
+                                      f"{head_dim}; use precision='fp32'")
         return torch.bfloat16
     low = all(t.dtype in (torch.bfloat16, torch.float16) for t in inputs)
-    return torch.bfloat16 if (low and head_dim in _TC_HEAD_DIMS) else torch.float32
+    return torch.bfloat16 if (low and _tc_head_ok(head_dim)) else torch.float32
 
 
 def _layer_forward(dt: torch.dtype, tfc, tfs, tfcs, w_fgh, b_fgh, w_out, b_out, num_heads: int, out=None,
@@ -877,6 +883,8 @@ class AdaAttnTransformerMultiHead(nn.Module):
         L0 = self.adaAttnHead[0]
         _check_activation(L0.activation)
         dt = _resolve_precision(precision or self.precision, L0.head_dim, *fs[: self.num_layers], activation=L0.activation)
+        if L0.head_dim not in _TC_HEAD_DIMS:
+            dt = torch.float32           # the style cache holds the streaming kernels' K / V' layout: wide heads cache in fp32
         bufs = []
         Bs, C, hs, ws_ = fs[0].shape
         for i in range(self.num_layers):

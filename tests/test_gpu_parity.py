@@ -68,7 +68,7 @@ def test_layer_fp32_vs_reference_golden(case, golden_index):
     assert e["max_abs"] <= fp32_tol(golden_index[case["name"]]["ref32_vs_ref64"]), e
 
 
-@pytest.mark.parametrize("case", [c for c in cases.LAYER_CASES if c["C"] // c["H"] in (64, 128) and "activation" not in c],
+@pytest.mark.parametrize("case", [c for c in cases.LAYER_CASES if c["C"] // c["H"] in (64, 128, 512) and "activation" not in c],
                          ids=lambda c: c["name"])
 def test_layer_bf16_vs_reference_golden(case, golden_index):
     fc, fs, fcs, sd = cases.layer_inputs(case)
@@ -382,10 +382,52 @@ def test_errors_on_device():
     x = torch.zeros(1, 512, 4, 4, device=DEV)
     with torch.no_grad(), pytest.raises(NotImplementedError):
         m(x, x, x)
-    m2 = M.AdaAttnMultiHead(512, 2).to(DEV)       # head_dim 256: fp32 kernels only
+    m2 = M.AdaAttnMultiHead(384, 2).to(DEV)       # head_dim 192: neither the streaming kernel nor a multiple of 128
     m2.precision = "bf16"
+    x2 = torch.zeros(1, 384, 4, 4, device=DEV)
     with torch.no_grad(), pytest.raises(NotImplementedError):
-        m2(x, x, x)
+        m2(x2, x2, x2)
+
+
+@pytest.mark.parametrize("H,B,hw,hsws", [(1, 2, (32, 32), (30, 30)), (2, 1, (24, 40), (16, 16)), (1, 1, (64, 64), (64, 64))])
+def test_wide_head_layers_on_the_tensor_cores(H, B, hw, hsws):
+    """head_dim 512 / 256 (1- and 2-head AdaAttnMultiHead: BASELINE configs[4] sweeps 1 / 4 / 8 heads): per-head
+    projections on the token GEMM + materialised tensor-core attention with split operands, against the float64 oracle;
+    ragged key counts, cross sizes, 4096 x 4096 tokens.  The fp32 SIMT kernels stay the reference-arithmetic path."""
+    case = dict(B=B, C=512, H=H, hw=hw, hsws=hsws, gain=1.0, seed=31 + H)
+    fc, fs, fcs, sd = cases.layer_inputs(case)
+    want = O.ada_attn_multi_head(fc, fs, fcs, sd, H)
+    m = build_layer(case, sd)
+    m.precision = "bf16"
+    t16 = [dev(x).bfloat16() for x in (fc, fs, fcs)]
+    with torch.no_grad():
+        got = m(dev(fc), dev(fs), dev(fcs))
+        auto = m(*t16)
+    assert got.dtype == torch.float32 and auto.dtype == torch.bfloat16
+    # (a) against the oracle on the inputs the kernels see (bf16 storage): what the PATH adds -- 2e-2 / 5e-3
+    want16 = O.ada_attn_multi_head(*[t.float().cpu().numpy().astype(np.float64) for t in t16], sd, H)
+    e16 = O.errors(got.cpu().numpy(), want16)
+    assert e16["max_abs_rel"] <= BF16_REL and e16["fro_rel"] <= 5e-3, e16
+    # (b) against the oracle on the unrounded inputs: the bf16 rounding of the feature maps in front of 256- / 512-wide
+    # logits (std ~ sqrt(d): sharper rows than at 64) costs up to 3e-2 by itself
+    e = O.errors(got.cpu().numpy(), want)
+    assert e["max_abs_rel"] <= 3.5e-2 and e["fro_rel"] <= 1.5e-2, e
+    ea = O.errors(auto.float().cpu().numpy(), want16)
+    assert ea["max_abs_rel"] <= BF16_REL, ea
+
+
+def test_single_head_modules_on_the_tensor_cores(golden_index):
+    """AdaAttN / AdaAttnTransformer (head_dim 512, adaDecoder.py:85-131, :209-232) with precision="bf16" against the
+    reference goldens (48 tokens: the small-fixture tolerance)."""
+    case = cases.SINGLE_HEAD_TRANSFORMER_CASES[0]
+    fc, fs, sd = cases.single_head_transformer_inputs(case)
+    m = M.AdaAttnTransformer()
+    m.load_state_dict(synth.to_torch(sd, torch.float32), strict=True)
+    m = set_precision(m.to(DEV).eval(), "bf16")
+    with torch.no_grad():
+        cs = m([dev(x) for x in fc], [dev(x) for x in fs])
+    e = O.errors(cases.pixel_sublattice(cs.float().cpu().numpy(), case["img_sub"]), load_golden(case["name"])["cs"])
+    assert e["max_abs_rel"] <= 4e-2, e
 
 
 # ---------------------------------------------------------------------------------------------------
