@@ -82,6 +82,9 @@ DECODER_CASES = [
 GRAD_CASES = [
     # d(loss)/d(inputs, weights) of one AdaAttnMultiHead layer, loss = sum(out * G); reference autograd in float64
     dict(name="grad_layer_c128_h2", kind="grad", B=2, C=128, H=2, hw=(10, 10), hsws=(8, 9), gain=1.0, seed=71),
+    # the shape of the training step (train_image.py: 256 x 256 images -> 32 x 32 tokens, 8 heads of 64); input
+    # gradients stored on every 13th token
+    dict(name="grad_layer_c512_h8_32x32_sub", kind="grad", B=2, C=512, H=8, hw=(32, 32), hsws=(32, 32), gain=1.0, seed=72, sub=13),
 ]
 
 VIT_CASES = [

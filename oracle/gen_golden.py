@@ -115,7 +115,10 @@ def main(prefix: str = ""):
             for k in cases.GRAD_KEYS[3:]:
                 grads[k] = named[k].grad
             for k, g in grads.items():
-                arrays[k.replace(".", "__")] = g.numpy().astype(np.float32)
+                a = g.numpy()
+                if "sub" in case and k in ("fc", "fs", "fcs"):
+                    a = cases.token_sublattice(a, case["sub"])
+                arrays[k.replace(".", "__")] = a.astype(np.float32)
                 meta[k] = summarize(g.numpy())
             meta["loss"] = float(loss)
         elif kind == "decoder":

@@ -434,6 +434,14 @@ def test_single_head_modules_on_the_tensor_cores(golden_index):
 # training step (BASELINE configs[4]): kernels forward, gradients against the reference's float64 autograd
 # ---------------------------------------------------------------------------------------------------
 
+def _as_golden(case, key, t):
+    """Gradient tensor -> numpy in the form the golden stores it (input gradients on every sub-th token)."""
+    a = t.float().cpu().numpy()
+    if "sub" in case and key in ("fc", "fs", "fcs"):
+        a = cases.token_sublattice(a, case["sub"])
+    return a
+
+
 @pytest.mark.parametrize("case", cases.GRAD_CASES, ids=lambda c: c["name"])
 @pytest.mark.parametrize("precision,tol", [("fp32", 2e-4)])
 def test_layer_gradients_vs_reference_autograd(case, precision, tol, golden_index):
@@ -455,7 +463,7 @@ def test_layer_gradients_vs_reference_autograd(case, precision, tol, golden_inde
     # gradient against its own range plus 1e-6 of the largest gradient in the layer
     scale = max(float(np.abs(g[k.replace(".", "__")]).max()) for k in got)
     for k, t in got.items():
-        eg = O.errors(t.float().cpu().numpy(), g[k.replace(".", "__")])
+        eg = O.errors(_as_golden(case, k, t), g[k.replace(".", "__")])
         assert eg["max_abs"] <= tol * eg["absmax"] + 1e-6 * scale, (k, eg)
 
 
@@ -497,7 +505,8 @@ def _check_kernel_grads(got, want, max_rel, fro_rel):
 @pytest.mark.parametrize("case", cases.GRAD_CASES, ids=lambda c: c["name"])
 def test_layer_backward_kernels_vs_reference_autograd(case, golden_index):
     """forward AND backward on own kernels (mhada_layer_backward: flash-style attention backward, the other
-    contractions on the tcgen05 GEMM) against the reference's float64 autograd gradients.  100 x 72 tokens: the bf16
+    contractions on the tcgen05 GEMM) against the reference's float64 autograd gradients, at the shape of the training
+    step (2 x 1024 tokens, 8 heads: 3e-2 / 2e-2) and on a small ragged fixture.  100 x 72 tokens: the bf16
     rounding of the INPUT feature maps alone moves the instance-norm statistics by a per cent at this token count
     (forward parity on these fixtures is 2-4e-2 too); measured 7e-2 max / 2e-2 Frobenius."""
     fc, fs, fcs, sd, G = cases.grad_inputs(case)
@@ -507,8 +516,9 @@ def test_layer_backward_kernels_vs_reference_autograd(case, golden_index):
     tin = [dev(a).requires_grad_(True) for a in (fc, fs, fcs)]
     _, got = _grads_of(m, tin, dev(G))
     g = load_golden(case["name"])
-    _check_kernel_grads({k: got[k].float().cpu().numpy() for k in cases.GRAD_KEYS},
-                        {k: g[k.replace(".", "__")] for k in cases.GRAD_KEYS}, 1.2e-1, 3.5e-2)
+    big = case["hw"][0] * case["hw"][1] >= 1024            # the training-step shape: 3e-2 / 2e-2
+    _check_kernel_grads({k: _as_golden(case, k, got[k]) for k in cases.GRAD_KEYS},
+                        {k: g[k.replace(".", "__")] for k in cases.GRAD_KEYS}, 3e-2 if big else 1.2e-1, 2e-2 if big else 3.5e-2)
 
 
 @pytest.mark.parametrize("B,H,hw,hsws,alias,max_rel,fro_rel", [(2, 8, (32, 32), (32, 32), False, 3e-2, 2e-2),

@@ -208,8 +208,16 @@ def test_reference_gradients_agree_with_oracle_finite_differences(case, golden_i
     eps = 1e-5
     for key, arr in (("fc", fc), ("fs", fs), ("fcs", fcs), ("g_list.1.weight", sd["g_list.1.weight"]),
                      ("out_conv.bias", sd["out_conv.bias"])):
-        v = rng.standard_normal(arr.shape)
         args = dict(fc=fc, fs=fs, fcs=fcs)
+        gk = g[key.replace(".", "__")].astype(np.float64)
+        if "sub" in case and key in args:
+            # input gradients are stored on every sub-th token: probe along a direction supported on those tokens
+            vs = rng.standard_normal(gk.shape)
+            v = np.zeros((arr.shape[0], arr.shape[1], arr.shape[2] * arr.shape[3]))
+            v[:, :, ::case["sub"]] = vs
+            v = v.reshape(arr.shape)
+        else:
+            vs = v = rng.standard_normal(arr.shape)
 
         def at(sign):
             if key in args:
@@ -221,5 +229,5 @@ def test_reference_gradients_agree_with_oracle_finite_differences(case, golden_i
             return loss(fc, fs, fcs, sd2)
 
         fd = (at(+1) - at(-1)) / (2 * eps)
-        an = float((g[key.replace(".", "__")].astype(np.float64) * v).sum())
+        an = float((gk * vs).sum())
         assert fd == pytest.approx(an, rel=2e-4, abs=1e-6 * abs(an) + 1e-6), key
