@@ -47,6 +47,16 @@ struct GemmParams {
     int split_rows;        // split-K: partial s is written at row s * split_rows of the f32 output (a multiple of 128)
 };
 
+#ifdef MHADA_GEMM_TRACE
+// development build only (-DMHADA_GEMM_TRACE, tools/trace_gemm.py): per CTA, cycles the three roles spend waiting
+__device__ unsigned long long mh_gemm_trace[512 * 8];
+#define GT_BEGIN(v) const long long v = clock64()
+#define GT_ADD(slot, v) gt[slot] += clock64() - v
+#else
+#define GT_BEGIN(v)
+#define GT_ADD(slot, v)
+#endif
+
 // v[i] = acc[i] + bias[col + i], i < 32: eight 16-byte loads (the same for every lane: L1 broadcast) instead of 32 scalar
 // ones; the launcher guarantees a 16-byte aligned bias pointer, col is a multiple of 32
 __device__ __forceinline__ void add_bias32(float (&v)[32], const uint32_t (&r)[32], const float* __restrict__ bias, int col) {
@@ -127,6 +137,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     if (warp == 0) {
         if (elect_one()) {
+#ifdef MHADA_GEMM_TRACE
+            long long gt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
             int g = 0;                                            // running k-tile counter of this CTA
             for (int it = worker; it < p.items; it += nworkers) {
                 const int sp = it / p.tiles_mn, r = it - sp * p.tiles_mn;       // K split, tile within the split
@@ -134,7 +147,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int k0 = sp * p.ktiles * GM_BK;
                 for (int kt = 0; kt < p.ktiles; ++kt, ++g) {
                     const int s = g % STAGES;
+                    GT_BEGIN(t0);
                     mbar_wait(&empty[s], ((g / STAGES) & 1) ^ 1);
+                    GT_ADD(3, t0);
                     uint8_t* a = smem + s * STAGE;
                     if (NCTA == 2) {
                         if (cta_rank == 0) mbar_arrive_expect_tx(&full[s], 2 * STAGE);      // the pair's bytes, one barrier
@@ -147,18 +162,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                 }
             }
+#ifdef MHADA_GEMM_TRACE
+            mh_gemm_trace[blockIdx.x * 8 + 3] = gt[3];
+#endif
         }
     } else if (warp == 1) {
         if (cta_rank == 0 && elect_one()) {
             constexpr uint32_t idesc = make_idesc_bf16(TM, BN, 0, 0);
+#ifdef MHADA_GEMM_TRACE
+            long long gt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            const long long tstart = clock64();
+#endif
             int g = 0, n = 0;
             for (int it = worker; it < p.items; it += nworkers, ++n) {
                 const int u = n & 1;
+                GT_BEGIN(t1);
                 mbar_wait(&acc_empty[u], ((n >> 1) & 1) ^ 1);     // the epilogue has drained this accumulator buffer
+                GT_ADD(1, t1);
                 tc_fence_after();
                 for (int kt = 0; kt < p.ktiles; ++kt, ++g) {
                     const int s = g % STAGES;
+                    GT_BEGIN(t2);
                     mbar_wait(&full[s], (g / STAGES) & 1);
+                    GT_ADD(2, t2);
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(smem + s * STAGE);
                     const uint64_t da = make_smem_desc(a_addr, 16, 1024);
@@ -174,6 +200,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (NCTA == 2) umma_commit_pair(&acc_full[u], 3);
                 else umma_commit(&acc_full[u]);
             }
+#ifdef MHADA_GEMM_TRACE
+            mh_gemm_trace[blockIdx.x * 8 + 0] = clock64() - tstart;
+            mh_gemm_trace[blockIdx.x * 8 + 1] = gt[1];
+            mh_gemm_trace[blockIdx.x * 8 + 2] = gt[2];
+            mh_gemm_trace[blockIdx.x * 8 + 7] = n;
+#endif
         }
     } else {
         // epilogue warps 2..9: TMEM lane quarter = warp % 4 (hardware rule), column half = (warp - 2) / 4
@@ -284,10 +316,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         } else {
         int n = 0;
+#ifdef MHADA_GEMM_TRACE
+        long long gt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        const long long tstart = clock64();
+#endif
         for (int it = worker; it < p.items; it += nworkers, ++n) {
             const int m0 = (it / p.ntiles) * TM + cta_rank * GM_BM, n0 = (it % p.ntiles) * BN + chalf * CW;
             const int u = n & 1;
+            GT_BEGIN(t5);
             mbar_wait(&acc_full[u], (n >> 1) & 1);
+            GT_ADD(5, t5);
             tc_fence_after();
 #pragma unroll 1
             for (int c = 0; c < CW; c += 32) {
@@ -313,8 +351,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     uint8_t* slab = stg + (nstore & 1) * (32 * 128);
                     if (half == 0) {
                         // the slab was the source of the store issued two stores ago: wait until it has been read
+                        GT_BEGIN(t6);
                         if (lane == 0) tma_store_wait_read<1>();
                         __syncwarp();
+                        GT_ADD(6, t6);
                     }
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
@@ -338,6 +378,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
             }
         }
+#ifdef MHADA_GEMM_TRACE
+        if (warp == 2 && lane == 0) {
+            mh_gemm_trace[blockIdx.x * 8 + 4] = clock64() - tstart;
+            mh_gemm_trace[blockIdx.x * 8 + 5] = gt[5];
+            mh_gemm_trace[blockIdx.x * 8 + 6] = gt[6];
+        }
+#endif
         }
         if (lane == 0) tma_store_wait<0>();
     }
@@ -439,7 +486,7 @@ int launch_gemm_bf16(const GemmDesc& d, cudaStream_t s) {
         // CTA pairs (256 x 256 tiles) when there is at least one full round of pair tiles; MHADA_GEMM_PAIR=0 keeps the
         // single-CTA kernel (A/B switch for measurements)
         static const bool pair_ok = [] { const char* e = getenv("MHADA_GEMM_PAIR"); return !(e && e[0] == '0'); }();
-        if (pair_ok && d.M >= 256 * (sm_count() / 2) / (d.N / 256)) return launch_gemm_bn<256, 4, 2>(d, 1, s);
+        if (pair_ok && d.M >= 256 * (sm_count() / 2) / (d.N / 256)) return launch_gemm_bn<256, 5, 2>(d, 1, s);
         return launch_gemm_bn<256, 3, 1>(d, 1, s);                   // 3 x 48 KB operand ring + 64 KB of staging slabs
     }
     return launch_gemm_bn<128, 4, 1>(d, 1, s);
@@ -504,3 +551,9 @@ int launch_gemm_bf16_splitk(const GemmDesc& d, void* ws, size_t ws_bytes, cudaSt
 }
 
 }  // namespace mh
+
+#ifdef MHADA_GEMM_TRACE
+extern "C" __attribute__((visibility("default"))) int mhada_debug_gemm_trace(unsigned long long* host_out, int n_ctas) {
+    return static_cast<int>(cudaMemcpyFromSymbol(host_out, mh::mh_gemm_trace, static_cast<size_t>(n_ctas) * 8 * sizeof(unsigned long long)));
+}
+#endif
