@@ -124,10 +124,12 @@ def test_abi_argument_checks_of_the_newer_entry_points(lib):
     rc = lib.mhada_layer_forward(_lib.BF16, aligned, aligned, aligned, aligned, aligned, None, None, 1, 4, 4, 512, 8,
                                  _lib.LAYER_COSINE, other, other, 1 << 30, None)
     assert rc == -2 and b"cosine" in lib.mhada_last_error()
-    # tensor-core path: head_dim 64 and 128 only
-    rc = lib.mhada_layer_forward(_lib.BF16, aligned, aligned, aligned, aligned, aligned, None, None, 1, 4, 4, 512, 2, 0,
+    # tensor-core path: head_dim 64, 128 and multiples of 128 (192 is neither)
+    rc = lib.mhada_layer_forward(_lib.BF16, aligned, aligned, aligned, aligned, aligned, None, None, 1, 4, 4, 384, 2, 0,
                                  other, other, 1 << 30, None)
     assert rc == -2 and b"head_dim" in lib.mhada_last_error()
+    # wide heads (256) pass the shape rules and need more workspace than the streaming path's layout
+    assert lib.mhada_layer_workspace(_lib.BF16, 1, 64, 64, 512, 2) > lib.mhada_layer_workspace(_lib.BF16, 1, 64, 64, 512, 8)
     a = _lib.AttnArgs()
     a.dtype = _lib.F32
     a.B, a.H, a.Nc, a.Ns, a.dqk, a.dv = 1, 1, 4, 4, 64, 64
