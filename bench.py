@@ -546,9 +546,10 @@ def measure(args, wl_name, ctx, steps, warmup, with_cpu_baseline):
 def measure_train(args, ctx, steps, warmup):
     """BASELINE configs[4]: one training step per GPU on its own batch (data parallel), gradients averaged with the
     bucketed all-reduce that is launched from autograd hooks DURING backward (sharding.OverlappedGradientAllReduce).
-    Forward: the CUDA kernels (bf16) for the six MHAda layers; ViT and decoder run their differentiable PyTorch op
-    sequence; backward of the layers = mhada_layer_backward (own kernels; MHADA_BACKWARD_IMPL=torch switches
-    to the fp32 PyTorch recompute for an A/B).
+    Forward: the CUDA kernels (bf16) for the six MHAda layers; the ViTs run their Linear layers and batch-axis attention
+    on own kernels, forward and backward (MHADA_VIT_TRAIN_IMPL=torch: plain PyTorch); the decoder runs its differentiable
+    PyTorch op sequence; backward of the layers = mhada_layer_backward (own kernels; MHADA_BACKWARD_IMPL=torch
+    switches to the fp32 PyTorch recompute for an A/B).
     The VGG loss network needs downloaded weights (absent offline): the loss is a synthetic stand-in with the same
     graph shape (pixel loss on cs against the content image + a feature term on fcs)."""
     import torch.distributed as dist
@@ -630,11 +631,13 @@ def measure_train(args, ctx, steps, warmup):
         "config": {"workload": wl["desc"], "images_per_gpu_per_step": B, "tokens": [wl["hw"][0] * wl["hw"][1]] * 2,
                    "parameters": n_params, "optimizer": "3 x Adam(lr=1e-4) (train_image.py:70-72)",
                    "loss": "synthetic (VGG19 weights cannot be downloaded offline): pixel term on cs + feature term on fcs",
-                   "forward": "MHAda layers on the bf16 CUDA kernels; ViT / decoder differentiable PyTorch ops",
+                   "forward": ("MHAda layers on the bf16 CUDA kernels; ViT Linear layers + batch attention on own kernels "
+                               "(tcgen05 token GEMM); LayerNorm / residuals / decoder = differentiable PyTorch ops"),
                    "backward": ("fp32 recompute of each layer with PyTorch ops (MHADA_BACKWARD_IMPL=torch)"
                                 if os.environ.get("MHADA_BACKWARD_IMPL") == "torch" else
                                 "mhada_layer_backward: flash-style attention backward kernels (V' = [V | V^2]), the other "
-                                "contractions on the tcgen05 token GEMM; ViT / decoder backward = PyTorch autograd"),
+                                "contractions on the tcgen05 token GEMM; ViT Linear / attention backward on own kernels; "
+                                "decoder backward = PyTorch autograd (cuDNN)"),
                    "gradient_sync": "bucketed (32 MB) all-reduce launched from autograd hooks during backward, NCCL"},
         "e2e": {"value": round(images / (ms_e2e * 1e-3), 2), "unit": "images/s",
                 "h2d_bytes_per_step": c_h.numel() * 4 + s_h.numel() * 4, "d2h_bytes_per_step": 4,
