@@ -39,6 +39,14 @@ struct ConvParams {
     int relu, out_padded;
 };
 
+// CTA-pair variant: the bytes land in THIS CTA's shared memory and are counted on the LEADER's barrier (ptx.cuh)
+__device__ __forceinline__ void tma_load_4d_pair(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(m), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
     asm volatile(
         "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
@@ -48,16 +56,19 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uin
 
 // Epilogue shared by both kernels (warps 2..9): TMEM lane quarter = warp % 4; the 256 accumulator columns (MT sub-tiles x
 // BN channels) are split in two halves between the two warps of a quarter.
-template <int BN>
+// NCTA = 2 (CTA pairs, Cout = 256): work item `it` of pair `worker` = pixel tiles 2 it and 2 it + 1, one per CTA.
+template <int BN, int NCTA = 1>
 __device__ __forceinline__ void conv_epilogue(const ConvParams& p, uint32_t tmem, uint64_t* acc_full, uint64_t* acc_empty,
-                                              int warp, int lane, int per_img) {
+                                              int warp, int lane, int per_img, int cta_rank = 0) {
     const int quarter = warp & 3;
     const int chalf = (warp - 2) >> 2;
     const int row = quarter * 32 + lane;
     const int Hp = p.H + 2, Wp = p.W + 2;
+    const int worker = static_cast<int>(blockIdx.x) / NCTA, nworkers = static_cast<int>(gridDim.x) / NCTA;
     int n = 0;
-    for (int it = blockIdx.x; it < p.items; it += gridDim.x, ++n) {
-        const int b = it / per_img, t = it % per_img;
+    for (int it = worker; it < p.items; it += nworkers, ++n) {
+        const int tile = it * NCTA + cta_rank;
+        const int b = tile / per_img, t = tile % per_img;       // b >= B: the odd tile out of the last pair (nothing to store)
         const int x0 = (t % p.tiles_x) * p.TW, y0 = (t / p.tiles_x) * p.TR;
         const int u = n & 1;
         mbar_wait(&acc_full[u], (n >> 1) & 1);
@@ -72,11 +83,14 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, uint32_t tmem
             if (cg + 32 == 128) {
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&acc_empty[u]);
+                if (lane == 0) {
+                    if (NCTA == 2) mbar_arrive_leader(&acc_empty[u]);
+                    else mbar_arrive(&acc_empty[u]);
+                }
             }
             const int pi = st * 128 + row;                    // pixel index inside the TW x TR block
             const int y = y0 + pi / p.TW, x = x0 + pi % p.TW;
-            if (y < p.H && x < p.W) {
+            if (b < p.B && y < p.H && x < p.W) {
                 uint32_t o[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
@@ -113,11 +127,18 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, uint32_t tmem
     }
 }
 
-template <int BN, int STAGES>
+// NCTA = 2 (BN = 256 only): a CTA pair (cluster of two) shares one MMA of M = 256 pixels (tcgen05.mma.cta_group::2): each
+// CTA loads the im2col box of ITS 128-pixel tile and HALF of the weight tile (32 KB per k-step instead of 48 KB), which
+// also makes room for a seven-stage ring; barriers as in gemm_tc.cu (bytes of both CTAs on the leader's `full`, multicast
+// commits, the epilogue warps of both CTAs arrive on the leader's `acc_empty`).
+template <int BN, int STAGES, int NCTA>
 __global__ void __launch_bounds__(CV_THREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const ConvParams p) {
     constexpr int MT = 256 / BN;
-    constexpr uint32_t A_BYTES = MT * 128 * CV_BK * 2, B_BYTES = BN * CV_BK * 2, STAGE = A_BYTES + B_BYTES;
+    static_assert(NCTA == 1 || MT == 1, "CTA pairs: one 128-pixel sub-tile per CTA");
+    constexpr uint32_t A_BYTES = MT * 128 * CV_BK * 2, B_BYTES = (BN / NCTA) * CV_BK * 2, STAGE = A_BYTES + B_BYTES;
+    const int cta_rank = NCTA == 2 ? static_cast<int>(cluster_ctarank()) : 0;
+    const int worker = static_cast<int>(blockIdx.x) / NCTA, nworkers = static_cast<int>(gridDim.x) / NCTA;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     __shared__ uint64_t full[STAGES], empty[STAGES], acc_full[2], acc_empty[2];
@@ -136,16 +157,22 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             }
             for (int u = 0; u < 2; ++u) {
                 mbar_init(&acc_full[u], 1);
-                mbar_init(&acc_empty[u], CV_EPI_WARPS);
+                mbar_init(&acc_empty[u], CV_EPI_WARPS * NCTA);
             }
             fence_mbar_init();
         }
         __syncwarp();
-        tmem_alloc(&tmem_slot, 512);
-        tmem_relinquish();
+        if (NCTA == 2) {
+            tmem_alloc2(&tmem_slot, 512);
+            tmem_relinquish2();
+        } else {
+            tmem_alloc(&tmem_slot, 512);
+            tmem_relinquish();
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if (NCTA == 2) cluster_sync_all();
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
     const int per_img = p.tiles_x * p.tiles_y;
@@ -153,25 +180,32 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     if (warp == 0) {
         if (elect_one()) {
             int g = 0;
-            for (int it = blockIdx.x; it < p.items; it += gridDim.x) {
-                const int b = it / per_img, t = it % per_img;
+            for (int it = worker; it < p.items; it += nworkers) {
+                const int tile = it * NCTA + cta_rank;
+                const int b = tile / per_img, t = tile % per_img;       // b >= B (odd tile out): the box is zero-filled
                 const int x0 = (t % p.tiles_x) * p.TW, y0 = (t / p.tiles_x) * p.TR;
                 for (int kt = 0; kt < p.ktiles; ++kt, ++g) {
                     const int tap = kt / p.cchunks, cc = kt % p.cchunks;
                     const int s = g % STAGES;
                     mbar_wait(&empty[s], ((g / STAGES) & 1) ^ 1);
-                    mbar_arrive_expect_tx(&full[s], STAGE);
                     uint8_t* a = smem + s * STAGE;
-                    tma_load_4d(a, &tmX, &full[s], cc * CV_BK, x0 + tap % 3, y0 + tap / 3, b);
-                    tma_load_2d(a + A_BYTES, &tmW, &full[s], kt * CV_BK, 0);
+                    if (NCTA == 2) {
+                        if (cta_rank == 0) mbar_arrive_expect_tx(&full[s], 2 * STAGE);
+                        tma_load_4d_pair(a, &tmX, &full[s], cc * CV_BK, x0 + tap % 3, y0 + tap / 3, b);
+                        tma_load_2d_pair(a + A_BYTES, &tmW, &full[s], kt * CV_BK, cta_rank * (BN / 2));
+                    } else {
+                        mbar_arrive_expect_tx(&full[s], STAGE);
+                        tma_load_4d(a, &tmX, &full[s], cc * CV_BK, x0 + tap % 3, y0 + tap / 3, b);
+                        tma_load_2d(a + A_BYTES, &tmW, &full[s], kt * CV_BK, 0);
+                    }
                 }
             }
         }
     } else if (warp == 1) {
-        if (elect_one()) {
-            constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+        if (cta_rank == 0 && elect_one()) {
+            constexpr uint32_t idesc = make_idesc_bf16(128 * NCTA, BN, 0, 0);
             int g = 0, n = 0;
-            for (int it = blockIdx.x; it < p.items; it += gridDim.x, ++n) {
+            for (int it = worker; it < p.items; it += nworkers, ++n) {
                 const int u = n & 1;
                 mbar_wait(&acc_empty[u], ((n >> 1) & 1) ^ 1);
                 tc_fence_after();
@@ -185,20 +219,29 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                     for (int t = 0; t < MT; ++t) {
                         const uint64_t da = make_smem_desc(a_addr + t * (128 * CV_BK * 2), 16, 1024);
 #pragma unroll
-                        for (int k = 0; k < CV_BK / 16; ++k)
-                            umma_ss(tmem + u * 256 + t * BN, desc_advance(da, k * 32), desc_advance(db, k * 32), idesc, (kt | k) != 0);
+                        for (int k = 0; k < CV_BK / 16; ++k) {
+                            if (NCTA == 2) umma_ss_pair(tmem + u * 256 + t * BN, desc_advance(da, k * 32), desc_advance(db, k * 32), idesc, (kt | k) != 0);
+                            else umma_ss(tmem + u * 256 + t * BN, desc_advance(da, k * 32), desc_advance(db, k * 32), idesc, (kt | k) != 0);
+                        }
                     }
-                    umma_commit(&empty[s]);
+                    if (NCTA == 2) umma_commit_pair(&empty[s], 3);
+                    else umma_commit(&empty[s]);
                 }
-                umma_commit(&acc_full[u]);
+                if (NCTA == 2) umma_commit_pair(&acc_full[u], 3);
+                else umma_commit(&acc_full[u]);
             }
         }
     } else {
-        conv_epilogue<BN>(p, tmem, acc_full, acc_empty, warp, lane, per_img);
+        conv_epilogue<BN, NCTA>(p, tmem, acc_full, acc_empty, warp, lane, per_img, cta_rank);
     }
     tc_fence_before();
-    __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem, 512);
+    if (NCTA == 2) {
+        cluster_sync_all();
+        if (warp == 1) tmem_dealloc2(tmem, 512);
+    } else {
+        __syncthreads();
+        if (warp == 1) tmem_dealloc(tmem, 512);
+    }
 }
 
 // HALO variant for Cout = 64 / 128 and W > 64 (decoder blocks 4..7).  With few output channels the A operand dominates
@@ -353,7 +396,7 @@ static int launch_conv_halo(const void* xp, const void* w, const float* bias, in
     return check_cuda(cudaGetLastError(), "conv3x3_halo launch");
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int NCTA = 1>
 static int launch_conv_bn(const void* xp, const void* w, const float* bias, int B, int H, int W, int Cin, int relu,
                           int out_padded, void* y, cudaStream_t s) {
     constexpr int MT = 256 / BN;
@@ -379,21 +422,35 @@ static int launch_conv_bn(const void* xp, const void* w, const float* bias, int 
     {
         uint64_t dims[2] = {static_cast<uint64_t>(9) * Cin, static_cast<uint64_t>(BN)};
         uint64_t str[1] = {static_cast<uint64_t>(9) * Cin * 2};
-        uint32_t box[2] = {CV_BK, BN};
+        uint32_t box[2] = {CV_BK, BN / NCTA};
         if (int e = make_tmap(&tmW, w, 2, 2, dims, str, box)) return e;
     }
     p.bias = bias; p.out = static_cast<__nv_bfloat16*>(y);
     p.B = B; p.H = H; p.W = W; p.Cin = Cin;
     p.tiles_x = (W + p.TW - 1) / p.TW; p.tiles_y = (H + p.TR - 1) / p.TR;
-    p.items = B * p.tiles_x * p.tiles_y;
+    p.items = (B * p.tiles_x * p.tiles_y + NCTA - 1) / NCTA;          // pair kernel: two pixel tiles per work item
     p.cchunks = Cin / CV_BK; p.ktiles = 9 * p.cchunks;
     p.relu = relu; p.out_padded = out_padded;
-    constexpr size_t smem = STAGES * (MT * 128 * CV_BK * 2 + BN * CV_BK * 2) + 1024;
+    constexpr size_t smem = STAGES * (MT * 128 * CV_BK * 2 + (BN / NCTA) * CV_BK * 2) + 1024;
     static DeviceOnce once;
-    if (int e = smem_attr_once(once, reinterpret_cast<const void*>(conv3x3_tc_kernel<BN, STAGES>), smem, "conv_tc smem attr")) return e;
-    const int n_sm = sm_count();
-    const int grid = p.items < n_sm ? p.items : n_sm;
-    conv3x3_tc_kernel<BN, STAGES><<<grid, CV_THREADS, smem, s>>>(tmX, tmW, p);
+    if (int e = smem_attr_once(once, reinterpret_cast<const void*>(conv3x3_tc_kernel<BN, STAGES, NCTA>), smem, "conv_tc smem attr")) return e;
+    const int n_workers = sm_count() / NCTA;
+    const int grid = (p.items < n_workers ? p.items : n_workers) * NCTA;
+    if (NCTA == 1) {
+        conv3x3_tc_kernel<BN, STAGES, NCTA><<<grid, CV_THREADS, smem, s>>>(tmX, tmW, p);
+    } else {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(static_cast<unsigned>(grid));
+        cfg.blockDim = dim3(CV_THREADS);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = NCTA; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        if (int e = check_cuda(cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<BN, STAGES, NCTA>, tmX, tmW, p), "conv3x3_tc pair launch")) return e;
+    }
     count_launch();
     return check_cuda(cudaGetLastError(), "conv3x3_tc launch");
 }
@@ -412,7 +469,12 @@ int launch_conv3x3_tc(const void* xp, const void* w, const float* bias, int B, i
     }();
     if (halo_mode && W > 64 && Cout == 128) return launch_conv_halo<128, 2>(xp, w, bias, B, H, W, Cin, relu, out_padded, y, halo_mode == 2, s);
     if (halo_mode && W > 64 && Cout == 64) return launch_conv_halo<64, 2>(xp, w, bias, B, H, W, Cin, relu, out_padded, y, halo_mode == 2, s);
-    if (Cout == 256) return launch_conv_bn<256, 4>(xp, w, bias, B, H, W, Cin, relu, out_padded, y, s);
+    if (Cout == 256) {
+        // MHADA_CONV_PAIR=0 keeps the single-CTA kernel (A/B switch); pairs need at least one pair of 128-pixel tiles
+        static const bool pair_ok = [] { const char* e = getenv("MHADA_CONV_PAIR"); return !(e && e[0] == '0'); }();
+        if (pair_ok && static_cast<long long>(B) * H * W >= 256) return launch_conv_bn<256, 7, 2>(xp, w, bias, B, H, W, Cin, relu, out_padded, y, s);
+        return launch_conv_bn<256, 4>(xp, w, bias, B, H, W, Cin, relu, out_padded, y, s);
+    }
     if (Cout == 128) return launch_conv_bn<128, 4>(xp, w, bias, B, H, W, Cin, relu, out_padded, y, s);
     return launch_conv_bn<64, 3>(xp, w, bias, B, H, W, Cin, relu, out_padded, y, s);
 }
