@@ -560,7 +560,11 @@ def measure_train(args, ctx, steps, warmup):
     vit_c, vit_s, model = build_models(wl, device)
     for m in (vit_c, vit_s, model):
         m.train()
-    opts = [torch.optim.Adam(m.parameters(), lr=1e-4) for m in (vit_c, vit_s, model)]       # train_image.py:70-72
+    # The whole step (forward, backward, gradient all-reduce, three Adam updates: ~1150 launches) is captured ONCE as a
+    # CUDA graph and replayed (MHADA_TRAIN_GRAPH=0: eager launch loop).  Every launch of libmhada_b200.so goes on the
+    # caller's stream without allocating or synchronising, so the autograd Functions capture like any PyTorch op.
+    use_graph = os.environ.get("MHADA_TRAIN_GRAPH", "1") != "0"
+    opts = [torch.optim.Adam(m.parameters(), lr=1e-4, capturable=use_graph) for m in (vit_c, vit_s, model)]   # train_image.py:70-72
     c_h, s_h = make_images(wl, seed=rank)
     c_d, s_d = c_h.to(device), s_h.to(device)
     sync = OverlappedGradientAllReduce([vit_c, vit_s, model]) if world > 1 else None
@@ -605,15 +609,52 @@ def measure_train(args, ctx, steps, warmup):
             ms = float(t.item())
         return ms
 
+    graph, static_loss, graph_note = None, None, None
+    if use_graph:
+        # eager steps first: warm-up of every cache / kernel attribute, and the exposed part of the all-reduce (events
+        # cannot be timed inside a graph)
+        side = torch.cuda.Stream(device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):
+            for _ in range(max(3, warmup)):
+                step(c_d, s_d, False)
+            for _ in range(5):
+                step(c_d, s_d, True)
+        torch.cuda.current_stream(device).wait_stream(side)
+        torch.cuda.synchronize()
+        tail_ms = sum(a.elapsed_time(b) for a, b in zip(ev["bwd_end"], ev["sync_end"])) / max(len(ev["bwd_end"]), 1)
+        ev["bwd_end"].clear(); ev["sync_end"].clear()
+        if world > 1:
+            dist.barrier()
+        try:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_loss = step(c_d, s_d, False)
+        except Exception as e:      # noqa: BLE001 -- a benchmark falls back to the eager loop and says so
+            graph, graph_note = None, f"capture failed, eager loop timed instead: {str(e).splitlines()[0][:160]}"
+            torch.cuda.synchronize()
+
+    def run_step(rec):
+        if graph is not None:
+            graph.replay()
+            return static_loss
+        return step(c_d, s_d, rec)
+
     sampler = ClockSampler(ctx["local"]) if rank == 0 else None
     if sampler:
         sampler.start()
-    ms_dev = timed(lambda rec: step(c_d, s_d, rec), steps, warmup)
+    ms_dev = timed(run_step, steps, warmup)
     clocks = sampler.stop() if sampler else None
-    tail_ms = sum(a.elapsed_time(b) for a, b in zip(ev["bwd_end"], ev["sync_end"])) / max(len(ev["bwd_end"]), 1)
+    if graph is None:
+        tail_ms = sum(a.elapsed_time(b) for a, b in zip(ev["bwd_end"], ev["sync_end"])) / max(len(ev["bwd_end"]), 1)
     ev["bwd_end"].clear(); ev["sync_end"].clear()
 
     def step_host(rec):
+        if graph is not None:
+            c_d.copy_(c_h, non_blocking=True)       # the graph reads its inputs from these buffers
+            s_d.copy_(s_h, non_blocking=True)
+            graph.replay()
+            return float(static_loss.detach())
         c = c_h.to(device, non_blocking=True)
         s = s_h.to(device, non_blocking=True)
         loss = step(c, s, rec)
@@ -638,13 +679,16 @@ def measure_train(args, ctx, steps, warmup):
                                 "mhada_layer_backward: flash-style attention backward kernels (V' = [V | V^2]), the other "
                                 "contractions on the tcgen05 token GEMM; ViT Linear / attention backward on own kernels; "
                                 "decoder backward = PyTorch autograd (cuDNN)"),
-                   "gradient_sync": "bucketed (32 MB) all-reduce launched from autograd hooks during backward, NCCL"},
+                   "gradient_sync": "bucketed (32 MB) all-reduce launched from autograd hooks during backward, NCCL",
+                   "launch": ("the whole step replayed as one CUDA graph" if graph is not None else
+                              ("eager launch loop" + (f" ({graph_note})" if graph_note else "")))},
         "e2e": {"value": round(images / (ms_e2e * 1e-3), 2), "unit": "images/s",
                 "h2d_bytes_per_step": c_h.numel() * 4 + s_h.numel() * 4, "d2h_bytes_per_step": 4,
                 "ms_per_step": round(ms_e2e / steps, 4)},
         "gradient_allreduce": {"exposed_ms_per_step": round(tail_ms, 4), "bytes": 4 * n_params,
                                "note": "device time between the end of backward and the end of the last bucket's "
-                                       "all-reduce + copy-back: what the overlap does NOT hide (0 at one GPU)"},
+                                       "all-reduce + copy-back: what the overlap does NOT hide (0 at one GPU); measured on "
+                                       "eager steps (events cannot be timed inside the replayed graph)"},
         "gpu_launches": None, "roofline": None, "clocks": clocks,
     }
 
