@@ -30,6 +30,11 @@ S.test_conv3x3_tc(2, 10, 14, 256, 256, 1)
 S.test_conv3x3_tc(1, 20, 28, 256, 128, 0)
 for args in ((300, 512, 192, "pos"), (70, 384, 64, "bf16"), (129, 512, 2048, "both"), (260, 2048, 512, "relu")):
     V.test_gemm(*args)
+V.test_gemm(20000, 512, 512, "resid")                 # CTA pairs (cluster of two, tcgen05.mma.cta_group::2), ragged last pair tile
+S.test_conv3x3_tc(3, 64, 64, 512, 256, 0)             # CTA-pair convolution
+S.test_attn_bwd(2, 2, 100, 72, 1.0)                   # flash-style backward kernels: ragged tiles
+S.test_attn_bwd(2, 2, 130, 1, 1.0)                    # one key
+V.test_batch_attn_bwd(3, 37, 2)
 V.test_layernorm(7, 128)
 V.test_batch_attn(5, 7)
 V.test_batch_attn(8, 64)
