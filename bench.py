@@ -673,12 +673,12 @@ def measure_train(args, ctx, steps, warmup):
                    "parameters": n_params, "optimizer": "3 x Adam(lr=1e-4) (train_image.py:70-72)",
                    "loss": "synthetic (VGG19 weights cannot be downloaded offline): pixel term on cs + feature term on fcs",
                    "forward": ("MHAda layers on the bf16 CUDA kernels; ViT Linear layers + batch attention on own kernels "
-                               "(tcgen05 token GEMM); LayerNorm / residuals / decoder = differentiable PyTorch ops"),
+                               "(tcgen05 token GEMM); decoder blocks on the inference kernels; LayerNorm / residuals = PyTorch ops"),
                    "backward": ("fp32 recompute of each layer with PyTorch ops (MHADA_BACKWARD_IMPL=torch)"
                                 if os.environ.get("MHADA_BACKWARD_IMPL") == "torch" else
                                 "mhada_layer_backward: flash-style attention backward kernels (V' = [V | V^2]), the other "
                                 "contractions on the tcgen05 token GEMM; ViT Linear / attention backward on own kernels; "
-                                "decoder backward = PyTorch autograd (cuDNN)"),
+                                "decoder backward = aten convolution / pad / bilinear backward ops (cuDNN) on bf16 channels_last"),
                    "gradient_sync": "bucketed (32 MB) all-reduce launched from autograd hooks during backward, NCCL",
                    "launch": ("the whole step replayed as one CUDA graph" if graph is not None else
                               ("eager launch loop" + (f" ({graph_note})" if graph_note else "")))},

@@ -765,6 +765,78 @@ def _conv3x3_relu(xp_nchw: torch.Tensor, w: torch.Tensor, b: torch.Tensor) -> to
     return torch.cudnn_convolution_relu(xp_nchw, w, b, (1, 1), (0, 0), (1, 1), 1)
 
 
+# ---- training path of the decoder: own kernels forward, library backward -----------------------------------------------
+# train_image.py:105-144 back-propagates through the decoder.  The forward of every block runs the same kernels as
+# inference (bf16, channels_last); the backward of the convolutions is aten.convolution_backward on those bf16
+# channels_last tensors (cuDNN tensor-core dgrad / wgrad, no NCHW <-> NHWC conversion: the r2 profile of the plain PyTorch
+# path had 1.5 ms of layout kernels and TF32 convolutions per cfg5 step), reflect-pad and bilinear backward are the aten
+# backward ops.  Own convolution-backward kernels are not built (DESIGN 9).  bf16 activations through nine ReLU blocks
+# move the gradients of the EARLY blocks by ~10 % against fp32 arithmetic -- exactly as much as PyTorch's own bf16
+# decoder does (tools/debug_decoder_train.py) -- so the path is taken only when the model runs in bf16.
+
+class _PadUpFn(torch.autograd.Function):
+    """[B,H,W,C] bf16 -> [B,Ho+2,Wo+2,C]: (x2 bilinear +) ReflectionPad2d(1) by pad_reflect_kernel."""
+
+    @staticmethod
+    def forward(ctx, x_tok, upsample):
+        ctx.upsample, ctx.in_shape = upsample, x_tok.shape
+        return _pad_reflect(x_tok.contiguous(), upsample)
+
+    @staticmethod
+    def backward(ctx, g):
+        B, H, W, C = ctx.in_shape
+        gn = g.permute(0, 3, 1, 2)                                        # NCHW view over channels_last memory
+        Ho, Wo = (2 * H, 2 * W) if ctx.upsample else (H, W)
+        dummy = gn.new_empty((B, C, Ho, Wo)).contiguous(memory_format=torch.channels_last)
+        gx = torch.ops.aten.reflection_pad2d_backward(gn, dummy, [1, 1, 1, 1])
+        if ctx.upsample:
+            gx = torch.ops.aten.upsample_bilinear2d_backward(gx, [Ho, Wo], [B, C, H, W], False, 2.0, 2.0)
+        return gx.permute(0, 2, 3, 1).contiguous(), None
+
+
+class _ConvReluFn(torch.autograd.Function):
+    """Reflect-padded [B,H+2,W+2,Cin] bf16 -> conv3x3 + bias + ReLU on tcgen05 (mhada_conv3x3) -> [B,H,W,Cout] bf16."""
+
+    @staticmethod
+    def forward(ctx, xp_tok, weight, bias, block):
+        w_packed, b32 = block._packed_tc()
+        y = _conv3x3_tc_relu(xp_tok, w_packed, b32, False)
+        ctx.save_for_backward(xp_tok, y, weight)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        xp_tok, y, weight = ctx.saved_tensors
+        gz = (g * (y > 0)).permute(0, 3, 1, 2)                            # ReLU backward; NCHW view, channels_last memory
+        w16 = weight.detach().to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        gxp, gw, gb = torch.ops.aten.convolution_backward(gz, xp_tok.permute(0, 3, 1, 2), w16, [weight.shape[0]], [1, 1], [0, 0],
+                                                          [1, 1], False, [0, 0], 1, [True, True, True])
+        return gxp.permute(0, 2, 3, 1).contiguous(), gw.to(weight.dtype), gb.to(weight.dtype), None
+
+
+class _ConvSmallReluFn(torch.autograd.Function):
+    """Last block (64 -> 3): UNPADDED [B,H,W,64] bf16 -> [B,3,H,W] bf16 by conv3x3_c64_small_kernel (pad resolved inside)."""
+
+    @staticmethod
+    def forward(ctx, x_tok, weight, bias):
+        y = _conv3x3_small_relu(x_tok.contiguous(), weight, bias)
+        ctx.save_for_backward(x_tok, y, weight)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x_tok, y, weight = ctx.saved_tensors
+        gz = (g * (y > 0)).contiguous(memory_format=torch.channels_last)
+        xp = _pad_reflect(x_tok.contiguous(), False).permute(0, 3, 1, 2)
+        w16 = weight.detach().to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        gxp, gw, gb = torch.ops.aten.convolution_backward(gz, xp, w16, [weight.shape[0]], [1, 1], [0, 0], [1, 1], False, [0, 0], 1,
+                                                          [True, True, True])
+        B, H, W, C = x_tok.shape
+        dummy = gxp.new_empty((B, C, H, W)).contiguous(memory_format=torch.channels_last)
+        gx = torch.ops.aten.reflection_pad2d_backward(gxp, dummy, [1, 1, 1, 1])
+        return gx.permute(0, 2, 3, 1).contiguous(), gw.to(weight.dtype), gb.to(weight.dtype)
+
+
 class Decoder(nn.Module):
     """Decoder.forward (conv.py:75-100).  bf16 path: own kernels only -- tcgen05 implicit-GEMM convolutions whose
     epilogue writes the next block's reflect-padded input, the fused x2-bilinear + pad kernel after the three
@@ -778,14 +850,43 @@ class Decoder(nn.Module):
                                    _ConvBlock(256, 256), _ConvBlock(256, 128, 2))
         self.conv2 = nn.Sequential(_ConvBlock(128, 128), _ConvBlock(128, 64, 2))
         self.conv3 = nn.Sequential(_ConvBlock(64, 64), _ConvBlock(64, 3))
+        # training: "kernels" = own kernels forward + aten backward ops (bf16 activations); "torch" = the plain PyTorch op
+        # sequence in the input's dtype; "auto" = kernels when the model runs in bf16 (precision "bf16", as
+        # set_precision(model, "bf16") sets it, or bf16 / fp16 features), else torch (MHADA_DECODER_TRAIN_IMPL sets the default)
+        self.train_impl = os.environ.get("MHADA_DECODER_TRAIN_IMPL", "auto")
+        self.precision = "auto"
 
     def _blocks(self):
         return [*self.conv1, *self.conv2, *self.conv3]
 
+    def _forward_train(self, fcs: torch.Tensor):
+        """Training (train_image.py:105-144): own kernels forward (bf16, channels_last), aten backward ops."""
+        x = fcs.permute(0, 2, 3, 1).to(torch.bfloat16)      # differentiable; no copy when fcs is bf16 channels_last already
+        blocks = self._blocks()
+        up = False
+        for i, blk in enumerate(blocks):
+            conv = blk.conv.conv
+            if conv.in_channels == 64 and conv.out_channels <= 8 and not blk.scale_factor and i == len(blocks) - 1 and not up:
+                y = _ConvSmallReluFn.apply(x, conv.weight, conv.bias)               # [B, 3, H, W]
+                return y if y.dtype == fcs.dtype else y.to(fcs.dtype)
+            xp = _PadUpFn.apply(x, up)
+            x = _ConvReluFn.apply(xp, conv.weight, conv.bias, blk.conv)
+            up = bool(blk.scale_factor)
+        y = x.permute(0, 3, 1, 2)
+        return y if y.dtype == fcs.dtype else y.to(fcs.dtype)
+
     def forward(self, fcs: torch.Tensor):
         _require_cuda(fcs)                                   # no CPU path (use the reference package on CPU)
         if _needs_grad(self, fcs):
-            # training (train_image.py:105-144): the plain differentiable PyTorch ops of conv.py:96-100 on the GPU
+            if self.train_impl not in ("auto", "kernels", "torch"):
+                raise ValueError(f"Unknown train_impl: {self.train_impl}")
+            tc_ok = fcs.shape[2] >= 2 and fcs.shape[3] >= 2 and all(
+                b.conv.conv.in_channels % 64 == 0 and (b.conv.conv.out_channels in (64, 128, 256) or i == 8)
+                for i, b in enumerate(self._blocks()))
+            low = self.precision == "bf16" or fcs.dtype in (torch.bfloat16, torch.float16)
+            if tc_ok and (self.train_impl == "kernels" or (self.train_impl == "auto" and low)):
+                return self._forward_train(fcs)
+            # the plain differentiable PyTorch ops of conv.py:96-100 on the GPU
             return self.conv3(self.conv2(self.conv1(fcs)))
         in_dtype = fcs.dtype
         if fcs.dtype not in (torch.float32, torch.bfloat16):

@@ -593,6 +593,41 @@ def test_forloss_gradient_matches_oracle_finite_difference():
         assert an == pytest.approx(fd, rel=2e-3, abs=1e-4 * abs(fd) + 1e-5), (idx, an, fd)
 
 
+@pytest.mark.parametrize("B,hw", [(2, (16, 16)), (1, (9, 14))])
+def test_decoder_training_path_vs_torch(B, hw):
+    """Decoder under autograd (train_image.py:105-144): own kernels forward (bf16, the inference kernels) + aten backward
+    ops, against the plain fp32 PyTorch op sequence of the same module.  Decoded image: 2e-2.  Gradients: bf16 activations
+    through nine ReLU blocks flip masks, so the gradients of the EARLY blocks sit ~0.10-0.12 (Frobenius) from the fp32
+    ones -- PyTorch's own bf16 decoder deviates by the same amount and as much from this path (measured,
+    tools/debug_decoder_train.py) -- while the last block's agree to < 1e-2: bounds 0.2 everywhere, 2e-2 on the last block."""
+    case = dict(cases.DECODER_CASES[0], B=B, hw=hw)
+    x, sd = cases.decoder_inputs(case)
+    m = M.Decoder()
+    m.load_state_dict({k[len("decoder."):]: v for k, v in synth.to_torch(sd, torch.float32).items()}, strict=True)
+    m = m.to(DEV).train()
+    G_ = torch.randn(B, 3, 8 * hw[0], 8 * hw[1], device=DEV)
+    res = {}
+    for impl in ("kernels", "torch"):
+        m.train_impl = impl
+        m.zero_grad(set_to_none=True)
+        xin = dev(x).requires_grad_(True)
+        out = m(xin)
+        assert out.dtype == torch.float32
+        (out.float() * G_).sum().backward()
+        res[impl] = (out.detach().float(), {"x": xin.grad, **{k: p.grad.clone() for k, p in m.named_parameters()}})
+    e = O.errors(res["kernels"][0].cpu().numpy(), res["torch"][0].cpu().numpy())
+    assert e["max_abs_rel"] <= 2e-2, e
+    for k, want in res["torch"][1].items():
+        got = res["kernels"][1][k]
+        assert torch.isfinite(got).all(), k
+        fro = float((got.float() - want.float()).norm() / want.float().norm())
+        assert fro <= (2e-2 if k.startswith("conv3.1.") else 0.2), (k, fro)
+    m.train_impl, m.precision = "auto", "auto"                     # fp32 features, precision not set: the fp32 torch path
+    m.zero_grad(set_to_none=True)
+    out = m(dev(x).requires_grad_(True))
+    assert torch.equal(out.detach().float(), res["torch"][0])
+
+
 def test_single_head_transformer_trains():
     """AdaAttnTransformer under autograd: every parameter receives a finite gradient."""
     case = cases.SINGLE_HEAD_TRANSFORMER_CASES[0]
