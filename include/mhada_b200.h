@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define MHADA_ABI_VERSION 11
+#define MHADA_ABI_VERSION 12
 
 #if defined(__GNUC__)
 #define MHADA_API __attribute__((visibility("default")))
@@ -201,6 +201,11 @@ MHADA_API int mhada_conv3x3(int dtype, const void* xp, const void* w, const floa
                             int Cout, int relu, int out_padded, void* y, mhada_stream_t stream);
 MHADA_API int mhada_pad_reflect(int dtype, const void* x, int B, int H, int W, int C, int upsample, void* y,
                                 mhada_stream_t stream);
+/*     backward of mhada_pad_reflect for the training step (train_image.py:139 through conv.py:26-27, :71):
+ *     dyp [B, Ho + 2, Wo + 2, C] (gradient of the padded, optionally up-sampled map) -> dx [B, H, W, C]; gather form,
+ *     deterministic. */
+MHADA_API int mhada_pad_reflect_bwd(int dtype, const void* dyp, int B, int H, int W, int C, int upsample, void* dx,
+                                    mhada_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * (7) ViT encoder -- replaces VisionTransformer.forward, MHAdaSTr/network/vit.py:148-169

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libmhada_b200.so")
 
 F32, BF16, U8 = 0, 1, 2
-ABI_VERSION = 11
+ABI_VERSION = 12
 VIT_MAX_LAYERS = 8
 PROJ_Q, PROJ_KV = 1, 2
 REUSE_FS_STATS = 1
@@ -125,6 +125,7 @@ SIGNATURES = {
     "mhada_conv3x3": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
                               c_void_p]),
     "mhada_pad_reflect": (c_int, [c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "mhada_pad_reflect_bwd": (c_int, [c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "mhada_layer_workspace": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "mhada_layer_forward": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                     c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -641,6 +641,18 @@ int mhada_pad_reflect(int dtype, const void* x, int B, int H, int W, int C, int 
     return launch_pad_reflect(dtype, x, B, H, W, C, upsample, y, static_cast<cudaStream_t>(stream));
 }
 
+int mhada_pad_reflect_bwd(int dtype, const void* dyp, int B, int H, int W, int C, int upsample, void* dx,
+                          mhada_stream_t stream) {
+    REQUIRE(dyp && dx, MHADA_ERR_ARG, "mhada_pad_reflect_bwd: null pointer");
+    REQUIRE(dtype == MHADA_F32 || dtype == MHADA_BF16, MHADA_ERR_ARG, "mhada_pad_reflect_bwd: bad dtype %d", dtype);
+    REQUIRE(B > 0 && H > 1 && W > 1 && C > 0, MHADA_ERR_ARG,
+            "mhada_pad_reflect_bwd: bad sizes B=%d H=%d W=%d C=%d (reflection needs H, W >= 2)", B, H, W, C);
+    REQUIRE(C % (dtype == MHADA_BF16 ? 8 : 4) == 0 && aligned16(dyp) && aligned16(dx), MHADA_ERR_ARG,
+            "mhada_pad_reflect_bwd: C must be a multiple of %d and pointers 16-byte aligned", dtype == MHADA_BF16 ? 8 : 4);
+    if (int e = device_check()) return e;
+    return launch_pad_reflect_bwd(dtype, dyp, B, H, W, C, upsample, dx, static_cast<cudaStream_t>(stream));
+}
+
 size_t mhada_layer_workspace(int dtype, int B, int Nc, int Ns, int C, int H) {
     if (B <= 0 || Nc <= 0 || Ns <= 0 || C <= 0 || H <= 0 || C % H != 0) return 0;
     return carve(dtype, B, Nc, Ns, C, H, nullptr).total;

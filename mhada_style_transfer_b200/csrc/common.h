@@ -144,6 +144,7 @@ int launch_conv3x3_small(const void* x, const float* w, const float* bias, int B
                          void* y, cudaStream_t s);
 // decoder glue
 int launch_pad_reflect(int dtype, const void* x, int B, int H, int W, int C, int upsample, void* y, cudaStream_t s);
+int launch_pad_reflect_bwd(int dtype, const void* gp, int B, int H, int W, int C, int upsample, void* dx, cudaStream_t s);
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

@@ -131,4 +131,79 @@ int launch_pad_reflect(int dtype, const void* x, int B, int H, int W, int C, int
     return check_cuda(cudaGetLastError(), "pad_reflect launch");
 }
 
+// ---- backward of the same op (training path of the decoder, train_image.py:139): dx[B, H, W, C] from the gradient of the
+// padded (and up-sampled) map dyp[B, Ho + 2, Wo + 2, C].  Gather form, one thread per (pixel, 16-byte channel vector), no
+// atomics: the gradient of pixel (u, v) of the UNPADDED up-sampled image is the interior value (u + 1, v + 1) plus the
+// ring positions ReflectionPad2d(1) filled from it (row 1 -> padded row 0, row Ho - 2 -> padded row Ho + 1, same for
+// columns); a source pixel i receives 0.75 / 0.25 of the up-sampled rows 2i-1 .. 2i+2 (align_corners = False, scale 2:
+// row 2k blends 0.25 (k-1) + 0.75 k, row 2k+1 blends 0.75 k + 0.25 min(k+1, H-1), row 0 copies row 0).
+template <typename T, bool UP>
+__global__ void __launch_bounds__(256) pad_reflect_bwd_kernel(const T* __restrict__ gp, T* __restrict__ dx, int B, int H, int W,
+                                                              int C) {
+    constexpr int VEC = PadVec<T>::VEC;
+    const int Ho = UP ? 2 * H : H, Wo = UP ? 2 * W : W;
+    const int cv = C / VEC;
+    const size_t t = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    if (t >= static_cast<size_t>(B) * H * W * cv) return;
+    const int c = static_cast<int>(t % cv) * VEC;
+    const int j = static_cast<int>((t / cv) % W), i = static_cast<int>((t / (static_cast<size_t>(cv) * W)) % H);
+    const int b = static_cast<int>(t / (static_cast<size_t>(cv) * W * H));
+    const T* gb = gp + static_cast<size_t>(b) * (Ho + 2) * (Wo + 2) * C + c;
+    float acc[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
+    auto folded = [&](int u, int v, float w) {          // acc += w * d(unpadded)[u][v]
+        int ys[3], xs[3], ny = 0, nx = 0;
+        ys[ny++] = u + 1;
+        if (u == 1) ys[ny++] = 0;
+        if (u == Ho - 2) ys[ny++] = Ho + 1;
+        xs[nx++] = v + 1;
+        if (v == 1) xs[nx++] = 0;
+        if (v == Wo - 2) xs[nx++] = Wo + 1;
+        for (int a = 0; a < ny; ++a)
+            for (int e = 0; e < nx; ++e) {
+                float val[VEC];
+                PadVec<T>::load(gb + (static_cast<size_t>(ys[a]) * (Wo + 2) + xs[e]) * C, val);
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) acc[k] = fmaf(w, val[k], acc[k]);
+            }
+    };
+    if (!UP) {
+        folded(i, j, 1.f);
+    } else {
+        int us[4], vs[4], nu = 0, nv = 0;
+        float wu[4], wv[4];
+        us[nu] = 2 * i; wu[nu++] = i == 0 ? 1.f : 0.75f;
+        us[nu] = 2 * i + 1; wu[nu++] = i == H - 1 ? 1.f : 0.75f;
+        if (i >= 1) { us[nu] = 2 * i - 1; wu[nu++] = 0.25f; }
+        if (i + 1 <= H - 1) { us[nu] = 2 * i + 2; wu[nu++] = 0.25f; }
+        vs[nv] = 2 * j; wv[nv++] = j == 0 ? 1.f : 0.75f;
+        vs[nv] = 2 * j + 1; wv[nv++] = j == W - 1 ? 1.f : 0.75f;
+        if (j >= 1) { vs[nv] = 2 * j - 1; wv[nv++] = 0.25f; }
+        if (j + 1 <= W - 1) { vs[nv] = 2 * j + 2; wv[nv++] = 0.25f; }
+        for (int a = 0; a < nu; ++a)
+            for (int e = 0; e < nv; ++e) folded(us[a], vs[e], wu[a] * wv[e]);
+    }
+    PadVec<T>::store(dx + ((static_cast<size_t>(b) * H + i) * W + j) * C + c, acc);
+}
+
+int launch_pad_reflect_bwd(int dtype, const void* gp, int B, int H, int W, int C, int upsample, void* dx, cudaStream_t s) {
+    const int vec = dtype == MHADA_BF16 ? 8 : 4;
+    const size_t n = static_cast<size_t>(B) * H * W * (C / vec);
+    const unsigned grid = static_cast<unsigned>((n + 255) / 256);
+    if (dtype == MHADA_BF16) {
+        auto g = static_cast<const __nv_bfloat16*>(gp);
+        auto o = static_cast<__nv_bfloat16*>(dx);
+        if (upsample) pad_reflect_bwd_kernel<__nv_bfloat16, true><<<grid, 256, 0, s>>>(g, o, B, H, W, C);
+        else pad_reflect_bwd_kernel<__nv_bfloat16, false><<<grid, 256, 0, s>>>(g, o, B, H, W, C);
+    } else {
+        auto g = static_cast<const float*>(gp);
+        auto o = static_cast<float*>(dx);
+        if (upsample) pad_reflect_bwd_kernel<float, true><<<grid, 256, 0, s>>>(g, o, B, H, W, C);
+        else pad_reflect_bwd_kernel<float, false><<<grid, 256, 0, s>>>(g, o, B, H, W, C);
+    }
+    count_launch();
+    return check_cuda(cudaGetLastError(), "pad_reflect_bwd launch");
+}
+
 }  // namespace mh

@@ -769,8 +769,8 @@ def _conv3x3_relu(xp_nchw: torch.Tensor, w: torch.Tensor, b: torch.Tensor) -> to
 # train_image.py:105-144 back-propagates through the decoder.  The forward of every block runs the same kernels as
 # inference (bf16, channels_last); the backward of the convolutions is aten.convolution_backward on those bf16
 # channels_last tensors (cuDNN tensor-core dgrad / wgrad, no NCHW <-> NHWC conversion: the r2 profile of the plain PyTorch
-# path had 1.5 ms of layout kernels and TF32 convolutions per cfg5 step), reflect-pad and bilinear backward are the aten
-# backward ops.  Own convolution-backward kernels are not built.  bf16 activations through nine ReLU blocks
+# path had 1.5 ms of layout kernels and TF32 convolutions per cfg5 step), reflect-pad (+ bilinear) backward is
+# pad_reflect_bwd_kernel.  Own convolution-backward kernels are not built.  bf16 activations through nine ReLU blocks
 # move the gradients of the EARLY blocks by ~10 % against fp32 arithmetic -- exactly as much as PyTorch's own bf16
 # decoder does (tools/debug_decoder_train.py) -- so the path is taken only when the model runs in bf16.
 
@@ -785,13 +785,12 @@ class _PadUpFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         B, H, W, C = ctx.in_shape
-        gn = g.permute(0, 3, 1, 2)                                        # NCHW view over channels_last memory
-        Ho, Wo = (2 * H, 2 * W) if ctx.upsample else (H, W)
-        dummy = gn.new_empty((B, C, Ho, Wo)).contiguous(memory_format=torch.channels_last)
-        gx = torch.ops.aten.reflection_pad2d_backward(gn, dummy, [1, 1, 1, 1])
-        if ctx.upsample:
-            gx = torch.ops.aten.upsample_bilinear2d_backward(gx, [Ho, Wo], [B, C, H, W], False, 2.0, 2.0)
-        return gx.permute(0, 2, 3, 1).contiguous(), None
+        g = g.contiguous()
+        dx = torch.empty((B, H, W, C), dtype=g.dtype, device=g.device)
+        with torch.cuda.device(g.device):
+            rc = _lib.lib().mhada_pad_reflect_bwd(_code(g.dtype), _ptr(g), B, H, W, C, 1 if ctx.upsample else 0, _ptr(dx), _stream())
+        _lib.check("mhada_pad_reflect_bwd", rc)
+        return dx, None
 
 
 class _ConvReluFn(torch.autograd.Function):
@@ -832,9 +831,12 @@ class _ConvSmallReluFn(torch.autograd.Function):
         gxp, gw, gb = torch.ops.aten.convolution_backward(gz, xp, w16, [weight.shape[0]], [1, 1], [0, 0], [1, 1], False, [0, 0], 1,
                                                           [True, True, True])
         B, H, W, C = x_tok.shape
-        dummy = gxp.new_empty((B, C, H, W)).contiguous(memory_format=torch.channels_last)
-        gx = torch.ops.aten.reflection_pad2d_backward(gxp, dummy, [1, 1, 1, 1])
-        return gx.permute(0, 2, 3, 1).contiguous(), gw.to(weight.dtype), gb.to(weight.dtype)
+        gxp = gxp.permute(0, 2, 3, 1).contiguous()
+        gx = torch.empty((B, H, W, C), dtype=gxp.dtype, device=gxp.device)
+        with torch.cuda.device(gxp.device):
+            rc = _lib.lib().mhada_pad_reflect_bwd(_code(gxp.dtype), _ptr(gxp), B, H, W, C, 0, _ptr(gx), _stream())
+        _lib.check("mhada_pad_reflect_bwd", rc)
+        return gx, gw.to(weight.dtype), gb.to(weight.dtype)
 
 
 class Decoder(nn.Module):

@@ -422,3 +422,22 @@ def test_attn_bwd(B, H, Nc, Ns, sharp):
         # everywhere (dO' travels as two bf16 terms) except at logits x16, where dv reaches 9e-2 max / 8e-3 Frobenius
         tol = 1e-1 if sharp > 2 else 2e-2
         assert e["max_abs"] <= tol * e["absmax"] + 5e-2 and (e["absmax"] < 1e-6 or e["fro_rel"] <= tol / 2), (name, e)
+
+
+@pytest.mark.parametrize("B,H,W,C,up", [(2, 5, 7, 64, 0), (1, 2, 2, 128, 1), (2, 9, 6, 64, 1), (1, 3, 3, 256, 0), (1, 16, 20, 64, 1),
+                                        (1, 1 + 1, 40, 8, 1)])
+def test_pad_reflect_bwd(B, H, W, C, up):
+    """mhada_pad_reflect_bwd against autograd of F.interpolate(x2, bilinear) + ReflectionPad2d(1) (conv.py:26-27, :71)."""
+    L = _lib.lib()
+    torch.manual_seed(B * 100 + H)
+    Ho, Wo = (2 * H, 2 * W) if up else (H, W)
+    g = torch.randn(B, Ho + 2, Wo + 2, C, device=G.DEV).bfloat16().contiguous()
+    dx = torch.empty(B, H, W, C, dtype=torch.bfloat16, device=G.DEV)
+    _lib.check("mhada_pad_reflect_bwd", L.mhada_pad_reflect_bwd(BF16, G.ptr(g), B, H, W, C, up, G.ptr(dx), G.stream()))
+    torch.cuda.synchronize()
+    x = torch.zeros(B, C, H, W, dtype=torch.float64, device=G.DEV, requires_grad=True)
+    y = torch.nn.functional.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False) if up else x
+    y = torch.nn.functional.pad(y, (1, 1, 1, 1), mode="reflect")
+    (y * g.double().permute(0, 3, 1, 2)).sum().backward()
+    e = O.errors(dx.float().cpu().numpy(), x.grad.permute(0, 2, 3, 1).cpu().numpy())
+    assert e["max_abs_rel"] <= 6e-3, e           # one bf16 rounding of the result
