@@ -564,7 +564,10 @@ def measure_train(args, ctx, steps, warmup):
     # CUDA graph and replayed (MHADA_TRAIN_GRAPH=0: eager launch loop).  Every launch of libmhada_b200.so goes on the
     # caller's stream without allocating or synchronising, so the autograd Functions capture like any PyTorch op.
     use_graph = os.environ.get("MHADA_TRAIN_GRAPH", "1") != "0"
-    opts = [torch.optim.Adam(m.parameters(), lr=1e-4, capturable=use_graph) for m in (vit_c, vit_s, model)]   # train_image.py:70-72
+    fused = os.environ.get("MHADA_TRAIN_FUSED_ADAM", "1") != "0"      # same update rule, one multi-tensor kernel per optimiser
+    # (fused=None leaves PyTorch's default, the foreach implementation; an explicit False would select the per-tensor loop)
+    opts = [torch.optim.Adam(m.parameters(), lr=1e-4, capturable=use_graph, fused=True if fused else None)
+            for m in (vit_c, vit_s, model)]                                                                # train_image.py:70-72
     c_h, s_h = make_images(wl, seed=rank)
     c_d, s_d = c_h.to(device), s_h.to(device)
     sync = OverlappedGradientAllReduce([vit_c, vit_s, model]) if world > 1 else None
@@ -670,7 +673,7 @@ def measure_train(args, ctx, steps, warmup):
         "steps": steps, "warmup": warmup, "ms_per_step": round(ms_dev / steps, 4), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": wl["desc"], "images_per_gpu_per_step": B, "tokens": [wl["hw"][0] * wl["hw"][1]] * 2,
-                   "parameters": n_params, "optimizer": "3 x Adam(lr=1e-4) (train_image.py:70-72)",
+                   "parameters": n_params, "optimizer": "3 x Adam(lr=1e-4) (train_image.py:70-72)" + (", fused multi-tensor implementation" if fused else ""),
                    "loss": "synthetic (VGG19 weights cannot be downloaded offline): pixel term on cs + feature term on fcs",
                    "forward": ("MHAda layers on the bf16 CUDA kernels; ViT Linear layers + batch attention on own kernels "
                                "(tcgen05 token GEMM); decoder blocks on the inference kernels; LayerNorm / residuals = PyTorch ops"),
