@@ -664,6 +664,20 @@ def measure_train(args, ctx, steps, warmup):
         return float(loss)                      # D2H of the step's result (the loss), synchronises like a logging trainer
 
     ms_e2e = timed(step_host, steps, max(3, warmup // 2))
+    if graph is not None and sync is not None:
+        # what the all-reduce costs inside the graph: the same step captured WITHOUT its collectives, timed the same way
+        # (after every reported measurement: the ranks' weights drift apart from here on)
+        try:
+            sync.enabled = False
+            g2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g2):
+                step(c_d, s_d, False)
+            ms_noar = timed(lambda rec: g2.replay(), steps, 3)
+            tail_ms = (ms_dev - ms_noar) / steps
+        except Exception:      # noqa: BLE001
+            tail_ms = None
+        finally:
+            sync.enabled = True
     if rank != 0:
         return None
     images = B * world * steps
@@ -688,10 +702,11 @@ def measure_train(args, ctx, steps, warmup):
         "e2e": {"value": round(images / (ms_e2e * 1e-3), 2), "unit": "images/s",
                 "h2d_bytes_per_step": c_h.numel() * 4 + s_h.numel() * 4, "d2h_bytes_per_step": 4,
                 "ms_per_step": round(ms_e2e / steps, 4)},
-        "gradient_allreduce": {"exposed_ms_per_step": round(tail_ms, 4), "bytes": 4 * n_params,
+        "gradient_allreduce": {"exposed_ms_per_step": round(tail_ms, 4) if tail_ms is not None else None, "bytes": 4 * n_params,
                                "note": "device time between the end of backward and the end of the last bucket's "
-                                       "all-reduce + copy-back: what the overlap does NOT hide (0 at one GPU); measured on "
-                                       "eager steps (events cannot be timed inside the replayed graph)"},
+                                       "all-reduce + copy-back: what the overlap does NOT hide (0 at one GPU); with the step "
+                                       "replayed as a CUDA graph: step time minus the time of the same graph captured "
+                                       "without its collectives"},
         "gpu_launches": None, "roofline": None, "clocks": clocks,
     }
 

@@ -131,6 +131,7 @@ class OverlappedGradientAllReduce:
         self._inflight = []            # (bucket index, flat tensor, work handle)
         self._handles = [p.register_post_accumulate_grad_hook(self._on_grad) for p in params]
         self.launched_in_backward = 0  # buckets whose all-reduce started before finish() (i.e. overlapped)
+        self.enabled = True            # False: hooks and finish() do nothing (timing a step without its collectives)
 
     def _launch(self, i):
         grads = [p.grad for p in self.buckets[i] if p.grad is not None]
@@ -141,6 +142,8 @@ class OverlappedGradientAllReduce:
         self._inflight.append((i, flat, work))
 
     def _on_grad(self, p):
+        if not self.enabled:
+            return
         i = self._bucket_of[id(p)]
         self._pending[i] -= 1
         if self._pending[i] == 0:
@@ -149,6 +152,8 @@ class OverlappedGradientAllReduce:
 
     def finish(self):
         """Wait for the collectives, write the averaged gradients back, re-arm for the next step."""
+        if not self.enabled:
+            return
         for i, n in enumerate(self._pending):          # buckets with parameters that got no gradient this step
             if 0 < n < len(self.buckets[i]) or (n == len(self.buckets[i]) and any(p.grad is not None for p in self.buckets[i])):
                 self._launch(i)
