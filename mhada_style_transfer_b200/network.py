@@ -17,8 +17,10 @@ Training (train_image.py:105-144): the FORWARD always runs the CUDA kernels.  Wh
 layers become autograd Functions.  On the bf16 path at head_dim 64 (the configuration every reference script uses) the
 BACKWARD runs own kernels too (mhada_layer_backward, SURVEY N4: flash-style attention backward with V' = [V~ | V~^2],
 the other contractions on the tcgen05 token GEMM).  Elsewhere (fp32 path, head_dim != 64, cosine, AdaAttN,
-AdaAttnForLoss) it recomputes the layer with PyTorch ops in fp32 and differentiates that.  The decoder takes the plain
-differentiable PyTorch path.  Gradients are checked against the reference's float64 autograd (tests/golden/grad_*).
+AdaAttnForLoss) it recomputes the layer with PyTorch ops in fp32 and differentiates that.  The decoder, when the model
+runs in bf16, runs its inference kernels forward with aten.convolution_backward + an own pad / up-sample backward kernel
+behind them (Decoder._forward_train); otherwise the plain differentiable PyTorch path.  Gradients are checked against the
+reference's float64 autograd (tests/golden/grad_*).
 """
 from __future__ import annotations
 
@@ -844,7 +846,9 @@ class Decoder(nn.Module):
     epilogue writes the next block's reflect-padded input, the fused x2-bilinear + pad kernel after the three
     up-sampling blocks, and the small 64 -> 3 kernel; activations stay channels_last.  fp32 path (the reference's
     arithmetic): the pad kernel + cuDNN fp32 convolutions.
-    CPU tensors raise (no CPU path); under autograd the plain differentiable PyTorch ops run on the GPU."""
+    CPU tensors raise (no CPU path).  Under autograd: the same kernels forward with a library convolution backward and an
+    own pad / up-sample backward kernel when the model runs in bf16 (_forward_train), else the plain differentiable
+    PyTorch ops on the GPU."""
 
     def __init__(self):
         super().__init__()
