@@ -126,3 +126,47 @@ def test_overlapped_gradient_allreduce_matches_full_batch():
         p.join(120)
         assert p.exitcode == 0
     assert q.get(timeout=10) == (True, True, True, True)
+
+
+def _disabled_worker(rank, world, port, q):
+    import os
+    import torch
+    import torch.distributed as dist
+    from mhada_style_transfer_b200.sharding import OverlappedGradientAllReduce
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    net = torch.nn.Linear(8, 4)
+    sync = OverlappedGradientAllReduce(net, bucket_bytes=64)
+    x = torch.full((2, 8), float(rank + 1))
+    sync.enabled = False                       # hooks and finish() do nothing: gradients stay local
+    net(x).sum().backward()
+    sync.finish()
+    local = net.weight.grad.clone()
+    net.zero_grad(set_to_none=True)
+    sync.enabled = True
+    net(x).sum().backward()
+    sync.finish()
+    q.put((rank, float(local[0, 0]), float(net.weight.grad[0, 0])))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_overlapped_allreduce_can_be_disabled_for_timing():
+    """bench.py times the captured training step without its collectives: `enabled = False` leaves the gradients local,
+    re-enabling restores the averaging."""
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_disabled_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    assert got[0][1] == 2.0 and got[1][1] == 4.0          # local gradients: 2 rows x (rank + 1)
+    assert got[0][2] == got[1][2] == 3.0                   # averaged over the two ranks
