@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define MHADA_ABI_VERSION 12
+#define MHADA_ABI_VERSION 13
 
 #if defined(__GNUC__)
 #define MHADA_API __attribute__((visibility("default")))
@@ -125,7 +125,12 @@ typedef struct mhada_attn_args {
                             style for every frame) */
     int activation;      /* MHADA_ACT_SOFTMAX (Softmax, adaDecoder.py:11-17) or MHADA_ACT_COSINE (CosineSimilarity,
                             adaDecoder.py:20-34: a = (cos(q, k) + 1) / sum_k (cos(q, k) + 1)); cosine is f32-path only */
+    void* scratch;       /* optional device scratch, 16-byte aligned: with mhada_attn_cosine_scratch(B or 1, H) bytes the
+                            cosine activation at dqk = dv = 64 and Ns >= 128 runs in CLOSED FORM, O(N d^2): A V' = (q^ . T +
+                            sum v') / (q^ . sum k^ + Ns) with T = sum_j k^_j (x) v'_j; NULL = the O(N^2 d) kernel */
+    size_t scratch_bytes;
 } mhada_attn_args;
+MHADA_API size_t mhada_attn_cosine_scratch(int B, int H);
 MHADA_API int mhada_attn(const mhada_attn_args* args, mhada_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------

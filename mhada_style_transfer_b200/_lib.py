@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libmhada_b200.so")
 
 F32, BF16, U8 = 0, 1, 2
-ABI_VERSION = 12
+ABI_VERSION = 13
 VIT_MAX_LAYERS = 8
 PROJ_Q, PROJ_KV = 1, 2
 REUSE_FS_STATS = 1
@@ -33,6 +33,7 @@ class AttnArgs(ctypes.Structure):
         ("q_mean", c_void_p), ("q_rstd", c_void_p), ("k_mean", c_void_p), ("k_rstd", c_void_p),
         ("kv_batch", c_int),
         ("activation", c_int),
+        ("scratch", c_void_p), ("scratch_bytes", c_size_t),
     ]
 
 
@@ -91,6 +92,7 @@ SIGNATURES = {
                            c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                            c_size_t, c_void_p]),
     "mhada_attn": (c_int, [POINTER(AttnArgs), c_void_p]),
+    "mhada_attn_cosine_scratch": (c_size_t, [c_int, c_int]),
     "mhada_debug_attn_trace": (c_int, [POINTER(AttnArgs), c_void_p, c_void_p]),
     "mhada_linear_workspace": (c_size_t, [c_int, c_int, c_int]),
     "mhada_linear": (c_int, [c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int,

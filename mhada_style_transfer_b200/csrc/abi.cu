@@ -23,8 +23,8 @@ size_t esize(int dtype) { return dtype == MHADA_BF16 ? 2 : 4; }
 
 struct LayerWs {
     float *mean_c, *rstd_c, *mean_s, *rstd_s, *mean_x, *rstd_x, *mu_v;
-    void *stats_ws, *proj_ws, *q, *k, *v, *heads, *lin_ws, *wide;
-    size_t stats_bytes, proj_bytes, lin_bytes, wide_bytes, total;
+    void *stats_ws, *proj_ws, *q, *k, *v, *heads, *lin_ws, *wide, *cos_ws;
+    size_t stats_bytes, proj_bytes, lin_bytes, wide_bytes, cos_bytes, total;
 };
 
 LayerWs carve(int dtype, int B, int Nc, int Ns, int C, int H, uint8_t* base) {
@@ -56,6 +56,8 @@ LayerWs carve(int dtype, int B, int Nc, int Ns, int C, int H, uint8_t* base) {
     w.v = take(wide ? 0 : static_cast<size_t>(B) * Ns * C * e * (dtype == MHADA_BF16 ? 2 : 1));
     w.wide_bytes = wide ? layer_wide_workspace(B, Nc, Ns, C, H) : 0;
     w.wide = take(w.wide_bytes);
+    w.cos_bytes = dtype == MHADA_F32 && d == 64 ? attn_cosine_scratch_bytes(B, H) : 0;      // closed-form cosine moments
+    w.cos_ws = take(w.cos_bytes);
     w.heads = take(static_cast<size_t>(B) * Nc * C * e);
     w.lin_bytes = dtype == MHADA_BF16 ? linear_bf16_workspace(C, C) : 0;
     w.lin_ws = take(w.lin_bytes);
@@ -251,6 +253,7 @@ int layer_impl(const char* who, int dtype, const void* fc, const void* fs, const
     a.x_mean = mean_x; a.x_rstd = rstd_x; a.mu_v = cache ? cv.mu_v : w.mu_v;
     a.kv_batch = cache ? Bs : B;
     a.activation = (flags & MHADA_LAYER_COSINE) ? MHADA_ACT_COSINE : MHADA_ACT_SOFTMAX;
+    a.scratch = w.cos_ws; a.scratch_bytes = w.cos_bytes;
     if (int e = attn_dispatch(a, s)) return e;
     }
     // (4) out_conv                                                           adaDecoder.py:202-205
@@ -361,6 +364,7 @@ int mhada_profile_stage(int stage, float* ms_total, int* brackets) {
 }
 
 int mhada_abi_version(void) { return MHADA_ABI_VERSION; }
+size_t mhada_attn_cosine_scratch(int B, int H) { return B > 0 && H > 0 ? attn_cosine_scratch_bytes(B, H) : 0; }
 const char* mhada_last_error(void) { return last_error(); }
 int mhada_device_check(void) { return device_check(); }
 int mhada_last_launch_count(void) { return g_launches; }

@@ -62,6 +62,7 @@ int launch_proj_f32(int parts, const float* fc, const float* fs, const float* me
                     const float* mean_s, const float* rstd_s, const float* w, const float* bias, int B, int Bs, int Nc,
                     int Ns, int H, int d, float* q, float* k, float* v, float* mu_v, cudaStream_t s);
 int launch_attn_f32(const mhada_attn_args& a, cudaStream_t s);
+size_t attn_cosine_scratch_bytes(int B, int H);   // closed-form cosine moments (head_dim 64), see simt_f32.cu
 int launch_linear_f32(const float* x, int ldx, const float* w, const float* bias, int M, int Cin, int Cout, float* y,
                       int ldy, cudaStream_t s);
 

@@ -375,6 +375,139 @@ __global__ void __launch_bounds__(256, 2) attn_f32_kernel(const AttnF32Params p)
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Cosine activation in CLOSED FORM (CosineSimilarity, adaDecoder.py:20-34), head_dim 64:
+//     a_ij = (q^_i . k^_j + 1) / sum_j (q^_i . k^_j + 1)        q^ = q / |q|, k^ = k / |k|
+//  => A V' = (q^_i . T + sV) / (q^_i . sK + Ns),   T = sum_j k^_j (x) v'_j  [64 x 128],  sK = sum_j k^_j,  sV = sum_j v'_j
+// i.e. O(N d^2) instead of O(N^2 d): one pass over the keys builds the moments of an (image, head), one pass over the
+// queries applies them (the N x N kernel above stays for other widths and for normalise-on-load).
+// ------------------------------------------------------------------------------------------------
+constexpr int COS_D = 64, COS_MOM = COS_D * 2 * COS_D + COS_D + 2 * COS_D;      // floats per (image, head)
+
+size_t attn_cosine_scratch_bytes(int B, int H) { return static_cast<size_t>(B) * H * COS_MOM * sizeof(float); }
+
+// grid (H, Bkv), 256 threads = 8 x 32: thread (ty, tx) owns rows ty*8.. of k^ and columns tx*4.. of v' = [v~ | v~^2]
+__global__ void __launch_bounds__(256) cosine_moments_kernel(const AttnF32Params p, float* __restrict__ scratch) {
+    __shared__ float ks[32][COS_D + 1];
+    __shared__ __align__(16) float vs[32][2 * COS_D];
+    const int h = blockIdx.x, b = blockIdx.y;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const float* kb = p.k + static_cast<size_t>(b) * p.Ns * p.ldk + h * COS_D;
+    const float* vb = p.v + static_cast<size_t>(b) * p.Ns * p.ldv + h * COS_D;
+    float acc[8][4], sk[8], sv[4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        sk[i] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) sv[j] = 0.f;
+    for (int k0 = 0; k0 < p.Ns; k0 += 32) {
+        // warp ty stages keys ty*4 .. ty*4+3: lane = two of the 64 channels; k is normalised here
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int r = ty * 4 + u, n = k0 + r;
+            float k0v = 0.f, k1v = 0.f, v0 = 0.f, v1 = 0.f;
+            if (n < p.Ns) {
+                k0v = __ldg(kb + static_cast<size_t>(n) * p.ldk + tx); k1v = __ldg(kb + static_cast<size_t>(n) * p.ldk + tx + 32);
+                v0 = __ldg(vb + static_cast<size_t>(n) * p.ldv + tx); v1 = __ldg(vb + static_cast<size_t>(n) * p.ldv + tx + 32);
+            }
+            float nn = fmaf(k0v, k0v, k1v * k1v);
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) nn += __shfl_xor_sync(0xffffffffu, nn, o);
+            const float inv = n < p.Ns ? 1.f / sqrtf(nn) : 0.f;
+            ks[r][tx] = k0v * inv; ks[r][tx + 32] = k1v * inv;
+            vs[r][tx] = v0; vs[r][tx + 32] = v1;
+            vs[r][COS_D + tx] = v0 * v0; vs[r][COS_D + tx + 32] = v1 * v1;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int kk = 0; kk < 32; ++kk) {
+            const float4 bv = *reinterpret_cast<const float4*>(&vs[kk][tx * 4]);
+            const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float a = ks[kk][ty * 8 + i];
+                if (tx == 0) sk[i] += a;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a, bb[j], acc[i][j]);
+            }
+            if (ty == 0) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) sv[j] += bb[j];
+            }
+        }
+        __syncthreads();
+    }
+    float* out = scratch + (static_cast<size_t>(b) * p.H + h) * COS_MOM;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        *reinterpret_cast<float4*>(out + (ty * 8 + i) * 2 * COS_D + tx * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    if (tx == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) out[COS_D * 2 * COS_D + ty * 8 + i] = sk[i];
+    }
+    if (ty == 0) *reinterpret_cast<float4*>(out + COS_D * 2 * COS_D + COS_D + tx * 4) = make_float4(sv[0], sv[1], sv[2], sv[3]);
+}
+
+// grid (ceil(Nc / 64), H, B), 256 threads: warp w applies the moments to query rows w, w + 8, ...; lane = 4 of the 128 columns
+__global__ void __launch_bounds__(256) cosine_apply_kernel(const AttnF32Params p, const float* __restrict__ scratch) {
+    __shared__ __align__(16) float T[COS_D][2 * COS_D];
+    __shared__ float sK[COS_D];
+    __shared__ __align__(16) float sV[2 * COS_D];
+    const int h = blockIdx.y, b = blockIdx.z, q0 = blockIdx.x * 64;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int bkv = p.kv_shared ? 0 : b;
+    const float* mom = scratch + (static_cast<size_t>(bkv) * p.H + h) * COS_MOM;
+    for (int e = threadIdx.x; e < COS_D * 2 * COS_D / 4; e += 256)
+        reinterpret_cast<float4*>(&T[0][0])[e] = __ldg(reinterpret_cast<const float4*>(mom) + e);
+    if (threadIdx.x < COS_D) sK[threadIdx.x] = __ldg(mom + COS_D * 2 * COS_D + threadIdx.x);
+    if (threadIdx.x < 2 * COS_D) sV[threadIdx.x] = __ldg(mom + COS_D * 2 * COS_D + COS_D + threadIdx.x);
+    __syncthreads();
+    for (int r = warp; r < 64; r += 8) {
+        const int n = q0 + r;
+        if (n >= p.Nc) break;
+        const float* qrow = p.q + (static_cast<size_t>(b) * p.Nc + n) * p.ldq + h * COS_D;
+        float qa = __ldg(qrow + lane), qb = __ldg(qrow + lane + 32);
+        float nn = fmaf(qa, qa, qb * qb);
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) nn += __shfl_xor_sync(0xffffffffu, nn, o);
+        const float inv = 1.f / sqrtf(nn);
+        qa *= inv; qb *= inv;
+        float den = fmaf(qa, sK[lane], qb * sK[lane + 32]);
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) den += __shfl_xor_sync(0xffffffffu, den, o);
+        den += static_cast<float>(p.Ns);
+        float acc[4] = {sV[lane * 4], sV[lane * 4 + 1], sV[lane * 4 + 2], sV[lane * 4 + 3]};
+#pragma unroll 8
+        for (int d = 0; d < COS_D; ++d) {
+            const float qd = __shfl_sync(0xffffffffu, d < 32 ? qa : qb, d & 31);
+            const float4 t = *reinterpret_cast<const float4*>(&T[d][lane * 4]);
+            acc[0] = fmaf(qd, t.x, acc[0]); acc[1] = fmaf(qd, t.y, acc[1]);
+            acc[2] = fmaf(qd, t.z, acc[2]); acc[3] = fmaf(qd, t.w, acc[3]);
+        }
+        const float rden = 1.f / den;
+        // lanes 0..15 hold M of channels lane*4.., lanes 16..31 hold E of channels (lane-16)*4..
+        float e4[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) e4[j] = __shfl_down_sync(0xffffffffu, acc[j], 16);
+        if (lane < 16) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int ch = h * COS_D + lane * 4 + j;
+                const float m = acc[j] * rden, e = e4[j] * rden;
+                const float sd = sqrtf(fmaxf(e - m * m, 1e-6f));
+                const size_t sidx = static_cast<size_t>(b) * p.H * COS_D + ch;
+                const float xn = (__ldg(p.x + (static_cast<size_t>(b) * p.Nc + n) * p.ldx + ch) - __ldg(p.x_mean + sidx)) *
+                                 __ldg(p.x_rstd + sidx);
+                const float mu = p.mu_v ? __ldg(p.mu_v + static_cast<size_t>(bkv) * p.H * COS_D + ch) : 0.f;
+                p.out[(static_cast<size_t>(b) * p.Nc + n) * p.ldo + ch] = fmaf(sd, xn, m + mu);
+            }
+        }
+    }
+}
+
 int launch_attn_f32(const mhada_attn_args& a, cudaStream_t s) {
     AttnF32Params p;
     p.q = static_cast<const float*>(a.q); p.k = static_cast<const float*>(a.k);
@@ -385,6 +518,19 @@ int launch_attn_f32(const mhada_attn_args& a, cudaStream_t s) {
     p.H = a.H; p.Nc = a.Nc; p.Ns = a.Ns; p.dqk = a.dqk; p.dv = a.dv;
     p.ldq = a.ldq; p.ldk = a.ldk; p.ldv = a.ldv; p.ldx = a.ldx; p.ldo = a.ldo;
     p.kv_shared = (a.kv_batch == 1 && a.B > 1) ? 1 : 0;
+    const int Bkv = p.kv_shared ? 1 : a.B;
+    // (not below 128 keys: nothing to gain there, and with a handful of keys Var = E - M^2 can vanish exactly -- one key:
+    // a = 1 -- which the N x N kernel reproduces bit for bit while the moments carry fp32 rounding noise into sqrt())
+    if (a.activation == MHADA_ACT_COSINE && a.Ns >= 128 && a.dqk == COS_D && a.dv == COS_D && !a.q_mean && !a.k_mean && a.scratch &&
+        a.scratch_bytes >= attn_cosine_scratch_bytes(Bkv, a.H) && (reinterpret_cast<uintptr_t>(a.scratch) & 15) == 0) {
+        // closed form: moments of every (image, head) over the keys, then one pass over the queries
+        float* scratch = static_cast<float*>(a.scratch);
+        cosine_moments_kernel<<<dim3(a.H, Bkv), 256, 0, s>>>(p, scratch);
+        count_launch();
+        cosine_apply_kernel<<<dim3((a.Nc + 63) / 64, a.H, a.B), 256, 0, s>>>(p, scratch);
+        count_launch();
+        return check_cuda(cudaGetLastError(), "attn_cosine launch");
+    }
     dim3 grid((a.Nc + TILE - 1) / TILE, (a.dv + TILE - 1) / TILE, a.B * a.H);
     if (a.activation == MHADA_ACT_COSINE)
         attn_f32_kernel<true><<<grid, 256, 0, s>>>(p);

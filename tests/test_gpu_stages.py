@@ -441,3 +441,56 @@ def test_pad_reflect_bwd(B, H, W, C, up):
     (y * g.double().permute(0, 3, 1, 2)).sum().backward()
     e = O.errors(dx.float().cpu().numpy(), x.grad.permute(0, 2, 3, 1).cpu().numpy())
     assert e["max_abs_rel"] <= 6e-3, e           # one bf16 rounding of the result
+
+
+@pytest.mark.parametrize("B,H,Nc,Ns,kv_batch", [(1, 1, 70, 1, 0), (2, 8, 300, 257, 0), (3, 2, 64, 1000, 1), (1, 8, 4096, 4096, 0)])
+def test_attn_cosine_closed_form(B, H, Nc, Ns, kv_batch):
+    """CosineSimilarity (adaDecoder.py:20-34) at head_dim 64 in closed form, O(N d^2): A V' = (q^ . T + sum v') / (q^ . sum k^ + Ns)
+    -- against the float64 definition a = (cos + 1) / sum(cos + 1) and against the O(N^2 d) kernel (no scratch given)."""
+    L = _lib.lib()
+    d = 64
+    Bkv = 1 if kv_batch == 1 else B
+    q = synth.bellish(1, (B, Nc, H * d), 0.3, 1.0)
+    k = synth.bellish(2, (Bkv, Ns, H * d), -0.2, 1.0)
+    v = synth.bellish(3, (Bkv, Ns, H * d), 0, 40.0)
+    x = synth.bellish(4, (B, Nc, H * d), 2.0, 30.0)
+    muv = synth.uniform(5, (Bkv, H * d), -3, 3)
+    tq, tk, tv, tx = (G.f32(a) for a in (q, k, v, x))
+    xm, xr = G.stats(tx, F32)
+    keep = G.f32(muv)
+    outs = []
+    for use_scratch in (True, False):
+        out = torch.empty(B, Nc, H * d, dtype=torch.float32, device=G.DEV)
+        a = _lib.AttnArgs()
+        a.dtype = F32
+        a.B, a.H, a.Nc, a.Ns, a.dqk, a.dv = B, H, Nc, Ns, d, d
+        a.q, a.k, a.v, a.x, a.out = tq.data_ptr(), tk.data_ptr(), tv.data_ptr(), tx.data_ptr(), out.data_ptr()
+        a.ldq = a.ldk = a.ldv = a.ldx = a.ldo = H * d
+        a.x_mean, a.x_rstd, a.mu_v = xm.data_ptr(), xr.data_ptr(), keep.data_ptr()
+        a.kv_batch, a.activation = kv_batch, _lib.ACT_COSINE
+        scratch = G.ws(L.mhada_attn_cosine_scratch(B, H))
+        if use_scratch:
+            a.scratch, a.scratch_bytes = scratch.data_ptr(), scratch.numel()
+        n0 = L.mhada_total_launch_count()
+        _lib.check("mhada_attn", L.mhada_attn(ctypes.byref(a), G.stream()))
+        torch.cuda.synchronize()
+        # moments + apply (from 128 keys up) vs the N x N kernel
+        assert L.mhada_total_launch_count() - n0 == (2 if use_scratch and Ns >= 128 else 1)
+        outs.append(out.cpu().numpy().astype(np.float64))
+    f = lambda z: z.astype(np.float32).astype(np.float64)
+    qf, kf, vf, xf, mf = f(q), f(k), f(v), f(x), f(muv)
+    xmn, xrn = xm.cpu().numpy().astype(np.float64), xr.cpu().numpy().astype(np.float64)
+    want = np.zeros((B, Nc, H * d))
+    for b in range(B):
+        bk = 0 if kv_batch == 1 else b
+        for h in range(H):
+            sl = slice(h * d, (h + 1) * d)
+            qh, kh, vh = qf[b][:, sl], kf[bk][:, sl], vf[bk][:, sl]
+            s = (qh @ kh.T) / (np.linalg.norm(qh, axis=1)[:, None] * np.linalg.norm(kh, axis=1)[None, :]) + 1.0
+            a_ = s / s.sum(1, keepdims=True)
+            m, e = a_ @ vh, a_ @ (vh * vh)
+            sd = np.sqrt(np.maximum(e - m * m, 1e-6))
+            want[b][:, sl] = sd * (xf[b][:, sl] - xmn[b, sl]) * xrn[b, sl] + m + mf[bk, sl]
+    for got in outs:
+        e = O.errors(got, want)
+        assert e["max_abs_rel"] < 2e-5, e

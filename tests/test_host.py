@@ -89,7 +89,7 @@ def test_library_exports_every_declared_symbol(lib):
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.mhada_abi_version() == _lib.ABI_VERSION == 12
+    assert lib.mhada_abi_version() == _lib.ABI_VERSION == 13
 
 
 def test_abi_rejects_without_gpu_or_bad_args(lib):
