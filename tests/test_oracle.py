@@ -231,3 +231,82 @@ def test_reference_gradients_agree_with_oracle_finite_differences(case, golden_i
         fd = (at(+1) - at(-1)) / (2 * eps)
         an = float((gk * vs).sum())
         assert fd == pytest.approx(an, rel=2e-4, abs=1e-6 * abs(an) + 1e-6), key
+
+
+def test_backward_formulas_of_the_kernels_match_autograd():
+    """SURVEY A.2 / DESIGN 4.7: the backward the B200 kernels implement -- written out in float64 with the CENTRED
+    quantities they use (V~ = V - mu_V, O' = [M~ | E~], dO' = [g - 2 M~ dVar | dVar], delta = dO'.O', dS = A (dA - delta),
+    dV = dV'_m + 2 V~ dV'_e, instance-norm backward) -- against torch.autograd of the reference's formulation
+    (adaDecoder.py:162-206).  Pins the claim that the centring needs no correction terms."""
+    torch.manual_seed(0)
+    B, H, d, Nc, Ns = 2, 2, 8, 12, 9
+    C = H * d
+    dd = torch.float64
+    fc = torch.randn(B, Nc, C, dtype=dd) * 3 + 1
+    fs = torch.randn(B, Ns, C, dtype=dd) * 2 + 5
+    fcs = torch.randn(B, Nc, C, dtype=dd) + 2
+    W = torch.randn(3, H, d, d, dtype=dd) * 0.3
+    bias = torch.randn(3, H, d, dtype=dd)
+    Wo = torch.randn(C, C, dtype=dd) * 0.1
+    bo = torch.randn(C, dtype=dd)
+    G = torch.randn(B, Nc, C, dtype=dd)
+
+    def inorm(x):
+        mu = x.mean(1, keepdim=True)
+        var = x.var(1, unbiased=False, keepdim=True)
+        return (x - mu) * torch.rsqrt(var + 1e-5)
+
+    def fwd(fc, fs, fcs, W, bias, Wo, bo):
+        xc, xs = inorm(fc).view(B, Nc, H, d), inorm(fs).view(B, Ns, H, d)
+        xr, xx = fs.view(B, Ns, H, d), inorm(fcs).view(B, Nc, H, d)
+        q = torch.einsum("bnhi,hoi->bhno", xc, W[0]) + bias[0][None, :, None, :]
+        k = torch.einsum("bnhi,hoi->bhno", xs, W[1]) + bias[1][None, :, None, :]
+        v = torch.einsum("bnhi,hoi->bhno", xr, W[2]) + bias[2][None, :, None, :]
+        a = torch.softmax(q @ k.transpose(2, 3), -1)
+        m, e = a @ v, a @ (v * v)
+        sd = torch.sqrt((e - m * m).clamp(min=1e-6))
+        y = (sd * xx.transpose(1, 2) + m).transpose(1, 2).reshape(B, Nc, C)
+        return y @ Wo.T + bo
+
+    leaves = [t.clone().requires_grad_(True) for t in (fc, fs, fcs, W, bias, Wo, bo)]
+    (fwd(*leaves) * G).sum().backward()
+    ref = [t.grad for t in leaves]
+
+    def stats(x):
+        return x.mean(1), torch.rsqrt(x.var(1, unbiased=False) + 1e-5)
+
+    (mc, rc), (ms, rs), (mx, rx) = stats(fc), stats(fs), stats(fcs)
+    xc, xs, xx = (fc - mc[:, None]) * rc[:, None], (fs - ms[:, None]) * rs[:, None], (fcs - mx[:, None]) * rx[:, None]
+    hv = lambda t, N: t.view(B, N, H, d).transpose(1, 2)
+    q = torch.einsum("bhni,hoi->bhno", hv(xc, Nc), W[0]) + bias[0][None, :, None, :]
+    k = torch.einsum("bhni,hoi->bhno", hv(xs, Ns), W[1]) + bias[1][None, :, None, :]
+    v = torch.einsum("bhni,hoi->bhno", hv(fs, Ns), W[2]) + bias[2][None, :, None, :]
+    muv = v.mean(2, keepdim=True)
+    vt = v - muv                                                        # the kernels only ever see the centred values
+    a = torch.softmax(q @ k.transpose(2, 3), -1)
+    Mt, Et = a @ vt, a @ (vt * vt)
+    var = Et - Mt * Mt
+    sd = torch.sqrt(var.clamp(min=1e-6))
+    cat = (sd * hv(xx, Nc) + Mt + muv).transpose(1, 2).reshape(B, Nc, C)
+    dcat = G @ Wo
+    dWo, dbo = G.reshape(-1, C).T @ cat.reshape(-1, C), G.sum((0, 1))
+    g = hv(dcat, Nc)
+    dxhat = g * sd
+    dvar = torch.where(var >= 1e-6, g * hv(xx, Nc) / (2 * sd), torch.zeros_like(g))
+    dM, dE = g - 2 * Mt * dvar, dvar
+    delta = (dM * Mt + dE * Et).sum(-1, keepdim=True)
+    dA = dM @ vt.transpose(2, 3) + dE @ (vt * vt).transpose(2, 3)
+    dS = a * (dA - delta)
+    dq, dk = dS @ k, dS.transpose(2, 3) @ q
+    dv = a.transpose(2, 3) @ dM + 2 * vt * (a.transpose(2, 3) @ dE)
+    gq = torch.einsum("bhno,hoi->bhni", dq, W[0])
+    gk = torch.einsum("bhno,hoi->bhni", dk, W[1])
+    gv = torch.einsum("bhno,hoi->bhni", dv, W[2])
+    dW = torch.stack([torch.einsum("bhno,bhni->hoi", dq, hv(xc, Nc)), torch.einsum("bhno,bhni->hoi", dk, hv(xs, Ns)),
+                      torch.einsum("bhno,bhni->hoi", dv, hv(fs, Ns))])
+    db = torch.stack([dq.sum((0, 2)), dk.sum((0, 2)), dv.sum((0, 2))])
+    tok = lambda t, N: t.transpose(1, 2).reshape(B, N, C)
+    inbwd = lambda g_, xh, r: r[:, None] * (g_ - g_.mean(1, keepdim=True) - xh * (g_ * xh).mean(1, keepdim=True))
+    mine = [inbwd(tok(gq, Nc), xc, rc), inbwd(tok(gk, Ns), xs, rs) + tok(gv, Ns), inbwd(tok(dxhat, Nc), xx, rx), dW, db, dWo, dbo]
+    for name, a_, b_ in zip("fc fs fcs W b Wo bo".split(), mine, ref):
+        assert float((a_ - b_).abs().max()) <= 1e-10 * max(1.0, float(b_.abs().max())), name
