@@ -238,6 +238,7 @@ def test_backward_formulas_of_the_kernels_match_autograd():
     quantities they use (V~ = V - mu_V, O' = [M~ | E~], dO' = [g - 2 M~ dVar | dVar], delta = dO'.O', dS = A (dA - delta),
     dV = dV'_m + 2 V~ dV'_e, instance-norm backward) -- against torch.autograd of the reference's formulation
     (adaDecoder.py:162-206).  Pins the claim that the centring needs no correction terms."""
+    import torch
     torch.manual_seed(0)
     B, H, d, Nc, Ns = 2, 2, 8, 12, 9
     C = H * d
