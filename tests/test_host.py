@@ -189,3 +189,20 @@ def test_backward_abi_argument_checks(lib):
     assert lib.mhada_colsum(None, 0, 4, 4, None, 0, None, None) == -1
     assert lib.mhada_gemm_splitk_workspace(512, 512, 8192) > 0 and lib.mhada_gemm_splitk_workspace(512, 500, 8192) == 0
     assert lib.mhada_gemm_bf16_splitk(None, 64, None, 64, 1, 128, 64, None, 128, None, 0, None) == -1
+
+
+def test_graph_wrapper_and_training_switches_reject_bad_arguments_on_the_host():
+    from mhada_style_transfer_b200.graphs import GraphedStyleTransfer
+    x = torch.zeros(1, 3, 16, 16)
+    with pytest.raises(ValueError, match="style mode"):
+        GraphedStyleTransfer(None, None, None, x, x, style="sometimes")
+    with pytest.raises(RuntimeError, match="CUDA"):
+        GraphedStyleTransfer(None, None, None, x, x)                      # no CPU path
+    d = M.Decoder()
+    assert d.train_impl in ("auto", "kernels", "torch") and d.precision == "auto"
+    from mhada_style_transfer_b200.network import set_precision
+    set_precision(M.AdaAttnTransformerMultiHead(), "bf16")               # reaches the decoder too
+    t = set_precision(M.AdaAttnTransformerMultiHead(), "bf16")
+    assert t.decoder.precision == "bf16" and all(l.precision == "bf16" for l in t.adaAttnHead)
+    with pytest.raises(ValueError):
+        set_precision(t, "fp16")
